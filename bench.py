@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- objects/s of the per-object pose-generation hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm (libgenpose_b200.so)
+    python bench.py --impl reference --gpus N ...             # reference's CPU path on the host cores
+
+A "step" is one pass of the full path (PointNet++ encoder x2 -> RK45 ScoreNet sampling, 50
+hypotheses/object -> EnergyNet scoring -> aggregation -> ScaleNet) over one batch of synthetic
+objects.  Workload = BASELINE.json configs[1]: 64 objects x 50 hypotheses per GPU, T0 = 0.55
+(scripts/eval_single.sh), random-init weights, synthetic clouds.  Multi-GPU: objects are sharded
+by rank, no collective on the data path, weak scaling (64 objects per GPU).
+
+`value`   : objects/s with the clouds already resident in HBM (CUDA events, max over ranks).
+`e2e`     : objects/s through the same public call with HOST (pinned) clouds: H2D copy of the clouds
+            and D2H read of the poses + lengths inside the timed region.
+`roofline`: the dominant kernel of this library (the fused ScoreNet/RK45 integrator), algorithmic FLOPs
+            (hoisted figure) / CUDA-event duration, against MEASURED_PEAKS.json.
+`cpu_baseline`: the oracle port (oracle/pose_oracle.py: the reference's torch-CPU + scipy path,
+            restated) timed on this box's host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "objects_per_sec_50hyp"
+UNIT = "objects/s"
+OBJECTS_PER_GPU = 64
+REPEAT = 50
+T0 = 0.55
+NUM_POINTS = 1024
+L2_FLUSH_BYTES = 256 << 20
+
+# algorithmic work of the ScoreNet RHS after hoisting, in FLOP
+ROW_EVAL_FLOP = 2 * 266752
+STAGE_SHARED_FLOP = 2 * 114688
+OBJECT_ONCE_FLOP = 2 * 786432
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    ap.add_argument("--objects", type=int, default=OBJECTS_PER_GPU, help="objects per GPU per step")
+    ap.add_argument("--mlp_mode", type=str, default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--cpu_sample_objects", type=int, default=8)
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.thread = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_step(state, n_objects):
+    """One bounded sample of the workload on the CPU: n_objects x 50 hypotheses through the oracle
+    port of the reference path (encoder x2, scipy RK45 sampler, energy, aggregation with sklearn
+    DBSCAN, ScaleNet).  Returns seconds."""
+    import torch
+    from oracle import pose_oracle as po
+    pts, center = state["pts"][:n_objects], state["center"][:n_objects]
+    torch.manual_seed(1)
+    noise = po.ve_prior((n_objects * REPEAT, 9), T=T0)
+    t0 = time.perf_counter()
+    po.full_pipeline(state["score_sd"], state["energy_sd"], state["scale_sd"], pts, center, noise,
+                     repeat_num=REPEAT, T0=T0, integrator="scipy")
+    return time.perf_counter() - t0
+
+
+def cpu_state(n_objects):
+    import torch
+    from genpose2_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    pts, center = synthetic.make_point_clouds(max(n_objects, 1), NUM_POINTS, seed=0)
+    return dict(pts=pts, center=center, score_sd=synthetic.random_gfobjectpose_state_dict(100),
+                energy_sd=synthetic.random_gfobjectpose_state_dict(200),
+                scale_sd=synthetic.random_scalenet_state_dict(300))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU reference; other ranks exit without work
+    import torch
+    n = args.cpu_sample_objects
+    st = cpu_state(n)
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_step(st, n)
+    times = [cpu_reference_step(st, n) for _ in range(args.steps)]
+    total = sum(times)
+    value = n * len(times) / total
+    cores = torch.get_num_threads()
+    sample = f"{n} objects x {REPEAT} hypotheses per step (full path incl. both encoders), {len(times)} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C2: {OBJECTS_PER_GPU} objects x {REPEAT} hypotheses, full path, T0={T0}",
+                   "sampled_objects_per_step": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from genpose2_b200 import _lib, samplers, synthetic
+    from genpose2_b200.pipeline import PosePipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (B200 arm) needs a GPU; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    B = args.objects
+    pipe = PosePipeline(device=f"cuda:{local_rank}", mlp_mode=args.mlp_mode).load_synthetic_weights((100, 200, 300))
+    # every rank owns its own contiguous slice of the global object list (weak scaling)
+    pts_all, center_all = synthetic.make_point_clouds(B * world, NUM_POINTS, seed=0)
+    pts_h = pts_all[rank * B:(rank + 1) * B].contiguous().pin_memory()
+    center_h = center_all[rank * B:(rank + 1) * B].contiguous().pin_memory()
+    pts_d, center_d = pts_h.to(dev), center_h.to(dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    out_pose_h = torch.empty((B, 4, 4), dtype=torch.float32).pin_memory()
+    out_len_h = torch.empty((B, 3), dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        return pipe({"pts": pts_d, "pts_center": center_d}, repeat_num=REPEAT, T0=T0)
+
+    def step_e2e():
+        p = pts_h.to(dev, non_blocking=True)
+        c = center_h.to(dev, non_blocking=True)
+        pose, length = pipe({"pts": p, "pts_center": c}, repeat_num=REPEAT, T0=T0)
+        out_pose_h.copy_(pose, non_blocking=True)
+        out_len_h.copy_(length, non_blocking=True)
+        return pose, length
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, sampler=None):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        if sampler:
+            sampler.start()
+        for s, e in evs:
+            flush.zero_()  # L2 flush between timed iterations (inputs are far smaller than the 126 MB L2)
+            s.record()
+            fn()
+            e.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        barrier()
+        total_ms = sum(s.elapsed_time(e) for s, e in evs)
+        if world > 1:
+            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms, clocks
+
+    torch.manual_seed(1234 + rank)
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    _lib.reset_launch_count()
+    total_ms, clocks = timed(step_resident, args.steps, ClockSampler(local_rank))
+    launches = _lib.launch_count()
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    for _ in range(2):
+        step_e2e()
+    e2e_ms, _ = timed(step_e2e, args.steps)
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    h2d = pts_h.numel() * 4 + center_h.numel() * 4
+    d2h = out_pose_h.numel() * 4 + out_len_h.numel() * 4
+
+    # ---- roofline of the dominant kernel of this library: the fused ScoreNet / RK45 integrator ----
+    peaks = measured_peaks()
+    score_net = pipe.score_agent.net
+    feat = pipe.score_agent.net(dict(pts=pts_d, pts_center=center_d), mode="pts_feature")
+    N = B * REPEAT
+    sdata = {"pts": torch.empty(N, 0), "pts_center": center_d.unsqueeze(1).expand(B, REPEAT, 3).reshape(N, 3).contiguous(),
+             "_gp_pts_feat_obj": feat, "_gp_rows_per_object": REPEAT}
+    torch.manual_seed(99)
+    noise = score_net.prior_fn((N, 9), T=T0)
+    prior = lambda shape, T=1.0: noise
+
+    def sampler_only():
+        return samplers.cond_ode_sampler(score_net, sdata, prior, score_net.sde_fn, device=dev, eps=1e-5, T=T0,
+                                         pose_mode="rot_matrix", return_trajectory=False)
+
+    for _ in range(3):
+        sampler_only()
+    torch.cuda.synchronize()
+    k_ms = []
+    for _ in range(max(5, min(args.steps, 20))):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        sampler_only()  # projection kernel (tiny) + the persistent integrator
+        e.record()
+        torch.cuda.synchronize()
+        k_ms.append(s.elapsed_time(e))
+    st = samplers.ode_stats()
+    nfev_total = st["nfev"] + 1  # + the denoise evaluation
+    flop = N * nfev_total * ROW_EVAL_FLOP + nfev_total * STAGE_SHARED_FLOP + B * OBJECT_ONCE_FLOP
+    k_med = sorted(k_ms)[len(k_ms) // 2]
+    achieved = flop / (k_med * 1e-3) / 1e12
+    peak = peaks["bf16_tflops_sustained"]
+    ffma_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # 148 SMs x 128 FP32 lanes x 2 FLOP x max SM clock
+    roofline = {
+        "bound": "tensor", "kernel": "ode_rk45_kernel (fused ScoreNet RHS + Dormand-Prince controller)",
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        "peak_source": f"{peaks['source']} bf16 dense, sustained",
+        "mlp_mode": args.mlp_mode, "kernel_ms": k_med, "nfev": nfev_total, "accepted": st["accepted"],
+        "rejected": st["rejected"], "algorithmic_flop_per_launch": flop,
+        "hyp_evals_per_s": N * nfev_total / (k_med * 1e-3),
+        "note": ("fp32 mode evaluates the MLPs with FFMA (no tensor cores): also quoted against the FP32 FFMA peak"
+                 if args.mlp_mode == "fp32" else "bf16 tcgen05 path"),
+        "ffma_peak_tflops": ffma_peak, "frac_of_ffma_peak": achieved / ffma_peak,
+    }
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n = args.cpu_sample_objects
+        stt = cpu_state(n)
+        cpu_reference_step(stt, min(n, 2))  # warm-up
+        reps = [cpu_reference_step(stt, n) for _ in range(3)]
+        med = sorted(reps)[1]
+        cpu_baseline = {"value": n / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"{n} objects x {REPEAT} hypotheses, full path incl. both encoders, median of 3 "
+                                  f"(oracle port: torch-CPU nets + scipy RK45 + sklearn DBSCAN)",
+                        "os_cpu_count": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.mlp_mode == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": f"C2: {B} objects x {REPEAT} hypotheses per GPU, full path "
+                                   f"(encoder x2 + RK45 ScoreNet sampling + EnergyNet + aggregation + ScaleNet), "
+                                   f"T0={T0}, rtol=atol=1e-5, {NUM_POINTS} pts/object, random-init weights",
+                       "objects_per_gpu": B, "hypotheses": REPEAT, "T0": T0, "l2": "flushed between timed steps "
+                       f"({L2_FLUSH_BYTES >> 20} MiB memset)", "parallelism": f"object-sharded x{world}, no collective on the data path"},
+            "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                      "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,446 @@
+// PointNet++ set-abstraction integer ops for sm_100a: farthest-point sampling, ball query,
+// gather and grouping.  Indices are bit-exact with the reference extension
+// (networks/pts_encoder/pointnet2_utils/pointnet2/src/{sampling,ball_query,group_points}_gpu.cu).
+//
+// Design (not a port): the reference keeps FPS distances in a global `temp` array, re-reads
+// xyz + temp from L1/L2 every iteration and reduces through a log2(BS)-deep shared-memory tree
+// with a barrier per level.  Here every point's coordinates and running distance live in
+// registers, the cloud is staged once into shared memory with vectorised loads, and the argmax
+// is two redux.sync instructions per warp plus ONE block barrier per sampled point.  The
+// reference's tie-break (ties are common: clouds are tiled with duplicates) is a property of its
+// reduction tree, so it is reproduced as an explicit total order instead of by mimicking the tree.
+#include "common.cuh"
+
+namespace gp {
+
+// ------------------------------------------------------------------------------------------
+// FPS
+// ------------------------------------------------------------------------------------------
+// Reference semantics (sampling_gpu.cu:93-209): thread `tid` of BS scans k = tid, tid+BS, ...
+// keeping the FIRST strict maximum; the tree then prefers the lower slot at every halving level.
+// The overall winner among equal distances is therefore the point with the smallest
+//      ord(k) = bitrev_{log2 BS}(k mod BS) * 2^SH + (k div BS)
+// (SURVEY.md Appendix A).  We maximise the 64-bit key (float_bits(dist), ~ord).
+struct FpsOrder {
+    int logBS;   // log2 of the reference block size
+    int SH;      // bits reserved for k div BS
+    __device__ __forceinline__ unsigned inv_ord(int k) const {
+        unsigned low = (unsigned)k & ((1u << logBS) - 1u);
+        unsigned rev = logBS ? (__brev(low) >> (32 - logBS)) : 0u;
+        unsigned ord = (rev << SH) | ((unsigned)k >> logBS);
+        return 0xFFFFFFFFu - ord;
+    }
+    __device__ __forceinline__ int index_of(unsigned inv) const {
+        unsigned ord = 0xFFFFFFFFu - inv;
+        unsigned rev = ord >> SH;
+        unsigned q = ord & ((1u << SH) - 1u);
+        unsigned low = logBS ? (__brev(rev) >> (32 - logBS)) : 0u;
+        return (int)((q << logBS) | low);
+    }
+};
+
+template <int NWARPS, int PPT, bool COORDS_IN_REGS>
+__global__ void __launch_bounds__(NWARPS * 32)
+fps_kernel(const float *__restrict__ xyz, int N, int m, FpsOrder order, int *__restrict__ idx,
+           float *__restrict__ new_xyz) {
+    constexpr int T = NWARPS * 32;
+    extern __shared__ __align__(16) float s_raw[];  // [3*N] AoS copy of this object's cloud
+    __shared__ uint2 s_part[2][32];
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const float *cloud = xyz + (size_t)b * N * 3;
+    int *out = idx + (size_t)b * m;
+    float *out_xyz = new_xyz ? new_xyz + (size_t)b * m * 3 : nullptr;
+
+    // stage the cloud: 16-byte loads when the object's base is aligned (N % 4 == 0)
+    const int nfl = N * 3;
+    if ((((size_t)b * nfl) & 3) == 0 && (nfl & 3) == 0 && ((uintptr_t)xyz & 15) == 0) {
+        const float4 *src = reinterpret_cast<const float4 *>(cloud);
+        float4 *dst = reinterpret_cast<float4 *>(s_raw);
+        for (int i = tid; i < nfl / 4; i += T) dst[i] = __ldg(src + i);
+    } else {
+        for (int i = tid; i < nfl; i += T) s_raw[i] = __ldg(cloud + i);
+    }
+    __syncthreads();
+
+    float px[COORDS_IN_REGS ? PPT : 1], py[COORDS_IN_REGS ? PPT : 1], pz[COORDS_IN_REGS ? PPT : 1];
+    float dist[PPT];
+    unsigned inv[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const int k = tid + i * T;
+        const bool valid = k < N;
+        if (COORDS_IN_REGS) {
+            px[i] = valid ? s_raw[3 * k + 0] : 0.f;
+            py[i] = valid ? s_raw[3 * k + 1] : 0.f;
+            pz[i] = valid ? s_raw[3 * k + 2] : 0.f;
+        }
+        dist[i] = valid ? 1e10f : 0.f;  // pointnet2_utils.py:32-34 fills temp with 1e10
+        inv[i] = valid ? order.inv_ord(k) : 0u;  // padded lanes can never win: key (0, 0)
+    }
+
+    int old = 0;
+    if (tid == 0) {
+        out[0] = 0;
+        if (out_xyz) {
+            out_xyz[0] = s_raw[0];
+            out_xyz[1] = s_raw[1];
+            out_xyz[2] = s_raw[2];
+        }
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int j = 1; j < m; ++j) {
+        const float x1 = s_raw[3 * old + 0], y1 = s_raw[3 * old + 1], z1 = s_raw[3 * old + 2];
+        unsigned best_hi = 0u, best_lo = 0u;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            float x2, y2, z2;
+            if (COORDS_IN_REGS) {
+                x2 = px[i]; y2 = py[i]; z2 = pz[i];
+            } else {
+                const int k = min(tid + i * T, N - 1);
+                x2 = s_raw[3 * k + 0]; y2 = s_raw[3 * k + 1]; z2 = s_raw[3 * k + 2];
+            }
+            const float d = sqdist_ref(x2 - x1, y2 - y1, z2 - z1);
+            const float d2 = fminf(d, dist[i]);
+            dist[i] = d2;
+            const unsigned hi = __float_as_uint(d2);
+            const bool gt = (hi > best_hi) || (hi == best_hi && inv[i] > best_lo);
+            best_hi = gt ? hi : best_hi;
+            best_lo = gt ? inv[i] : best_lo;
+        }
+        unsigned whi = __reduce_max_sync(0xffffffffu, best_hi);
+        unsigned wlo = __reduce_max_sync(0xffffffffu, best_hi == whi ? best_lo : 0u);
+        if (NWARPS > 1) {
+            if (lane == 0) s_part[j & 1][warp] = make_uint2(whi, wlo);
+            __syncthreads();
+            uint2 p = lane < NWARPS ? s_part[j & 1][lane] : make_uint2(0u, 0u);
+            whi = __reduce_max_sync(0xffffffffu, p.x);
+            wlo = __reduce_max_sync(0xffffffffu, p.x == whi ? p.y : 0u);
+        }
+        old = order.index_of(wlo);
+        if (tid == 0) {
+            out[j] = old;
+            if (out_xyz) {
+                out_xyz[3 * j + 0] = s_raw[3 * old + 0];
+                out_xyz[3 * j + 1] = s_raw[3 * old + 1];
+                out_xyz[3 * j + 2] = s_raw[3 * old + 2];
+            }
+        }
+    }
+}
+
+static int ref_block_size(int n) {  // cuda_utils.h:10-14 opt_n_threads
+    int p = 0;
+    while ((2 << p) <= n) ++p;  // largest power of two <= n
+    int bs = 1 << p;
+    return bs > 1024 ? 1024 : bs;
+}
+
+template <int NWARPS, int PPT, bool REGS>
+static int launch_fps(const float *xyz, int B, int N, int m, FpsOrder order, int *idx,
+                      float *new_xyz, cudaStream_t st) {
+    size_t smem = (size_t)N * 3 * sizeof(float);
+    smem = (smem + 15) & ~(size_t)15;
+    auto kern = fps_kernel<NWARPS, PPT, REGS>;
+    if (smem > 48 * 1024) GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B, NWARPS * 32, smem, st>>>(xyz, N, m, order, idx, new_xyz);
+    GP_CHECK_LAUNCH("gp_fps");
+    return GP_OK;
+}
+
+}  // namespace gp
+
+using namespace gp;
+
+extern "C" int gp_fps(const float *xyz, int B, int N, int m, int32_t *idx, float *new_xyz,
+                      gp_stream_t s) {
+    GP_REQUIRE(xyz && idx, "gp_fps: null pointer");
+    GP_REQUIRE(B >= 0 && N >= 1 && m >= 0, "gp_fps: bad sizes B=%d N=%d m=%d", B, N, m);
+    if (B == 0 || m == 0) return GP_OK;
+    if (N > 16384) {
+        set_error("gp_fps: N=%d > 16384 is not supported (cloud must fit in shared memory)", N);
+        return GP_ERR_UNSUPPORTED;
+    }
+    const int BS = ref_block_size(N);
+    FpsOrder order;
+    order.logBS = 0;
+    while ((1 << order.logBS) < BS) ++order.logBS;
+    const int J = (N + BS - 1) / BS;
+    order.SH = 0;
+    while ((1 << order.SH) < J) ++order.SH;
+    cudaStream_t st = as_stream(s);
+    if (N <= 32) return launch_fps<1, 1, true>(xyz, B, N, m, order, idx, new_xyz, st);
+    if (N <= 64) return launch_fps<1, 2, true>(xyz, B, N, m, order, idx, new_xyz, st);
+    if (N <= 128) return launch_fps<1, 4, true>(xyz, B, N, m, order, idx, new_xyz, st);
+    if (N <= 256) return launch_fps<2, 4, true>(xyz, B, N, m, order, idx, new_xyz, st);
+    if (N <= 512) return launch_fps<4, 4, true>(xyz, B, N, m, order, idx, new_xyz, st);
+    if (N <= 1024) return launch_fps<8, 4, true>(xyz, B, N, m, order, idx, new_xyz, st);
+    if (N <= 2048) return launch_fps<16, 4, true>(xyz, B, N, m, order, idx, new_xyz, st);
+    if (N <= 4096) return launch_fps<32, 4, true>(xyz, B, N, m, order, idx, new_xyz, st);
+    if (N <= 8192) return launch_fps<32, 8, false>(xyz, B, N, m, order, idx, new_xyz, st);
+    return launch_fps<32, 16, false>(xyz, B, N, m, order, idx, new_xyz, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// gather:  out[b,c,j] = points[b,c,idx[b,j]]     (sampling_gpu.cu:8-24)
+// ------------------------------------------------------------------------------------------
+namespace gp {
+__global__ void gather_kernel(const float *__restrict__ points, const int *__restrict__ idx, int C,
+                              int N, int m, float *__restrict__ out) {
+    const int b = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const int id = __ldg(idx + (size_t)b * m + j);
+    const float *src = points + (size_t)b * C * N + id;
+    float *dst = out + (size_t)b * C * m + j;
+    for (int c = 0; c < C; ++c) dst[(size_t)c * m] = __ldg(src + (size_t)c * N);
+}
+}  // namespace gp
+
+extern "C" int gp_gather(const float *points, const int32_t *idx, int B, int C, int N, int m,
+                         float *out, gp_stream_t s) {
+    GP_REQUIRE(points && idx && out, "gp_gather: null pointer");
+    GP_REQUIRE(B >= 0 && C >= 0 && N >= 1 && m >= 0, "gp_gather: bad sizes");
+    if (B == 0 || C == 0 || m == 0) return GP_OK;
+    GP_REQUIRE(B <= 65535, "gp_gather: B=%d > 65535", B);
+    dim3 grid((m + 127) / 128, B);
+    gather_kernel<<<grid, 128, 0, as_stream(s)>>>(points, idx, C, N, m, out);
+    GP_CHECK_LAUNCH("gp_gather");
+    return GP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// ball query (one or two radii per scan)       (ball_query_gpu.cu:9-45)
+// ------------------------------------------------------------------------------------------
+namespace gp {
+
+constexpr int BQ_WARPS = 8;
+constexpr int BQ_CPW = 8;                       // centres per warp
+constexpr int BQ_CPB = BQ_WARPS * BQ_CPW;       // centres per block
+constexpr int BQ_CHUNK = 4096;                  // points staged per pass (48 KB, SoA)
+
+template <bool TWO>
+__global__ void __launch_bounds__(BQ_WARPS * 32)
+ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz, int N, int M,
+                  float r0sq, int ns0, int *__restrict__ idx0, float r1sq, int ns1,
+                  int *__restrict__ idx1) {
+    extern __shared__ __align__(16) float s_pts[];  // sx[CH] sy[CH] sz[CH]
+    const int CH = min(N, BQ_CHUNK);
+    float *sx = s_pts, *sy = s_pts + CH, *sz = s_pts + 2 * CH;
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *cloud = xyz + (size_t)b * N * 3;
+    const unsigned lt = (1u << lane) - 1u;
+
+    const int c_first = blockIdx.x * BQ_CPB + warp * BQ_CPW;
+    float cx[BQ_CPW], cy[BQ_CPW], cz[BQ_CPW];
+    int cnt0[BQ_CPW], first0[BQ_CPW], cnt1[BQ_CPW], first1[BQ_CPW];
+#pragma unroll
+    for (int c = 0; c < BQ_CPW; ++c) {
+        const int i = min(c_first + c, M - 1);
+        const float *p = new_xyz + ((size_t)b * M + i) * 3;
+        cx[c] = __ldg(p + 0); cy[c] = __ldg(p + 1); cz[c] = __ldg(p + 2);
+        cnt0[c] = cnt1[c] = 0;
+        first0[c] = first1[c] = 0;
+    }
+
+    for (int base = 0; base < N; base += CH) {
+        const int n_here = min(CH, N - base);
+        if (base) __syncthreads();
+        // stage chunk: coalesced AoS read -> SoA shared
+        for (int i = tid; i < n_here * 3; i += BQ_WARPS * 32) {
+            const float v = __ldg(cloud + (size_t)base * 3 + i);
+            const int k = i / 3, a = i - 3 * k;
+            (a == 0 ? sx : (a == 1 ? sy : sz))[k] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < BQ_CPW; ++c) {
+            if (c_first + c >= M) break;
+            const bool need0 = cnt0[c] < ns0;
+            const bool need1 = TWO && cnt1[c] < ns1;
+            if (!need0 && !need1) continue;
+            int *o0 = idx0 + ((size_t)b * M + c_first + c) * ns0;
+            int *o1 = TWO ? idx1 + ((size_t)b * M + c_first + c) * ns1 : nullptr;
+            int n0 = cnt0[c], n1 = cnt1[c];
+            for (int k0 = 0; k0 < n_here; k0 += 32) {
+                const int k = k0 + lane;
+                const bool valid = k < n_here;
+                const int kk = valid ? k : 0;
+                // reference: (new_x - x)^2 + (new_y - y)^2 + (new_z - z)^2, fma pattern in sqdist_ref
+                const float d2 = sqdist_ref(cx[c] - sx[kk], cy[c] - sy[kk], cz[c] - sz[kk]);
+                const unsigned m0 = __ballot_sync(0xffffffffu, valid && d2 < r0sq);
+                if (n0 < ns0 && m0) {
+                    if (n0 == 0) first0[c] = base + k0 + __ffs(m0) - 1;
+                    const int pos = n0 + __popc(m0 & lt);
+                    if (((m0 >> lane) & 1u) && pos < ns0) o0[pos] = base + k;
+                    n0 += __popc(m0);
+                }
+                if (TWO) {
+                    const unsigned m1 = __ballot_sync(0xffffffffu, valid && d2 < r1sq);
+                    if (n1 < ns1 && m1) {
+                        if (n1 == 0) first1[c] = base + k0 + __ffs(m1) - 1;
+                        const int pos = n1 + __popc(m1 & lt);
+                        if (((m1 >> lane) & 1u) && pos < ns1) o1[pos] = base + k;
+                        n1 += __popc(m1);
+                    }
+                }
+                if (n0 >= ns0 && (!TWO || n1 >= ns1)) break;
+            }
+            cnt0[c] = n0;
+            cnt1[c] = n1;
+        }
+    }
+    // back-fill: first hit replicated into the unused slots; all zeros if the ball is empty
+#pragma unroll
+    for (int c = 0; c < BQ_CPW; ++c) {
+        if (c_first + c >= M) break;
+        int *o0 = idx0 + ((size_t)b * M + c_first + c) * ns0;
+        for (int sl = min(cnt0[c], ns0) + lane; sl < ns0; sl += 32) o0[sl] = cnt0[c] ? first0[c] : 0;
+        if (TWO) {
+            int *o1 = idx1 + ((size_t)b * M + c_first + c) * ns1;
+            for (int sl = min(cnt1[c], ns1) + lane; sl < ns1; sl += 32) o1[sl] = cnt1[c] ? first1[c] : 0;
+        }
+    }
+}
+
+template <bool TWO>
+static int launch_bq(const float *new_xyz, const float *xyz, int B, int N, int M, float r0,
+                     int ns0, int *idx0, float r1, int ns1, int *idx1, cudaStream_t st) {
+    const int CH = N < BQ_CHUNK ? N : BQ_CHUNK;
+    size_t smem = (size_t)CH * 3 * sizeof(float);
+    dim3 grid((M + BQ_CPB - 1) / BQ_CPB, B);
+    // radius2 = radius * radius in float32 (ball_query_gpu.cu:23)
+    const float r0sq = r0 * r0, r1sq = r1 * r1;
+    ball_query_kernel<TWO><<<grid, BQ_WARPS * 32, smem, st>>>(new_xyz, xyz, N, M, r0sq, ns0, idx0,
+                                                              r1sq, ns1, idx1);
+    GP_CHECK_LAUNCH("gp_ball_query");
+    return GP_OK;
+}
+}  // namespace gp
+
+extern "C" int gp_ball_query(const float *new_xyz, const float *xyz, int B, int N, int M,
+                             float radius, int nsample, int32_t *idx, gp_stream_t s) {
+    GP_REQUIRE(new_xyz && xyz && idx, "gp_ball_query: null pointer");
+    GP_REQUIRE(B >= 0 && N >= 1 && M >= 0 && nsample >= 1, "gp_ball_query: bad sizes");
+    if (B == 0 || M == 0) return GP_OK;
+    GP_REQUIRE(B <= 65535, "gp_ball_query: B=%d > 65535", B);
+    return launch_bq<false>(new_xyz, xyz, B, N, M, radius, nsample, idx, 0.f, 0, nullptr, as_stream(s));
+}
+
+extern "C" int gp_ball_query2(const float *new_xyz, const float *xyz, int B, int N, int M,
+                              float radius0, int nsample0, int32_t *idx0, float radius1,
+                              int nsample1, int32_t *idx1, gp_stream_t s) {
+    GP_REQUIRE(new_xyz && xyz && idx0 && idx1, "gp_ball_query2: null pointer");
+    GP_REQUIRE(B >= 0 && N >= 1 && M >= 0 && nsample0 >= 1 && nsample1 >= 1, "gp_ball_query2: bad sizes");
+    if (B == 0 || M == 0) return GP_OK;
+    GP_REQUIRE(B <= 65535, "gp_ball_query2: B=%d > 65535", B);
+    return launch_bq<true>(new_xyz, xyz, B, N, M, radius0, nsample0, idx0, radius1, nsample1, idx1,
+                           as_stream(s));
+}
+
+// ------------------------------------------------------------------------------------------
+// grouping: out[b,c,p,s] = points[b,c,idx[b,p,s]]          (group_points_gpu.cu:47-66)
+// and the fused QueryAndGroup tail (pointnet2_utils.py:279-296)
+// ------------------------------------------------------------------------------------------
+namespace gp {
+
+constexpr int GR_CC = 8;  // channels per thread (amortises the idx load)
+
+// One thread owns 4 consecutive (p,s) slots (16-byte store) for GR_CC channels.
+// FUSED: channel 0..2 = xyz[idx] - new_xyz, channel 3.. = features[idx].
+template <bool FUSED>
+__global__ void __launch_bounds__(256)
+group_kernel(const float *__restrict__ points, const float *__restrict__ xyz,
+             const float *__restrict__ new_xyz, const int *__restrict__ idx, int C, int N, int M,
+             int ns, float *__restrict__ out) {
+    const int b = blockIdx.z;
+    const int total = M * ns;  // multiple of 4 (checked on the host)
+    const int q4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (q4 >= total) return;
+    const int4 id = __ldg(reinterpret_cast<const int4 *>(idx + (size_t)b * total + q4));
+    const int Ctot = FUSED ? C + 3 : C;
+    const int c0 = blockIdx.y * GR_CC;
+    const int c1 = min(c0 + GR_CC, Ctot);
+    for (int c = c0; c < c1; ++c) {
+        float4 v;
+        if (FUSED && c < 3) {
+            const float *px = xyz + (size_t)b * N * 3 + c;
+            // ns % 4 == 0 here, so the four slots share one centre
+            const float ctr = __ldg(new_xyz + ((size_t)b * M + q4 / ns) * 3 + c);
+            v.x = __ldg(px + 3 * id.x) - ctr;
+            v.y = __ldg(px + 3 * id.y) - ctr;
+            v.z = __ldg(px + 3 * id.z) - ctr;
+            v.w = __ldg(px + 3 * id.w) - ctr;
+        } else {
+            const float *src = points + ((size_t)b * C + (FUSED ? c - 3 : c)) * N;
+            v.x = __ldg(src + id.x);
+            v.y = __ldg(src + id.y);
+            v.z = __ldg(src + id.z);
+            v.w = __ldg(src + id.w);
+        }
+        *reinterpret_cast<float4 *>(out + ((size_t)b * Ctot + c) * total + q4) = v;
+    }
+}
+
+// scalar fallback for M*ns (or ns, fused) not divisible by 4
+template <bool FUSED>
+__global__ void group_kernel_scalar(const float *__restrict__ points, const float *__restrict__ xyz,
+                                    const float *__restrict__ new_xyz, const int *__restrict__ idx,
+                                    int C, int N, int M, int ns, float *__restrict__ out) {
+    const int b = blockIdx.z;
+    const int total = M * ns;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= total) return;
+    const int id = __ldg(idx + (size_t)b * total + q);
+    const int Ctot = FUSED ? C + 3 : C;
+    const int c0 = blockIdx.y * GR_CC, c1 = min(c0 + GR_CC, Ctot);
+    for (int c = c0; c < c1; ++c) {
+        float v;
+        if (FUSED && c < 3)
+            v = __ldg(xyz + ((size_t)b * N + id) * 3 + c) - __ldg(new_xyz + ((size_t)b * M + q / ns) * 3 + c);
+        else
+            v = __ldg(points + ((size_t)b * C + (FUSED ? c - 3 : c)) * N + id);
+        out[((size_t)b * Ctot + c) * total + q] = v;
+    }
+}
+
+template <bool FUSED>
+static int launch_group(const float *points, const float *xyz, const float *new_xyz, const int *idx,
+                        int B, int C, int N, int M, int ns, float *out, cudaStream_t st) {
+    const int Ctot = FUSED ? C + 3 : C;
+    const int total = M * ns;
+    const bool vec = (ns % 4 == 0) && (((uintptr_t)idx & 15) == 0) && (((uintptr_t)out & 15) == 0);
+    if (vec) {
+        dim3 grid((total / 4 + 255) / 256, (Ctot + GR_CC - 1) / GR_CC, B);
+        group_kernel<FUSED><<<grid, 256, 0, st>>>(points, xyz, new_xyz, idx, C, N, M, ns, out);
+    } else {
+        dim3 grid((total + 255) / 256, (Ctot + GR_CC - 1) / GR_CC, B);
+        group_kernel_scalar<FUSED><<<grid, 256, 0, st>>>(points, xyz, new_xyz, idx, C, N, M, ns, out);
+    }
+    GP_CHECK_LAUNCH(FUSED ? "gp_query_group" : "gp_group");
+    return GP_OK;
+}
+}  // namespace gp
+
+extern "C" int gp_group(const float *points, const int32_t *idx, int B, int C, int N, int M,
+                        int nsample, float *out, gp_stream_t s) {
+    GP_REQUIRE(points && idx && out, "gp_group: null pointer");
+    GP_REQUIRE(B >= 0 && C >= 0 && N >= 1 && M >= 0 && nsample >= 0, "gp_group: bad sizes");
+    if (B == 0 || C == 0 || M == 0 || nsample == 0) return GP_OK;
+    GP_REQUIRE(B <= 65535 && (C + GR_CC - 1) / GR_CC <= 65535, "gp_group: B or C too large");
+    return launch_group<false>(points, nullptr, nullptr, idx, B, C, N, M, nsample, out, as_stream(s));
+}
+
+extern "C" int gp_query_group(const float *xyz, const float *new_xyz, const float *features,
+                              const int32_t *idx, int B, int C, int N, int M, int nsample,
+                              float *out, gp_stream_t s) {
+    GP_REQUIRE(xyz && new_xyz && idx && out, "gp_query_group: null pointer");
+    GP_REQUIRE(C == 0 || features, "gp_query_group: features is NULL but C=%d", C);
+    GP_REQUIRE(B >= 0 && C >= 0 && N >= 1 && M >= 0 && nsample >= 0, "gp_query_group: bad sizes");
+    if (B == 0 || M == 0 || nsample == 0) return GP_OK;
+    GP_REQUIRE(B <= 65535, "gp_query_group: B too large");
+    return launch_group<true>(features, xyz, new_xyz, idx, B, C, N, M, nsample, out, as_stream(s));
+}

@@ -1,0 +1,861 @@
+// ScoreNet / EnergyNet trunk kernels (FP32 path): weight packing, per-object head projection,
+// single evaluation, energy scoring, the device-resident Dormand-Prince (scipy-RK45-faithful)
+// integrator fused with the ScoreNet RHS, and the fixed-step predictor-corrector sampler.
+#include <cooperative_groups.h>
+#include <cuda_bf16.h>
+
+#include "trunk.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace gp {
+
+// ------------------------------------------------------------------------------------------
+// packing
+// ------------------------------------------------------------------------------------------
+struct RawTrunk {
+    gp_trunk_params p;
+};
+
+__global__ void pack_trunk_kernel(RawTrunk raw, float *__restrict__ P) {
+    const gp_trunk_params &p = raw.p;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < TrunkLayout::END; i += stride) {
+        float v = 0.f;
+        if (i < TrunkLayout::B1) {  // W1T[k][n] = pose_w0[n][k]
+            const size_t k = i / 256, n = i % 256;
+            v = p.pose_w0[n * 9 + k];
+        } else if (i < TrunkLayout::W2T) {
+            v = p.pose_b0[i - TrunkLayout::B1];
+        } else if (i < TrunkLayout::B2) {  // W2T[k][n] = pose_w1[n][k]
+            const size_t j = i - TrunkLayout::W2T, k = j / 256, n = j % 256;
+            v = p.pose_w1[n * 256 + k];
+        } else if (i < TrunkLayout::FOUR) {
+            v = p.pose_b1[i - TrunkLayout::B2];
+        } else if (i < TrunkLayout::WTT) {
+            v = p.fourier_w[i - TrunkLayout::FOUR];
+        } else if (i < TrunkLayout::BT) {  // WTT[k][j] = t_w[j][k]
+            const size_t j = i - TrunkLayout::WTT, k = j / 128, n = j % 128;
+            v = p.t_w[n * 128 + k];
+        } else if (i < TrunkLayout::WHP) {
+            v = p.t_b[i - TrunkLayout::BT];
+        } else if (i < TrunkLayout::WHT) {  // WHP[k][h*256+j] = head_w0[h][j][1152+k]
+            const size_t j = i - TrunkLayout::WHP, k = j / 768, n = j % 768;
+            v = p.head_w0[n / 256][(n % 256) * 1408 + 1152 + k];
+        } else if (i < TrunkLayout::WHF) {  // WHT[k][h*256+j] = head_w0[h][j][1024+k]
+            const size_t j = i - TrunkLayout::WHT, k = j / 768, n = j % 768;
+            v = p.head_w0[n / 256][(n % 256) * 1408 + 1024 + k];
+        } else if (i < TrunkLayout::BH) {  // WHF[n][c] = head_w0[h][j][c]
+            const size_t j = i - TrunkLayout::WHF, n = j / 1024, c = j % 1024;
+            v = p.head_w0[n / 256][(n % 256) * 1408 + c];
+        } else if (i < TrunkLayout::WO) {
+            const size_t n = i - TrunkLayout::BH;
+            v = p.head_b0[n / 256][n % 256];
+        } else if (i < TrunkLayout::BO) {  // WO[n][o] = head_w1[h][o][j]
+            const size_t j = i - TrunkLayout::WO, n = j / 4, o = j % 4;
+            v = o < 3 ? p.head_w1[n / 256][o * 256 + (n % 256)] : 0.f;
+        } else if (i < TrunkLayout::F32_END) {
+            const size_t c = i - TrunkLayout::BO;
+            v = c < 9 ? p.head_b1[c / 3][c % 3] : 0.f;
+        } else if (i < TrunkLayout::WHP_BF16) {  // two bf16 per float slot: W2[n][k], K contiguous
+            const size_t e = (i - TrunkLayout::W2_BF16) * 2;
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(p.pose_w1[e], p.pose_w1[e + 1]);
+            v = *reinterpret_cast<float *>(&h2);
+        } else {  // WHP[n][k] = head_w0[h][j][1152+k]
+            const size_t e = (i - TrunkLayout::WHP_BF16) * 2, n = e / 256, k = e % 256;
+            const float *src = p.head_w0[n / 256] + (n % 256) * 1408 + 1152 + k;
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(src[0], src[1]);
+            v = *reinterpret_cast<float *>(&h2);
+        }
+        P[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-object projection  proj[b][n] = bh[n] + sum_c WHF[n][c] * pts_feat[b][c]
+// block: 8 warps; 8 objects x 64 outputs per block; one warp per output, lanes stride c.
+// ------------------------------------------------------------------------------------------
+constexpr int PJ_OBJ = 8, PJ_OUT = 64;
+__global__ void __launch_bounds__(256)
+project_kernel(const float *__restrict__ P, const float *__restrict__ feat, int B, float *__restrict__ proj) {
+    __shared__ __align__(16) float s_f[PJ_OBJ][1024];
+    const int b0 = blockIdx.y * PJ_OBJ, n0 = blockIdx.x * PJ_OUT;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < PJ_OBJ * 256; i += 256) {
+        const int o = i >> 8, c4 = i & 255;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b0 + o < B) v = __ldg(reinterpret_cast<const float4 *>(feat + (size_t)(b0 + o) * 1024) + c4);
+        reinterpret_cast<float4 *>(&s_f[o][0])[c4] = v;
+    }
+    __syncthreads();
+    for (int j = warp; j < PJ_OUT; j += 8) {
+        const int n = n0 + j;
+        const float4 *w = reinterpret_cast<const float4 *>(P + TrunkLayout::WHF + (size_t)n * 1024);
+        float acc[PJ_OBJ];
+#pragma unroll
+        for (int o = 0; o < PJ_OBJ; ++o) acc[o] = 0.f;
+#pragma unroll 2
+        for (int c4 = lane; c4 < 256; c4 += 32) {
+            const float4 wv = __ldg(w + c4);
+#pragma unroll
+            for (int o = 0; o < PJ_OBJ; ++o) {
+                const float4 f = reinterpret_cast<const float4 *>(&s_f[o][0])[c4];
+                acc[o] = fmaf(f.x, wv.x, acc[o]);
+                acc[o] = fmaf(f.y, wv.y, acc[o]);
+                acc[o] = fmaf(f.z, wv.z, acc[o]);
+                acc[o] = fmaf(f.w, wv.w, acc[o]);
+            }
+        }
+        const float bias = __ldg(P + TrunkLayout::BH + n);
+#pragma unroll
+        for (int o = 0; o < PJ_OBJ; ++o) {
+            float v = acc[o];
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+            if (lane == 0 && b0 + o < B) proj[(size_t)(b0 + o) * 768 + n] = v + bias;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// single evaluation / energy: one CTA per tile; rows may carry different t (handled by runs)
+// ------------------------------------------------------------------------------------------
+template <int RPT>
+struct EvalSmem {
+    TileSmem<RPT> tile;
+    float tq[768];
+    float four[128];
+    float tfeat[128];
+    float times[8];
+    float trow[4 * RPT];
+};
+
+// MODE 0: score = f/(std+1e-7) -> out [N,9];  MODE 1: energy [N,2] from f64 poses
+template <int RPT, int MODE>
+__global__ void __launch_bounds__(256, 1)
+eval_kernel(const float *__restrict__ P, const float *__restrict__ proj, const float *__restrict__ x,
+            const double *__restrict__ poses, const float *__restrict__ center,
+            const float *__restrict__ t, int N, int rpo, float *__restrict__ out) {
+    constexpr int RT = 4 * RPT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EvalSmem<RPT> &S = *reinterpret_cast<EvalSmem<RPT> *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int r0 = blockIdx.x * RT;
+    float w1col[9], b1v;
+    load_w1col(P, w1col, b1v);
+    for (int i = tid; i < RT * 12; i += 256) {
+        const int r = i / 12, c = i - 12 * r;
+        float v = 0.f;
+        if (r0 + r < N && c < 9) {
+            if (MODE == 0) {
+                v = x[(size_t)(r0 + r) * 9 + c];
+            } else {
+                // pose_samples.type_as(f32) then [:, -3:] -= pts_center (posenet_agent.py:668-694)
+                v = (float)poses[(size_t)(r0 + r) * 9 + c];
+                if (c >= 6) v = v - center[(size_t)(r0 + r) * 3 + (c - 6)];
+            }
+        }
+        S.tile.x[i] = v;
+    }
+    for (int r = tid; r < RT; r += 256) {
+        S.tile.obj[r] = (r0 + r < N) ? (r0 + r) / rpo : -1;
+        S.trow[r] = (r0 + r < N) ? t[r0 + r] : 0.f;
+    }
+    __syncthreads();
+    const int nrows = min(RT, N - r0);
+    int run0 = 0;
+    while (run0 < nrows) {  // maximal runs of equal t share one t-branch evaluation
+        const float tv = S.trow[run0];
+        int run1 = run0 + 1;
+        while (run1 < nrows && S.trow[run1] == tv) ++run1;
+        if (tid == 0) S.times[0] = tv;
+        __syncthreads();
+        compute_tq(P, S.times, 1, S.four, S.tfeat, S.tq);
+        tile_forward<RPT>(P, proj, S.tile, S.tq, w1col, b1v);
+        const float std = sigma_f32(tv);
+        if (MODE == 0) {
+            for (int i = tid; i < (run1 - run0) * 9; i += 256) {
+                const int r = run0 + i / 9, c = i % 9;
+                out[(size_t)(r0 + r) * 9 + c] = S.tile.out[0][r * 12 + c] / (std + 1e-7f);
+            }
+        } else {
+            for (int r = run0 + tid; r < run1; r += 256) {
+                float er = 0.f, et = 0.f;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) er += S.tile.x[r * 12 + c] * (S.tile.out[0][r * 12 + c] / std);
+#pragma unroll
+                for (int c = 6; c < 9; ++c) et += S.tile.x[r * 12 + c] * (S.tile.out[0][r * 12 + c] / std);
+                out[(size_t)(r0 + r) * 2 + 0] = er;
+                out[(size_t)(r0 + r) * 2 + 1] = et;
+            }
+        }
+        __syncthreads();
+        run0 = run1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Dormand-Prince 5(4) with scipy's controller, device resident.
+// ------------------------------------------------------------------------------------------
+__constant__ double c_C[6] = {0.0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0};
+__constant__ double c_A[6][5] = {
+    {0, 0, 0, 0, 0},
+    {1.0 / 5, 0, 0, 0, 0},
+    {3.0 / 40, 9.0 / 40, 0, 0, 0},
+    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0},
+    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0},
+    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656}};
+__constant__ double c_B[6] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
+__constant__ double c_E[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
+
+struct OdeArgs {
+    const float *P;
+    const float *proj;
+    const double *x0;
+    const float *center;
+    int N, rpo;
+    double T, eps, rtol, atol;
+    int denoise;
+    double *x_out;
+    double *traj;
+    int max_traj;
+    double *stats;
+    // workspace
+    double *y[2];     // current / candidate state   [N][9]
+    double *K[8];     // stage derivatives, K[0..6] + one spare for FSAL rotation  [N][9]
+    double *part;     // [2][3][ntiles] partial sums
+    int ntiles;
+};
+
+template <int RPT>
+struct OdeSmem {
+    TileSmem<RPT> tile;
+    float tq[6 * 768];
+    float four[6 * 128];
+    float tfeat[6 * 128];
+    float times[8];
+    double red[8];
+    double bc[4];
+};
+
+// sum part[0..ntiles) in a fixed order; identical in every CTA
+__device__ __forceinline__ double grid_total(const double *part, int ntiles, double *s_red) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < ntiles; i += blockDim.x) v += __ldcg(part + i);
+    return block_sum(v, s_red);
+}
+
+template <int RPT>
+__global__ void __launch_bounds__(256, 1) ode_rk45_kernel(OdeArgs a) {
+    constexpr int RT = 4 * RPT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    OdeSmem<RPT> &S = *reinterpret_cast<OdeSmem<RPT> *>(smem_raw);
+    cg::grid_group grid = cg::this_grid();
+    const int tid = threadIdx.x;
+    const float *P = a.P;
+    const int N = a.N;
+    const double n_total = (double)N * 9.0;
+    float w1col[9], b1v;
+    load_w1col(P, w1col, b1v);
+
+    const double direction = (a.eps > a.T) ? 1.0 : ((a.eps < a.T) ? -1.0 : 1.0);
+    const double t_bound = a.eps;
+    double *ycur = a.y[0], *ynew = a.y[1];
+    int kidx[7] = {0, 1, 2, 3, 4, 5, 6};  // K buffers: kidx[0] holds f(t, y) (FSAL)
+    int kspare = 7;
+    double nfev = 0, n_acc = 0, n_rej = 0;
+    int status = 0;
+    int pbuf = 0;
+
+    // One RHS evaluation over this CTA's tiles.
+    //  kind 0: x = y0 (init from a.x0, also writes ycur), K[kidx[0]] = f; partials d0^2, d1^2
+    //  kind 1: x = y + h0*dir*f0 -> f1 into K[kidx[1]]; partial d2^2 (numerator)
+    //  kind 2: the six stages of one RK step (needs S.tq for 6 times); partial err^2
+    //  kind 3: denoise + finalise into x_out
+    auto stage_eval = [&](int tile, int tq_slot, double t_stage, int kdst) {
+        // inputs already in S.tile.x; computes K[kdst] rows of this tile
+        tile_forward<RPT>(P, a.proj, S.tile, S.tq + tq_slot * 768, w1col, b1v);
+        const float tf = (float)t_stage;
+        const float std = sigma_f32(tf);
+        const double g = diffusion_f64(t_stage);
+        const double coef = 0.5 * (g * g);
+        const int r0 = tile * RT;
+        double *Kd = a.K[kdst];
+        for (int i = tid; i < RT * 9; i += 256) {
+            const int r = i / 9, c = i - 9 * r;
+            if (r0 + r < N) {
+                const float sc = S.tile.out[0][r * 12 + c] / (std + 1e-7f);  // scorenet.py:262-264
+                Kd[(size_t)(r0 + r) * 9 + c] = 0.0 - coef * (double)sc;      // samplers.py:219
+            }
+        }
+        __syncthreads();
+    };
+    auto set_obj = [&](int tile) {
+        const int r0 = tile * RT;
+        for (int r = tid; r < RT; r += 256) S.tile.obj[r] = (r0 + r < N) ? (r0 + r) / a.rpo : -1;
+    };
+
+    // ---- f0 = fun(T, y0), d0, d1 (select_initial_step, common.py:68-134) ----
+    double t = a.T;
+    if (tid == 0) S.times[0] = (float)t;
+    __syncthreads();
+    compute_tq(P, S.times, 1, S.four, S.tfeat, S.tq);
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const int r0 = tile * RT;
+        set_obj(tile);
+        for (int i = tid; i < RT * 12; i += 256) {
+            const int r = i / 12, c = i - 12 * r;
+            float v = 0.f;
+            if (r0 + r < N && c < 9) {
+                const double yv = a.x0[(size_t)(r0 + r) * 9 + c];
+                ycur[(size_t)(r0 + r) * 9 + c] = yv;
+                if (a.traj) a.traj[(size_t)(r0 + r) * 9 + c] = yv;
+                v = (float)yv;
+            }
+            S.tile.x[i] = v;
+        }
+        __syncthreads();
+        stage_eval(tile, 0, t, kidx[0]);
+        double s0 = 0.0, s1 = 0.0;
+        for (int i = tid; i < RT * 9; i += 256) {
+            const int r = i / 9;
+            if (r0 + r < N) {
+                const size_t g = (size_t)r0 * 9 + i;
+                const double yv = ycur[g], fv = a.K[kidx[0]][g];
+                const double sc = a.atol + fabs(yv) * a.rtol;
+                s0 += (yv / sc) * (yv / sc);
+                s1 += (fv / sc) * (fv / sc);
+            }
+        }
+        s0 = block_sum(s0, S.red);
+        s1 = block_sum(s1, S.red);
+        if (tid == 0) {
+            a.part[(pbuf * 3 + 0) * a.ntiles + tile] = s0;
+            a.part[(pbuf * 3 + 1) * a.ntiles + tile] = s1;
+        }
+    }
+    nfev += 1;
+    grid.sync();
+    const double d0 = sqrt(grid_total(a.part + (pbuf * 3 + 0) * a.ntiles, a.ntiles, S.red) / n_total);
+    const double d1 = sqrt(grid_total(a.part + (pbuf * 3 + 1) * a.ntiles, a.ntiles, S.red) / n_total);
+    pbuf ^= 1;
+    const double interval = fabs(t_bound - a.T);
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    h0 = fmin(h0, interval);
+
+    // ---- f1 = fun(t0 + h0*dir, y0 + h0*dir*f0), d2 ----
+    {
+        const double t1 = t + h0 * direction;
+        if (tid == 0) S.times[0] = (float)t1;
+        __syncthreads();
+        compute_tq(P, S.times, 1, S.four, S.tfeat, S.tq);
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            const int r0 = tile * RT;
+            set_obj(tile);
+            for (int i = tid; i < RT * 12; i += 256) {
+                const int r = i / 12, c = i - 12 * r;
+                float v = 0.f;
+                if (r0 + r < N && c < 9) {
+                    const size_t g = (size_t)(r0 + r) * 9 + c;
+                    v = (float)(ycur[g] + h0 * direction * a.K[kidx[0]][g]);
+                }
+                S.tile.x[i] = v;
+            }
+            __syncthreads();
+            stage_eval(tile, 0, t1, kidx[1]);
+            double s2 = 0.0;
+            for (int i = tid; i < RT * 9; i += 256) {
+                const int r = i / 9;
+                if (r0 + r < N) {
+                    const size_t g = (size_t)r0 * 9 + i;
+                    const double sc = a.atol + fabs(ycur[g]) * a.rtol;
+                    const double d = (a.K[kidx[1]][g] - a.K[kidx[0]][g]) / sc;
+                    s2 += d * d;
+                }
+            }
+            s2 = block_sum(s2, S.red);
+            if (tid == 0) a.part[(pbuf * 3 + 0) * a.ntiles + tile] = s2;
+        }
+        nfev += 1;
+        grid.sync();
+    }
+    const double d2 = sqrt(grid_total(a.part + (pbuf * 3 + 0) * a.ntiles, a.ntiles, S.red) / n_total) / h0;
+    pbuf ^= 1;
+    double h1;
+    if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+    else h1 = pow(0.01 / fmax(d1, d2), 1.0 / 5.0);
+    double h_abs = fmin(fmin(100.0 * h0, h1), interval);
+    const double h_initial = h_abs;
+    double h_last = 0.0;
+
+    // ---- main loop (ivp.py while status is None; rk.py _step_impl) ----
+    long attempts = 0;
+    while (direction * (t - t_bound) < 0.0 && status == 0) {
+        const double min_step = 10.0 * fabs(nextafter(t, direction * INFINITY) - t);
+        if (h_abs < min_step) h_abs = min_step;  // max_step = inf
+        bool step_rejected = false;
+        while (true) {
+            if (h_abs < min_step) { status = -1; break; }
+            if (++attempts > 100000) { status = -2; break; }
+            double h = h_abs * direction;
+            double t_new = t + h;
+            if (direction * (t_new - t_bound) > 0.0) t_new = t_bound;
+            h = t_new - t;
+            h_abs = fabs(h);
+
+            if (tid < 5) S.times[tid] = (float)(t + c_C[tid + 1] * h);
+            if (tid == 5) S.times[5] = (float)(t + h);
+            __syncthreads();
+            compute_tq(P, S.times, 6, S.four, S.tfeat, S.tq);
+
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                const int r0 = tile * RT;
+                set_obj(tile);
+                // rk_step (rk.py:14-78)
+                for (int s = 1; s <= 6; ++s) {
+                    for (int i = tid; i < RT * 12; i += 256) {
+                        const int r = i / 12, c = i - 12 * r;
+                        float v = 0.f;
+                        if (r0 + r < N && c < 9) {
+                            const size_t g = (size_t)(r0 + r) * 9 + c;
+                            double acc = 0.0;
+                            if (s < 6) {
+                                for (int j = 0; j < s; ++j) acc += a.K[kidx[j]][g] * c_A[s][j];
+                                v = (float)(ycur[g] + acc * h);  // dy = dot(K[:s].T, a[:s]) * h
+                            } else {
+                                for (int j = 0; j < 6; ++j) acc += a.K[kidx[j]][g] * c_B[j];
+                                const double yn = ycur[g] + h * acc;  // y_new = y + h * dot(K[:-1].T, B)
+                                ynew[g] = yn;
+                                v = (float)yn;
+                            }
+                        }
+                        S.tile.x[i] = v;
+                    }
+                    __syncthreads();
+                    const double ts = (s < 6) ? t + c_C[s] * h : t + h;
+                    stage_eval(tile, s - 1, ts, kidx[s]);
+                }
+                // error estimate (rk.py:139-147)
+                double se = 0.0;
+                for (int i = tid; i < RT * 9; i += 256) {
+                    const int r = i / 9;
+                    if (r0 + r < N) {
+                        const size_t g = (size_t)r0 * 9 + i;
+                        double e = 0.0;
+                        for (int j = 0; j < 7; ++j) e += a.K[kidx[j]][g] * c_E[j];
+                        e *= h;
+                        const double sc = a.atol + fmax(fabs(ycur[g]), fabs(ynew[g])) * a.rtol;
+                        se += (e / sc) * (e / sc);
+                        if (a.traj && (int)n_acc + 1 < a.max_traj)  // speculative: kept only if accepted
+                            a.traj[((size_t)((int)n_acc + 1) * N) * 9 + g] = ynew[g];
+                    }
+                }
+                se = block_sum(se, S.red);
+                if (tid == 0) a.part[(pbuf * 3 + 0) * a.ntiles + tile] = se;
+            }
+            nfev += 6;
+            grid.sync();
+            const double error_norm = sqrt(grid_total(a.part + (pbuf * 3 + 0) * a.ntiles, a.ntiles, S.red) / n_total);
+            pbuf ^= 1;
+            if (error_norm < 1.0) {
+                double factor = (error_norm == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(error_norm, -0.2));
+                if (step_rejected) factor = fmin(1.0, factor);
+                h_abs *= factor;
+                // accept: y <- y_new, f <- f_new (FSAL: K[6] becomes K[0]); pointer rotation only
+                double *ty = ycur; ycur = ynew; ynew = ty;
+                const int k0 = kidx[0]; kidx[0] = kidx[6]; kidx[6] = k0;
+                (void)kspare;
+                t = t_new;
+                h_last = h;
+                n_acc += 1;
+                break;
+            } else {
+                // max(MIN_FACTOR, SAFETY * norm ** exponent): python max() keeps 0.2 when the rhs is NaN
+                const double f = 0.9 * pow(error_norm, -0.2);
+                h_abs *= (f > 0.2) ? f : 0.2;
+                step_rejected = true;
+                n_rej += 1;
+            }
+        }
+    }
+
+    // ---- denoise (samplers.py:238-249), Gram-Schmidt and centre (:251-257) ----
+    {
+        const float eps_f = (float)a.eps;
+        if (a.denoise) {
+            if (tid == 0) S.times[0] = eps_f;
+            __syncthreads();
+            compute_tq(P, S.times, 1, S.four, S.tfeat, S.tq);
+        }
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            const int r0 = tile * RT;
+            if (a.denoise) {
+                set_obj(tile);
+                for (int i = tid; i < RT * 12; i += 256) {
+                    const int r = i / 12, c = i - 12 * r;
+                    float v = 0.f;
+                    if (r0 + r < N && c < 9) v = (float)ycur[(size_t)(r0 + r) * 9 + c];
+                    S.tile.x[i] = v;
+                }
+                __syncthreads();
+                tile_forward<RPT>(P, a.proj, S.tile, S.tq, w1col, b1v);
+            }
+            for (int r = tid; r < RT; r += 256) {
+                if (r0 + r >= N) continue;
+                double v[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) v[c] = ycur[(size_t)(r0 + r) * 9 + c];
+                if (a.denoise) {
+                    const float std = sigma_f32(eps_f);
+                    const float dif = diffusion_f32(eps_f);
+                    const float step = (float)((1.0 - a.eps) / 1000.0);
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) {
+                        const float grad = S.tile.out[0][r * 12 + c] / (std + 1e-7f);
+                        const float drift = 0.f - (dif * dif) * grad;
+                        v[c] = v[c] + (double)(drift * step);
+                    }
+                }
+                gram_schmidt6<double>(v);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[6 + c] += (double)a.center[(size_t)(r0 + r) * 3 + c];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) a.x_out[(size_t)(r0 + r) * 9 + c] = v[c];
+            }
+            __syncthreads();
+        }
+        if (a.denoise) nfev += 0;  // the denoise evaluation is outside the solver's nfev
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        a.stats[GP_STAT_NFEV] = nfev;
+        a.stats[GP_STAT_ACCEPTED] = n_acc;
+        a.stats[GP_STAT_REJECTED] = n_rej;
+        a.stats[GP_STAT_STATUS] = (double)status;
+        a.stats[GP_STAT_T_FINAL] = t;
+        a.stats[GP_STAT_H_INITIAL] = h_initial;
+        a.stats[GP_STAT_H_LAST] = h_last;
+    }
+}
+
+// xs = normalise(traj) + centre, transposed to [N,S,9]            (samplers.py:251-255)
+__global__ void traj_finalize_kernel(const double *__restrict__ traj, const float *__restrict__ center,
+                                     int S, int N, double *__restrict__ xs) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)S * N) return;
+    const int s = (int)(i / N), r = (int)(i % N);
+    double v[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) v[c] = traj[i * 9 + c];
+    gram_schmidt6<double>(v);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[6 + c] += (double)center[(size_t)r * 3 + c];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) xs[((size_t)r * S + s) * 9 + c] = v[c];
+}
+
+// ------------------------------------------------------------------------------------------
+// predictor-corrector sampler (samplers.py:113-177), float32 like the reference
+// ------------------------------------------------------------------------------------------
+struct PcArgs {
+    const float *P, *proj, *x0, *noise, *center, *time_steps;
+    int N, rpo, num_steps;
+    double snr;
+    float *xs, *mean_x;
+    float *x;      // [N][9] state
+    double *part;  // [2][ntiles]
+    int ntiles;
+};
+
+template <int RPT>
+__global__ void __launch_bounds__(256, 1) pc_kernel(PcArgs a) {
+    constexpr int RT = 4 * RPT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    OdeSmem<RPT> &S = *reinterpret_cast<OdeSmem<RPT> *>(smem_raw);
+    cg::grid_group grid = cg::this_grid();
+    const int tid = threadIdx.x, N = a.N;
+    const float *P = a.P;
+    float w1col[9], b1v;
+    load_w1col(P, w1col, b1v);
+    // grad of this CTA's tiles stays in global scratch between the two halves of a step: reuse
+    // mean_x as scratch for grad (it is overwritten with the real mean_x at the end of each step).
+    float *grad = a.mean_x;
+    const float step_size = a.time_steps[0] - a.time_steps[1];
+    const float sqrt_step = sqrtf(step_size);
+    int pbuf = 0;
+    for (int it = 0; it < a.num_steps; ++it) {
+        const float tv = a.time_steps[it];
+        if (tid == 0) S.times[0] = tv;
+        __syncthreads();
+        compute_tq(P, S.times, 1, S.four, S.tfeat, S.tq);
+        const float std = sigma_f32(tv);
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            const int r0 = tile * RT;
+            for (int r = tid; r < RT; r += 256) S.tile.obj[r] = (r0 + r < N) ? (r0 + r) / a.rpo : -1;
+            for (int i = tid; i < RT * 12; i += 256) {
+                const int r = i / 12, c = i - 12 * r;
+                float v = 0.f;
+                if (r0 + r < N && c < 9) v = (it == 0 ? a.x0 : a.x)[(size_t)(r0 + r) * 9 + c];
+                S.tile.x[i] = v;
+            }
+            __syncthreads();
+            tile_forward<RPT>(P, a.proj, S.tile, S.tq, w1col, b1v);
+            double sn = 0.0;
+            for (int r = tid; r < RT; r += 256) {
+                if (r0 + r >= N) continue;
+                float ss = 0.f;
+#pragma unroll
+                for (int c = 0; c < 9; ++c) {
+                    const float gv = S.tile.out[0][r * 12 + c] / (std + 1e-7f);
+                    grad[(size_t)(r0 + r) * 9 + c] = gv;
+                    ss += gv * gv;
+                }
+                sn += (double)sqrtf(ss);
+            }
+            sn = block_sum(sn, S.red);
+            if (tid == 0) a.part[pbuf * a.ntiles + tile] = sn;
+            __syncthreads();
+        }
+        grid.sync();
+        const float grad_norm = (float)(grid_total(a.part + pbuf * a.ntiles, a.ntiles, S.red) / (double)N);
+        pbuf ^= 1;
+        // langevin_step_size = 2 * (snr * sqrt(9) / grad_norm) ** 2      (samplers.py:143-144).
+        // np.float64 / Tensor dispatches to Tensor.__rtruediv__ = reciprocal() * other.
+        const float q = (1.0f / grad_norm) * (float)(a.snr * 3.0);
+        const float lang = 2.f * (q * q);
+        const float sq2l = sqrtf(2.f * lang);
+        const float dif = diffusion_f32(tv);
+        const float *z1 = a.noise + ((size_t)it * 2 + 0) * N * 9;
+        const float *z2 = a.noise + ((size_t)it * 2 + 1) * N * 9;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            const int r0 = tile * RT;
+            for (int r = tid; r < RT; r += 256) {
+                if (r0 + r >= N) continue;
+                const size_t g = (size_t)(r0 + r) * 9;
+                float x[9], gr[9], m[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) {
+                    gr[c] = grad[g + c];
+                    const float xv = (it == 0 ? a.x0 : a.x)[g + c];
+                    x[c] = (xv + lang * gr[c]) + sq2l * z1[g + c];
+                }
+                const float na = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+                const float nb = sqrtf(x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);
+                x[0] /= na; x[1] /= na; x[2] /= na;
+                x[3] /= nb; x[4] /= nb; x[5] /= nb;
+#pragma unroll
+                for (int c = 0; c < 9; ++c) {
+                    const float drift = 0.f - (dif * dif) * gr[c];
+                    m[c] = x[c] + drift * step_size;
+                    x[c] = m[c] + (dif * sqrt_step) * z2[g + c];
+                }
+                gram_schmidt6<float>(x);
+#pragma unroll
+                for (int c = 0; c < 9; ++c) a.x[g + c] = x[c];
+                if (a.xs) {
+#pragma unroll
+                    for (int c = 0; c < 9; ++c)
+                        a.xs[((size_t)(r0 + r) * a.num_steps + it) * 9 + c] = x[c] + (c >= 6 ? a.center[(size_t)(r0 + r) * 3 + c - 6] : 0.f);
+                }
+                if (it == a.num_steps - 1) {
+#pragma unroll
+                    for (int c = 6; c < 9; ++c) m[c] += a.center[(size_t)(r0 + r) * 3 + c - 6];
+                    gram_schmidt6<float>(m);
+                }
+#pragma unroll
+                for (int c = 0; c < 9; ++c) a.mean_x[g + c] = m[c];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int coop_grid_limit(const void *kern, size_t smem) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess) return 0;
+    return per_sm * num_sms();
+}
+
+template <int RPT>
+static int launch_ode(OdeArgs &a, cudaStream_t st) {
+    constexpr int RT = 4 * RPT;
+    a.ntiles = (a.N + RT - 1) / RT;
+    const size_t smem = sizeof(OdeSmem<RPT>);
+    auto kern = ode_rk45_kernel<RPT>;
+    GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int limit = coop_grid_limit((const void *)kern, smem);
+    if (limit <= 0) { set_error("gp_scorenet_ode: kernel cannot be made resident"); return GP_ERR_LAUNCH; }
+    int grid = a.ntiles < limit ? a.ntiles : limit;
+    void *params[] = {&a};
+    GP_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(256), params, smem, st));
+    count_launch();
+    return GP_OK;
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace gp
+
+using namespace gp;
+
+extern "C" size_t gp_trunk_packed_bytes(void) { return TrunkLayout::END * sizeof(float); }
+
+extern "C" int gp_trunk_pack(const gp_trunk_params *raw, void *packed, gp_stream_t s) {
+    GP_REQUIRE(raw && packed, "gp_trunk_pack: null pointer");
+    GP_REQUIRE(raw->pose_w0 && raw->pose_b0 && raw->pose_w1 && raw->pose_b1 && raw->fourier_w && raw->t_w && raw->t_b,
+               "gp_trunk_pack: null parameter");
+    for (int h = 0; h < 3; ++h)
+        GP_REQUIRE(raw->head_w0[h] && raw->head_b0[h] && raw->head_w1[h] && raw->head_b1[h], "gp_trunk_pack: null head %d", h);
+    GP_REQUIRE(((uintptr_t)packed & 15) == 0, "gp_trunk_pack: packed must be 16-byte aligned");
+    RawTrunk r;
+    r.p = *raw;
+    pack_trunk_kernel<<<num_sms() * 4, 256, 0, as_stream(s)>>>(r, (float *)packed);
+    GP_CHECK_LAUNCH("gp_trunk_pack");
+    return GP_OK;
+}
+
+extern "C" int gp_trunk_project(const void *packed, const float *pts_feat, int B, float *proj, gp_stream_t s) {
+    GP_REQUIRE(packed && pts_feat && proj, "gp_trunk_project: null pointer");
+    GP_REQUIRE(B >= 0, "gp_trunk_project: B < 0");
+    if (B == 0) return GP_OK;
+    GP_REQUIRE(((uintptr_t)pts_feat & 15) == 0, "gp_trunk_project: pts_feat must be 16-byte aligned");
+    dim3 grid(768 / PJ_OUT, (B + PJ_OBJ - 1) / PJ_OBJ);
+    project_kernel<<<grid, 256, 0, as_stream(s)>>>((const float *)packed, pts_feat, B, proj);
+    GP_CHECK_LAUNCH("gp_trunk_project");
+    return GP_OK;
+}
+
+template <int MODE>
+static int launch_eval(const void *packed, const float *proj, const float *x, const double *poses,
+                       const float *center, const float *t, int N, int rpo, float *out, cudaStream_t st,
+                       const char *name) {
+    if (N == 0) return GP_OK;
+    if (N <= 16 * num_sms()) {
+        constexpr int RPT = 4;
+        const size_t smem = sizeof(EvalSmem<RPT>);
+        auto kern = eval_kernel<RPT, MODE>;
+        GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(N + 15) / 16, 256, smem, st>>>((const float *)packed, proj, x, poses, center, t, N, rpo, out);
+    } else {
+        constexpr int RPT = 8;
+        const size_t smem = sizeof(EvalSmem<RPT>);
+        auto kern = eval_kernel<RPT, MODE>;
+        GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(N + 31) / 32, 256, smem, st>>>((const float *)packed, proj, x, poses, center, t, N, rpo, out);
+    }
+    GP_CHECK_LAUNCH(name);
+    return GP_OK;
+}
+
+extern "C" int gp_scorenet_eval(const void *packed, const float *proj, const float *x, const float *t,
+                                int N, int rows_per_object, float *score, gp_stream_t s) {
+    GP_REQUIRE(packed && proj && x && t && score, "gp_scorenet_eval: null pointer");
+    GP_REQUIRE(N >= 0 && rows_per_object >= 1, "gp_scorenet_eval: bad sizes");
+    return launch_eval<0>(packed, proj, x, nullptr, nullptr, t, N, rows_per_object, score, as_stream(s), "gp_scorenet_eval");
+}
+
+extern "C" int gp_energy(const void *packed, const float *proj, const double *poses, const float *pts_center,
+                         const float *t_rows, int N, int rows_per_object, float *energy, gp_stream_t s) {
+    GP_REQUIRE(packed && proj && poses && pts_center && t_rows && energy, "gp_energy: null pointer");
+    GP_REQUIRE(N >= 0 && rows_per_object >= 1, "gp_energy: bad sizes");
+    return launch_eval<1>(packed, proj, nullptr, poses, pts_center, t_rows, N, rows_per_object, energy, as_stream(s), "gp_energy");
+}
+
+extern "C" size_t gp_scorenet_ode_workspace_bytes(int N) {
+    if (N < 0) return 0;
+    const size_t state = align256((size_t)N * 9 * sizeof(double));
+    const size_t ntiles_max = (size_t)(N + 7) / 8 + 1;
+    return state * 10 + align256(2 * 3 * ntiles_max * sizeof(double)) + 256;
+}
+
+extern "C" int gp_scorenet_ode(const void *packed, const float *proj, const double *x0, const float *pts_center,
+                               int N, int rows_per_object, double T, double eps, double rtol, double atol,
+                               int denoise, double *x_out, double *traj, int max_traj, double *stats,
+                               void *workspace, size_t workspace_bytes, int mode, gp_stream_t s) {
+    GP_REQUIRE(packed && proj && x0 && pts_center && x_out && stats && workspace, "gp_scorenet_ode: null pointer");
+    GP_REQUIRE(N >= 1 && rows_per_object >= 1, "gp_scorenet_ode: bad sizes N=%d rows_per_object=%d", N, rows_per_object);
+    GP_REQUIRE(rtol > 0 && atol > 0, "gp_scorenet_ode: tolerances must be positive");
+    GP_REQUIRE(traj == nullptr || max_traj >= 1, "gp_scorenet_ode: max_traj < 1");
+    if (workspace_bytes < gp_scorenet_ode_workspace_bytes(N)) {
+        set_error("gp_scorenet_ode: workspace too small (%zu < %zu)", workspace_bytes, gp_scorenet_ode_workspace_bytes(N));
+        return GP_ERR_WORKSPACE;
+    }
+    if (mode != 0) {
+        set_error("gp_scorenet_ode: mode %d not available in this build (0 = fp32)", mode);
+        return GP_ERR_UNSUPPORTED;
+    }
+    // scipy validate_tol: rtol is clamped to 100 * EPS
+    if (rtol < 100 * 2.220446049250313e-16) rtol = 100 * 2.220446049250313e-16;
+    OdeArgs a;
+    a.P = (const float *)packed; a.proj = proj; a.x0 = x0; a.center = pts_center;
+    a.N = N; a.rpo = rows_per_object; a.T = T; a.eps = eps; a.rtol = rtol; a.atol = atol;
+    a.denoise = denoise; a.x_out = x_out; a.traj = traj; a.max_traj = max_traj; a.stats = stats;
+    unsigned char *w = (unsigned char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    const size_t state = align256((size_t)N * 9 * sizeof(double));
+    a.y[0] = (double *)w; w += state;
+    a.y[1] = (double *)w; w += state;
+    for (int k = 0; k < 8; ++k) { a.K[k] = (double *)w; w += state; }
+    a.part = (double *)w;
+    cudaStream_t st = as_stream(s);
+    const int sms = num_sms();
+    if (N <= 8 * sms) return launch_ode<2>(a, st);
+    if (N <= 16 * sms) return launch_ode<4>(a, st);
+    return launch_ode<8>(a, st);
+}
+
+extern "C" int gp_traj_finalize(const double *traj, const float *pts_center, int S, int N, double *xs, gp_stream_t s) {
+    GP_REQUIRE(traj && pts_center && xs, "gp_traj_finalize: null pointer");
+    GP_REQUIRE(S >= 0 && N >= 0, "gp_traj_finalize: bad sizes");
+    if (S == 0 || N == 0) return GP_OK;
+    const size_t total = (size_t)S * N;
+    traj_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(s)>>>(traj, pts_center, S, N, xs);
+    GP_CHECK_LAUNCH("gp_traj_finalize");
+    return GP_OK;
+}
+
+extern "C" size_t gp_scorenet_pc_workspace_bytes(int N) {
+    if (N < 0) return 0;
+    return align256((size_t)N * 9 * sizeof(float)) + align256(2 * ((size_t)(N + 7) / 8 + 1) * sizeof(double)) + 256;
+}
+
+template <int RPT>
+static int launch_pc(PcArgs &a, cudaStream_t st) {
+    constexpr int RT = 4 * RPT;
+    a.ntiles = (a.N + RT - 1) / RT;
+    const size_t smem = sizeof(OdeSmem<RPT>);
+    auto kern = pc_kernel<RPT>;
+    GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int limit = coop_grid_limit((const void *)kern, smem);
+    if (limit <= 0) { set_error("gp_scorenet_pc: kernel cannot be made resident"); return GP_ERR_LAUNCH; }
+    int grid = a.ntiles < limit ? a.ntiles : limit;
+    void *params[] = {&a};
+    GP_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(256), params, smem, st));
+    count_launch();
+    return GP_OK;
+}
+
+extern "C" int gp_scorenet_pc(const void *packed, const float *proj, const float *x0, const float *noise,
+                              const float *pts_center, const float *time_steps, int N, int rows_per_object,
+                              int num_steps, double snr, float *xs, float *mean_x, void *workspace,
+                              size_t workspace_bytes, gp_stream_t s) {
+    GP_REQUIRE(packed && proj && x0 && noise && pts_center && time_steps && mean_x && workspace, "gp_scorenet_pc: null pointer");
+    GP_REQUIRE(N >= 1 && rows_per_object >= 1 && num_steps >= 2, "gp_scorenet_pc: bad sizes");
+    if (workspace_bytes < gp_scorenet_pc_workspace_bytes(N)) {
+        set_error("gp_scorenet_pc: workspace too small");
+        return GP_ERR_WORKSPACE;
+    }
+    PcArgs a;
+    a.P = (const float *)packed; a.proj = proj; a.x0 = x0; a.noise = noise; a.center = pts_center;
+    a.time_steps = time_steps; a.N = N; a.rpo = rows_per_object; a.num_steps = num_steps; a.snr = snr;
+    a.xs = xs; a.mean_x = mean_x;
+    unsigned char *w = (unsigned char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    a.x = (float *)w; w += align256((size_t)N * 9 * sizeof(float));
+    a.part = (double *)w;
+    cudaStream_t st = as_stream(s);
+    const int sms = num_sms();
+    if (N <= 8 * sms) return launch_pc<2>(a, st);
+    if (N <= 16 * sms) return launch_pc<4>(a, st);
+    return launch_pc<8>(a, st);
+}

@@ -1,0 +1,101 @@
+"""The per-object pose-generation path end to end, in the order the reference runners execute it
+(runners/evaluation_single.py:404-420, runners/evaluation_tracking.py:110-216):
+
+    score_agent.pred_func  ->  energy_agent.get_energy(T=1e-5)  ->  aggregate_pose  ->  scale_agent.pred_scale_func
+
+plus the object sharding used for multi-GPU runs: objects are split into contiguous ranges, one
+process per GPU, no collective inside the path, one gather of [B,4,4] + [B,3] at the end
+(SURVEY.md section 8(e)).
+"""
+import copy
+
+import torch
+import torch.distributed as dist
+
+from . import synthetic
+from .aggregation import aggregate_pose
+from .config import get_config
+from .posenet_agent import PoseNet
+from .rotation import matrix_to_rotation_6d_cols
+
+
+def shard_range(num_objects, rank, world_size):
+    """Contiguous object range [lo, hi) of `rank`: the first `num_objects %
+    world_size` ranks get one extra object."""
+    base, rem = divmod(num_objects, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_results(pose, length, group=None):
+    """All ranks contribute their [b_local,4,4] / [b_local,3] shard; rank 0 gets the concatenation
+    (ragged shards allowed).  Works with NCCL (device tensors) and gloo (CPU tensors)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return pose, length
+    world = dist.get_world_size(group)
+    flat = torch.cat([pose.reshape(pose.shape[0], 16), length.reshape(length.shape[0], 3)], dim=1).contiguous()
+    counts = [torch.zeros(1, dtype=torch.int64, device=flat.device) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([flat.shape[0]], dtype=torch.int64, device=flat.device), group=group)
+    counts = [int(c.item()) for c in counts]
+    mx = max(counts)
+    padded = torch.zeros((mx, 19), dtype=flat.dtype, device=flat.device)
+    padded[: flat.shape[0]] = flat
+    bufs = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(bufs, padded, group=group)
+    full = torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+    return full[:, :16].reshape(-1, 4, 4), full[:, 16:]
+
+
+class PosePipeline:
+    """score + energy + scale agents wired together; every stage runs on libgenpose_b200.so."""
+
+    def __init__(self, cfg=None, device="cuda", mlp_mode="fp32"):
+        cfg = copy.copy(cfg) if cfg is not None else get_config()
+        cfg.device = device
+        cfg.mlp_mode = mlp_mode
+        if not getattr(cfg, "sampler_mode", None):
+            cfg.sampler_mode = ["ode"]
+        self.cfg = cfg
+        c = copy.copy(cfg); c.agent_type = "score"
+        self.score_agent = PoseNet(c)
+        c = copy.copy(cfg); c.agent_type = "energy"
+        self.energy_agent = PoseNet(c)
+        c = copy.copy(cfg); c.agent_type = "scale"
+        self.scale_agent = PoseNet(c)
+
+    def load_state_dicts(self, score_sd, energy_sd, scale_sd):
+        self.score_agent.net.load_state_dict(score_sd)
+        self.energy_agent.net.load_state_dict(energy_sd)
+        self.scale_agent.net.load_state_dict(scale_sd)
+        return self
+
+    def load_synthetic_weights(self, seeds=(100, 200, 300)):
+        return self.load_state_dicts(synthetic.random_gfobjectpose_state_dict(seeds[0]),
+                                     synthetic.random_gfobjectpose_state_dict(seeds[1]),
+                                     synthetic.random_scalenet_state_dict(seeds[2]))
+
+    @torch.no_grad()
+    def __call__(self, data, repeat_num=None, T0=None, init_x=None, return_all=False):
+        """data{'pts' [B,N,3] f32 cuda, 'pts_center' [B,3]} -> (aggregated_pose [B,4,4] f32, length [B,3] f32)."""
+        cfg = self.cfg
+        R = cfg.eval_repeat_num if repeat_num is None else repeat_num
+        T0 = cfg.T0 if T0 is None else T0
+        pred_pose, pred_q, geometry = self.score_agent.pred_func(
+            data=data, repeat_num=R, T0=T0, init_x=init_x, save_path=None, return_geometry=True)
+        score_feat = data["pts_feat"]
+        energy = self.energy_agent.get_energy(data=data, pose_samples=pred_pose, T=1e-5, mode="test",
+                                              extract_feature=True, geometry=geometry)
+        agg = aggregate_pose(pred_pose, energy, eval_repeat_num=R, retain_ratio=cfg.retain_ratio,
+                             clustering=cfg.clustering, clustering_eps=cfg.clustering_eps,
+                             clustering_minpts=cfg.clustering_minpts)
+        _, length = self.scale_agent.pred_scale_func({"pts_feat": score_feat, "rgb_feat": None,
+                                                      "axes": agg[:, :3, :3]})
+        if return_all:
+            return dict(pred_pose=pred_pose, pred_pose_q_wxyz=pred_q, energy=energy, aggregated_pose=agg,
+                        length=length, pts_feat=score_feat)
+        return agg, length
+
+    @staticmethod
+    def next_init_x(aggregated_pose):
+        """Tracking feedback (evaluation_tracking.py:210-214): aggregated pose re-encoded as 6D + t."""
+        return torch.cat([matrix_to_rotation_6d_cols(aggregated_pose[:, :3, :3]), aggregated_pose[:, :3, 3]], dim=-1)

@@ -1,0 +1,139 @@
+"""Drop-in for networks/pts_encoder/pointnet2_utils/pointnet2/pointnet2_utils.py (inference side).
+
+Same names, argument order, dtypes and shapes as the reference (`furthest_point_sample`,
+`gather_operation`, `ball_query`, `grouping_operation`, `QueryAndGroup`, `GroupAll`), backed by
+libgenpose_b200.so.  Indices are bit-exact with the reference extension.  Backward passes are out
+of scope (training is not on the hot path) and raise.
+"""
+from typing import Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def furthest_point_sample(xyz: torch.Tensor, npoint: int) -> torch.Tensor:
+    """pointnet2_utils.py:16-37.  xyz (B, N, 3) f32 -> (B, npoint) int32."""
+    assert xyz.is_contiguous()
+    _lib.check_cuda(xyz, "xyz", torch.float32)
+    B, N, _ = xyz.size()
+    output = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
+    _lib.call("gp_fps", _lib.ptr(xyz), B, N, int(npoint), _lib.ptr(output), None, device=xyz.device)
+    return output
+
+
+def furthest_point_sample_gather(xyz: torch.Tensor, npoint: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """FPS fused with the gather of pointnet2_modules.py:43-47: returns (idx, new_xyz (B,npoint,3))."""
+    assert xyz.is_contiguous()
+    _lib.check_cuda(xyz, "xyz", torch.float32)
+    B, N, _ = xyz.size()
+    idx = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
+    new_xyz = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz.device)
+    _lib.call("gp_fps", _lib.ptr(xyz), B, N, int(npoint), _lib.ptr(idx), _lib.ptr(new_xyz), device=xyz.device)
+    return idx, new_xyz
+
+
+def gather_operation(features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """pointnet2_utils.py:50-72.  features (B, C, N), idx (B, npoint) -> (B, C, npoint)."""
+    assert features.is_contiguous()
+    assert idx.is_contiguous()
+    _lib.check_cuda(features, "features", torch.float32)
+    _lib.check_cuda(idx, "idx", torch.int32)
+    B, npoint = idx.size()
+    _, C, N = features.size()
+    output = torch.empty((B, C, npoint), dtype=torch.float32, device=features.device)
+    _lib.call("gp_gather", _lib.ptr(features), _lib.ptr(idx), B, C, N, npoint, _lib.ptr(output),
+              device=features.device)
+    return output
+
+
+def ball_query(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
+    """pointnet2_utils.py:229-253.  -> idx (B, npoint, nsample) int32."""
+    assert new_xyz.is_contiguous()
+    assert xyz.is_contiguous()
+    _lib.check_cuda(xyz, "xyz", torch.float32)
+    _lib.check_cuda(new_xyz, "new_xyz", torch.float32)
+    B, N, _ = xyz.size()
+    npoint = new_xyz.size(1)
+    idx = torch.empty((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
+    _lib.call("gp_ball_query", _lib.ptr(new_xyz), _lib.ptr(xyz), B, N, npoint, float(radius), int(nsample),
+              _lib.ptr(idx), device=xyz.device)
+    return idx
+
+
+def ball_query2(radii, nsamples, xyz: torch.Tensor, new_xyz: torch.Tensor):
+    """Both radii of an MSG level in one scan of the cloud -> (idx0, idx1)."""
+    _lib.check_cuda(xyz, "xyz", torch.float32)
+    _lib.check_cuda(new_xyz, "new_xyz", torch.float32)
+    B, N, _ = xyz.size()
+    npoint = new_xyz.size(1)
+    idx0 = torch.empty((B, npoint, nsamples[0]), dtype=torch.int32, device=xyz.device)
+    idx1 = torch.empty((B, npoint, nsamples[1]), dtype=torch.int32, device=xyz.device)
+    _lib.call("gp_ball_query2", _lib.ptr(new_xyz), _lib.ptr(xyz), B, N, npoint, float(radii[0]),
+              int(nsamples[0]), _lib.ptr(idx0), float(radii[1]), int(nsamples[1]), _lib.ptr(idx1),
+              device=xyz.device)
+    return idx0, idx1
+
+
+def grouping_operation(features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """pointnet2_utils.py:179-203.  features (B, C, N), idx (B, npoint, nsample) -> (B, C, npoint, nsample)."""
+    assert features.is_contiguous()
+    assert idx.is_contiguous()
+    _lib.check_cuda(features, "features", torch.float32)
+    _lib.check_cuda(idx, "idx", torch.int32)
+    B, nfeatures, nsample = idx.size()
+    _, C, N = features.size()
+    output = torch.empty((B, C, nfeatures, nsample), dtype=torch.float32, device=features.device)
+    _lib.call("gp_group", _lib.ptr(features), _lib.ptr(idx), B, C, N, nfeatures, nsample, _lib.ptr(output),
+              device=features.device)
+    return output
+
+
+def query_group(xyz, new_xyz, features, idx) -> torch.Tensor:
+    """Fused tail of QueryAndGroup.forward (pointnet2_utils.py:279-296): (B, 3 + C, npoint, nsample)."""
+    _lib.check_cuda(xyz, "xyz", torch.float32)
+    _lib.check_cuda(new_xyz, "new_xyz", torch.float32)
+    _lib.check_cuda(idx, "idx", torch.int32)
+    B, N, _ = xyz.size()
+    _, M, ns = idx.size()
+    C = 0
+    if features is not None:
+        _lib.check_cuda(features, "features", torch.float32)
+        C = features.size(1)
+    out = torch.empty((B, 3 + C, M, ns), dtype=torch.float32, device=xyz.device)
+    _lib.call("gp_query_group", _lib.ptr(xyz), _lib.ptr(new_xyz), _lib.ptr(features), _lib.ptr(idx), B, C, N, M,
+              ns, _lib.ptr(out), device=xyz.device)
+    return out
+
+
+class QueryAndGroup(nn.Module):
+    """pointnet2_utils.py:259-298."""
+
+    def __init__(self, radius: float, nsample: int, use_xyz: bool = True):
+        super().__init__()
+        self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
+
+    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
+        idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
+        if features is not None and not self.use_xyz:
+            return grouping_operation(features, idx)
+        assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
+        return query_group(xyz, new_xyz, features, idx)
+
+
+class GroupAll(nn.Module):
+    """pointnet2_utils.py:301-328 (pure views/concat, no kernel needed)."""
+
+    def __init__(self, use_xyz: bool = True):
+        super().__init__()
+        self.use_xyz = use_xyz
+
+    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
+        grouped_xyz = xyz.transpose(1, 2).unsqueeze(2)
+        if features is not None:
+            grouped_features = features.unsqueeze(2)
+            if self.use_xyz:
+                return torch.cat([grouped_xyz, grouped_features], dim=1)
+            return grouped_features
+        return grouped_xyz

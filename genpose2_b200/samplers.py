@@ -1,0 +1,127 @@
+"""Drop-ins for `cond_ode_sampler` and `cond_pc_sampler`
+(networks/gf_algorithms/samplers.py:180-258, 113-177): same signatures, same returned shapes and
+dtypes (the ODE sampler returns float64 like scipy's state), same consumption of the global CPU
+generator for the initial noise (`prior` is called exactly as the reference calls it).
+
+What changes: the scipy `solve_ivp` host loop with a host<->device round trip per RHS evaluation
+(samplers.py:204-234) is one persistent device kernel (gp_scorenet_ode); the 500-step PC loop is
+one persistent kernel (gp_scorenet_pc).
+"""
+import warnings
+
+import numpy as np
+import torch
+
+from . import _lib
+from .scorenet import _object_features
+
+POSE_DIM = 9  # get_pose_dim("rot_matrix"), utils/genpose_utils.py:34-35
+MAX_TRAJ = 512  # accepted-step slots recorded when the trajectory is requested
+
+last_ode_stats = {}  # statistics of the most recent cond_ode_sampler call (nfev, accepted, ...)
+
+
+def _score_net(score_model):
+    net = getattr(score_model, "pose_score_net", score_model)
+    if not hasattr(net, "packed"):
+        raise TypeError("score_model must be a genpose2_b200 GFObjectPose / PoseScoreNet (no fallback path)")
+    return net
+
+
+def _mlp_mode(score_model):
+    cfg = getattr(score_model, "cfg", None)
+    mode = getattr(cfg, "mlp_mode", "fp32") if cfg is not None else "fp32"
+    return {"fp32": 0, "bf16": 1}[mode]
+
+
+def cond_ode_sampler(score_model, data, prior, sde_coeff, atol=1e-5, rtol=1e-5, device="cuda", eps=1e-5,
+                     T=1.0, num_steps=None, pose_mode="quat_wxyz", denoise=True, init_x=None,
+                     return_trajectory=True):
+    """-> (xs [N, S, 9] f64, x [N, 9] f64).  `return_trajectory=False` (not in the reference) skips
+    recording the accepted steps and returns xs = x[:, None]."""
+    if pose_mode != "rot_matrix":
+        raise NotImplementedError("accelerated sampler supports pose_mode='rot_matrix' only")
+    if num_steps is not None:
+        raise NotImplementedError("num_steps (dense output on a fixed grid) is row f2 of the scope table")
+    net = _score_net(score_model)
+    batch_size = data["pts"].shape[0]
+    noise = prior((batch_size, POSE_DIM), T=T).to(device)  # CPU generator, like samplers.py:197-201
+    x0 = noise if init_x is None else init_x + noise
+    dev = x0.device
+    x0 = x0.to(torch.float64).contiguous()  # scipy casts y0 to float64
+    feat, rpo = _object_features(data, batch_size)
+    proj = net.project(feat.to(dev))
+    center = _lib.check_cuda(data["pts_center"].to(torch.float32).contiguous(), "pts_center", torch.float32)
+
+    x_out = torch.empty((batch_size, POSE_DIM), dtype=torch.float64, device=dev)
+    stats = torch.zeros(_lib.GP_STAT_COUNT, dtype=torch.float64, device=dev)
+    ws_bytes = _lib.load().gp_scorenet_ode_workspace_bytes(batch_size)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    traj = None
+    if return_trajectory:
+        traj = torch.empty((MAX_TRAJ, batch_size, POSE_DIM), dtype=torch.float64, device=dev)
+    _lib.call("gp_scorenet_ode", _lib.ptr(net.packed()), _lib.ptr(proj), _lib.ptr(x0), _lib.ptr(center),
+              batch_size, rpo, float(T), float(eps), float(rtol), float(atol), 1 if denoise else 0,
+              _lib.ptr(x_out), _lib.ptr(traj), MAX_TRAJ if traj is not None else 0, _lib.ptr(stats),
+              _lib.ptr(ws), ws_bytes, _mlp_mode(score_model), device=dev)
+    if return_trajectory:
+        st = stats.cpu()
+        S = int(st[_lib.STAT_ACCEPTED].item()) + 1
+        if S > MAX_TRAJ:
+            raise RuntimeError(f"trajectory longer than {MAX_TRAJ} accepted steps")
+        xs = torch.empty((batch_size, S, POSE_DIM), dtype=torch.float64, device=dev)
+        _lib.call("gp_traj_finalize", _lib.ptr(traj), _lib.ptr(center), S, batch_size, _lib.ptr(xs), device=dev)
+        _record_stats(st)
+    else:
+        xs = x_out.unsqueeze(1)
+        last_ode_stats.clear()
+        last_ode_stats["device_stats"] = stats
+    return xs, x_out
+
+
+def _record_stats(st):
+    last_ode_stats.clear()
+    last_ode_stats.update(
+        nfev=int(st[_lib.STAT_NFEV]), accepted=int(st[_lib.STAT_ACCEPTED]), rejected=int(st[_lib.STAT_REJECTED]),
+        status=int(st[_lib.STAT_STATUS]), t_final=float(st[_lib.STAT_T_FINAL]),
+        h_initial=float(st[_lib.STAT_H_INITIAL]), h_last=float(st[_lib.STAT_H_LAST]))
+    if last_ode_stats["status"] != 0:
+        # the reference ignores solve_ivp's status as well (samplers.py:226-236); say so loudly
+        warnings.warn(f"device RK45 ended with status {last_ode_stats['status']} "
+                      "(-1: step size underflow, -2: attempt cap)")
+
+
+def ode_stats():
+    """Statistics of the last cond_ode_sampler call as a dict (synchronises if still on device)."""
+    if "device_stats" in last_ode_stats:
+        _record_stats(last_ode_stats["device_stats"].cpu())
+    return dict(last_ode_stats)
+
+
+def cond_pc_sampler(score_model, data, prior, sde_coeff, num_steps=500, snr=0.16, device="cuda", eps=1e-5,
+                    pose_mode="quat_wxyz", init_x=None, noise=None):
+    """-> (xs [N, num_steps, 9] f32, mean_x [N, 9] f32).  `noise` (not in the reference):
+    [num_steps, 2, N, 9] tensor replacing the per-step `torch.randn_like` draws; by default they are
+    drawn with torch on `device` in the reference's call order."""
+    if pose_mode != "rot_matrix":
+        raise NotImplementedError("accelerated sampler supports pose_mode='rot_matrix' only")
+    net = _score_net(score_model)
+    batch_size = data["pts"].shape[0]
+    x0 = prior((batch_size, POSE_DIM)).to(device) if init_x is None else init_x
+    dev = x0.device
+    x0 = x0.to(torch.float32).contiguous()
+    time_steps = torch.linspace(1.0, eps, num_steps, device=dev)
+    if noise is None:
+        noise = torch.stack([torch.stack([torch.randn_like(x0), torch.randn_like(x0)]) for _ in range(num_steps)])
+    noise = _lib.check_cuda(noise.to(dev, torch.float32).contiguous(), "noise", torch.float32)
+    feat, rpo = _object_features(data, batch_size)
+    proj = net.project(feat.to(dev))
+    center = _lib.check_cuda(data["pts_center"].to(torch.float32).contiguous(), "pts_center", torch.float32)
+    xs = torch.empty((batch_size, num_steps, POSE_DIM), dtype=torch.float32, device=dev)
+    mean_x = torch.empty((batch_size, POSE_DIM), dtype=torch.float32, device=dev)
+    ws_bytes = _lib.load().gp_scorenet_pc_workspace_bytes(batch_size)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _lib.call("gp_scorenet_pc", _lib.ptr(net.packed()), _lib.ptr(proj), _lib.ptr(x0), _lib.ptr(noise),
+              _lib.ptr(center), _lib.ptr(time_steps), batch_size, rpo, int(num_steps), float(snr), _lib.ptr(xs),
+              _lib.ptr(mean_x), _lib.ptr(ws), ws_bytes, device=dev)
+    return xs, mean_x

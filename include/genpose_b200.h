@@ -1,0 +1,224 @@
+/*
+ * genpose_b200.h -- C ABI of libgenpose_b200.so: hand-written sm_100a CUDA kernels for the
+ * per-object pose-generation hot path of GenPose++ (reference: PythonerJOJO/GenPose2).
+ *
+ * Conventions:
+ *   - plain device pointers + sizes + an explicit cudaStream_t (passed as void*); no torch types;
+ *   - the CALLER allocates every output and workspace (sizes from the gp_*_bytes() queries);
+ *   - no hidden global state, re-entrant, the device is the one the pointers live on;
+ *   - every entry returns 0 on success, a negative gp_status on bad arguments, or a positive
+ *     cudaError_t if a launch failed.  Nothing ever calls exit() (the reference does:
+ *     sampling_gpu.cu:248-252, ball_query_gpu.cu:62-65).  gp_last_error() gives the message.
+ *   - all tensors are contiguous, float32 / int32 / float64 as stated per argument.
+ *
+ * Each entry cites the reference interface it replaces (paths relative to the reference root;
+ * P2 = networks/pts_encoder/pointnet2_utils/pointnet2).
+ */
+#ifndef GENPOSE_B200_H
+#define GENPOSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *gp_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define GP_API __attribute__((visibility("default")))
+#else
+#define GP_API
+#endif
+
+enum gp_status {
+    GP_OK = 0,
+    GP_ERR_BAD_ARG = -1,
+    GP_ERR_UNSUPPORTED = -2,
+    GP_ERR_WORKSPACE = -3,
+    GP_ERR_LAUNCH = -4
+};
+
+/* ABI version of this header (bumped on any signature change). */
+GP_API int gp_version(void);
+/* Message of the last failing call on this host thread (thread-local, never NULL). */
+GP_API const char *gp_last_error(void);
+/* Number of kernels launched by this library on this host thread since the last reset. */
+GP_API long long gp_launch_count(void);
+GP_API void gp_launch_count_reset(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * (1) PointNet++ set-abstraction integer ops.  Indices are bit-exact with the reference ext.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces pointnet2_cuda.furthest_point_sampling_wrapper(b, n, m, points, temp, idx)
+ * (P2/src/sampling.cpp:40-51 -> sampling_gpu.cu:93-253; Python: P2/pointnet2_utils.py:16-37).
+ * xyz [B,N,3] f32 -> idx [B,m] i32.  No `temp` scratch: distances live in registers.
+ * new_xyz (optional, may be NULL) [B,m,3] f32 receives xyz[b, idx[b,j], :] -- the fused
+ * gather_operation of pointnet2_modules.py:43-47. */
+GP_API int gp_fps(const float *xyz, int B, int N, int m, int32_t *idx, float *new_xyz, gp_stream_t s);
+
+/* Replaces pointnet2_cuda.gather_points_wrapper(b, c, n, npoints, points, idx, out)
+ * (P2/src/sampling.cpp:13-25 -> sampling_gpu.cu:8-43).  points [B,C,N], idx [B,m] -> out [B,C,m]. */
+GP_API int gp_gather(const float *points, const int32_t *idx, int B, int C, int N, int m, float *out,
+              gp_stream_t s);
+
+/* Replaces pointnet2_cuda.ball_query_wrapper(b, n, m, radius, nsample, new_xyz, xyz, idx)
+ * (P2/src/ball_query.cpp:16-27 -> ball_query_gpu.cu:9-66).  xyz [B,N,3], new_xyz [B,M,3] ->
+ * idx [B,M,nsample] i32.  Every slot is written (the caller need not zero-initialise). */
+GP_API int gp_ball_query(const float *new_xyz, const float *xyz, int B, int N, int M, float radius,
+                  int nsample, int32_t *idx, gp_stream_t s);
+
+/* Two radii in one scan of the cloud (the MSG grouper pair of pointnet2_modules.py:104-121). */
+GP_API int gp_ball_query2(const float *new_xyz, const float *xyz, int B, int N, int M, float radius0,
+                   int nsample0, int32_t *idx0, float radius1, int nsample1, int32_t *idx1,
+                   gp_stream_t s);
+
+/* Replaces pointnet2_cuda.group_points_wrapper(b, c, n, npoints, nsample, points, idx, out)
+ * (P2/src/group_points.cpp:26-37 -> group_points_gpu.cu:47-89).
+ * points [B,C,N], idx [B,M,nsample] -> out [B,C,M,nsample]. */
+GP_API int gp_group(const float *points, const int32_t *idx, int B, int C, int N, int M, int nsample,
+             float *out, gp_stream_t s);
+
+/* Replaces QueryAndGroup.forward after the ball query (P2/pointnet2_utils.py:279-296): the two
+ * grouping_operation calls, the xyz transpose, the recentring and the concat, in one pass.
+ * xyz [B,N,3], new_xyz [B,M,3], features [B,C,N] (NULL when C == 0), idx [B,M,nsample] ->
+ * out [B,3+C,M,nsample] with out[:, :3] = xyz[idx] - new_xyz and out[:, 3:] = features[idx]. */
+GP_API int gp_query_group(const float *xyz, const float *new_xyz, const float *features,
+                   const int32_t *idx, int B, int C, int N, int M, int nsample, float *out,
+                   gp_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
+ * (2)(3) ScoreNet / EnergyNet trunk.  Raw parameters in the reference's state-dict layout
+ * (SURVEY.md section 5): nn.Linear weights are [out,in] row-major.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gp_trunk_params {
+    const float *pose_w0;    /* pose_encoder.0.weight [256,9]    (scorenet.py:133-138) */
+    const float *pose_b0;    /* pose_encoder.0.bias   [256] */
+    const float *pose_w1;    /* pose_encoder.2.weight [256,256] */
+    const float *pose_b1;    /* pose_encoder.2.bias   [256] */
+    const float *fourier_w;  /* t_encoder.0.W         [64]       (scorenet.py:77-88) */
+    const float *t_w;        /* t_encoder.1.weight    [128,128] */
+    const float *t_b;        /* t_encoder.1.bias      [128] */
+    const float *head_w0[3]; /* fusion_tail_{rot_x,rot_y,trans}.0.weight [256,1408] */
+    const float *head_b0[3]; /* ....0.bias [256] */
+    const float *head_w1[3]; /* ....2.weight [3,256] */
+    const float *head_b1[3]; /* ....2.bias [3] */
+} gp_trunk_params;
+
+/* Bytes of the packed trunk (re-laid-out weights the kernels read; caller-allocated, device). */
+GP_API size_t gp_trunk_packed_bytes(void);
+/* Packs `raw` (device pointers) into `packed`.  Do once per checkpoint. */
+GP_API int gp_trunk_pack(const gp_trunk_params *raw, void *packed, gp_stream_t s);
+
+/* Per-object hoisted head projection: proj[b, 0:768] = head_w0[:, :1024] @ pts_feat[b] + head_b0
+ * (the pts_feat columns of scorenet.py:249,259-261, constant over hypotheses and ODE stages).
+ * pts_feat [B,1024] f32 -> proj [B,768] f32. */
+GP_API int gp_trunk_project(const void *packed, const float *pts_feat, int B, float *proj, gp_stream_t s);
+
+/* One PoseScoreNet.forward (scorenet.py:215-275): x [N,9] f32, t [N] f32 (one value per row),
+ * proj [B,768] with row i belonging to object i / rows_per_object -> score [N,9] f32
+ * (= f_theta / (std + 1e-7)).  Used by GFObjectPose.forward(mode="score") (posenet.py:305-307). */
+GP_API int gp_scorenet_eval(const void *packed, const float *proj, const float *x, const float *t, int N,
+                     int rows_per_object, float *score, gp_stream_t s);
+
+/* Integrator statistics written by gp_scorenet_ode (device, 16 doubles). */
+enum gp_ode_stat {
+    GP_STAT_NFEV = 0,      /* RHS evaluations inside the solver (scipy res.nfev) */
+    GP_STAT_ACCEPTED = 1,  /* accepted steps (res.t.size - 1) */
+    GP_STAT_REJECTED = 2,
+    GP_STAT_STATUS = 3,    /* 0 finished, -1 step size underflow, -2 attempt cap hit */
+    GP_STAT_T_FINAL = 4,
+    GP_STAT_H_INITIAL = 5,
+    GP_STAT_H_LAST = 6,
+    GP_STAT_COUNT = 16
+};
+
+/* Bytes of device workspace gp_scorenet_ode needs for N rows. */
+GP_API size_t gp_scorenet_ode_workspace_bytes(int N);
+
+/* Replaces cond_ode_sampler (networks/gf_algorithms/samplers.py:180-258) including the host
+ * scipy.integrate.solve_ivp(RK45) loop (samplers.py:226-234), the denoise step (:238-249),
+ * Gram-Schmidt (:251-257) and `+ pts_center`: a device-resident Dormand-Prince 5(4) integrator
+ * with scipy's step-size control shared over the flattened batch, fused with the ScoreNet RHS.
+ *   x0          [N,9] f64   initial state  (= prior(T) [+ init_x], samplers.py:197-201)
+ *   proj        [B,768] f32 from gp_trunk_project;   row i -> object i / rows_per_object
+ *   pts_center  [N,3] f32
+ *   T, eps, rtol, atol      as in the reference call (posenet.py:253-266)
+ *   denoise     0/1
+ *   x_out       [N,9] f64   final pose (normalised rotation, centre added)
+ *   traj        NULL, or [max_traj, N, 9] f64: raw state after every accepted step, slot 0 = x0
+ *   stats       [GP_STAT_COUNT] f64 (device)
+ *   mode        0 = fp32 (FFMA) MLP, 1 = bf16 tensor-core MLP (tcgen05)
+ */
+GP_API int gp_scorenet_ode(const void *packed, const float *proj, const double *x0,
+                    const float *pts_center, int N, int rows_per_object, double T, double eps,
+                    double rtol, double atol, int denoise, double *x_out, double *traj,
+                    int max_traj, double *stats, void *workspace, size_t workspace_bytes, int mode,
+                    gp_stream_t s);
+
+/* Post-processing of a recorded trajectory into the reference's `xs` (samplers.py:251-255):
+ * traj [S,N,9] f64 raw -> xs [N,S,9] f64 with Gram-Schmidt on the rotation part and the centre
+ * added. */
+GP_API int gp_traj_finalize(const double *traj, const float *pts_center, int S, int N, double *xs,
+                     gp_stream_t s);
+
+/* Replaces cond_pc_sampler (samplers.py:113-177): num_steps x {Langevin corrector, Euler-Maruyama
+ * predictor}, time grid linspace(1, eps, num_steps), one batch-wide step-size reduction per step.
+ *   x0 [N,9] f32; noise [num_steps,2,N,9] f32 (the torch.randn_like draws in call order);
+ *   time_steps [num_steps] f32 (device) = torch.linspace(1.0, eps, num_steps) (samplers.py:129);
+ *   xs NULL or [N,num_steps,9] f32; mean_x [N,9] f32. */
+GP_API size_t gp_scorenet_pc_workspace_bytes(int N);
+GP_API int gp_scorenet_pc(const void *packed, const float *proj, const float *x0, const float *noise,
+                   const float *pts_center, const float *time_steps, int N, int rows_per_object,
+                   int num_steps, double snr, float *xs, float *mean_x, void *workspace,
+                   size_t workspace_bytes, gp_stream_t s);
+
+/* Replaces PoseNet.get_energy's network call + PoseEnergyNet.get_energy
+ * (posenet_agent.py:660-705, energynet.py:151-208; energy_mode=IP, s_theta_mode=score,
+ * norm_energy=identical).  poses [N,9] f64 camera frame; the centre is subtracted from the
+ * translation (posenet_agent.py:694), the pose cast to f32 (:668-670).  t_rows [N] f32.
+ * -> energy [N,2] f32 = [E_rot, E_trans]. */
+GP_API int gp_energy(const void *packed, const float *proj, const double *poses, const float *pts_center,
+              const float *t_rows, int N, int rows_per_object, float *energy, gp_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
+ * (4) Energy-ranked outlier rejection + quaternion averaging + DBSCAN, and the ScaleNet head.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces sort_poses_by_energy (networks/reward.py:131-155) + the aggregation block
+ * (runners/evaluation_single.py:179-215 = evaluation_tracking.py:146-183 = infer.py:158-194):
+ * rot / trans ranked independently by their energy channel, top `retain` kept, 6D -> quaternion,
+ * eigen-average (utils/misc.py:295-317), DBSCAN(eps, min_samples) on the rows of the
+ * 1 - <qi,qj>^2 matrix, largest cluster re-averaged, mean translation.
+ *   poses [B,R,9] f64, energy [B,R,2] f32 -> pose_out [B,4,4] f32;
+ *   labels_out NULL or [B,retain] i32 (DBSCAN labels, for inspection);
+ *   sorted_out NULL or [B,R,9] f64 (sort_poses_by_energy's first return value).
+ * Requires R <= 64 and retain <= 32. */
+GP_API int gp_aggregate(const double *poses, const float *energy, int B, int R, int retain,
+                 int clustering, double clustering_eps, int min_samples, float *pose_out,
+                 int32_t *labels_out, double *sorted_out, gp_stream_t s);
+
+typedef struct gp_scalenet_params {
+    const float *axes_w0; /* axes_encoder.0.weight [256,180] (networks/scalenet.py:20-25) */
+    const float *axes_b0;
+    const float *axes_w1; /* axes_encoder.2.weight [256,256] */
+    const float *axes_b1;
+    const float *tail_w0; /* fusion_tail_length.0.weight [256,1280] */
+    const float *tail_b0;
+    const float *tail_w1; /* fusion_tail_length.2.weight [3,256] */
+    const float *tail_b1;
+} gp_scalenet_params;
+
+/* Replaces ScaleNet.forward (networks/scalenet.py:33-49) + encode_axes
+ * (utils/genpose_utils.py:8-18).  axes [B,3,3] f32 (row stride `axes_stride` floats, so the
+ * [:3,:3] block of a [B,4,4] pose can be passed with stride 4 and batch stride 16),
+ * pts_feat [B,1024] -> length [B,3]. */
+GP_API int gp_scalenet(const gp_scalenet_params *p, const float *axes, int axes_batch_stride,
+                int axes_row_stride, const float *pts_feat, int B, float *length, gp_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENPOSE_B200_H */

@@ -1,0 +1,195 @@
+"""CPU: the C-ABI library loads and exports every symbol include/genpose_b200.h declares (no
+compute without a GPU), the host mirror has the reference's state-dict layout and config keys,
+unsupported configurations raise instead of falling back, and the multi-GPU sharding logic works
+over gloo with world_size 2."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from genpose2_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "genpose_b200.h")).read()
+    declared = set(re.findall(r"GP_API [^;(]*?\b(gp_[a-z0-9_]+)\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib2 = _lib.load()
+    assert lib2.gp_version() == 1
+    assert lib2.gp_trunk_packed_bytes() > 4 * (768 * 1024 + 256 * 768)
+    assert lib2.gp_scorenet_ode_workspace_bytes(3200) >= 10 * 3200 * 9 * 8
+
+
+def test_bad_arguments_return_status_not_exit():
+    from genpose2_b200 import _lib
+    lib = _lib.load()
+    rc = lib.gp_fps(None, 1, 16, 4, None, None, None)
+    assert rc == -1 and b"null" in lib.gp_last_error()
+    rc = lib.gp_aggregate(ctypes.c_void_p(8), ctypes.c_void_p(8), 1, 100, 20, 1, 0.05, 3, ctypes.c_void_p(8), None, None, None)
+    assert rc == -1 and b"R=100" in lib.gp_last_error()
+
+
+def test_cpu_tensors_are_rejected_no_fallback():
+    from genpose2_b200 import pointnet2_utils as pu
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        pu.furthest_point_sample(torch.randn(1, 8, 3), 2)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        pu.ball_query(0.1, 4, torch.randn(1, 8, 3), torch.randn(1, 2, 3))
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from genpose2_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU / PyTorch fallback"):
+        _lib.load()
+
+
+def test_state_dict_layout_matches_reference_layout():
+    """the synthetic state dicts were loaded with strict load_state_dict into the REFERENCE modules
+    by tests/golden/make_golden.py; here the same dicts must load strictly into the mirror."""
+    from genpose2_b200 import synthetic
+    from genpose2_b200.config import get_config
+    from genpose2_b200.posenet import GFObjectPose
+    from genpose2_b200.scalenet import ScaleNet
+    from genpose2_b200.sde import init_sde
+    cfg = get_config()
+    cfg.device = "cpu"
+    for agent_type in ("score", "energy"):
+        cfg.agent_type = agent_type
+        net = GFObjectPose(cfg, *init_sde("ve"))
+        sd = synthetic.random_gfobjectpose_state_dict(1)
+        assert set(net.state_dict().keys()) == set(sd.keys())
+        net.load_state_dict(sd, strict=True)
+        assert sum(p.numel() for p in net.parameters()) == 3776937  # SURVEY.md 8(c) probe
+    sn = ScaleNet(1024, 0, 180)
+    sn.load_state_dict(synthetic.random_scalenet_state_dict(2), strict=True)
+    assert sum(p.numel() for p in sn.parameters()) == 440835
+
+
+def test_config_keys_and_unsupported_modes_raise():
+    from genpose2_b200.config import get_config
+    from genpose2_b200.posenet import GFObjectPose
+    from genpose2_b200.sde import init_sde
+    cfg = get_config()
+    for key, val in dict(pose_mode="rot_matrix", sde_mode="ve", regression_head="Rx_Ry_and_T", pts_encoder="pointnet2",
+                         energy_mode="IP", s_theta_mode="score", norm_energy="identical", scale_embedding=180,
+                         num_points=1024, eval_repeat_num=50, retain_ratio=0.4, clustering=1, clustering_eps=0.05,
+                         clustering_minpts=0.1667, seed=0, T0=1.0).items():
+        assert getattr(cfg, key) == val, key
+    assert get_config(["--T0", "0.55", "--sampler_mode", "ode"]).T0 == 0.55
+    with pytest.raises(NotImplementedError):
+        init_sde("vp")
+    cfg.device = "cpu"
+    for key, bad in (("dino", "pointwise"), ("pts_encoder", "pointnet"), ("regression_head", "RT"), ("pose_mode", "quat_wxyz")):
+        c = get_config()
+        c.device = "cpu"
+        setattr(c, key, bad)
+        with pytest.raises(NotImplementedError):
+            GFObjectPose(c, *init_sde("ve"))
+    c = get_config()
+    c.device = "cpu"
+    c.agent_type = "energy"
+    c.energy_mode = "L2"
+    with pytest.raises(NotImplementedError):
+        GFObjectPose(c, *init_sde("ve"))
+
+
+def test_sde_matches_oracle():
+    from genpose2_b200 import sde
+    from oracle import pose_oracle as po
+    prior, marg, sde_fn, eps, T = sde.init_sde("ve")
+    assert eps == 1e-5 and T == 1.0
+    t = torch.tensor([[0.3], [0.9]])
+    assert torch.equal(marg(None, t)[1], po.ve_marginal_std(t))
+    assert torch.equal(sde_fn(t)[1], po.ve_sde(t)[1])
+    torch.manual_seed(3)
+    a = prior((4, 9), T=0.55)
+    torch.manual_seed(3)
+    assert torch.equal(a, po.ve_prior((4, 9), T=0.55))
+
+
+def test_shard_range_partitions_contiguously():
+    from genpose2_b200.pipeline import shard_range
+    for n in (0, 1, 7, 64, 8192, 8191):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["GP_ROOT"])
+from genpose2_b200.pipeline import gather_results, shard_range
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["GP_PORT"],
+                        rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+B = 7  # ragged: 4 + 3
+lo, hi = shard_range(B, rank, world)
+g = torch.Generator().manual_seed(0)
+pose_full = torch.randn(B, 4, 4, generator=g); length_full = torch.randn(B, 3, generator=g)
+pose, length = gather_results(pose_full[lo:hi].clone(), length_full[lo:hi].clone())
+assert torch.equal(pose, pose_full) and torch.equal(length, length_full), (rank, pose.shape)
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_gather_results_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", GP_PORT=str(port), GP_ROOT=ROOT)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out.decode()
+
+
+def test_oracle_pointnet2_matches_bruteforce_numpy():
+    """the C restatement itself: FPS against a direct numpy transcription for a power-of-two N
+    without ties (where the tree tie-break cannot matter), ball query against a brute-force scan."""
+    import numpy as np
+    from oracle import pointnet2_oracle as pn
+    rng = np.random.default_rng(0)
+    xyz = rng.normal(size=(2, 256, 3)).astype(np.float32)
+    idx = pn.furthest_point_sample(xyz, 40)
+    for b in range(2):
+        d = np.full(256, 1e10, np.float32)
+        cur = 0
+        for j in range(1, 40):
+            diff = xyz[b] - xyz[b, cur]
+            dist = (diff[:, 1] * diff[:, 1]).astype(np.float32)
+            dist = (diff[:, 0].astype(np.float64) * diff[:, 0] + dist).astype(np.float32)  # one fma
+            dist = (diff[:, 2].astype(np.float64) * diff[:, 2] + dist).astype(np.float32)
+            d = np.minimum(d, dist)
+            cur = int(np.argmax(d))
+            assert idx[b, j] == cur
+    new_xyz = np.take_along_axis(xyz, idx[..., None].astype(np.int64), 1)
+    bq = pn.ball_query(0.9, 6, xyz, new_xyz)
+    for b in range(2):
+        for i in range(40):
+            diff = new_xyz[b, i] - xyz[b]
+            d2 = (diff ** 2).sum(1)
+            hits = np.nonzero(d2 < np.float32(0.9) ** 2 * 0.999)[0]
+            got = bq[b, i]
+            n = min(len(hits), 6)
+            assert set(got[:n]) <= set(np.nonzero(d2 < np.float32(0.9) ** 2 * 1.001)[0])
+            assert (got[n:] == got[0]).all() or len(hits) >= 6
+    assert pn.fps_block_size(1000) == 512 and pn.fps_block_size(1024) == 1024 and pn.fps_block_size(5000) == 1024

@@ -1,0 +1,72 @@
+"""GPU: energy-ranked outlier rejection + quaternion averaging + DBSCAN (gp_aggregate) and the
+ScaleNet head (gp_scalenet) vs the golden fixtures produced by the reference functions + sklearn."""
+import numpy as np
+import pytest
+import torch
+
+from genpose2_b200 import synthetic
+from oracle import pose_oracle as po
+from tests.util import geodesic_mats, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sort_poses_by_energy_matches_reference():
+    from genpose2_b200.aggregation import sort_poses_by_energy
+    g = load_golden("aggregate_clusters")
+    sp, se = sort_poses_by_energy(torch.from_numpy(g["poses"]).cuda(), torch.from_numpy(g["energy"]).cuda())
+    np.testing.assert_array_equal(sp.cpu().numpy(), g["sorted_pose"])
+    np.testing.assert_array_equal(se.cpu().numpy(), g["sorted_energy"])
+
+
+def test_aggregate_clusters_matches_reference():
+    from genpose2_b200.aggregation import aggregate_pose
+    g = load_golden("aggregate_clusters")
+    out, labels = aggregate_pose(torch.from_numpy(g["poses"]).cuda(), torch.from_numpy(g["energy"]).cuda(),
+                                 eval_repeat_num=50, return_labels=True)
+    np.testing.assert_array_equal(labels.cpu().numpy(), g["labels"])
+    want = g["aggregated_pose"]
+    got = out.cpu().numpy()
+    assert got.dtype == np.float32 and got.shape == want.shape
+    assert geodesic_mats(got[:, :3, :3].astype(np.float64), want[:, :3, :3].astype(np.float64)).max() < 1e-5
+    np.testing.assert_allclose(got[:, :3, 3], want[:, :3, 3], rtol=0, atol=1e-6)
+    np.testing.assert_array_equal(got[:, 3], np.tile(np.array([0, 0, 0, 1], np.float32), (got.shape[0], 1)))
+
+
+def test_aggregate_random_vs_oracle_many_objects():
+    """many objects, several jitter levels (cluster / no cluster / multi-cluster), no-clustering flag"""
+    from genpose2_b200.aggregation import aggregate_pose
+    for seed, jitter in ((1, 1.0), (2, 4.0), (3, 12.0)):
+        poses = synthetic.make_cluster_quaternion_poses(40, 50, seed=seed, jitter_deg=jitter)
+        energy = torch.randn(40, 50, 2, generator=torch.Generator().manual_seed(seed))
+        for clustering in (1, 0):
+            want, wl = po.aggregate_pose(poses, energy, clustering=bool(clustering))
+            got, gl = aggregate_pose(poses.cuda(), energy.cuda(), eval_repeat_num=50, clustering=clustering,
+                                     return_labels=True)
+            if clustering:
+                np.testing.assert_array_equal(gl.cpu().numpy(), wl)
+            g, w = got.cpu().numpy().astype(np.float64), want.numpy().astype(np.float64)
+            assert geodesic_mats(g[:, :3, :3], w[:, :3, :3]).max() < 1e-5
+            np.testing.assert_allclose(g[:, :3, 3], w[:, :3, 3], rtol=0, atol=1e-6)
+
+
+def test_scalenet_matches_reference_golden():
+    from genpose2_b200.scalenet import ScaleNet
+    g = load_golden("scalenet_b5")
+    net = ScaleNet(1024, 0, 180).cuda()
+    net.load_state_dict(synthetic.random_scalenet_state_dict(int(g["scale_seed"])))
+    out = net({"pts_feat": torch.from_numpy(g["feat"]).cuda(), "axes": torch.from_numpy(g["axes"]).cuda()})
+    np.testing.assert_allclose(out.cpu().numpy(), g["length"], rtol=2e-5, atol=2e-6)
+    # strided axes view of a [B,4,4] pose
+    pose = torch.zeros(5, 4, 4, device="cuda")
+    pose[:, :3, :3] = torch.from_numpy(g["axes"]).cuda()
+    out2 = net({"pts_feat": torch.from_numpy(g["feat"]).cuda(), "axes": pose[:, :3, :3]})
+    assert torch.equal(out, out2)
+    # larger batch path (8 objects per block)
+    B = 1300
+    gen = torch.Generator().manual_seed(0)
+    feat = torch.relu(torch.randn(B, 1024, generator=gen))
+    axes = torch.from_numpy(synthetic._random_rotations(np.random.default_rng(0), B)).float()
+    want = po.scalenet_forward(synthetic.random_scalenet_state_dict(int(g["scale_seed"])), axes, feat)
+    got = net({"pts_feat": feat.cuda(), "axes": axes.cuda()}).cpu()
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=2e-5, atol=2e-6)

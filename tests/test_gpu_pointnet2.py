@@ -1,0 +1,173 @@
+"""GPU: FPS / ball query / gather / grouping through the C ABI vs (i) the C restatement in oracle/
+and (ii) the reference's own CUDA extension (oracle/_ref) -- indices must be bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from genpose2_b200 import synthetic
+from oracle import pointnet2_oracle as po
+from tests.util import ref_ext
+
+pytestmark = pytest.mark.gpu
+
+
+def clouds(B, N, seed, dup_fraction=0.5):
+    pts, _ = synthetic.make_point_clouds(B, N, seed=seed, dup_fraction=dup_fraction)
+    return pts.cuda().contiguous()
+
+
+def ref_fps(ext, xyz, m):
+    B, N, _ = xyz.shape
+    out = torch.empty((B, m), dtype=torch.int32, device="cuda")
+    temp = torch.full((B, N), 1e10, dtype=torch.float32, device="cuda")
+    ext.furthest_point_sampling_wrapper(B, N, m, xyz, temp, out)
+    return out
+
+
+def ref_bq(ext, radius, ns, xyz, new_xyz):
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    idx = torch.zeros((B, M, ns), dtype=torch.int32, device="cuda")
+    ext.ball_query_wrapper(B, N, M, radius, ns, new_xyz, xyz, idx)
+    return idx
+
+
+@pytest.mark.parametrize("N", [1, 2, 5, 33, 64, 128, 256, 512, 1000, 1024, 1500, 2048, 4096])
+def test_fps_bit_exact_vs_oracle(N):
+    from genpose2_b200 import pointnet2_utils as pu
+    B = 6 if N <= 1024 else 2
+    xyz = clouds(B, N, seed=N) if N >= 300 else torch.randn(B, N, 3, device="cuda")
+    if N >= 8:
+        xyz[0, N // 2:] = xyz[0, : N - N // 2]  # exact duplicates: ties everywhere
+        xyz[1] = xyz[1, 0]  # all points identical
+    m = max(1, N // 2)
+    got = pu.furthest_point_sample(xyz, m).cpu().numpy()
+    want = po.furthest_point_sample(xyz.cpu().numpy(), m)
+    np.testing.assert_array_equal(got, want)
+    idx2, new_xyz = pu.furthest_point_sample_gather(xyz, m)
+    np.testing.assert_array_equal(idx2.cpu().numpy(), want)
+    np.testing.assert_array_equal(new_xyz.cpu().numpy(), np.take_along_axis(xyz.cpu().numpy(), want[..., None].astype(np.int64), 1))
+
+
+@pytest.mark.parametrize("N,B", [(1024, 64), (1000, 8), (2048, 32), (4096, 16), (8192, 8), (16384, 4)])
+def test_fps_bit_exact_vs_reference_ext(N, B):
+    ext = ref_ext()
+    if ext is None:
+        pytest.skip("reference extension (oracle/_ref) not loadable")
+    from genpose2_b200 import pointnet2_utils as pu
+    xyz = clouds(B, N, seed=100 + N)
+    m = N // 2
+    got = pu.furthest_point_sample(xyz, m)
+    want = ref_fps(ext, xyz, m)
+    assert torch.equal(got, want)
+
+
+def test_fps_encoder_levels_vs_reference_ext():
+    """the four FPS levels of the encoder (1024->512->256->128->64), each on the previous level's output"""
+    ext = ref_ext()
+    from genpose2_b200 import pointnet2_utils as pu
+    xyz = clouds(64, 1024, seed=7)
+    for m in (512, 256, 128, 64):
+        idx, new_xyz = pu.furthest_point_sample_gather(xyz, m)
+        want = po.furthest_point_sample(xyz.cpu().numpy(), m) if ext is None else ref_fps(ext, xyz, m).cpu().numpy()
+        np.testing.assert_array_equal(idx.cpu().numpy(), want)
+        xyz = new_xyz
+
+
+@pytest.mark.parametrize("N,M,radius,ns", [(1024, 512, 0.01, 16), (1024, 512, 0.02, 32), (512, 256, 0.04, 32),
+                                           (128, 64, 0.16, 32), (1000, 77, 0.03, 5), (5000, 300, 0.02, 16),
+                                           (64, 64, 1e-6, 8)])
+def test_ball_query_bit_exact(N, M, radius, ns):
+    from genpose2_b200 import pointnet2_utils as pu
+    ext = ref_ext()
+    B = 5
+    xyz = clouds(B, N, seed=N + M)
+    idx = pu.furthest_point_sample(xyz, M)
+    new_xyz = torch.gather(xyz, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    new_xyz[0, 0] += 10.0  # an empty ball -> all zeros
+    got = pu.ball_query(radius, ns, xyz, new_xyz)
+    want = po.ball_query(radius, ns, xyz.cpu().numpy(), new_xyz.cpu().numpy())
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    assert (got[0, 0] == 0).all()
+    if ext is not None:
+        assert torch.equal(got, ref_bq(ext, radius, ns, xyz, new_xyz))
+    g0, g1 = pu.ball_query2([radius, radius * 2], [ns, ns * 2], xyz, new_xyz)
+    assert torch.equal(g0, got)
+    np.testing.assert_array_equal(g1.cpu().numpy(), po.ball_query(radius * 2, ns * 2, xyz.cpu().numpy(), new_xyz.cpu().numpy()))
+
+
+def test_gather_group_match_oracle_and_reference():
+    from genpose2_b200 import pointnet2_utils as pu
+    ext = ref_ext()
+    B, C, N, M, ns = 3, 37, 513, 100, 12
+    feats = torch.randn(B, C, N, device="cuda")
+    idx = torch.randint(0, N, (B, M), dtype=torch.int32, device="cuda")
+    g = pu.gather_operation(feats, idx)
+    np.testing.assert_array_equal(g.cpu().numpy(), po.gather_operation(feats.cpu().numpy(), idx.cpu().numpy()))
+    gi = torch.randint(0, N, (B, M, ns), dtype=torch.int32, device="cuda")
+    out = pu.grouping_operation(feats, gi)
+    np.testing.assert_array_equal(out.cpu().numpy(), po.grouping_operation(feats.cpu().numpy(), gi.cpu().numpy()))
+    gi5 = torch.randint(0, N, (B, M, 5), dtype=torch.int32, device="cuda")  # scalar fallback (ns % 4 != 0)
+    out5 = pu.grouping_operation(feats, gi5)
+    np.testing.assert_array_equal(out5.cpu().numpy(), po.grouping_operation(feats.cpu().numpy(), gi5.cpu().numpy()))
+    if ext is not None:
+        ref = torch.empty_like(out)
+        ext.group_points_wrapper(B, C, N, M, ns, feats, gi, ref)
+        assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("C", [0, 96])
+def test_query_group_matches_reference_composition(C):
+    """QueryAndGroup.forward (pointnet2_utils.py:279-296) composed from the oracle pieces."""
+    from genpose2_b200 import pointnet2_utils as pu
+    B, N, M, ns = 4, 512, 256, 16
+    xyz = clouds(B, N, seed=3)
+    idx, new_xyz = pu.furthest_point_sample_gather(xyz, M)
+    feats = torch.randn(B, C, N, device="cuda") if C else None
+    bq = pu.ball_query(0.03, ns, xyz, new_xyz)
+    got = pu.QueryAndGroup(0.03, ns)(xyz, new_xyz, feats).cpu()
+    gx = torch.from_numpy(po.grouping_operation(xyz.cpu().transpose(1, 2).contiguous().numpy(), bq.cpu().numpy()))
+    gx = gx - new_xyz.cpu().transpose(1, 2).unsqueeze(-1)
+    want = gx if not C else torch.cat([gx, torch.from_numpy(po.grouping_operation(feats.cpu().numpy(), bq.cpu().numpy()))], 1)
+    assert torch.equal(got, want)
+
+
+def test_full_size_properties_c3_sweep():
+    """BASELINE config 3 sizes (256 objects, N up to 16384): size-independent FPS / ball-query
+    properties, plus bit-exactness vs the reference ext when it is present."""
+    from genpose2_b200 import pointnet2_utils as pu
+    ext = ref_ext()
+    for N, B in ((1024, 256), (4096, 256), (16384, 64)):
+        xyz = clouds(B, N, seed=N + 1, dup_fraction=0.0) * 1.0
+        m = N // 2
+        idx, new_xyz = pu.furthest_point_sample_gather(xyz, m)
+        assert (idx[:, 0] == 0).all() and int(idx.min()) >= 0 and int(idx.max()) < N
+        srt = torch.sort(idx.long(), dim=1)[0]
+        assert (srt[:, 1:] != srt[:, :-1]).all(), "FPS must not repeat a point while distinct points remain"
+        # farthest-point property on a prefix: the distance of pick j to the earlier picks is non-increasing
+        p = new_xyz[:, :64]
+        d = (p[:, :, None].double() - p[:, None].double()).norm(dim=-1)
+        mins = torch.stack([d[:, j, :j].min(dim=1)[0] for j in range(1, 64)], dim=1)
+        assert (mins[:, 1:] <= mins[:, :-1] + 1e-6).all()
+        r, ns = 0.02 * (1024 / N) ** 0.5, 16
+        bq = pu.ball_query(r, ns, xyz, new_xyz[:, :512].contiguous())
+        g = torch.gather(xyz, 1, bq.long().reshape(B, -1, 1).expand(-1, -1, 3)).reshape(B, 512, ns, 3)
+        dist = (g - new_xyz[:, :512, None]).norm(dim=-1)
+        assert (dist < r * 1.0001).all()  # every returned index is inside the ball (centres are cloud points)
+        assert (bq[:, :, 1:] >= bq[:, :, :1]).all()  # ordered scan with first-hit back-fill
+        if ext is not None:
+            assert torch.equal(idx, ref_fps(ext, xyz, m))
+            assert torch.equal(bq, ref_bq(ext, r, ns, xyz, new_xyz[:, :512].contiguous()))
+
+
+def test_edge_cases_and_errors():
+    from genpose2_b200 import pointnet2_utils as pu
+    xyz = torch.randn(2, 16, 3, device="cuda")
+    assert pu.furthest_point_sample(xyz, 1).tolist() == [[0], [0]]
+    assert pu.furthest_point_sample(torch.randn(0, 16, 3, device="cuda"), 4).shape == (0, 4)
+    with pytest.raises(RuntimeError):
+        pu.furthest_point_sample(torch.randn(1, 20000, 3, device="cuda"), 4)  # documented limit
+    with pytest.raises(RuntimeError):
+        pu.furthest_point_sample(torch.randn(2, 16, 3), 4)  # CPU tensor: no fallback
+    with pytest.raises(TypeError):
+        pu.gather_operation(torch.randn(1, 3, 8, device="cuda"), torch.zeros(1, 4, dtype=torch.int64, device="cuda"))
