@@ -144,7 +144,7 @@ static int launch_fps(const float *xyz, int B, int N, int m, FpsOrder order, int
     size_t smem = (size_t)N * 3 * sizeof(float);
     smem = (smem + 15) & ~(size_t)15;
     auto kern = fps_kernel<NWARPS, PPT, REGS>;
-    if (smem > 48 * 1024) GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<B, NWARPS * 32, smem, st>>>(xyz, N, m, order, idx, new_xyz);
     GP_CHECK_LAUNCH("gp_fps");
     return GP_OK;
@@ -156,9 +156,9 @@ using namespace gp;
 
 extern "C" int gp_fps(const float *xyz, int B, int N, int m, int32_t *idx, float *new_xyz,
                       gp_stream_t s) {
-    GP_REQUIRE(xyz && idx, "gp_fps: null pointer");
     GP_REQUIRE(B >= 0 && N >= 1 && m >= 0, "gp_fps: bad sizes B=%d N=%d m=%d", B, N, m);
     if (B == 0 || m == 0) return GP_OK;
+    GP_REQUIRE(xyz && idx, "gp_fps: null pointer");
     if (N > 16384) {
         set_error("gp_fps: N=%d > 16384 is not supported (cloud must fit in shared memory)", N);
         return GP_ERR_UNSUPPORTED;

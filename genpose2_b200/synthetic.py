@@ -149,7 +149,7 @@ def make_point_clouds(num_objects, num_points=1024, seed=0, dup_fraction=0.1, sc
             p = p_cam
         p = p[:N] + rng.normal(0.0, 1e-3, size=(N, 3))
         if rng.uniform() < dup_fraction:
-            K = int(rng.integers(300, min(900, N - 1) + 1))
+            K = int(rng.integers(max(1, (3 * N) // 10), max(2, (9 * N) // 10) + 1)) if N < 1000 else int(rng.integers(300, 901))
             # sample_points: ids = concat(tile(arange(K), N // K), choice(K, N % K))
             ids = np.concatenate(
                 [np.tile(np.arange(K), N // K), rng.choice(K, N % K, replace=False)]

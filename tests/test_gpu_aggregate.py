@@ -19,6 +19,22 @@ def test_sort_poses_by_energy_matches_reference():
     np.testing.assert_array_equal(se.cpu().numpy(), g["sorted_energy"])
 
 
+def test_sort_ties_are_stable_descending():
+    """torch.sort(stable=False) leaves the order of equal energies unspecified; gp_aggregate is
+    stable-descending (equal keys keep hypothesis order)."""
+    from genpose2_b200.aggregation import sort_poses_by_energy
+    poses = torch.arange(2 * 10 * 9, dtype=torch.float64).reshape(2, 10, 9).cuda()
+    energy = torch.tensor([3., 1., 3., 2., 1., 3., 0., 2., 9., 1.]).repeat(2, 1).unsqueeze(-1).repeat(1, 1, 2).cuda()
+    energy[1, :, 1] = -energy[1, :, 1]
+    sp, se = sort_poses_by_energy(poses, energy)
+    order = [8, 0, 2, 5, 3, 7, 1, 4, 9, 6]
+    assert sp[0, :, 0].tolist() == [poses[0, i, 0].item() for i in order]
+    assert sp[0, :, 8].tolist() == [poses[0, i, 8].item() for i in order]
+    rev = [6, 1, 4, 9, 3, 7, 0, 2, 5, 8]
+    assert sp[1, :, 8].tolist() == [poses[1, i, 8].item() for i in rev]
+    assert sp[1, :, 5].tolist() == [poses[1, i, 5].item() for i in order]
+
+
 def test_aggregate_clusters_matches_reference():
     from genpose2_b200.aggregation import aggregate_pose
     g = load_golden("aggregate_clusters")

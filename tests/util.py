@@ -24,8 +24,11 @@ def rot_from_6d(x):
 
 
 def geodesic_mats(Ra, Rb):
-    tr = np.einsum("bij,bij->b", Ra, Rb)
-    return np.arccos(np.clip((tr - 1) / 2, -1, 1))
+    """rotation angle between Ra and Rb.  ||Ra - Rb||_F = 2 sqrt(2) |sin(theta / 2)|: unlike
+    arccos((tr - 1) / 2) this stays accurate for tiny angles (arccos turns a 6e-8 float32 rounding
+    of the trace into a 2e-4 rad 'error')."""
+    d = np.linalg.norm((np.asarray(Ra, np.float64) - np.asarray(Rb, np.float64)).reshape(-1, 9), axis=1)
+    return 2.0 * np.arcsin(np.clip(d / (2.0 * np.sqrt(2.0)), 0.0, 1.0))
 
 
 def geodesic_6d(x, y):
