@@ -49,7 +49,7 @@ SIGNATURES = {
     "gp_trunk_packed_bytes": (c_size_t, []),
     "gp_trunk_pack": (c_int, [ctypes.POINTER(TrunkParams), c_void_p, c_void_p]),
     "gp_trunk_project": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
-    "gp_scorenet_eval": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "gp_scorenet_eval": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "gp_scorenet_ode_workspace_bytes": (c_size_t, [c_int]),
     "gp_scorenet_ode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_double,
                                 c_double, c_double, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
@@ -57,8 +57,8 @@ SIGNATURES = {
     "gp_traj_finalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "gp_scorenet_pc_workspace_bytes": (c_size_t, [c_int]),
     "gp_scorenet_pc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                               c_int, c_double, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "gp_energy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+                               c_int, c_double, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "gp_energy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "gp_aggregate": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_int, c_void_p,
                              c_void_p, c_void_p, c_void_p]),
     "gp_scalenet": (c_int, [ctypes.POINTER(ScaleNetParams), c_void_p, c_int, c_int, c_void_p, c_int,

@@ -4,7 +4,7 @@
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
-#include "trunk.cuh"
+#include "trunk_tc.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -57,13 +57,22 @@ __global__ void pack_trunk_kernel(RawTrunk raw, float *__restrict__ P) {
         } else if (i < TrunkLayout::F32_END) {
             const size_t c = i - TrunkLayout::BO;
             v = c < 9 ? p.head_b1[c / 3][c % 3] : 0.f;
-        } else if (i < TrunkLayout::WHP_BF16) {  // two bf16 per float slot: W2[n][k], K contiguous
-            const size_t e = (i - TrunkLayout::W2_BF16) * 2;
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(p.pose_w1[e], p.pose_w1[e + 1]);
-            v = *reinterpret_cast<float *>(&h2);
-        } else {  // WHP[n][k] = head_w0[h][j][1152+k]
-            const size_t e = (i - TrunkLayout::WHP_BF16) * 2, n = e / 256, k = e % 256;
-            const float *src = p.head_w0[n / 256] + (n % 256) * 1408 + 1152 + k;
+        } else if (i < TrunkLayout::W_TC) {
+            v = 0.f;  // alignment padding
+        } else {
+            // destination float slot -> byte offset inside chunk c -> (row n, 16-byte chunk, element pair)
+            const size_t f = i - TrunkLayout::W_TC;
+            const size_t c = f / (256 * 64 / 2), o = (f % (256 * 64 / 2)) * 4;
+            const size_t n = o / 128, wb = o % 128;
+            const size_t logical16 = (wb / 16) ^ (n & 7);      // undo the SWIZZLE_128B XOR
+            const size_t kk = logical16 * 8 + (wb % 16) / 2;    // k inside the 64-wide atom
+            const float *src;
+            if (c < 4) {
+                src = p.pose_w1 + n * 256 + c * 64 + kk;       // W2[n][k]
+            } else {
+                const size_t h = (c - 4) / 4, a = (c - 4) % 4;
+                src = p.head_w0[h] + n * 1408 + 1152 + a * 64 + kk;  // head h, pose_feat columns
+            }
             __nv_bfloat162 h2 = __floats2bfloat162_rn(src[0], src[1]);
             v = *reinterpret_cast<float *>(&h2);
         }
@@ -118,32 +127,62 @@ project_kernel(const float *__restrict__ P, const float *__restrict__ feat, int 
 }
 
 // ------------------------------------------------------------------------------------------
-// single evaluation / energy: one CTA per tile; rows may carry different t (handled by runs)
+// Evaluator policies: how one tile of rows gets its f_theta.  SimtEval<RPT>: FP32 FFMA, 4*RPT rows,
+// 256 threads.  TcEval: bf16 tcgen05, 128 rows, 320 threads (trunk_tc.cuh).  Both expose the same
+// shared-memory members (x, out, obj, tq, four, tfeat, times, red) to the integrator code.
 // ------------------------------------------------------------------------------------------
 template <int RPT>
-struct EvalSmem {
-    TileSmem<RPT> tile;
-    float tq[768];
-    float four[128];
-    float tfeat[128];
-    float times[8];
-    float trow[4 * RPT];
+struct SimtEval {
+    static constexpr int RT = 4 * RPT;
+    static constexpr int NT = 256;
+    using Smem = TileSmem<RPT>;
+    struct Ctx {
+        float w1col[9];
+        float b1v;
+    };
+    static constexpr size_t smem_bytes() { return sizeof(Smem); }
+    static __device__ __forceinline__ Smem &smem(unsigned char *raw) { return *reinterpret_cast<Smem *>(raw); }
+    static __device__ __forceinline__ void setup(Smem &, Ctx &c, const float *P) { load_w1col(P, c.w1col, c.b1v); }
+    static __device__ __forceinline__ void teardown(Smem &, Ctx &) {}
+    static __device__ __forceinline__ void forward(const float *P, const float *proj, Smem &S, Ctx &c, const float *tq) {
+        tile_forward<RPT>(P, proj, S, tq, c.w1col, c.b1v);
+    }
 };
 
+struct TcEval {
+    static constexpr int RT = tc::RT;
+    static constexpr int NT = tc::NTHREADS;
+    using Smem = tc::Smem;
+    using Ctx = tc::State;
+    static constexpr size_t smem_bytes() { return sizeof(Smem) + 1024; }
+    static __device__ __forceinline__ Smem &smem(unsigned char *raw) {
+        return *reinterpret_cast<Smem *>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    }
+    static __device__ __forceinline__ void setup(Smem &S, Ctx &c, const float *P) { tc::setup(S, c, P); }
+    static __device__ __forceinline__ void teardown(Smem &S, Ctx &c) { tc::teardown(S, c); }
+    static __device__ __forceinline__ void forward(const float *P, const float *proj, Smem &S, Ctx &c, const float *tq) {
+        tc::forward(P, proj, S, c, tq);
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// single evaluation / energy: one CTA per tile; rows may carry different t (handled by runs)
 // MODE 0: score = f/(std+1e-7) -> out [N,9];  MODE 1: energy [N,2] from f64 poses
-template <int RPT, int MODE>
-__global__ void __launch_bounds__(256, 1)
+// ------------------------------------------------------------------------------------------
+template <class EV, int MODE>
+__global__ void __launch_bounds__(EV::NT, 1)
 eval_kernel(const float *__restrict__ P, const float *__restrict__ proj, const float *__restrict__ x,
             const double *__restrict__ poses, const float *__restrict__ center,
             const float *__restrict__ t, int N, int rpo, float *__restrict__ out) {
-    constexpr int RT = 4 * RPT;
+    constexpr int RT = EV::RT, NT = EV::NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    EvalSmem<RPT> &S = *reinterpret_cast<EvalSmem<RPT> *>(smem_raw);
+    typename EV::Smem &S = EV::smem(smem_raw);
+    typename EV::Ctx ctx;
     const int tid = threadIdx.x;
     const int r0 = blockIdx.x * RT;
-    float w1col[9], b1v;
-    load_w1col(P, w1col, b1v);
-    for (int i = tid; i < RT * 12; i += 256) {
+    EV::setup(S, ctx, P);
+    __shared__ float s_trow[EV::RT];
+    for (int i = tid; i < RT * 12; i += NT) {
         const int r = i / 12, c = i - 12 * r;
         float v = 0.f;
         if (r0 + r < N && c < 9) {
@@ -155,36 +194,36 @@ eval_kernel(const float *__restrict__ P, const float *__restrict__ proj, const f
                 if (c >= 6) v = v - center[(size_t)(r0 + r) * 3 + (c - 6)];
             }
         }
-        S.tile.x[i] = v;
+        S.x[i] = v;
     }
-    for (int r = tid; r < RT; r += 256) {
-        S.tile.obj[r] = (r0 + r < N) ? (r0 + r) / rpo : -1;
-        S.trow[r] = (r0 + r < N) ? t[r0 + r] : 0.f;
+    for (int r = tid; r < RT; r += NT) {
+        S.obj[r] = (r0 + r < N) ? (r0 + r) / rpo : -1;
+        s_trow[r] = (r0 + r < N) ? t[r0 + r] : 0.f;
     }
     __syncthreads();
     const int nrows = min(RT, N - r0);
     int run0 = 0;
     while (run0 < nrows) {  // maximal runs of equal t share one t-branch evaluation
-        const float tv = S.trow[run0];
+        const float tv = s_trow[run0];
         int run1 = run0 + 1;
-        while (run1 < nrows && S.trow[run1] == tv) ++run1;
+        while (run1 < nrows && s_trow[run1] == tv) ++run1;
         if (tid == 0) S.times[0] = tv;
         __syncthreads();
         compute_tq(P, S.times, 1, S.four, S.tfeat, S.tq);
-        tile_forward<RPT>(P, proj, S.tile, S.tq, w1col, b1v);
+        EV::forward(P, proj, S, ctx, S.tq);
         const float std = sigma_f32(tv);
         if (MODE == 0) {
-            for (int i = tid; i < (run1 - run0) * 9; i += 256) {
+            for (int i = tid; i < (run1 - run0) * 9; i += NT) {
                 const int r = run0 + i / 9, c = i % 9;
-                out[(size_t)(r0 + r) * 9 + c] = S.tile.out[0][r * 12 + c] / (std + 1e-7f);
+                out[(size_t)(r0 + r) * 9 + c] = S.out[0][r * 12 + c] / (std + 1e-7f);
             }
         } else {
-            for (int r = run0 + tid; r < run1; r += 256) {
+            for (int r = run0 + tid; r < run1; r += NT) {
                 float er = 0.f, et = 0.f;
 #pragma unroll
-                for (int c = 0; c < 6; ++c) er += S.tile.x[r * 12 + c] * (S.tile.out[0][r * 12 + c] / std);
+                for (int c = 0; c < 6; ++c) er += S.x[r * 12 + c] * (S.out[0][r * 12 + c] / std);
 #pragma unroll
-                for (int c = 6; c < 9; ++c) et += S.tile.x[r * 12 + c] * (S.tile.out[0][r * 12 + c] / std);
+                for (int c = 6; c < 9; ++c) et += S.x[r * 12 + c] * (S.out[0][r * 12 + c] / std);
                 out[(size_t)(r0 + r) * 2 + 0] = er;
                 out[(size_t)(r0 + r) * 2 + 1] = et;
             }
@@ -192,6 +231,7 @@ eval_kernel(const float *__restrict__ P, const float *__restrict__ proj, const f
         __syncthreads();
         run0 = run1;
     }
+    EV::teardown(S, ctx);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -222,20 +262,9 @@ struct OdeArgs {
     double *stats;
     // workspace
     double *y[2];     // current / candidate state   [N][9]
-    double *K[8];     // stage derivatives, K[0..6] + one spare for FSAL rotation  [N][9]
+    double *K[7];     // stage derivatives K[0..6]    [N][9]
     double *part;     // [2][3][ntiles] partial sums
     int ntiles;
-};
-
-template <int RPT>
-struct OdeSmem {
-    TileSmem<RPT> tile;
-    float tq[6 * 768];
-    float four[6 * 128];
-    float tfeat[6 * 128];
-    float times[8];
-    double red[8];
-    double bc[4];
 };
 
 // sum part[0..ntiles) in a fixed order; identical in every CTA
@@ -245,54 +274,48 @@ __device__ __forceinline__ double grid_total(const double *part, int ntiles, dou
     return block_sum(v, s_red);
 }
 
-template <int RPT>
-__global__ void __launch_bounds__(256, 1) ode_rk45_kernel(OdeArgs a) {
-    constexpr int RT = 4 * RPT;
+template <class EV>
+__global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
+    constexpr int RT = EV::RT, NT = EV::NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    OdeSmem<RPT> &S = *reinterpret_cast<OdeSmem<RPT> *>(smem_raw);
+    typename EV::Smem &S = EV::smem(smem_raw);
+    typename EV::Ctx ctx;
     cg::grid_group grid = cg::this_grid();
     const int tid = threadIdx.x;
     const float *P = a.P;
     const int N = a.N;
     const double n_total = (double)N * 9.0;
-    float w1col[9], b1v;
-    load_w1col(P, w1col, b1v);
+    EV::setup(S, ctx, P);
 
     const double direction = (a.eps > a.T) ? 1.0 : ((a.eps < a.T) ? -1.0 : 1.0);
     const double t_bound = a.eps;
     double *ycur = a.y[0], *ynew = a.y[1];
     int kidx[7] = {0, 1, 2, 3, 4, 5, 6};  // K buffers: kidx[0] holds f(t, y) (FSAL)
-    int kspare = 7;
     double nfev = 0, n_acc = 0, n_rej = 0;
     int status = 0;
     int pbuf = 0;
 
-    // One RHS evaluation over this CTA's tiles.
-    //  kind 0: x = y0 (init from a.x0, also writes ycur), K[kidx[0]] = f; partials d0^2, d1^2
-    //  kind 1: x = y + h0*dir*f0 -> f1 into K[kidx[1]]; partial d2^2 (numerator)
-    //  kind 2: the six stages of one RK step (needs S.tq for 6 times); partial err^2
-    //  kind 3: denoise + finalise into x_out
+    // RHS of the rows whose float32 inputs sit in S.x -> K[kdst] (float64), scipy's `fun`
     auto stage_eval = [&](int tile, int tq_slot, double t_stage, int kdst) {
-        // inputs already in S.tile.x; computes K[kdst] rows of this tile
-        tile_forward<RPT>(P, a.proj, S.tile, S.tq + tq_slot * 768, w1col, b1v);
+        EV::forward(P, a.proj, S, ctx, S.tq + tq_slot * 768);
         const float tf = (float)t_stage;
         const float std = sigma_f32(tf);
         const double g = diffusion_f64(t_stage);
         const double coef = 0.5 * (g * g);
         const int r0 = tile * RT;
         double *Kd = a.K[kdst];
-        for (int i = tid; i < RT * 9; i += 256) {
+        for (int i = tid; i < RT * 9; i += NT) {
             const int r = i / 9, c = i - 9 * r;
             if (r0 + r < N) {
-                const float sc = S.tile.out[0][r * 12 + c] / (std + 1e-7f);  // scorenet.py:262-264
-                Kd[(size_t)(r0 + r) * 9 + c] = 0.0 - coef * (double)sc;      // samplers.py:219
+                const float sc = S.out[0][r * 12 + c] / (std + 1e-7f);  // scorenet.py:262-264
+                Kd[(size_t)(r0 + r) * 9 + c] = 0.0 - coef * (double)sc;  // samplers.py:219
             }
         }
         __syncthreads();
     };
     auto set_obj = [&](int tile) {
         const int r0 = tile * RT;
-        for (int r = tid; r < RT; r += 256) S.tile.obj[r] = (r0 + r < N) ? (r0 + r) / a.rpo : -1;
+        for (int r = tid; r < RT; r += NT) S.obj[r] = (r0 + r < N) ? (r0 + r) / a.rpo : -1;
     };
 
     // ---- f0 = fun(T, y0), d0, d1 (select_initial_step, common.py:68-134) ----
@@ -303,7 +326,7 @@ __global__ void __launch_bounds__(256, 1) ode_rk45_kernel(OdeArgs a) {
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const int r0 = tile * RT;
         set_obj(tile);
-        for (int i = tid; i < RT * 12; i += 256) {
+        for (int i = tid; i < RT * 12; i += NT) {
             const int r = i / 12, c = i - 12 * r;
             float v = 0.f;
             if (r0 + r < N && c < 9) {
@@ -312,12 +335,12 @@ __global__ void __launch_bounds__(256, 1) ode_rk45_kernel(OdeArgs a) {
                 if (a.traj) a.traj[(size_t)(r0 + r) * 9 + c] = yv;
                 v = (float)yv;
             }
-            S.tile.x[i] = v;
+            S.x[i] = v;
         }
         __syncthreads();
         stage_eval(tile, 0, t, kidx[0]);
         double s0 = 0.0, s1 = 0.0;
-        for (int i = tid; i < RT * 9; i += 256) {
+        for (int i = tid; i < RT * 9; i += NT) {
             const int r = i / 9;
             if (r0 + r < N) {
                 const size_t g = (size_t)r0 * 9 + i;
@@ -352,19 +375,19 @@ __global__ void __launch_bounds__(256, 1) ode_rk45_kernel(OdeArgs a) {
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             const int r0 = tile * RT;
             set_obj(tile);
-            for (int i = tid; i < RT * 12; i += 256) {
+            for (int i = tid; i < RT * 12; i += NT) {
                 const int r = i / 12, c = i - 12 * r;
                 float v = 0.f;
                 if (r0 + r < N && c < 9) {
                     const size_t g = (size_t)(r0 + r) * 9 + c;
                     v = (float)(ycur[g] + h0 * direction * a.K[kidx[0]][g]);
                 }
-                S.tile.x[i] = v;
+                S.x[i] = v;
             }
             __syncthreads();
             stage_eval(tile, 0, t1, kidx[1]);
             double s2 = 0.0;
-            for (int i = tid; i < RT * 9; i += 256) {
+            for (int i = tid; i < RT * 9; i += NT) {
                 const int r = i / 9;
                 if (r0 + r < N) {
                     const size_t g = (size_t)r0 * 9 + i;
@@ -413,7 +436,7 @@ __global__ void __launch_bounds__(256, 1) ode_rk45_kernel(OdeArgs a) {
                 set_obj(tile);
                 // rk_step (rk.py:14-78)
                 for (int s = 1; s <= 6; ++s) {
-                    for (int i = tid; i < RT * 12; i += 256) {
+                    for (int i = tid; i < RT * 12; i += NT) {
                         const int r = i / 12, c = i - 12 * r;
                         float v = 0.f;
                         if (r0 + r < N && c < 9) {
@@ -429,7 +452,7 @@ __global__ void __launch_bounds__(256, 1) ode_rk45_kernel(OdeArgs a) {
                                 v = (float)yn;
                             }
                         }
-                        S.tile.x[i] = v;
+                        S.x[i] = v;
                     }
                     __syncthreads();
                     const double ts = (s < 6) ? t + c_C[s] * h : t + h;
@@ -437,7 +460,7 @@ __global__ void __launch_bounds__(256, 1) ode_rk45_kernel(OdeArgs a) {
                 }
                 // error estimate (rk.py:139-147)
                 double se = 0.0;
-                for (int i = tid; i < RT * 9; i += 256) {
+                for (int i = tid; i < RT * 9; i += NT) {
                     const int r = i / 9;
                     if (r0 + r < N) {
                         const size_t g = (size_t)r0 * 9 + i;
@@ -464,7 +487,6 @@ __global__ void __launch_bounds__(256, 1) ode_rk45_kernel(OdeArgs a) {
                 // accept: y <- y_new, f <- f_new (FSAL: K[6] becomes K[0]); pointer rotation only
                 double *ty = ycur; ycur = ynew; ynew = ty;
                 const int k0 = kidx[0]; kidx[0] = kidx[6]; kidx[6] = k0;
-                (void)kspare;
                 t = t_new;
                 h_last = h;
                 n_acc += 1;
@@ -491,16 +513,16 @@ __global__ void __launch_bounds__(256, 1) ode_rk45_kernel(OdeArgs a) {
             const int r0 = tile * RT;
             if (a.denoise) {
                 set_obj(tile);
-                for (int i = tid; i < RT * 12; i += 256) {
+                for (int i = tid; i < RT * 12; i += NT) {
                     const int r = i / 12, c = i - 12 * r;
                     float v = 0.f;
                     if (r0 + r < N && c < 9) v = (float)ycur[(size_t)(r0 + r) * 9 + c];
-                    S.tile.x[i] = v;
+                    S.x[i] = v;
                 }
                 __syncthreads();
-                tile_forward<RPT>(P, a.proj, S.tile, S.tq, w1col, b1v);
+                EV::forward(P, a.proj, S, ctx, S.tq);
             }
-            for (int r = tid; r < RT; r += 256) {
+            for (int r = tid; r < RT; r += NT) {
                 if (r0 + r >= N) continue;
                 double v[9];
 #pragma unroll
@@ -511,7 +533,7 @@ __global__ void __launch_bounds__(256, 1) ode_rk45_kernel(OdeArgs a) {
                     const float step = (float)((1.0 - a.eps) / 1000.0);
 #pragma unroll
                     for (int c = 0; c < 9; ++c) {
-                        const float grad = S.tile.out[0][r * 12 + c] / (std + 1e-7f);
+                        const float grad = S.out[0][r * 12 + c] / (std + 1e-7f);
                         const float drift = 0.f - (dif * dif) * grad;
                         v[c] = v[c] + (double)(drift * step);
                     }
@@ -524,7 +546,6 @@ __global__ void __launch_bounds__(256, 1) ode_rk45_kernel(OdeArgs a) {
             }
             __syncthreads();
         }
-        if (a.denoise) nfev += 0;  // the denoise evaluation is outside the solver's nfev
     }
     if (blockIdx.x == 0 && tid == 0) {
         a.stats[GP_STAT_NFEV] = nfev;
@@ -535,6 +556,7 @@ __global__ void __launch_bounds__(256, 1) ode_rk45_kernel(OdeArgs a) {
         a.stats[GP_STAT_H_INITIAL] = h_initial;
         a.stats[GP_STAT_H_LAST] = h_last;
     }
+    EV::teardown(S, ctx);
 }
 
 // xs = normalise(traj) + centre, transposed to [N,S,9]            (samplers.py:251-255)
@@ -566,16 +588,16 @@ struct PcArgs {
     int ntiles;
 };
 
-template <int RPT>
-__global__ void __launch_bounds__(256, 1) pc_kernel(PcArgs a) {
-    constexpr int RT = 4 * RPT;
+template <class EV>
+__global__ void __launch_bounds__(EV::NT, 1) pc_kernel(PcArgs a) {
+    constexpr int RT = EV::RT, NT = EV::NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    OdeSmem<RPT> &S = *reinterpret_cast<OdeSmem<RPT> *>(smem_raw);
+    typename EV::Smem &S = EV::smem(smem_raw);
+    typename EV::Ctx ctx;
     cg::grid_group grid = cg::this_grid();
     const int tid = threadIdx.x, N = a.N;
     const float *P = a.P;
-    float w1col[9], b1v;
-    load_w1col(P, w1col, b1v);
+    EV::setup(S, ctx, P);
     // grad of this CTA's tiles stays in global scratch between the two halves of a step: reuse
     // mean_x as scratch for grad (it is overwritten with the real mean_x at the end of each step).
     float *grad = a.mean_x;
@@ -590,22 +612,22 @@ __global__ void __launch_bounds__(256, 1) pc_kernel(PcArgs a) {
         const float std = sigma_f32(tv);
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             const int r0 = tile * RT;
-            for (int r = tid; r < RT; r += 256) S.tile.obj[r] = (r0 + r < N) ? (r0 + r) / a.rpo : -1;
-            for (int i = tid; i < RT * 12; i += 256) {
+            for (int r = tid; r < RT; r += NT) S.obj[r] = (r0 + r < N) ? (r0 + r) / a.rpo : -1;
+            for (int i = tid; i < RT * 12; i += NT) {
                 const int r = i / 12, c = i - 12 * r;
                 float v = 0.f;
                 if (r0 + r < N && c < 9) v = (it == 0 ? a.x0 : a.x)[(size_t)(r0 + r) * 9 + c];
-                S.tile.x[i] = v;
+                S.x[i] = v;
             }
             __syncthreads();
-            tile_forward<RPT>(P, a.proj, S.tile, S.tq, w1col, b1v);
+            EV::forward(P, a.proj, S, ctx, S.tq);
             double sn = 0.0;
-            for (int r = tid; r < RT; r += 256) {
+            for (int r = tid; r < RT; r += NT) {
                 if (r0 + r >= N) continue;
                 float ss = 0.f;
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {
-                    const float gv = S.tile.out[0][r * 12 + c] / (std + 1e-7f);
+                    const float gv = S.out[0][r * 12 + c] / (std + 1e-7f);
                     grad[(size_t)(r0 + r) * 9 + c] = gv;
                     ss += gv * gv;
                 }
@@ -628,7 +650,7 @@ __global__ void __launch_bounds__(256, 1) pc_kernel(PcArgs a) {
         const float *z2 = a.noise + ((size_t)it * 2 + 1) * N * 9;
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             const int r0 = tile * RT;
-            for (int r = tid; r < RT; r += 256) {
+            for (int r = tid; r < RT; r += NT) {
                 if (r0 + r >= N) continue;
                 const size_t g = (size_t)(r0 + r) * 9;
                 float x[9], gr[9], m[9];
@@ -667,29 +689,29 @@ __global__ void __launch_bounds__(256, 1) pc_kernel(PcArgs a) {
         }
         __syncthreads();
     }
+    EV::teardown(S, ctx);
 }
 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static int coop_grid_limit(const void *kern, size_t smem) {
+static int coop_grid_limit(const void *kern, int threads, size_t smem) {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess) return 0;
     return per_sm * num_sms();
 }
 
-template <int RPT>
+template <class EV>
 static int launch_ode(OdeArgs &a, cudaStream_t st) {
-    constexpr int RT = 4 * RPT;
-    a.ntiles = (a.N + RT - 1) / RT;
-    const size_t smem = sizeof(OdeSmem<RPT>);
-    auto kern = ode_rk45_kernel<RPT>;
+    a.ntiles = (a.N + EV::RT - 1) / EV::RT;
+    const size_t smem = EV::smem_bytes();
+    auto kern = ode_rk45_kernel<EV>;
     GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int limit = coop_grid_limit((const void *)kern, smem);
+    int limit = coop_grid_limit((const void *)kern, EV::NT, smem);
     if (limit <= 0) { set_error("gp_scorenet_ode: kernel cannot be made resident"); return GP_ERR_LAUNCH; }
     int grid = a.ntiles < limit ? a.ntiles : limit;
     void *params[] = {&a};
-    GP_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(256), params, smem, st));
+    GP_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(EV::NT), params, smem, st));
     count_launch();
     return GP_OK;
 }
@@ -717,9 +739,9 @@ extern "C" int gp_trunk_pack(const gp_trunk_params *raw, void *packed, gp_stream
 }
 
 extern "C" int gp_trunk_project(const void *packed, const float *pts_feat, int B, float *proj, gp_stream_t s) {
-    GP_REQUIRE(packed && pts_feat && proj, "gp_trunk_project: null pointer");
     GP_REQUIRE(B >= 0, "gp_trunk_project: B < 0");
     if (B == 0) return GP_OK;
+    GP_REQUIRE(packed && pts_feat && proj, "gp_trunk_project: null pointer");
     GP_REQUIRE(((uintptr_t)pts_feat & 15) == 0, "gp_trunk_project: pts_feat must be 16-byte aligned");
     dim3 grid(768 / PJ_OUT, (B + PJ_OBJ - 1) / PJ_OBJ);
     project_kernel<<<grid, 256, 0, as_stream(s)>>>((const float *)packed, pts_feat, B, proj);
@@ -727,47 +749,53 @@ extern "C" int gp_trunk_project(const void *packed, const float *pts_feat, int B
     return GP_OK;
 }
 
+template <class EV, int MODE>
+static int launch_eval_ev(const void *packed, const float *proj, const float *x, const double *poses,
+                          const float *center, const float *t, int N, int rpo, float *out, cudaStream_t st) {
+    const size_t smem = EV::smem_bytes();
+    auto kern = eval_kernel<EV, MODE>;
+    GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(N + EV::RT - 1) / EV::RT, EV::NT, smem, st>>>((const float *)packed, proj, x, poses, center, t, N, rpo, out);
+    return GP_OK;
+}
+
 template <int MODE>
 static int launch_eval(const void *packed, const float *proj, const float *x, const double *poses,
-                       const float *center, const float *t, int N, int rpo, float *out, cudaStream_t st,
-                       const char *name) {
+                       const float *center, const float *t, int N, int rpo, float *out, int mode,
+                       cudaStream_t st, const char *name) {
     if (N == 0) return GP_OK;
-    if (N <= 16 * num_sms()) {
-        constexpr int RPT = 4;
-        const size_t smem = sizeof(EvalSmem<RPT>);
-        auto kern = eval_kernel<RPT, MODE>;
-        GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(N + 15) / 16, 256, smem, st>>>((const float *)packed, proj, x, poses, center, t, N, rpo, out);
-    } else {
-        constexpr int RPT = 8;
-        const size_t smem = sizeof(EvalSmem<RPT>);
-        auto kern = eval_kernel<RPT, MODE>;
-        GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(N + 31) / 32, 256, smem, st>>>((const float *)packed, proj, x, poses, center, t, N, rpo, out);
-    }
+    int rc;
+    if (mode == 1) rc = launch_eval_ev<TcEval, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
+    else if (N <= 16 * num_sms()) rc = launch_eval_ev<SimtEval<4>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
+    else rc = launch_eval_ev<SimtEval<8>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
+    if (rc != GP_OK) return rc;
     GP_CHECK_LAUNCH(name);
     return GP_OK;
 }
 
 extern "C" int gp_scorenet_eval(const void *packed, const float *proj, const float *x, const float *t,
-                                int N, int rows_per_object, float *score, gp_stream_t s) {
-    GP_REQUIRE(packed && proj && x && t && score, "gp_scorenet_eval: null pointer");
+                                int N, int rows_per_object, float *score, int mode, gp_stream_t s) {
     GP_REQUIRE(N >= 0 && rows_per_object >= 1, "gp_scorenet_eval: bad sizes");
-    return launch_eval<0>(packed, proj, x, nullptr, nullptr, t, N, rows_per_object, score, as_stream(s), "gp_scorenet_eval");
+    if (N == 0) return GP_OK;
+    GP_REQUIRE(packed && proj && x && t && score, "gp_scorenet_eval: null pointer");
+    GP_REQUIRE(mode == 0 || mode == 1, "gp_scorenet_eval: mode must be 0 (fp32) or 1 (bf16 tensor cores)");
+    return launch_eval<0>(packed, proj, x, nullptr, nullptr, t, N, rows_per_object, score, mode, as_stream(s), "gp_scorenet_eval");
 }
 
 extern "C" int gp_energy(const void *packed, const float *proj, const double *poses, const float *pts_center,
-                         const float *t_rows, int N, int rows_per_object, float *energy, gp_stream_t s) {
-    GP_REQUIRE(packed && proj && poses && pts_center && t_rows && energy, "gp_energy: null pointer");
+                         const float *t_rows, int N, int rows_per_object, float *energy, int mode, gp_stream_t s) {
     GP_REQUIRE(N >= 0 && rows_per_object >= 1, "gp_energy: bad sizes");
-    return launch_eval<1>(packed, proj, nullptr, poses, pts_center, t_rows, N, rows_per_object, energy, as_stream(s), "gp_energy");
+    if (N == 0) return GP_OK;
+    GP_REQUIRE(packed && proj && poses && pts_center && t_rows && energy, "gp_energy: null pointer");
+    GP_REQUIRE(mode == 0 || mode == 1, "gp_energy: mode must be 0 (fp32) or 1 (bf16 tensor cores)");
+    return launch_eval<1>(packed, proj, nullptr, poses, pts_center, t_rows, N, rows_per_object, energy, mode, as_stream(s), "gp_energy");
 }
 
 extern "C" size_t gp_scorenet_ode_workspace_bytes(int N) {
     if (N < 0) return 0;
     const size_t state = align256((size_t)N * 9 * sizeof(double));
     const size_t ntiles_max = (size_t)(N + 7) / 8 + 1;
-    return state * 10 + align256(2 * 3 * ntiles_max * sizeof(double)) + 256;
+    return state * 9 + align256(2 * 3 * ntiles_max * sizeof(double)) + 256;
 }
 
 extern "C" int gp_scorenet_ode(const void *packed, const float *proj, const double *x0, const float *pts_center,
@@ -778,13 +806,10 @@ extern "C" int gp_scorenet_ode(const void *packed, const float *proj, const doub
     GP_REQUIRE(N >= 1 && rows_per_object >= 1, "gp_scorenet_ode: bad sizes N=%d rows_per_object=%d", N, rows_per_object);
     GP_REQUIRE(rtol > 0 && atol > 0, "gp_scorenet_ode: tolerances must be positive");
     GP_REQUIRE(traj == nullptr || max_traj >= 1, "gp_scorenet_ode: max_traj < 1");
+    GP_REQUIRE(mode == 0 || mode == 1, "gp_scorenet_ode: mode must be 0 (fp32) or 1 (bf16 tensor cores)");
     if (workspace_bytes < gp_scorenet_ode_workspace_bytes(N)) {
         set_error("gp_scorenet_ode: workspace too small (%zu < %zu)", workspace_bytes, gp_scorenet_ode_workspace_bytes(N));
         return GP_ERR_WORKSPACE;
-    }
-    if (mode != 0) {
-        set_error("gp_scorenet_ode: mode %d not available in this build (0 = fp32)", mode);
-        return GP_ERR_UNSUPPORTED;
     }
     // scipy validate_tol: rtol is clamped to 100 * EPS
     if (rtol < 100 * 2.220446049250313e-16) rtol = 100 * 2.220446049250313e-16;
@@ -796,19 +821,20 @@ extern "C" int gp_scorenet_ode(const void *packed, const float *proj, const doub
     const size_t state = align256((size_t)N * 9 * sizeof(double));
     a.y[0] = (double *)w; w += state;
     a.y[1] = (double *)w; w += state;
-    for (int k = 0; k < 8; ++k) { a.K[k] = (double *)w; w += state; }
+    for (int k = 0; k < 7; ++k) { a.K[k] = (double *)w; w += state; }
     a.part = (double *)w;
     cudaStream_t st = as_stream(s);
     const int sms = num_sms();
-    if (N <= 8 * sms) return launch_ode<2>(a, st);
-    if (N <= 16 * sms) return launch_ode<4>(a, st);
-    return launch_ode<8>(a, st);
+    if (mode == 1) return launch_ode<TcEval>(a, st);
+    if (N <= 8 * sms) return launch_ode<SimtEval<2>>(a, st);
+    if (N <= 16 * sms) return launch_ode<SimtEval<4>>(a, st);
+    return launch_ode<SimtEval<8>>(a, st);
 }
 
 extern "C" int gp_traj_finalize(const double *traj, const float *pts_center, int S, int N, double *xs, gp_stream_t s) {
-    GP_REQUIRE(traj && pts_center && xs, "gp_traj_finalize: null pointer");
     GP_REQUIRE(S >= 0 && N >= 0, "gp_traj_finalize: bad sizes");
     if (S == 0 || N == 0) return GP_OK;
+    GP_REQUIRE(traj && pts_center && xs, "gp_traj_finalize: null pointer");
     const size_t total = (size_t)S * N;
     traj_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(s)>>>(traj, pts_center, S, N, xs);
     GP_CHECK_LAUNCH("gp_traj_finalize");
@@ -820,18 +846,17 @@ extern "C" size_t gp_scorenet_pc_workspace_bytes(int N) {
     return align256((size_t)N * 9 * sizeof(float)) + align256(2 * ((size_t)(N + 7) / 8 + 1) * sizeof(double)) + 256;
 }
 
-template <int RPT>
+template <class EV>
 static int launch_pc(PcArgs &a, cudaStream_t st) {
-    constexpr int RT = 4 * RPT;
-    a.ntiles = (a.N + RT - 1) / RT;
-    const size_t smem = sizeof(OdeSmem<RPT>);
-    auto kern = pc_kernel<RPT>;
+    a.ntiles = (a.N + EV::RT - 1) / EV::RT;
+    const size_t smem = EV::smem_bytes();
+    auto kern = pc_kernel<EV>;
     GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int limit = coop_grid_limit((const void *)kern, smem);
+    int limit = coop_grid_limit((const void *)kern, EV::NT, smem);
     if (limit <= 0) { set_error("gp_scorenet_pc: kernel cannot be made resident"); return GP_ERR_LAUNCH; }
     int grid = a.ntiles < limit ? a.ntiles : limit;
     void *params[] = {&a};
-    GP_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(256), params, smem, st));
+    GP_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(EV::NT), params, smem, st));
     count_launch();
     return GP_OK;
 }
@@ -839,9 +864,10 @@ static int launch_pc(PcArgs &a, cudaStream_t st) {
 extern "C" int gp_scorenet_pc(const void *packed, const float *proj, const float *x0, const float *noise,
                               const float *pts_center, const float *time_steps, int N, int rows_per_object,
                               int num_steps, double snr, float *xs, float *mean_x, void *workspace,
-                              size_t workspace_bytes, gp_stream_t s) {
+                              size_t workspace_bytes, int mode, gp_stream_t s) {
     GP_REQUIRE(packed && proj && x0 && noise && pts_center && time_steps && mean_x && workspace, "gp_scorenet_pc: null pointer");
     GP_REQUIRE(N >= 1 && rows_per_object >= 1 && num_steps >= 2, "gp_scorenet_pc: bad sizes");
+    GP_REQUIRE(mode == 0 || mode == 1, "gp_scorenet_pc: mode must be 0 (fp32) or 1 (bf16 tensor cores)");
     if (workspace_bytes < gp_scorenet_pc_workspace_bytes(N)) {
         set_error("gp_scorenet_pc: workspace too small");
         return GP_ERR_WORKSPACE;
@@ -855,7 +881,8 @@ extern "C" int gp_scorenet_pc(const void *packed, const float *proj, const float
     a.part = (double *)w;
     cudaStream_t st = as_stream(s);
     const int sms = num_sms();
-    if (N <= 8 * sms) return launch_pc<2>(a, st);
-    if (N <= 16 * sms) return launch_pc<4>(a, st);
-    return launch_pc<8>(a, st);
+    if (mode == 1) return launch_pc<TcEval>(a, st);
+    if (N <= 8 * sms) return launch_pc<SimtEval<2>>(a, st);
+    if (N <= 16 * sms) return launch_pc<SimtEval<4>>(a, st);
+    return launch_pc<SimtEval<8>>(a, st);
 }

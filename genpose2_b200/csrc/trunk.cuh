@@ -28,10 +28,11 @@ struct TrunkLayout {
     static constexpr size_t WO = BH + 768;                     // [768][4]    (3 used) out weights
     static constexpr size_t BO = WO + 768 * 4;                 // [12]        (9 used)
     static constexpr size_t F32_END = BO + 12;
-    // bf16 operands for the tensor-core path (tcgen05): element offsets counted in floats
-    static constexpr size_t W2_BF16 = F32_END;                 // [256 n][256 k] bf16, K-major
-    static constexpr size_t WHP_BF16 = W2_BF16 + 256 * 256 / 2;  // [768 n][256 k] bf16, K-major
-    static constexpr size_t END = WHP_BF16 + 768 * 256 / 2;
+    // bf16 B operands for the tensor-core path (tcgen05), as 16 ready-to-copy shared-memory images of
+    // [256 n][64 k] bf16 in the canonical K-major SWIZZLE_128B layout (32 KB each): chunks 0-3 = W2
+    // k-atoms, chunks 4+4h+a = head h k-atom a.  Offsets counted in floats; 1024-byte aligned.
+    static constexpr size_t W_TC = (F32_END + 255) / 256 * 256;
+    static constexpr size_t END = W_TC + 16 * (256 * 64 / 2);
 };
 
 constexpr float kFloatPi = 3.14159265358979323846f;  // np.pi cast to float32 by torch
@@ -111,6 +112,12 @@ struct TileSmem {
     float x[RT * 12];       // input poses, padded rows
     float out[2][RT * 12];  // per-half-warp-pair partial head outputs
     int obj[RT];            // object index of each row (-1: padding row)
+    float tq[6 * 768];      // t-branch of up to 6 stage times
+    float four[6 * 128];
+    float tfeat[6 * 128];
+    float times[8];
+    double red[16];
+    float trow[RT];
 };
 
 template <int RPT>
@@ -248,8 +255,8 @@ __device__ __forceinline__ void load_w1col(const float *__restrict__ P, float (&
     b1v = __ldg(P + TrunkLayout::B1 + n);
 }
 
-// deterministic block-wide sum of one double per thread (256 threads); result valid in all threads
-__device__ __forceinline__ double block_sum(double v, double *s_red /*[8]*/) {
+// deterministic block-wide sum of one double per thread (<= 16 warps); result valid in all threads
+__device__ __forceinline__ double block_sum(double v, double *s_red /*[16]*/) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

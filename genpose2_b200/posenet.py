@@ -37,6 +37,7 @@ class GFObjectPose(nn.Module):
                 s_theta_mode=cfg.s_theta_mode, norm_energy=cfg.norm_energy)
         else:
             raise NotImplementedError(f"agent_type={cfg.agent_type!r}")
+        self.pose_score_net.mlp_mode = getattr(cfg, "mlp_mode", "fp32")
 
     def extract_pts_feature(self, data, geometry=None, return_geometry=False):
         """posenet.py:127-228 with dino=none: pts_encoder(pts) -> [bs,1024]."""

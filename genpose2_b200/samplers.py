@@ -29,9 +29,8 @@ def _score_net(score_model):
 
 
 def _mlp_mode(score_model):
-    cfg = getattr(score_model, "cfg", None)
-    mode = getattr(cfg, "mlp_mode", "fp32") if cfg is not None else "fp32"
-    return {"fp32": 0, "bf16": 1}[mode]
+    from .scorenet import MLP_MODES
+    return MLP_MODES[_score_net(score_model).mlp_mode]
 
 
 def cond_ode_sampler(score_model, data, prior, sde_coeff, atol=1e-5, rtol=1e-5, device="cuda", eps=1e-5,
@@ -123,5 +122,5 @@ def cond_pc_sampler(score_model, data, prior, sde_coeff, num_steps=500, snr=0.16
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     _lib.call("gp_scorenet_pc", _lib.ptr(net.packed()), _lib.ptr(proj), _lib.ptr(x0), _lib.ptr(noise),
               _lib.ptr(center), _lib.ptr(time_steps), batch_size, rpo, int(num_steps), float(snr), _lib.ptr(xs),
-              _lib.ptr(mean_x), _lib.ptr(ws), ws_bytes, device=dev)
+              _lib.ptr(mean_x), _lib.ptr(ws), ws_bytes, _mlp_mode(score_model), device=dev)
     return xs, mean_x

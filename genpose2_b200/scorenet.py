@@ -15,6 +15,9 @@ import torch.nn as nn
 from . import _lib
 
 
+MLP_MODES = {"fp32": 0, "bf16": 1}
+
+
 def zero_module(module):
     """scorenet.py:15-21"""
     for p in module.parameters():
@@ -51,6 +54,7 @@ class _Trunk(nn.Module):
             setattr(self, f"fusion_tail_{name}",
                     nn.Sequential(nn.Linear(128 + 256 + 1024, 256), self.act, zero_module(nn.Linear(256, 3))))
         self.marginal_prob_func = marginal_prob_func
+        self.mlp_mode = "fp32"  # "fp32": FFMA MLP; "bf16": tcgen05 tensor-core MLP (set by GFObjectPose from cfg.mlp_mode)
         self._packed = None
         self._packed_key = None
 
@@ -125,7 +129,7 @@ class PoseScoreNet(_Trunk):
         t = data["t"].reshape(-1).to(torch.float32).contiguous()
         out = torch.empty((N, 9), dtype=torch.float32, device=x.device)
         _lib.call("gp_scorenet_eval", _lib.ptr(self.packed()), _lib.ptr(proj), _lib.ptr(x), _lib.ptr(t), N, rpo,
-                  _lib.ptr(out), device=x.device)
+                  _lib.ptr(out), MLP_MODES[self.mlp_mode], device=x.device)
         return out
 
 
@@ -143,7 +147,8 @@ class PoseEnergyNet(_Trunk):
         N = poses_f64.shape[0]
         out = torch.empty((N, 2), dtype=torch.float32, device=poses_f64.device)
         _lib.call("gp_energy", _lib.ptr(self.packed()), _lib.ptr(proj), _lib.ptr(poses_f64), _lib.ptr(pts_center),
-                  _lib.ptr(t_rows), N, int(rows_per_object), _lib.ptr(out), device=poses_f64.device)
+                  _lib.ptr(t_rows), N, int(rows_per_object), _lib.ptr(out), MLP_MODES[self.mlp_mode],
+                  device=poses_f64.device)
         return out
 
     def forward(self, data, return_item="score"):

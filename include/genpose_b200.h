@@ -119,9 +119,10 @@ GP_API int gp_trunk_project(const void *packed, const float *pts_feat, int B, fl
 
 /* One PoseScoreNet.forward (scorenet.py:215-275): x [N,9] f32, t [N] f32 (one value per row),
  * proj [B,768] with row i belonging to object i / rows_per_object -> score [N,9] f32
- * (= f_theta / (std + 1e-7)).  Used by GFObjectPose.forward(mode="score") (posenet.py:305-307). */
+ * (= f_theta / (std + 1e-7)).  Used by GFObjectPose.forward(mode="score") (posenet.py:305-307).
+ * mode: 0 = fp32 (FFMA) MLP, 1 = bf16 tensor-core MLP (tcgen05), as for gp_scorenet_ode. */
 GP_API int gp_scorenet_eval(const void *packed, const float *proj, const float *x, const float *t, int N,
-                     int rows_per_object, float *score, gp_stream_t s);
+                     int rows_per_object, float *score, int mode, gp_stream_t s);
 
 /* Integrator statistics written by gp_scorenet_ode (device, 16 doubles). */
 enum gp_ode_stat {
@@ -173,7 +174,7 @@ GP_API size_t gp_scorenet_pc_workspace_bytes(int N);
 GP_API int gp_scorenet_pc(const void *packed, const float *proj, const float *x0, const float *noise,
                    const float *pts_center, const float *time_steps, int N, int rows_per_object,
                    int num_steps, double snr, float *xs, float *mean_x, void *workspace,
-                   size_t workspace_bytes, gp_stream_t s);
+                   size_t workspace_bytes, int mode, gp_stream_t s);
 
 /* Replaces PoseNet.get_energy's network call + PoseEnergyNet.get_energy
  * (posenet_agent.py:660-705, energynet.py:151-208; energy_mode=IP, s_theta_mode=score,
@@ -181,7 +182,7 @@ GP_API int gp_scorenet_pc(const void *packed, const float *proj, const float *x0
  * translation (posenet_agent.py:694), the pose cast to f32 (:668-670).  t_rows [N] f32.
  * -> energy [N,2] f32 = [E_rot, E_trans]. */
 GP_API int gp_energy(const void *packed, const float *proj, const double *poses, const float *pts_center,
-              const float *t_rows, int N, int rows_per_object, float *energy, gp_stream_t s);
+              const float *t_rows, int N, int rows_per_object, float *energy, int mode, gp_stream_t s);
 
 /* ---------------------------------------------------------------------------------------------
  * (4) Energy-ranked outlier rejection + quaternion averaging + DBSCAN, and the ScaleNet head.

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     lib2 = _lib.load()
     assert lib2.gp_version() == 1
     assert lib2.gp_trunk_packed_bytes() > 4 * (768 * 1024 + 256 * 768)
-    assert lib2.gp_scorenet_ode_workspace_bytes(3200) >= 10 * 3200 * 9 * 8
+    assert lib2.gp_scorenet_ode_workspace_bytes(3200) >= 9 * 3200 * 9 * 8
 
 
 def test_bad_arguments_return_status_not_exit():
