@@ -38,6 +38,8 @@ T0 = 0.55
 NUM_POINTS = 1024
 L2_FLUSH_BYTES = 256 << 20
 
+NCU_DRAM_BYTES_PER_LAUNCH = {"fp32": 2270464 + 22784, "bf16": 1782784 + 12544}  # profiles/README.md
+
 # algorithmic work of the ScoreNet RHS after hoisting, in FLOP
 ROW_EVAL_FLOP = 2 * 266752
 STAGE_SHARED_FLOP = 2 * 114688
@@ -54,6 +56,7 @@ def parse():
     ap.add_argument("--mlp_mode", type=str, default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--cpu_sample_objects", type=int, default=8)
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--single_mode", action="store_true", help="skip the measurement of the other mlp_mode")
     return ap.parse_args()
 
 
@@ -184,7 +187,6 @@ def run_b200(args):
     _lib.load()
 
     B = args.objects
-    pipe = PosePipeline(device=f"cuda:{local_rank}", mlp_mode=args.mlp_mode).load_synthetic_weights((100, 200, 300))
     # every rank owns its own contiguous slice of the global object list (weak scaling)
     pts_all, center_all = synthetic.make_point_clouds(B * world, NUM_POINTS, seed=0)
     pts_h = pts_all[rank * B:(rank + 1) * B].contiguous().pin_memory()
@@ -193,17 +195,7 @@ def run_b200(args):
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     out_pose_h = torch.empty((B, 4, 4), dtype=torch.float32).pin_memory()
     out_len_h = torch.empty((B, 3), dtype=torch.float32).pin_memory()
-
-    def step_resident():
-        return pipe({"pts": pts_d, "pts_center": center_d}, repeat_num=REPEAT, T0=T0)
-
-    def step_e2e():
-        p = pts_h.to(dev, non_blocking=True)
-        c = center_h.to(dev, non_blocking=True)
-        pose, length = pipe({"pts": p, "pts_center": c}, repeat_num=REPEAT, T0=T0)
-        out_pose_h.copy_(pose, non_blocking=True)
-        out_len_h.copy_(length, non_blocking=True)
-        return pose, length
+    peaks = measured_peaks()
 
     def barrier():
         if world > 1:
@@ -230,67 +222,92 @@ def run_b200(args):
             total_ms = float(t.item())
         return total_ms, clocks
 
-    torch.manual_seed(1234 + rank)
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    torch.cuda.synchronize()
-    _lib.reset_launch_count()
-    total_ms, clocks = timed(step_resident, args.steps, ClockSampler(local_rank))
-    launches = _lib.launch_count()
-    value = world * B * args.steps / (total_ms * 1e-3)
+    def measure(mlp_mode, with_e2e, with_clocks):
+        pipe = PosePipeline(device=f"cuda:{local_rank}", mlp_mode=mlp_mode).load_synthetic_weights((100, 200, 300))
 
-    for _ in range(2):
-        step_e2e()
-    e2e_ms, _ = timed(step_e2e, args.steps)
-    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+        def step_resident():
+            return pipe({"pts": pts_d, "pts_center": center_d}, repeat_num=REPEAT, T0=T0)
+
+        def step_e2e():
+            p = pts_h.to(dev, non_blocking=True)
+            c = center_h.to(dev, non_blocking=True)
+            pose, length = pipe({"pts": p, "pts_center": c}, repeat_num=REPEAT, T0=T0)
+            out_pose_h.copy_(pose, non_blocking=True)
+            out_len_h.copy_(length, non_blocking=True)
+            return pose, length
+
+        torch.manual_seed(1234 + rank)
+        for _ in range(max(args.warmup, 3)):
+            step_resident()
+        torch.cuda.synchronize()
+        _lib.reset_launch_count()
+        total_ms, clocks = timed(step_resident, args.steps, ClockSampler(local_rank) if with_clocks else None)
+        res = {"launches": _lib.launch_count(), "total_ms": total_ms, "clocks": clocks,
+               "value": world * B * args.steps / (total_ms * 1e-3)}
+        if with_e2e:
+            for _ in range(2):
+                step_e2e()
+            e2e_ms, _ = timed(step_e2e, args.steps)
+            res["e2e_ms"] = e2e_ms
+            res["e2e_value"] = world * B * args.steps / (e2e_ms * 1e-3)
+
+        # ---- roofline of the dominant kernel of this library: the fused ScoreNet / RK45 integrator ----
+        score_net = pipe.score_agent.net
+        feat = score_net(dict(pts=pts_d, pts_center=center_d), mode="pts_feature")
+        N = B * REPEAT
+        sdata = {"pts": torch.empty(N, 0), "pts_center": center_d.unsqueeze(1).expand(B, REPEAT, 3).reshape(N, 3).contiguous(),
+                 "_gp_pts_feat_obj": feat, "_gp_rows_per_object": REPEAT}
+        torch.manual_seed(99)
+        noise = score_net.prior_fn((N, 9), T=T0)
+        prior = lambda shape, T=1.0: noise
+
+        def sampler_only():
+            return samplers.cond_ode_sampler(score_net, sdata, prior, score_net.sde_fn, device=dev, eps=1e-5, T=T0,
+                                             pose_mode="rot_matrix", return_trajectory=False)
+
+        for _ in range(3):
+            sampler_only()
+        torch.cuda.synchronize()
+        k_ms = []
+        for _ in range(max(5, min(args.steps, 20))):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            sampler_only()  # projection kernel (tiny) + the persistent integrator
+            e.record()
+            torch.cuda.synchronize()
+            k_ms.append(s.elapsed_time(e))
+        st = samplers.ode_stats()
+        nfev_total = st["nfev"] + 1  # + the denoise evaluation
+        flop = N * nfev_total * ROW_EVAL_FLOP + nfev_total * STAGE_SHARED_FLOP + B * OBJECT_ONCE_FLOP
+        k_med = sorted(k_ms)[len(k_ms) // 2]
+        achieved = flop / (k_med * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        ffma_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # 148 SMs x 128 FP32 lanes x 2 FLOP x max SM clock
+        res["roofline"] = {
+            "bound": "tensor", "kernel": "ode_rk45_kernel<%s> (fused ScoreNet RHS + Dormand-Prince controller)"
+                                         % ("TcEval: tcgen05 bf16" if mlp_mode == "bf16" else "SimtEval: FFMA fp32"),
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture of the same
+            # workload (profiles/README.md, round 1): weights and state are L2-resident, the kernel is not HBM bound
+            "traffic": NCU_DRAM_BYTES_PER_LAUNCH[mlp_mode],
+            "peak_source": f"{peaks['source']} bf16 dense, sustained",
+            "mlp_mode": mlp_mode, "kernel_ms": k_med, "nfev": nfev_total, "accepted": st["accepted"],
+            "rejected": st["rejected"], "algorithmic_flop_per_launch": flop,
+            "hyp_evals_per_s": N * nfev_total / (k_med * 1e-3),
+            "note": ("fp32 mode evaluates the MLPs with FFMA (no tensor cores): also quoted against the FP32 FFMA peak"
+                     if mlp_mode == "fp32" else "bf16 operands on tcgen05, fp32 accumulation in TMEM"),
+            "ffma_peak_tflops": ffma_peak, "frac_of_ffma_peak": achieved / ffma_peak,
+        }
+        return res
+
+    main_res = measure(args.mlp_mode, True, True)
+    other_mode = "bf16" if args.mlp_mode == "fp32" else "fp32"
+    other_res = measure(other_mode, False, False) if not args.single_mode else None
+    value, total_ms, clocks, launches = main_res["value"], main_res["total_ms"], main_res["clocks"], main_res["launches"]
+    e2e_value, e2e_ms, roofline = main_res["e2e_value"], main_res["e2e_ms"], main_res["roofline"]
     h2d = pts_h.numel() * 4 + center_h.numel() * 4
     d2h = out_pose_h.numel() * 4 + out_len_h.numel() * 4
-
-    # ---- roofline of the dominant kernel of this library: the fused ScoreNet / RK45 integrator ----
-    peaks = measured_peaks()
-    score_net = pipe.score_agent.net
-    feat = pipe.score_agent.net(dict(pts=pts_d, pts_center=center_d), mode="pts_feature")
-    N = B * REPEAT
-    sdata = {"pts": torch.empty(N, 0), "pts_center": center_d.unsqueeze(1).expand(B, REPEAT, 3).reshape(N, 3).contiguous(),
-             "_gp_pts_feat_obj": feat, "_gp_rows_per_object": REPEAT}
-    torch.manual_seed(99)
-    noise = score_net.prior_fn((N, 9), T=T0)
-    prior = lambda shape, T=1.0: noise
-
-    def sampler_only():
-        return samplers.cond_ode_sampler(score_net, sdata, prior, score_net.sde_fn, device=dev, eps=1e-5, T=T0,
-                                         pose_mode="rot_matrix", return_trajectory=False)
-
-    for _ in range(3):
-        sampler_only()
-    torch.cuda.synchronize()
-    k_ms = []
-    for _ in range(max(5, min(args.steps, 20))):
-        flush.zero_()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        sampler_only()  # projection kernel (tiny) + the persistent integrator
-        e.record()
-        torch.cuda.synchronize()
-        k_ms.append(s.elapsed_time(e))
-    st = samplers.ode_stats()
-    nfev_total = st["nfev"] + 1  # + the denoise evaluation
-    flop = N * nfev_total * ROW_EVAL_FLOP + nfev_total * STAGE_SHARED_FLOP + B * OBJECT_ONCE_FLOP
-    k_med = sorted(k_ms)[len(k_ms) // 2]
-    achieved = flop / (k_med * 1e-3) / 1e12
-    peak = peaks["bf16_tflops_sustained"]
-    ffma_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # 148 SMs x 128 FP32 lanes x 2 FLOP x max SM clock
-    roofline = {
-        "bound": "tensor", "kernel": "ode_rk45_kernel (fused ScoreNet RHS + Dormand-Prince controller)",
-        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-        "peak_source": f"{peaks['source']} bf16 dense, sustained",
-        "mlp_mode": args.mlp_mode, "kernel_ms": k_med, "nfev": nfev_total, "accepted": st["accepted"],
-        "rejected": st["rejected"], "algorithmic_flop_per_launch": flop,
-        "hyp_evals_per_s": N * nfev_total / (k_med * 1e-3),
-        "note": ("fp32 mode evaluates the MLPs with FFMA (no tensor cores): also quoted against the FP32 FFMA peak"
-                 if args.mlp_mode == "fp32" else "bf16 tcgen05 path"),
-        "ffma_peak_tflops": ffma_peak, "frac_of_ffma_peak": achieved / ffma_peak,
-    }
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -318,6 +335,9 @@ def run_b200(args):
                                       "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
+        if other_res is not None:
+            line["other_mode"] = {"mlp_mode": other_mode, "value": other_res["value"], "unit": UNIT,
+                                  "ms_per_step": other_res["total_ms"] / args.steps, "roofline": other_res["roofline"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

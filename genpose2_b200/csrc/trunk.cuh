@@ -123,12 +123,19 @@ struct TileSmem {
 template <int RPT>
 __device__ __forceinline__ void gemm256(const float *__restrict__ Wt, int ldw, const float *s_h,
                                         int row0, float (&acc)[RPT][4]) {
+    // weights for k..k+3 are fetched one iteration ahead (register double buffering): the L2/L1
+    // latency of the streamed weight rows is the dominant stall of this loop otherwise
+    float4 w0 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)0 * ldw));
+    float4 w1 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)1 * ldw));
+    float4 w2 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)2 * ldw));
+    float4 w3 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)3 * ldw));
 #pragma unroll 2
     for (int k = 0; k < 256; k += 4) {
-        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)(k + 0) * ldw));
-        const float4 w1 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)(k + 1) * ldw));
-        const float4 w2 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)(k + 2) * ldw));
-        const float4 w3 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)(k + 3) * ldw));
+        const int kn = (k + 4 < 256) ? k + 4 : k;
+        const float4 n0 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)(kn + 0) * ldw));
+        const float4 n1 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)(kn + 1) * ldw));
+        const float4 n2 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)(kn + 2) * ldw));
+        const float4 n3 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)(kn + 3) * ldw));
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
             const float4 a = *reinterpret_cast<const float4 *>(s_h + (row0 + i) * HS + k);
@@ -149,6 +156,7 @@ __device__ __forceinline__ void gemm256(const float *__restrict__ Wt, int ldw, c
             acc[i][2] = fmaf(a.w, w3.z, acc[i][2]);
             acc[i][3] = fmaf(a.w, w3.w, acc[i][3]);
         }
+        w0 = n0; w1 = n1; w2 = n2; w3 = n3;
     }
 }
 
