@@ -444,3 +444,90 @@ extern "C" int gp_query_group(const float *xyz, const float *new_xyz, const floa
     GP_REQUIRE(B <= 65535, "gp_query_group: B too large");
     return launch_group<true>(features, xyz, new_xyz, idx, B, C, N, M, nsample, out, as_stream(s));
 }
+
+// ------------------------------------------------------------------------------------------
+// channels-last ("rows") variants used by the drop-in encoder: one GEMM row per (centre, sample)
+// ------------------------------------------------------------------------------------------
+namespace gp {
+
+// out[(b*M + p)*ns + s][0:3] = xyz[b, idx[b,p,s]] - new_xyz[b,p];  out[..][3:3+C] = feat[b, idx[b,p,s], :]
+// (the same values QueryAndGroup.forward produces, P2/pointnet2_utils.py:279-296, stored row-major per
+// sample instead of [B, 3+C, M, ns]); columns 3+C .. ld-1 are zero-filled.
+// One warp per row: lanes copy the feature row with 16-byte accesses when C % 4 == 0.
+__global__ void __launch_bounds__(256)
+group_rows_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz,
+                  const float *__restrict__ feat, const int *__restrict__ idx, int C, int N, int M, int ns,
+                  int ld, long long rows_total, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows_total) return;
+    const long long bp = row / ns;           // b*M + p
+    const int b = (int)(bp / M);
+    const int id = __ldg(idx + row);
+    float *o = out + row * ld;
+    if (lane < 3) o[lane] = __ldg(xyz + ((size_t)b * N + id) * 3 + lane) - __ldg(new_xyz + bp * 3 + lane);
+    if (C > 0) {
+        const float *src = feat + ((size_t)b * N + id) * C;
+        // destination starts at column 3: scalar stores (rows are short), 16-byte loads when aligned
+        if ((C & 3) == 0 && (((uintptr_t)feat) & 15) == 0) {
+            for (int c4 = lane; c4 < C / 4; c4 += 32) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + c4);
+                float *d = o + 3 + 4 * c4;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        } else {
+            for (int c = lane; c < C; c += 32) o[3 + c] = __ldg(src + c);
+        }
+    }
+    for (int c = 3 + C + lane; c < ld; c += 32) o[c] = 0.f;
+}
+
+// out[g*ld_out + c] = max_s h[(g*ns + s)*C + c]      (F.max_pool2d over nsample, pointnet2_modules.py:59-61)
+__global__ void __launch_bounds__(256)
+maxpool_rows_kernel(const float *__restrict__ h, long long G, int ns, int C, int ld_out, float *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over G * C/4 (vector) or G*C
+    const int C4 = C >> 2;
+    if ((C & 3) == 0 && (ld_out & 3) == 0 && ((uintptr_t)h & 15) == 0 && ((uintptr_t)out & 15) == 0) {
+        if (i >= G * C4) return;
+        const long long g = i / C4;
+        const int c4 = (int)(i - g * C4);
+        const float4 *p = reinterpret_cast<const float4 *>(h + g * ns * (long long)C) + c4;
+        float4 m = __ldg(p);
+        for (int s = 1; s < ns; ++s) {
+            const float4 v = __ldg(p + (size_t)s * C4);
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+        *reinterpret_cast<float4 *>(out + g * ld_out + 4 * c4) = m;
+    } else {
+        if (i >= G * C) return;
+        const long long g = i / C;
+        const int c = (int)(i - g * C);
+        float m = h[g * ns * (long long)C + c];
+        for (int s = 1; s < ns; ++s) m = fmaxf(m, h[(g * ns + s) * (long long)C + c]);
+        out[g * ld_out + c] = m;
+    }
+}
+}  // namespace gp
+
+extern "C" int gp_group_rows(const float *xyz, const float *new_xyz, const float *feat_cl, const int32_t *idx,
+                             int B, int C, int N, int M, int nsample, int ld_out, float *out, gp_stream_t s) {
+    GP_REQUIRE(B >= 0 && C >= 0 && N >= 1 && M >= 0 && nsample >= 0 && ld_out >= 3 + C, "gp_group_rows: bad sizes");
+    const long long rows = (long long)B * M * nsample;
+    if (rows == 0) return GP_OK;
+    GP_REQUIRE(xyz && new_xyz && idx && out && (C == 0 || feat_cl), "gp_group_rows: null pointer");
+    GP_REQUIRE((rows + 7) / 8 < 2147483647LL, "gp_group_rows: too many rows");
+    group_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(s)>>>(xyz, new_xyz, feat_cl, idx, C, N, M, nsample,
+                                                                            ld_out, rows, out);
+    GP_CHECK_LAUNCH("gp_group_rows");
+    return GP_OK;
+}
+
+extern "C" int gp_maxpool_rows(const float *h, long long G, int nsample, int C, int ld_out, float *out, gp_stream_t s) {
+    GP_REQUIRE(G >= 0 && nsample >= 1 && C >= 1 && ld_out >= C, "gp_maxpool_rows: bad sizes");
+    if (G == 0) return GP_OK;
+    GP_REQUIRE(h && out, "gp_maxpool_rows: null pointer");
+    const long long work = ((C & 3) == 0 && (ld_out & 3) == 0) ? G * (C >> 2) : G * C;
+    maxpool_rows_kernel<<<(unsigned)((work + 255) / 256), 256, 0, as_stream(s)>>>(h, G, nsample, C, ld_out, out);
+    GP_CHECK_LAUNCH("gp_maxpool_rows");
+    return GP_OK;
+}

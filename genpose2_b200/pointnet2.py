@@ -12,9 +12,10 @@ level, instead of the reference's FPS, 3 gathers / transposes, 2 ball queries an
 The geometry (FPS / ball-query indices) depends on xyz only, so `forward` can return it and accept
 it back: the score and the energy encoder see the same cloud and share one geometry pass.
 
-The per-scale SharedMLP (conv1x1 + BatchNorm(eval) + ReLU, pytorch_utils.py:5-33) followed by the
-max-pool is "next" row f1 of SURVEY.md section 8 and still goes through torch (cuBLAS fp32
-matmul with BatchNorm folded into the weights).
+The per-scale SharedMLP (conv1x1 + BatchNorm(eval) + ReLU, pytorch_utils.py:5-33) is "next" row f1 of
+SURVEY.md section 8: activations are kept channels-last (one GEMM row per sample), each layer is one
+library GEMM with bias + ReLU in its epilogue (cuBLASLt, fp32, BatchNorm folded into the weights), and
+the gather into rows and the max-pool over the samples are kernels of libgenpose_b200.so.
 """
 from typing import List, Optional
 
@@ -72,13 +73,33 @@ class SharedMLP(nn.Module):
             self.add_module(f"layer{i}", _Conv2d(spec[i], spec[i + 1]))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x (B, C, M, ns) -> (B, Cout, M): conv+BN+ReLU stack then max over ns."""
+        """Reference layout: x (B, C, M, ns) -> (B, Cout, M): conv+BN+ReLU stack then max over ns."""
         B, C, M, ns = x.shape
-        h = x.reshape(B, C, M * ns)
+        rows = x.permute(0, 2, 3, 1).reshape(B * M * ns, C)
+        h = self.forward_rows(rows)
+        return pu.maxpool_rows(h, B * M, ns).view(B, M, -1).permute(0, 2, 1).contiguous()
+
+    def _folded_layers(self):
+        """BatchNorm(eval) folded into the 1x1 convs, cached until a parameter / buffer changes."""
+        ts = []
         for i in range(self.n_layers):
-            w, b = getattr(self, f"layer{i}").folded()
-            h = torch.relu_(torch.baddbmm(b[None, :, None], w.unsqueeze(0).expand(B, -1, -1), h))
-        return h.view(B, -1, M, ns).amax(dim=3)
+            l = getattr(self, f"layer{i}")
+            ts += [l.conv.weight, l.bn.bn.weight, l.bn.bn.bias, l.bn.bn.running_mean, l.bn.bn.running_var]
+        key = tuple((t.data_ptr(), t._version) for t in ts)
+        if getattr(self, "_fold_key", None) != key:
+            with torch.no_grad():
+                self._fold = [tuple(t.contiguous() for t in getattr(self, f"layer{i}").folded())
+                              for i in range(self.n_layers)]
+            self._fold_key = key
+        return self._fold
+
+    def forward_rows(self, rows: torch.Tensor) -> torch.Tensor:
+        """Channels-last: rows (R, Cin) -> (R, Cout); each layer is relu(rows @ W^T + b) with the bias and
+        the ReLU in the GEMM epilogue (cuBLASLt through torch._addmm_activation) -- SURVEY section 8 row f1."""
+        h = rows
+        for w, b in self._folded_layers():
+            h = torch._addmm_activation(b, h, w.t())
+        return h
 
 
 class PointnetSAModuleMSG(nn.Module):
@@ -92,22 +113,43 @@ class PointnetSAModuleMSG(nn.Module):
         self.mlps = nn.ModuleList([SharedMLP([spec[0] + 3] + spec[1:]) for spec in mlps])
 
     def forward(self, xyz, features=None, geometry=None):
-        """xyz (B,N,3), features (B,C,N) -> new_xyz (B,npoint,3), new_features (B,sum Cout,npoint), geometry"""
-        outs = []
+        """Reference layout (pointnet2_modules.py:19-74): xyz (B,N,3), features (B,C,N) ->
+        new_xyz (B,npoint,3), new_features (B,sum Cout,npoint), geometry."""
+        feat_cl = None if features is None else features.transpose(1, 2).contiguous()
+        new_xyz, out_cl, geometry = self.forward_cl(xyz, feat_cl, geometry)
+        return new_xyz, out_cl.transpose(1, 2).contiguous(), geometry
+
+    def forward_cl(self, xyz, feat_cl=None, geometry=None):
+        """Channels-last fast path: feat_cl (B,N,C) -> new_xyz (B,npoint,3), out (B,npoint,sum Cout).
+        FPS+gather, one two-radius ball query, then per scale: fused gather into GEMM rows, the SharedMLP
+        as a row-major GEMM chain, max-pool over the samples written straight into the concatenated output."""
+        B = xyz.shape[0]
+        couts = [getattr(m, f"layer{m.n_layers - 1}").conv.out_channels for m in self.mlps]
         if self.npoint is not None:
             if geometry is None:
                 idx, new_xyz = pu.furthest_point_sample_gather(xyz, self.npoint)
                 bq = pu.ball_query2(self.radii, self.nsamples, xyz, new_xyz)
                 geometry = (idx, new_xyz, bq)
             idx, new_xyz, bq = geometry
-            for i in range(len(self.mlps)):
-                grouped = pu.query_group(xyz, new_xyz, features, bq[i])
-                outs.append(self.mlps[i](grouped))
-        else:
-            new_xyz = None
-            for i in range(len(self.mlps)):
-                outs.append(self.mlps[i](self.groupers[i](xyz, None, features)))
-        return new_xyz, torch.cat(outs, dim=1), geometry
+            M = self.npoint
+            out = torch.empty((B, M, sum(couts)), dtype=torch.float32, device=xyz.device)
+            off = 0
+            for i, mlp in enumerate(self.mlps):
+                rows = pu.group_rows(xyz, new_xyz, feat_cl, bq[i])
+                h = mlp.forward_rows(rows)
+                pu.maxpool_rows(h, B * M, self.nsamples[i], out=out.view(B * M, -1)[:, off:off + couts[i]])
+                off += couts[i]
+            return new_xyz, out, geometry
+        # GroupAll (pointnet2_utils.py:306-328): every point of the level is one sample of a single group
+        N = xyz.shape[1]
+        rows = (xyz if feat_cl is None else torch.cat([xyz, feat_cl], dim=-1)).reshape(B * N, -1)
+        out = torch.empty((B, 1, sum(couts)), dtype=torch.float32, device=xyz.device)
+        off = 0
+        for i, mlp in enumerate(self.mlps):
+            h = mlp.forward_rows(rows)
+            pu.maxpool_rows(h, B, N, out=out.view(B, -1)[:, off:off + couts[i]])
+            off += couts[i]
+        return None, out, geometry
 
 
 class Pointnet2ClsMSG(nn.Module):
@@ -131,11 +173,12 @@ class Pointnet2ClsMSG(nn.Module):
     def forward(self, pointcloud: torch.Tensor, geometry: Optional[list] = None, return_geometry=False):
         """pointcloud (B, N, 3 + C) -> (B, 1024).  `geometry`: per-level FPS / ball-query results of an
         earlier call on the same cloud (they depend on xyz only)."""
-        xyz, features = self._break_up_pc(pointcloud)
+        xyz = pointcloud[..., 0:3].contiguous()
+        feat_cl = pointcloud[..., 3:].contiguous() if pointcloud.size(-1) > 3 else None
         geo_out = []
         for k, sa in enumerate(self.SA_modules):
             g = None if geometry is None else geometry[k]
-            xyz, features, g = sa(xyz, features, g)
+            xyz, feat_cl, g = sa.forward_cl(xyz, feat_cl, g)
             geo_out.append(g)
-        out = features.squeeze(-1)
+        out = feat_cl.squeeze(1)
         return (out, geo_out) if return_geometry else out

@@ -107,6 +107,38 @@ def query_group(xyz, new_xyz, features, idx) -> torch.Tensor:
     return out
 
 
+def group_rows(xyz, new_xyz, feat_cl, idx) -> torch.Tensor:
+    """Channels-last QueryAndGroup tail: one row per (centre, sample): [B*M*ns, 3 + C] with
+    row = [xyz[idx] - new_xyz | feat_cl[idx]]; feat_cl is [B, N, C] (channels last) or None."""
+    _lib.check_cuda(xyz, "xyz", torch.float32)
+    _lib.check_cuda(new_xyz, "new_xyz", torch.float32)
+    _lib.check_cuda(idx, "idx", torch.int32)
+    B, N, _ = xyz.size()
+    _, M, ns = idx.size()
+    C = 0
+    if feat_cl is not None:
+        _lib.check_cuda(feat_cl, "feat_cl", torch.float32)
+        C = feat_cl.size(2)
+    out = torch.empty((B * M * ns, 3 + C), dtype=torch.float32, device=xyz.device)
+    _lib.call("gp_group_rows", _lib.ptr(xyz), _lib.ptr(new_xyz), _lib.ptr(feat_cl), _lib.ptr(idx), B, C, N, M, ns,
+              3 + C, _lib.ptr(out), device=xyz.device)
+    return out
+
+
+def maxpool_rows(h, groups, nsample, out=None):
+    """max over the `nsample` consecutive rows of each group: h [groups*nsample, C] -> out [groups, C]
+    (`out` may be a column slice of a wider row-major tensor: both MSG scales land in one tensor)."""
+    _lib.check_cuda(h, "h", torch.float32)
+    C = h.size(1)
+    if out is None:
+        out = torch.empty((groups, C), dtype=torch.float32, device=h.device)
+    if out.stride(-1) != 1 or out.dtype != torch.float32:
+        raise ValueError("out must be float32 with unit inner stride")
+    _lib.call("gp_maxpool_rows", _lib.ptr(h), int(groups), int(nsample), C, int(out.stride(-2)), _lib.ptr(out),
+              device=h.device)
+    return out
+
+
 class QueryAndGroup(nn.Module):
     """pointnet2_utils.py:259-298."""
 

@@ -89,6 +89,18 @@ GP_API int gp_query_group(const float *xyz, const float *new_xyz, const float *f
                    const int32_t *idx, int B, int C, int N, int M, int nsample, float *out,
                    gp_stream_t s);
 
+/* Channels-last ("one GEMM row per sample") form of the same QueryAndGroup tail, used by the drop-in
+ * encoder so that the SharedMLP (conv1x1 + BN + ReLU, P2/pytorch_utils.py:5-33) is a plain row-major
+ * GEMM chain.  feat_cl is [B,N,C] (channels last; NULL when C == 0), out is [B*M*nsample, ld_out] with
+ * out[row, 0:3] = xyz[idx] - new_xyz, out[row, 3:3+C] = feat_cl[idx, :], zero padding up to ld_out. */
+GP_API int gp_group_rows(const float *xyz, const float *new_xyz, const float *feat_cl, const int32_t *idx,
+                  int B, int C, int N, int M, int nsample, int ld_out, float *out, gp_stream_t s);
+
+/* Replaces F.max_pool2d(new_features, kernel_size=[1, nsample]) (P2/pointnet2_modules.py:59-61) on the
+ * channels-last layout: h [G*nsample, C] -> out[g, 0:C] = max over the nsample rows of group g
+ * (out has row stride ld_out so both MSG scales can land in one concatenated tensor). */
+GP_API int gp_maxpool_rows(const float *h, long long G, int nsample, int C, int ld_out, float *out, gp_stream_t s);
+
 /* ---------------------------------------------------------------------------------------------
  * (2)(3) ScoreNet / EnergyNet trunk.  Raw parameters in the reference's state-dict layout
  * (SURVEY.md section 5): nn.Linear weights are [out,in] row-major.

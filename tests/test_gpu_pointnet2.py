@@ -171,3 +171,23 @@ def test_edge_cases_and_errors():
         pu.furthest_point_sample(torch.randn(2, 16, 3), 4)  # CPU tensor: no fallback
     with pytest.raises(TypeError):
         pu.gather_operation(torch.randn(1, 3, 8, device="cuda"), torch.zeros(1, 4, dtype=torch.int64, device="cuda"))
+
+
+def test_group_rows_and_maxpool_rows():
+    """channels-last gather / max-pool vs the reference-layout ops"""
+    from genpose2_b200 import pointnet2_utils as pu
+    B, N, M, ns = 3, 512, 128, 16
+    xyz = clouds(B, N, seed=11)
+    idx, new_xyz = pu.furthest_point_sample_gather(xyz, M)
+    bq = pu.ball_query(0.05, ns, xyz, new_xyz)
+    for C in (0, 7, 96):
+        feats = torch.randn(B, C, N, device="cuda") if C else None
+        want = pu.query_group(xyz, new_xyz, feats, bq)  # [B, 3+C, M, ns]
+        got = pu.group_rows(xyz, new_xyz, None if feats is None else feats.transpose(1, 2).contiguous(), bq)
+        assert torch.equal(got.view(B, M, ns, 3 + C).permute(0, 3, 1, 2), want)
+        h = torch.randn(B * M * ns, 40, device="cuda")
+        out = torch.zeros(B * M, 100, device="cuda")
+        pu.maxpool_rows(h, B * M, ns, out=out[:, 20:60])
+        assert torch.equal(out[:, 20:60], h.view(B * M, ns, 40).amax(1)) and (out[:, :20] == 0).all() and (out[:, 60:] == 0).all()
+        h3 = torch.randn(B * M * ns, 3, device="cuda")  # scalar path
+        assert torch.equal(pu.maxpool_rows(h3, B * M, ns), h3.view(B * M, ns, 3).amax(1))
