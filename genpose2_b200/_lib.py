@@ -49,6 +49,10 @@ SIGNATURES = {
     "gp_group_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p]),
     "gp_maxpool_rows": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "gp_gemm_packed_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "gp_gemm_pack": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "gp_gemm_bias_relu": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                  c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "gp_trunk_packed_bytes": (c_size_t, []),
     "gp_trunk_pack": (c_int, [ctypes.POINTER(TrunkParams), c_void_p, c_void_p]),
     "gp_trunk_project": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

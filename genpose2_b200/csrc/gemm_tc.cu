@@ -1,0 +1,327 @@
+// Y = relu(X . W^T + b) on the 5th-gen tensor cores (tcgen05 + TMEM), optionally fused with the max-pool
+// over `pool_ns` consecutive rows: the SharedMLP layer of a PointNet++ set-abstraction scale
+// (P2/pytorch_utils.py:5-33: conv1x1 + BatchNorm(eval, folded) + ReLU; P2/pointnet2_modules.py:59-61)
+// on channels-last rows.
+//
+// Operands are bf16 with fp32 accumulation in TMEM.  NPASS = 1: plain bf16 (bf16 mode).  NPASS = 3: every
+// fp32 value is split x = hi + lo (two bf16) and the product is accumulated as hi*hi + lo*hi + hi*lo:
+// 16 mantissa bits per operand, relative error ~2^-16 per product -- the fp32-mode encoder path.
+//
+// CTA = 128 rows x BN (<= 256) columns, K streamed in chunks of 64 through NS shared-memory stages:
+//   warps 0-3  A loaders (one row per thread: 16-byte global loads, hi/lo split, swizzled 16-byte smem
+//              stores) during the main loop, epilogue afterwards (tcgen05.ld, bias, ReLU, store / pool)
+//   warp 4     TMA producer: cp.async.bulk of the pre-packed, pre-swizzled weight chunk images
+//   warp 5     MMA issuer: tcgen05.mma.kind::f16 M128 x BN x K16, commits to mbarriers
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace gp {
+namespace gemm {
+
+constexpr int BM = 128;
+constexpr int KC = 64;                   // k per chunk (128 bytes of bf16: one SWIZZLE_128B atom row)
+constexpr int A_TILE = BM * 128;         // 16 KB
+constexpr int B_TILE_MAX = 256 * 128;    // 32 KB
+constexpr int NTHREADS = 192;
+
+struct Args {
+    const float *X;        // [R, ldx]
+    long long R;
+    int ldx;               // floats per row (multiple of 4); columns >= K hold zeros or meet zero weights
+    const uint8_t *Wp;     // packed weights
+    const float *bias;     // [N]
+    int N, K;
+    float *Y;              // [R, ldy] or nullptr when pooling
+    int ldy;
+    int pool_ns;           // 0: no pooling
+    float *pooled;         // [R / pool_ns, ld_pooled], zero-initialised by the caller
+    int ld_pooled;
+    int nchunks;           // ceil(K / 64)
+};
+
+__host__ __device__ inline int bn_of_tile(int N, int j) {  // columns of n-tile j, rounded up to 16
+    int rem = N - 256 * j;
+    if (rem > 256) rem = 256;
+    return (rem + 15) & ~15;
+}
+__host__ __device__ inline size_t tile_image_bytes(int bn) { return (size_t)bn * 128; }
+// packed layout: for n-tile j, for chunk c: hi image [bn x 128 B] then (NPASS == 3) lo image
+__host__ __device__ inline size_t packed_tile_offset(int N, int nchunks, int npass, int j) {
+    size_t off = 0;
+    const int images = npass == 3 ? 2 : 1;
+    for (int t = 0; t < j; ++t) off += (size_t)nchunks * images * tile_image_bytes(bn_of_tile(N, t));
+    return off;
+}
+
+__global__ void pack_weights_kernel(const float *__restrict__ W, int N, int K, int npass, int nchunks,
+                                    uint8_t *__restrict__ out, size_t total_bytes) {
+    // one thread per 4 bytes (two bf16) of the packed buffer
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const int images = npass == 3 ? 2 : 1;
+    const int ntiles = (N + 255) / 256;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_bytes / 4; i += stride) {
+        size_t o = i * 4;
+        int j = 0;
+        size_t toff = 0;
+        for (; j < ntiles; ++j) {
+            const size_t sz = (size_t)nchunks * images * tile_image_bytes(bn_of_tile(N, j));
+            if (o < toff + sz) break;
+            toff += sz;
+        }
+        const int bn = bn_of_tile(N, j);
+        const size_t img = tile_image_bytes(bn);
+        const size_t rel = o - toff;
+        const int c = (int)(rel / (images * img));
+        const size_t in_c = rel % (images * img);
+        const int which = (int)(in_c / img);  // 0 hi, 1 lo
+        const size_t ob = in_c % img;
+        const int nl = (int)(ob / 128), wb = (int)(ob % 128);
+        const int logical16 = (wb / 16) ^ (nl & 7);
+        const int kk = logical16 * 8 + (wb % 16) / 2;
+        const int n = 256 * j + nl;
+        float v[2];
+        for (int e = 0; e < 2; ++e) {
+            const int k = c * KC + kk + e;
+            float w = (n < N && k < K) ? W[(size_t)n * K + k] : 0.f;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+            v[e] = which == 0 ? __bfloat162float(hi) : (w - __bfloat162float(hi));
+        }
+        __nv_bfloat162 p = __floats2bfloat162_rn(v[0], v[1]);
+        *reinterpret_cast<uint32_t *>(out + o) = *reinterpret_cast<uint32_t *>(&p);
+    }
+}
+
+template <int NPASS>
+struct Cfg {
+    static constexpr int IMAGES = NPASS == 3 ? 2 : 1;
+    static constexpr int NS = NPASS == 3 ? 2 : 4;
+    static constexpr int STAGE_BYTES = IMAGES * (A_TILE + B_TILE_MAX);
+    static constexpr size_t SMEM = (size_t)NS * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int NPASS>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_bias_relu_kernel(Args a) {
+    using C = Cfg<NPASS>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // stage s: [A_hi | A_lo | B_hi | B_lo]
+    auto a_img = [&](int s, int which) { return base + (size_t)s * C::STAGE_BYTES + (size_t)which * A_TILE; };
+    auto b_img = [&](int s, int which) { return base + (size_t)s * C::STAGE_BYTES + (size_t)C::IMAGES * A_TILE + (size_t)which * B_TILE_MAX; };
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(base + (size_t)C::NS * C::STAGE_BYTES);
+    unsigned long long *a_full = bars, *b_full = bars + C::NS, *empty = bars + 2 * C::NS, *d_full = bars + 3 * C::NS;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * C::NS + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long row0 = (long long)blockIdx.x * BM;
+    const int jt = blockIdx.y;
+    const int bn = bn_of_tile(a.N, jt);
+    const int n0 = 256 * jt;
+
+    if (tid == 0) {
+        for (int s = 0; s < C::NS; ++s) {
+            tc::mbar_init(&a_full[s], 4);   // one elected lane per loader warp
+            tc::mbar_init(&b_full[s], 1);
+            tc::mbar_init(&empty[s], 1);
+        }
+        tc::mbar_init(d_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 5) tc::tmem_alloc(tmem_slot, 256);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 4) {
+        // ------------------------- A loaders -------------------------
+        const int r = tid;  // 0..127
+        const long long grow = row0 + r;
+        const bool row_ok = grow < a.R;
+        const float *xrow = a.X + (row_ok ? grow : 0) * (long long)a.ldx;
+        for (int c = 0; c < a.nchunks; ++c) {
+            const int s = c % C::NS;
+            if (c >= C::NS) tc::mbar_wait(&empty[s], ((c / C::NS) + 1) & 1);
+            float4 v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int k = c * KC + 4 * j;
+                v[j] = (row_ok && k < a.ldx) ? __ldg(reinterpret_cast<const float4 *>(xrow + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            uint8_t *hi_row = a_img(s, 0) + r * 128;
+            uint8_t *lo_row = a_img(s, 1) + r * 128;
+#pragma unroll
+            for (int j8 = 0; j8 < 8; ++j8) {  // 8 bf16 = one 16-byte swizzle unit
+                const float4 p = v[2 * j8], q = v[2 * j8 + 1];
+                const __nv_bfloat162 h0 = __floats2bfloat162_rn(p.x, p.y), h1 = __floats2bfloat162_rn(p.z, p.w);
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(q.x, q.y), h3 = __floats2bfloat162_rn(q.z, q.w);
+                uint4 pk;
+                pk.x = *reinterpret_cast<const uint32_t *>(&h0); pk.y = *reinterpret_cast<const uint32_t *>(&h1);
+                pk.z = *reinterpret_cast<const uint32_t *>(&h2); pk.w = *reinterpret_cast<const uint32_t *>(&h3);
+                const int sw = (j8 ^ (r & 7)) << 4;
+                *reinterpret_cast<uint4 *>(hi_row + sw) = pk;
+                if (NPASS == 3) {
+                    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+                    const float2 f2 = __bfloat1622float2(h2), f3 = __bfloat1622float2(h3);
+                    const __nv_bfloat162 l0 = __floats2bfloat162_rn(p.x - f0.x, p.y - f0.y), l1 = __floats2bfloat162_rn(p.z - f1.x, p.w - f1.y);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(q.x - f2.x, q.y - f2.y), l3 = __floats2bfloat162_rn(q.z - f3.x, q.w - f3.y);
+                    uint4 pl;
+                    pl.x = *reinterpret_cast<const uint32_t *>(&l0); pl.y = *reinterpret_cast<const uint32_t *>(&l1);
+                    pl.z = *reinterpret_cast<const uint32_t *>(&l2); pl.w = *reinterpret_cast<const uint32_t *>(&l3);
+                    *reinterpret_cast<uint4 *>(lo_row + sw) = pl;
+                }
+            }
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&a_full[s]);
+        }
+        // ------------------------- epilogue -------------------------
+        tc::mbar_wait(d_full, 0);
+        tc::tc_fence_after();
+        const uint32_t lane_addr = tmem + ((uint32_t)(32 * warp) << 16);
+        const int ns = a.pool_ns;
+        for (int g = 0; g < bn / 32 + ((bn & 31) ? 1 : 0); ++g) {
+            uint32_t rv[32];
+            tc::tmem_ld32(lane_addr + g * 32, rv);
+            float out[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = n0 + g * 32 + j;
+                const float bv = n < a.N ? __ldg(a.bias + n) : 0.f;
+                out[j] = (n < a.N && row_ok) ? fmaxf(__uint_as_float(rv[j]) + bv, 0.f) : 0.f;
+            }
+            if (ns == 0) {
+                if (row_ok) {
+                    float *yrow = a.Y + grow * (long long)a.ldy + n0 + g * 32;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const int n = n0 + g * 32 + 4 * j4;
+                        if (n + 4 <= a.ldy)  // ldy % 4 == 0: a vector is fully inside or fully outside
+                            *reinterpret_cast<float4 *>(yrow + 4 * j4) = make_float4(out[4 * j4], out[4 * j4 + 1], out[4 * j4 + 2], out[4 * j4 + 3]);
+                    }
+                }
+            } else {
+                // max over the pool_ns consecutive rows of each group.  Values are >= 0 after the ReLU, so the
+                // float order equals the unsigned order of the bit patterns: one redux.sync per column.
+                const int gl = ns < 32 ? ns : 32;                  // lanes per sub-group
+                const unsigned mask = gl == 32 ? 0xffffffffu : (((1u << gl) - 1u) << ((lane / gl) * gl));
+                const int per_lane = 32 / gl;                      // result columns kept by each lane
+                float keep[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const unsigned m = __reduce_max_sync(mask, __float_as_uint(out[j]));
+                    if ((lane % gl) == (j % gl)) keep[(j / gl) & 3] = __uint_as_float(m);
+                }
+                if (row_ok) {
+                    const long long grp = grow / ns;
+                    for (int q = 0; q < per_lane && q < 4; ++q) {
+                        const int n = n0 + g * 32 + q * gl + (lane % gl);
+                        if (n < a.N) {
+                            float *dst = a.pooled + grp * (long long)a.ld_pooled + n;
+                            if (ns <= 32) *dst = keep[q];
+                            else atomicMax(reinterpret_cast<int *>(dst), __float_as_int(keep[q]));
+                        }
+                    }
+                }
+            }
+        }
+        tc::tc_fence_before();
+    } else if (warp == 4) {
+        // ------------------------- TMA producer (weights) -------------------------
+        if (lane == 0) {
+            const size_t img = tile_image_bytes(bn);
+            const uint8_t *src = a.Wp + packed_tile_offset(a.N, a.nchunks, NPASS, jt);
+            for (int c = 0; c < a.nchunks; ++c) {
+                const int s = c % C::NS;
+                if (c >= C::NS) tc::mbar_wait(&empty[s], ((c / C::NS) + 1) & 1);
+                tc::mbar_arrive_expect_tx(&b_full[s], (uint32_t)(C::IMAGES * img));
+                for (int w = 0; w < C::IMAGES; ++w)
+                    tc::bulk_g2s(b_img(s, w), src + ((size_t)c * C::IMAGES + w) * img, (uint32_t)img, &b_full[s]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------- MMA issuer -------------------------
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(128, (uint32_t)bn);
+            for (int c = 0; c < a.nchunks; ++c) {
+                const int s = c % C::NS;
+                const uint32_t ph = (c / C::NS) & 1;
+                tc::mbar_wait(&a_full[s], ph);
+                tc::mbar_wait(&b_full[s], ph);
+                tc::tc_fence_after();
+                const uint32_t ahi = tc::smem_u32(a_img(s, 0)), alo = tc::smem_u32(a_img(s, 1));
+                const uint32_t bhi = tc::smem_u32(b_img(s, 0)), blo = tc::smem_u32(b_img(s, 1));
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    tc::umma_bf16(tmem, tc::make_desc(ahi + kk * 32), tc::make_desc(bhi + kk * 32), idesc, (c | kk) ? 1u : 0u);
+                    if (NPASS == 3) {
+                        tc::umma_bf16(tmem, tc::make_desc(alo + kk * 32), tc::make_desc(bhi + kk * 32), idesc, 1u);
+                        tc::umma_bf16(tmem, tc::make_desc(ahi + kk * 32), tc::make_desc(blo + kk * 32), idesc, 1u);
+                    }
+                }
+                tc::umma_commit(&empty[s]);
+            }
+            tc::umma_commit(d_full);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 5) tc::tmem_dealloc(tmem, 256);
+}
+
+template <int NPASS>
+static int launch(const Args &a, cudaStream_t st) {
+    auto kern = gemm_bias_relu_kernel<NPASS>;
+    GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<NPASS>::SMEM));
+    dim3 grid((unsigned)((a.R + BM - 1) / BM), (unsigned)((a.N + 255) / 256));
+    kern<<<grid, NTHREADS, Cfg<NPASS>::SMEM, st>>>(a);
+    GP_CHECK_LAUNCH("gp_gemm_bias_relu");
+    return GP_OK;
+}
+
+}  // namespace gemm
+}  // namespace gp
+
+using namespace gp;
+
+extern "C" size_t gp_gemm_packed_bytes(int N, int K, int npass) {
+    if (N < 1 || K < 1 || (npass != 1 && npass != 3)) return 0;
+    const int nchunks = (K + gemm::KC - 1) / gemm::KC;
+    return gemm::packed_tile_offset(N, nchunks, npass, (N + 255) / 256);
+}
+
+extern "C" int gp_gemm_pack(const float *W, int N, int K, int npass, void *packed, gp_stream_t s) {
+    GP_REQUIRE(W && packed, "gp_gemm_pack: null pointer");
+    GP_REQUIRE(N >= 1 && K >= 1 && (npass == 1 || npass == 3), "gp_gemm_pack: bad arguments");
+    GP_REQUIRE(((uintptr_t)packed & 15) == 0, "gp_gemm_pack: packed must be 16-byte aligned");
+    const int nchunks = (K + gemm::KC - 1) / gemm::KC;
+    const size_t total = gp_gemm_packed_bytes(N, K, npass);
+    gemm::pack_weights_kernel<<<num_sms() * 4, 256, 0, as_stream(s)>>>(W, N, K, npass, nchunks, (uint8_t *)packed, total);
+    GP_CHECK_LAUNCH("gp_gemm_pack");
+    return GP_OK;
+}
+
+extern "C" int gp_gemm_bias_relu(const float *X, long long R, int ldx, const void *packed, const float *bias, int N,
+                                 int K, int npass, float *Y, int ldy, int pool_ns, float *pooled, int ld_pooled,
+                                 gp_stream_t s) {
+    GP_REQUIRE(R >= 0 && N >= 1 && K >= 1 && (npass == 1 || npass == 3), "gp_gemm_bias_relu: bad arguments");
+    if (R == 0) return GP_OK;
+    GP_REQUIRE(X && packed && bias, "gp_gemm_bias_relu: null pointer");
+    GP_REQUIRE(ldx >= 4 && (ldx & 3) == 0 && ((uintptr_t)X & 15) == 0, "gp_gemm_bias_relu: X rows must be 16-byte aligned (ldx %% 4 == 0)");
+    GP_REQUIRE(((uintptr_t)packed & 15) == 0, "gp_gemm_bias_relu: packed must be 16-byte aligned");
+    if (pool_ns == 0) {
+        GP_REQUIRE(Y && ldy >= N && ldy <= ((N + 31) & ~31) && (ldy & 3) == 0 && ((uintptr_t)Y & 15) == 0,
+                   "gp_gemm_bias_relu: bad Y / ldy (need N <= ldy <= round_up(N, 32), ldy %% 4 == 0)");
+    } else {
+        GP_REQUIRE(pooled && ld_pooled >= N, "gp_gemm_bias_relu: bad pooled output");
+        GP_REQUIRE(pool_ns >= 1 && ((pool_ns <= 32 && 32 % pool_ns == 0) || pool_ns % 32 == 0) && R % pool_ns == 0,
+                   "gp_gemm_bias_relu: pool_ns=%d must divide 32 or be a multiple of 32, and divide R", pool_ns);
+        GP_REQUIRE(pool_ns >= 8, "gp_gemm_bias_relu: pool_ns < 8 not supported");
+    }
+    gemm::Args a;
+    a.X = X; a.R = R; a.ldx = ldx; a.Wp = (const uint8_t *)packed; a.bias = bias; a.N = N; a.K = K;
+    a.Y = Y; a.ldy = ldy; a.pool_ns = pool_ns; a.pooled = pooled; a.ld_pooled = ld_pooled;
+    a.nchunks = (K + gemm::KC - 1) / gemm::KC;
+    return npass == 3 ? gemm::launch<3>(a, as_stream(s)) : gemm::launch<1>(a, as_stream(s));
+}

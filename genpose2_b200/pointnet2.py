@@ -93,12 +93,38 @@ class SharedMLP(nn.Module):
             self._fold_key = key
         return self._fold
 
+    def _tc_layers(self, npass):
+        """(packed weights, bias, N, K) per layer for the tcgen05 GEMM, cached like the folded weights."""
+        fold = self._folded_layers()
+        key = (self._fold_key, npass)
+        if getattr(self, "_tc_key", None) != key:
+            self._tc = [(pu.gemm_pack(w, npass), b, w.shape[0], w.shape[1]) for w, b in fold]
+            self._tc_key = key
+        return self._tc
+
+    def forward_rows_pooled(self, rows, groups, nsample, out, gemm_mode):
+        """rows (R, ld) -> SharedMLP -> max over `nsample` rows per group, written into `out` (groups, Cout).
+        gemm_mode: "cublas" (fp32 library GEMM), "bf16x3" (tcgen05, split-bf16, fp32-class) or "bf16" (tcgen05)."""
+        if gemm_mode == "cublas":
+            h = self.forward_rows(rows)
+            return pu.maxpool_rows(h, groups, nsample, out=out)
+        npass = {"bf16x3": 3, "bf16": 1}[gemm_mode]
+        layers = self._tc_layers(npass)
+        h = rows
+        for i, (packed, b, N, K) in enumerate(layers):
+            if i + 1 < len(layers):
+                h = pu.gemm_bias_relu(h, packed, b, N, K, npass)
+            else:
+                out.zero_()
+                pu.gemm_bias_relu(h, packed, b, N, K, npass, pool_ns=nsample, pooled_out=out)
+        return out
+
     def forward_rows(self, rows: torch.Tensor) -> torch.Tensor:
         """Channels-last: rows (R, Cin) -> (R, Cout); each layer is relu(rows @ W^T + b) with the bias and
         the ReLU in the GEMM epilogue (cuBLASLt through torch._addmm_activation) -- SURVEY section 8 row f1."""
         h = rows
         for w, b in self._folded_layers():
-            h = torch._addmm_activation(b, h, w.t())
+            h = torch._addmm_activation(b, h[:, : w.shape[1]] if h.shape[1] != w.shape[1] else h, w.t())
         return h
 
 
@@ -108,6 +134,7 @@ class PointnetSAModuleMSG(nn.Module):
     def __init__(self, *, npoint, radii, nsamples, mlps):
         super().__init__()
         self.npoint, self.radii, self.nsamples = npoint, radii, nsamples
+        self.gemm_mode = "cublas"  # "cublas" | "bf16x3" | "bf16" (see SharedMLP.forward_rows_pooled)
         self.groupers = nn.ModuleList(
             [pu.QueryAndGroup(r, n) if npoint is not None else pu.GroupAll() for r, n in zip(radii, nsamples)])
         self.mlps = nn.ModuleList([SharedMLP([spec[0] + 3] + spec[1:]) for spec in mlps])
@@ -135,19 +162,23 @@ class PointnetSAModuleMSG(nn.Module):
             out = torch.empty((B, M, sum(couts)), dtype=torch.float32, device=xyz.device)
             off = 0
             for i, mlp in enumerate(self.mlps):
-                rows = pu.group_rows(xyz, new_xyz, feat_cl, bq[i])
-                h = mlp.forward_rows(rows)
-                pu.maxpool_rows(h, B * M, self.nsamples[i], out=out.view(B * M, -1)[:, off:off + couts[i]])
+                rows = pu.group_rows(xyz, new_xyz, feat_cl, bq[i], pad_to=1 if self.gemm_mode == "cublas" else 4)
+                mlp.forward_rows_pooled(rows, B * M, self.nsamples[i], out.view(B * M, -1)[:, off:off + couts[i]],
+                                        self.gemm_mode)
                 off += couts[i]
             return new_xyz, out, geometry
         # GroupAll (pointnet2_utils.py:306-328): every point of the level is one sample of a single group
         N = xyz.shape[1]
-        rows = (xyz if feat_cl is None else torch.cat([xyz, feat_cl], dim=-1)).reshape(B * N, -1)
+        parts = [xyz] if feat_cl is None else [xyz, feat_cl]
+        width = sum(p.shape[-1] for p in parts)
+        if self.gemm_mode != "cublas" and width % 4:
+            parts.append(torch.zeros((B, N, 4 - width % 4), dtype=torch.float32, device=xyz.device))
+        rows = torch.cat(parts, dim=-1).reshape(B * N, -1)
         out = torch.empty((B, 1, sum(couts)), dtype=torch.float32, device=xyz.device)
         off = 0
+        gm = self.gemm_mode if (self.gemm_mode == "cublas" or N % 32 == 0 or 32 % N == 0) else "cublas"
         for i, mlp in enumerate(self.mlps):
-            h = mlp.forward_rows(rows)
-            pu.maxpool_rows(h, B, N, out=out.view(B, -1)[:, off:off + couts[i]])
+            mlp.forward_rows_pooled(rows, B, N, out.view(B, -1)[:, off:off + couts[i]], gm)
             off += couts[i]
         return None, out, geometry
 
@@ -163,6 +194,15 @@ class Pointnet2ClsMSG(nn.Module):
             self.SA_modules.append(PointnetSAModuleMSG(
                 npoint=cfg["NPOINTS"][k], radii=cfg["RADIUS"][k], nsamples=cfg["NSAMPLE"][k], mlps=mlps))
             channel_in = sum(m[-1] for m in mlps)
+
+    def set_gemm_mode(self, mode):
+        """SharedMLP GEMM engine for every level: "cublas" (fp32 library GEMM), "bf16x3" (tcgen05 split-bf16,
+        fp32-class accuracy) or "bf16" (tcgen05 bf16)."""
+        if mode not in ("cublas", "bf16x3", "bf16"):
+            raise ValueError(mode)
+        for sa in self.SA_modules:
+            sa.gemm_mode = mode
+        return self
 
     @staticmethod
     def _break_up_pc(pc):

@@ -107,9 +107,10 @@ def query_group(xyz, new_xyz, features, idx) -> torch.Tensor:
     return out
 
 
-def group_rows(xyz, new_xyz, feat_cl, idx) -> torch.Tensor:
-    """Channels-last QueryAndGroup tail: one row per (centre, sample): [B*M*ns, 3 + C] with
-    row = [xyz[idx] - new_xyz | feat_cl[idx]]; feat_cl is [B, N, C] (channels last) or None."""
+def group_rows(xyz, new_xyz, feat_cl, idx, pad_to=1) -> torch.Tensor:
+    """Channels-last QueryAndGroup tail: one row per (centre, sample): [B*M*ns, ld] with
+    row = [xyz[idx] - new_xyz | feat_cl[idx] | zeros]; feat_cl is [B, N, C] (channels last) or None;
+    ld = 3 + C rounded up to a multiple of `pad_to`."""
     _lib.check_cuda(xyz, "xyz", torch.float32)
     _lib.check_cuda(new_xyz, "new_xyz", torch.float32)
     _lib.check_cuda(idx, "idx", torch.int32)
@@ -119,9 +120,10 @@ def group_rows(xyz, new_xyz, feat_cl, idx) -> torch.Tensor:
     if feat_cl is not None:
         _lib.check_cuda(feat_cl, "feat_cl", torch.float32)
         C = feat_cl.size(2)
-    out = torch.empty((B * M * ns, 3 + C), dtype=torch.float32, device=xyz.device)
+    ld = (3 + C + pad_to - 1) // pad_to * pad_to
+    out = torch.empty((B * M * ns, ld), dtype=torch.float32, device=xyz.device)
     _lib.call("gp_group_rows", _lib.ptr(xyz), _lib.ptr(new_xyz), _lib.ptr(feat_cl), _lib.ptr(idx), B, C, N, M, ns,
-              3 + C, _lib.ptr(out), device=xyz.device)
+              ld, _lib.ptr(out), device=xyz.device)
     return out
 
 
@@ -137,6 +139,37 @@ def maxpool_rows(h, groups, nsample, out=None):
     _lib.call("gp_maxpool_rows", _lib.ptr(h), int(groups), int(nsample), C, int(out.stride(-2)), _lib.ptr(out),
               device=h.device)
     return out
+
+
+def gemm_pack(weight: torch.Tensor, npass: int) -> torch.Tensor:
+    """Pack W [N, K] fp32 into the pre-swizzled bf16 (npass=1) / bf16 hi+lo (npass=3) chunk images the
+    tcgen05 GEMM streams with TMA (gp_gemm_pack).  Do once per checkpoint."""
+    w = _lib.check_cuda(weight.detach().to(torch.float32).contiguous(), "weight", torch.float32)
+    N, K = w.shape
+    nbytes = _lib.load().gp_gemm_packed_bytes(N, K, npass)
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    _lib.call("gp_gemm_pack", _lib.ptr(w), N, K, npass, _lib.ptr(packed), device=w.device)
+    return packed
+
+
+def gemm_bias_relu(x, packed, bias, N, K, npass, pool_ns=0, pooled_out=None):
+    """relu(x @ W^T + bias) on the tensor cores (gp_gemm_bias_relu).  x [R, ldx] fp32 with ldx % 4 == 0.
+    pool_ns == 0 -> returns y [R, round_up(N, 32)] (columns >= N are zero);
+    pool_ns  > 0 -> max over each pool_ns consecutive rows into `pooled_out` (zero-initialised,
+    [R / pool_ns, >= N] row-major, may be a column slice) and returns it."""
+    _lib.check_cuda(x, "x", torch.float32)
+    R, ldx = x.shape
+    if pool_ns:
+        if pooled_out is None:
+            pooled_out = torch.zeros((R // pool_ns, N), dtype=torch.float32, device=x.device)
+        _lib.call("gp_gemm_bias_relu", _lib.ptr(x), R, ldx, _lib.ptr(packed), _lib.ptr(bias), N, K, npass, None, 0,
+                  int(pool_ns), _lib.ptr(pooled_out), int(pooled_out.stride(-2)), device=x.device)
+        return pooled_out
+    ldy = (N + 31) // 32 * 32
+    y = torch.empty((R, ldy), dtype=torch.float32, device=x.device)
+    _lib.call("gp_gemm_bias_relu", _lib.ptr(x), R, ldx, _lib.ptr(packed), _lib.ptr(bias), N, K, npass, _lib.ptr(y), ldy,
+              0, None, 0, device=x.device)
+    return y
 
 
 class QueryAndGroup(nn.Module):

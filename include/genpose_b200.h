@@ -101,6 +101,21 @@ GP_API int gp_group_rows(const float *xyz, const float *new_xyz, const float *fe
  * (out has row stride ld_out so both MSG scales can land in one concatenated tensor). */
 GP_API int gp_maxpool_rows(const float *h, long long G, int nsample, int C, int ld_out, float *out, gp_stream_t s);
 
+/* One SharedMLP layer (P2/pytorch_utils.py:5-33: conv1x1 + BatchNorm(eval) folded + ReLU) on channels-last
+ * rows, on the tcgen05 tensor cores: Y = relu(X . W^T + bias), optionally fused with the max-pool over
+ * `pool_ns` consecutive rows (P2/pointnet2_modules.py:59-61).
+ *   npass = 1: bf16 operands (bf16 mode);  npass = 3: fp32 values split into hi + lo bf16 and accumulated
+ *   as hi*hi + lo*hi + hi*lo (16 mantissa bits per operand, fp32 accumulation) -- the fp32-mode path.
+ *   W [N,K] fp32 row-major is packed once per checkpoint with gp_gemm_pack (gp_gemm_packed_bytes bytes).
+ *   X [R, ldx] fp32, ldx %% 4 == 0, columns K..ldx-1 must be finite (they meet zero weights).
+ *   pool_ns == 0: Y [R, ldy] with ldy = round_up(N, 32); columns N..ldy-1 are written as zeros.
+ *   pool_ns  > 0: pooled [R / pool_ns, ld_pooled] (zero-initialised by the caller) receives the max. */
+GP_API size_t gp_gemm_packed_bytes(int N, int K, int npass);
+GP_API int gp_gemm_pack(const float *W, int N, int K, int npass, void *packed, gp_stream_t s);
+GP_API int gp_gemm_bias_relu(const float *X, long long R, int ldx, const void *packed, const float *bias, int N,
+                      int K, int npass, float *Y, int ldy, int pool_ns, float *pooled, int ld_pooled,
+                      gp_stream_t s);
+
 /* ---------------------------------------------------------------------------------------------
  * (2)(3) ScoreNet / EnergyNet trunk.  Raw parameters in the reference's state-dict layout
  * (SURVEY.md section 5): nn.Linear weights are [out,in] row-major.

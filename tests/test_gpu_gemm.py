@@ -1,0 +1,54 @@
+"""GPU: the tcgen05 SharedMLP-layer GEMM (gp_gemm_bias_relu) vs a float64 torch reference, and the
+encoder with its three GEMM engines vs the CPU restatement."""
+import numpy as np
+import pytest
+import torch
+
+from genpose2_b200 import synthetic
+from oracle import pose_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("R,K,N,ldx", [(128, 64, 256, 64), (1000, 99, 64, 100), (4096, 259, 196, 260),
+                                       (2048, 515, 384, 516), (640, 1027, 512, 1028), (300, 3, 16, 4),
+                                       (256, 32, 96, 32)])
+@pytest.mark.parametrize("npass", [3, 1])
+def test_gemm_bias_relu_matches_float64(R, K, N, ldx, npass):
+    from genpose2_b200 import pointnet2_utils as pu
+    g = torch.Generator().manual_seed(R + K + N)
+    x = torch.zeros(R, ldx)
+    x[:, :K] = torch.randn(R, K, generator=g)
+    x[:, K:] = 7.0  # padding columns must only ever meet zero weights
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) * 0.1
+    want = torch.relu(x[:, :K].double() @ w.double().t() + b.double())
+    packed = pu.gemm_pack(w.cuda(), npass)
+    y = pu.gemm_bias_relu(x.cuda(), packed, b.cuda(), N, K, npass)
+    assert y.shape == (R, (N + 31) // 32 * 32)
+    assert (y[:, N:] == 0).all()
+    err = float((y[:, :N].double().cpu() - want).abs().max() / want.abs().max())
+    tol = 5e-5 if npass == 3 else 2e-2
+    assert err < tol, err
+    for ns in (16, 32, 64):
+        if R % ns:
+            continue
+        out = torch.zeros(R // ns, N + 8, device="cuda")
+        pu.gemm_bias_relu(x.cuda(), packed, b.cuda(), N, K, npass, pool_ns=ns, pooled_out=out[:, 4:4 + N])
+        assert torch.equal(out[:, 4:4 + N], y[:, :N].view(R // ns, ns, N).amax(1)), ns
+        assert (out[:, :4] == 0).all() and (out[:, 4 + N:] == 0).all()
+
+
+@pytest.mark.parametrize("mode,tol", [("cublas", 1e-4), ("bf16x3", 2e-4), ("bf16", 5e-2)])
+def test_encoder_gemm_engines_vs_cpu_restatement(mode, tol):
+    from genpose2_b200.pointnet2 import Pointnet2ClsMSG
+    sd = synthetic.random_encoder_state_dict(7, prefix="")
+    enc = Pointnet2ClsMSG(0).cuda().eval().set_gemm_mode(mode)
+    enc.load_state_dict(sd)
+    pts, _ = synthetic.make_point_clouds(3, 1024, seed=9, dup_fraction=0.5)
+    with torch.no_grad():
+        got = enc(pts.cuda())
+    want = po.pointnet2_encoder({"pts_encoder." + k: v for k, v in sd.items()}, pts)
+    err = float((got.cpu() - want).abs().max() / want.abs().max())
+    print(f"encoder {mode}: max rel err {err:.3e}")
+    assert err < tol, err
