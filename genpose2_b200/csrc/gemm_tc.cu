@@ -91,6 +91,34 @@ __global__ void pack_weights_kernel(const float *__restrict__ W, int N, int K, i
     }
 }
 
+// pooled epilogue for one 32-column group: GL lanes form one pooling sub-group
+template <int GL>
+__device__ __forceinline__ void pool_store(const float (&out)[32], int lane, bool row_ok, long long grow, int ns,
+                                           int nbase, const Args &a) {
+    constexpr int PER_LANE = 32 / GL;
+    const unsigned mask = GL == 32 ? 0xffffffffu : (((1u << GL) - 1u) << ((lane / GL) * GL));
+    float keep[PER_LANE];
+#pragma unroll
+    for (int q = 0; q < PER_LANE; ++q) keep[q] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const unsigned m = __reduce_max_sync(mask, __float_as_uint(out[j]));
+        if ((lane % GL) == (j % GL)) keep[j / GL] = __uint_as_float(m);
+    }
+    if (row_ok) {
+        const long long grp = grow / ns;
+#pragma unroll
+        for (int q = 0; q < PER_LANE; ++q) {
+            const int n = nbase + q * GL + (lane % GL);
+            if (n < a.N) {
+                float *dst = a.pooled + grp * (long long)a.ld_pooled + n;
+                if (ns <= 32) *dst = keep[q];
+                else atomicMax(reinterpret_cast<int *>(dst), __float_as_int(keep[q]));
+            }
+        }
+    }
+}
+
 template <int NPASS>
 struct Cfg {
     static constexpr int IMAGES = NPASS == 3 ? 2 : 1;
@@ -135,40 +163,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bias_relu_kernel(Args a) {
 
     if (warp < 4) {
         // ------------------------- A loaders -------------------------
-        const int r = tid;  // 0..127
+        // Coalesced: in pass i a warp reads two rows' 256-byte chunks (lanes 0-15 row 2i, lanes 16-31 row 2i+1,
+        // 16 bytes per lane = 4 full 128-byte lines per instruction), converts its 4 floats to bf16 hi (+ lo)
+        // and writes 8 bytes into the swizzled operand row.
+        const int jv = lane & 15;                         // 16-byte vector inside the 256-byte chunk
+        const int sub = lane >> 4;                        // which of the two rows of this pass
+        const int r = tid;                                // epilogue row (TMEM lane) of this thread
         const long long grow = row0 + r;
         const bool row_ok = grow < a.R;
-        const float *xrow = a.X + (row_ok ? grow : 0) * (long long)a.ldx;
         for (int c = 0; c < a.nchunks; ++c) {
             const int s = c % C::NS;
             if (c >= C::NS) tc::mbar_wait(&empty[s], ((c / C::NS) + 1) & 1);
+            const int k = c * KC + 4 * jv;
+            const bool k_ok = k < a.ldx;
             float4 v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int k = c * KC + 4 * j;
-                v[j] = (row_ok && k < a.ldx) ? __ldg(reinterpret_cast<const float4 *>(xrow + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 16; ++i) {
+                const long long lr = row0 + 32 * warp + 2 * i + sub;
+                v[i] = (k_ok && lr < a.R) ? __ldg(reinterpret_cast<const float4 *>(a.X + lr * (long long)a.ldx + k))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            uint8_t *hi_row = a_img(s, 0) + r * 128;
-            uint8_t *lo_row = a_img(s, 1) + r * 128;
+            uint8_t *hi_img = a_img(s, 0), *lo_img = a_img(s, 1);
 #pragma unroll
-            for (int j8 = 0; j8 < 8; ++j8) {  // 8 bf16 = one 16-byte swizzle unit
-                const float4 p = v[2 * j8], q = v[2 * j8 + 1];
+            for (int i = 0; i < 16; ++i) {
+                const int rl = 32 * warp + 2 * i + sub;   // row inside the tile
+                const int off = rl * 128 + (((jv >> 1) ^ (rl & 7)) << 4) + ((jv & 1) << 3);
+                const float4 p = v[i];
                 const __nv_bfloat162 h0 = __floats2bfloat162_rn(p.x, p.y), h1 = __floats2bfloat162_rn(p.z, p.w);
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(q.x, q.y), h3 = __floats2bfloat162_rn(q.z, q.w);
-                uint4 pk;
+                uint2 pk;
                 pk.x = *reinterpret_cast<const uint32_t *>(&h0); pk.y = *reinterpret_cast<const uint32_t *>(&h1);
-                pk.z = *reinterpret_cast<const uint32_t *>(&h2); pk.w = *reinterpret_cast<const uint32_t *>(&h3);
-                const int sw = (j8 ^ (r & 7)) << 4;
-                *reinterpret_cast<uint4 *>(hi_row + sw) = pk;
+                *reinterpret_cast<uint2 *>(hi_img + off) = pk;
                 if (NPASS == 3) {
                     const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-                    const float2 f2 = __bfloat1622float2(h2), f3 = __bfloat1622float2(h3);
-                    const __nv_bfloat162 l0 = __floats2bfloat162_rn(p.x - f0.x, p.y - f0.y), l1 = __floats2bfloat162_rn(p.z - f1.x, p.w - f1.y);
-                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(q.x - f2.x, q.y - f2.y), l3 = __floats2bfloat162_rn(q.z - f3.x, q.w - f3.y);
-                    uint4 pl;
+                    const __nv_bfloat162 l0 = __floats2bfloat162_rn(p.x - f0.x, p.y - f0.y);
+                    const __nv_bfloat162 l1 = __floats2bfloat162_rn(p.z - f1.x, p.w - f1.y);
+                    uint2 pl;
                     pl.x = *reinterpret_cast<const uint32_t *>(&l0); pl.y = *reinterpret_cast<const uint32_t *>(&l1);
-                    pl.z = *reinterpret_cast<const uint32_t *>(&l2); pl.w = *reinterpret_cast<const uint32_t *>(&l3);
-                    *reinterpret_cast<uint4 *>(lo_row + sw) = pl;
+                    *reinterpret_cast<uint2 *>(lo_img + off) = pl;
                 }
             }
             tc::fence_proxy_async();
@@ -191,38 +222,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bias_relu_kernel(Args a) {
                 out[j] = (n < a.N && row_ok) ? fmaxf(__uint_as_float(rv[j]) + bv, 0.f) : 0.f;
             }
             if (ns == 0) {
-                if (row_ok) {
-                    float *yrow = a.Y + grow * (long long)a.ldy + n0 + g * 32;
+                // transpose the warp's 32 x 32 block through shared memory (the operand stages are free once
+                // d_full has fired) so that every store instruction writes one full 128-byte line of one row
+                float *stg = reinterpret_cast<float *>(base) + warp * (32 * 33);
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const int n = n0 + g * 32 + 4 * j4;
-                        if (n + 4 <= a.ldy)  // ldy % 4 == 0: a vector is fully inside or fully outside
-                            *reinterpret_cast<float4 *>(yrow + 4 * j4) = make_float4(out[4 * j4], out[4 * j4 + 1], out[4 * j4 + 2], out[4 * j4 + 3]);
-                    }
+                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = out[j];
+                __syncwarp();
+                const int ncol = n0 + g * 32 + lane;
+                if (ncol < a.ldy) {
+                    const long long rbase = row0 + 32 * warp;
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; ++rr)
+                        if (rbase + rr < a.R) a.Y[(rbase + rr) * (long long)a.ldy + ncol] = stg[rr * 33 + lane];
                 }
+                __syncwarp();
             } else {
                 // max over the pool_ns consecutive rows of each group.  Values are >= 0 after the ReLU, so the
                 // float order equals the unsigned order of the bit patterns: one redux.sync per column.
-                const int gl = ns < 32 ? ns : 32;                  // lanes per sub-group
-                const unsigned mask = gl == 32 ? 0xffffffffu : (((1u << gl) - 1u) << ((lane / gl) * gl));
-                const int per_lane = 32 / gl;                      // result columns kept by each lane
-                float keep[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const unsigned m = __reduce_max_sync(mask, __float_as_uint(out[j]));
-                    if ((lane % gl) == (j % gl)) keep[(j / gl) & 3] = __uint_as_float(m);
-                }
-                if (row_ok) {
-                    const long long grp = grow / ns;
-                    for (int q = 0; q < per_lane && q < 4; ++q) {
-                        const int n = n0 + g * 32 + q * gl + (lane % gl);
-                        if (n < a.N) {
-                            float *dst = a.pooled + grp * (long long)a.ld_pooled + n;
-                            if (ns <= 32) *dst = keep[q];
-                            else atomicMax(reinterpret_cast<int *>(dst), __float_as_int(keep[q]));
-                        }
-                    }
-                }
+                if (ns >= 32) pool_store<32>(out, lane, row_ok, grow, ns, n0 + g * 32, a);
+                else if (ns == 16) pool_store<16>(out, lane, row_ok, grow, ns, n0 + g * 32, a);
+                else pool_store<8>(out, lane, row_ok, grow, ns, n0 + g * 32, a);
             }
         }
         tc::tc_fence_before();
@@ -317,7 +336,7 @@ extern "C" int gp_gemm_bias_relu(const float *X, long long R, int ldx, const voi
         GP_REQUIRE(pooled && ld_pooled >= N, "gp_gemm_bias_relu: bad pooled output");
         GP_REQUIRE(pool_ns >= 1 && ((pool_ns <= 32 && 32 % pool_ns == 0) || pool_ns % 32 == 0) && R % pool_ns == 0,
                    "gp_gemm_bias_relu: pool_ns=%d must divide 32 or be a multiple of 32, and divide R", pool_ns);
-        GP_REQUIRE(pool_ns >= 8, "gp_gemm_bias_relu: pool_ns < 8 not supported");
+        GP_REQUIRE(pool_ns == 8 || pool_ns == 16 || pool_ns % 32 == 0, "gp_gemm_bias_relu: pool_ns must be 8, 16 or a multiple of 32");
     }
     gemm::Args a;
     a.X = X; a.R = R; a.ldx = ldx; a.Wp = (const uint8_t *)packed; a.bias = bias; a.N = N; a.K = K;
