@@ -171,18 +171,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bias_relu_kernel(Args a) {
         const int r = tid;                                // epilogue row (TMEM lane) of this thread
         const long long grow = row0 + r;
         const bool row_ok = grow < a.R;
-        for (int c = 0; c < a.nchunks; ++c) {
-            const int s = c % C::NS;
-            if (c >= C::NS) tc::mbar_wait(&empty[s], ((c / C::NS) + 1) & 1);
+        // register double buffering: the global loads of chunk c+1 are in flight while chunk c is converted
+        // (the rows come from HBM; without this the loader is latency bound)
+        auto load_chunk = [&](int c, float4 (&v)[16]) {
             const int k = c * KC + 4 * jv;
             const bool k_ok = k < a.ldx;
-            float4 v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const long long lr = row0 + 32 * warp + 2 * i + sub;
                 v[i] = (k_ok && lr < a.R) ? __ldg(reinterpret_cast<const float4 *>(a.X + lr * (long long)a.ldx + k))
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        };
+        auto convert_store = [&](int s, const float4 (&v)[16]) {
             uint8_t *hi_img = a_img(s, 0), *lo_img = a_img(s, 1);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -202,9 +203,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bias_relu_kernel(Args a) {
                     *reinterpret_cast<uint2 *>(lo_img + off) = pl;
                 }
             }
-            tc::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&a_full[s]);
+        };
+        float4 va[16], vb[16];
+        load_chunk(0, va);
+        for (int c = 0; c < a.nchunks; c += 2) {
+            if (c + 1 < a.nchunks) load_chunk(c + 1, vb);
+            {
+                const int s = c % C::NS;
+                if (c >= C::NS) tc::mbar_wait(&empty[s], ((c / C::NS) + 1) & 1);
+                convert_store(s, va);
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&a_full[s]);
+            }
+            if (c + 1 < a.nchunks) {
+                if (c + 2 < a.nchunks) load_chunk(c + 2, va);
+                const int c1 = c + 1, s = c1 % C::NS;
+                if (c1 >= C::NS) tc::mbar_wait(&empty[s], ((c1 / C::NS) + 1) & 1);
+                convert_store(s, vb);
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&a_full[s]);
+            }
         }
         // ------------------------- epilogue -------------------------
         tc::mbar_wait(d_full, 0);

@@ -531,3 +531,116 @@ extern "C" int gp_maxpool_rows(const float *h, long long G, int nsample, int C, 
     GP_CHECK_LAUNCH("gp_maxpool_rows");
     return GP_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// First set-abstraction level fused end to end (no point features yet: 3 input channels):
+// gather (xyz[idx] - new_xyz) -> 3 -> C1 -> C2 -> C3 SharedMLP (BatchNorm folded, ReLU) -> max over
+// the nsample rows of each centre.  One thread per (centre, sample) row, FP32 FFMA, weights broadcast
+// from shared memory as float4, pooling with one redux.sync per channel.  The channels are far too
+// narrow for a tensor-core tile (16..64), and nothing is materialised in HBM.
+// ------------------------------------------------------------------------------------------
+namespace gp {
+
+template <int C1, int C2, int C3>
+struct SaSmallSmem {
+    float w0[3][C1], b0[C1];
+    float w1[C1][C2], b1[C2];
+    float w2[C2][C3], b2[C3];
+};
+
+template <int CIN, int COUT>
+__device__ __forceinline__ void dense_relu(const float (&in)[CIN], const float *w /*[CIN][COUT]*/, const float *b,
+                                           float (&out)[COUT]) {
+#pragma unroll
+    for (int n = 0; n < COUT; n += 4) {
+        const float4 bv = *reinterpret_cast<const float4 *>(b + n);
+        out[n] = bv.x; out[n + 1] = bv.y; out[n + 2] = bv.z; out[n + 3] = bv.w;
+    }
+#pragma unroll
+    for (int k = 0; k < CIN; ++k) {
+#pragma unroll
+        for (int n = 0; n < COUT; n += 4) {
+            const float4 wv = *reinterpret_cast<const float4 *>(w + k * COUT + n);
+            out[n] = fmaf(in[k], wv.x, out[n]);
+            out[n + 1] = fmaf(in[k], wv.y, out[n + 1]);
+            out[n + 2] = fmaf(in[k], wv.z, out[n + 2]);
+            out[n + 3] = fmaf(in[k], wv.w, out[n + 3]);
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < COUT; ++n) out[n] = fmaxf(out[n], 0.f);
+}
+
+template <int C1, int C2, int C3, int NS>
+__global__ void __launch_bounds__(256)
+sa_small_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz, const int *__restrict__ idx,
+                int N, int M, long long rows_total, const float *__restrict__ w0, const float *__restrict__ b0,
+                const float *__restrict__ w1, const float *__restrict__ b1, const float *__restrict__ w2,
+                const float *__restrict__ b2, float *__restrict__ out, int ld_out) {
+    __shared__ __align__(16) SaSmallSmem<C1, C2, C3> S;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // stage the (folded) weights transposed to [k][n]
+    for (int i = tid; i < 3 * C1; i += 256) S.w0[i / C1][i % C1] = __ldg(w0 + (i % C1) * 3 + i / C1);
+    for (int i = tid; i < C1 * C2; i += 256) S.w1[i / C2][i % C2] = __ldg(w1 + (i % C2) * C1 + i / C2);
+    for (int i = tid; i < C2 * C3; i += 256) S.w2[i / C3][i % C3] = __ldg(w2 + (i % C3) * C2 + i / C3);
+    for (int i = tid; i < C1; i += 256) S.b0[i] = __ldg(b0 + i);
+    for (int i = tid; i < C2; i += 256) S.b1[i] = __ldg(b1 + i);
+    for (int i = tid; i < C3; i += 256) S.b2[i] = __ldg(b2 + i);
+    __syncthreads();
+    const long long row = (long long)blockIdx.x * 256 + tid;
+    const bool ok = row < rows_total;
+    const long long rr = ok ? row : rows_total - 1;
+    const long long bp = rr / NS;           // b*M + p
+    const int b = (int)(bp / M);
+    const int id = __ldg(idx + rr);
+    float a0[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) a0[c] = __ldg(xyz + ((size_t)b * N + id) * 3 + c) - __ldg(new_xyz + bp * 3 + c);
+    float h1[C1], h2[C2], h3[C3];
+    dense_relu<3, C1>(a0, &S.w0[0][0], S.b0, h1);
+    dense_relu<C1, C2>(h1, &S.w1[0][0], S.b1, h2);
+    dense_relu<C2, C3>(h2, &S.w2[0][0], S.b2, h3);
+    // max over the NS rows of the centre: values >= 0, so unsigned order of the bit patterns == float order
+    constexpr int GL = NS < 32 ? NS : 32;
+    const unsigned mask = GL == 32 ? 0xffffffffu : (((1u << GL) - 1u) << ((lane / GL) * GL));
+    float keep[C3 / GL > 0 ? C3 / GL : 1];
+#pragma unroll
+    for (int n = 0; n < C3; ++n) {
+        const unsigned m = __reduce_max_sync(mask, ok ? __float_as_uint(h3[n]) : 0u);
+        if ((lane % GL) == (n % GL)) keep[n / GL] = __uint_as_float(m);
+    }
+    if (ok) {
+        float *dst = out + bp * (long long)ld_out;
+#pragma unroll
+        for (int q = 0; q < C3 / GL; ++q) dst[q * GL + (lane % GL)] = keep[q];
+    }
+}
+
+template <int C1, int C2, int C3>
+static int launch_sa_small(const float *xyz, const float *new_xyz, const int *idx, int B, int N, int M, int ns,
+                           const float *const *w, const float *const *b, float *out, int ld_out, cudaStream_t st) {
+    const long long rows = (long long)B * M * ns;
+    const unsigned grid = (unsigned)((rows + 255) / 256);
+    if (ns == 16)
+        sa_small_kernel<C1, C2, C3, 16><<<grid, 256, 0, st>>>(xyz, new_xyz, idx, N, M, rows, w[0], b[0], w[1], b[1], w[2], b[2], out, ld_out);
+    else
+        sa_small_kernel<C1, C2, C3, 32><<<grid, 256, 0, st>>>(xyz, new_xyz, idx, N, M, rows, w[0], b[0], w[1], b[1], w[2], b[2], out, ld_out);
+    GP_CHECK_LAUNCH("gp_sa_small_mlp");
+    return GP_OK;
+}
+}  // namespace gp
+
+extern "C" int gp_sa_small_mlp(const float *xyz, const float *new_xyz, const int32_t *idx, int B, int N, int M,
+                               int nsample, const float *const *weights, const float *const *biases, int C1, int C2,
+                               int C3, float *out, int ld_out, gp_stream_t s) {
+    GP_REQUIRE(B >= 0 && N >= 1 && M >= 0 && (nsample == 16 || nsample == 32), "gp_sa_small_mlp: nsample must be 16 or 32");
+    if ((long long)B * M == 0) return GP_OK;
+    GP_REQUIRE(xyz && new_xyz && idx && weights && biases && out && ld_out >= C3, "gp_sa_small_mlp: null pointer / bad ld_out");
+    for (int i = 0; i < 3; ++i) GP_REQUIRE(weights[i] && biases[i], "gp_sa_small_mlp: null layer %d", i);
+    if (C1 == 16 && C2 == 16 && C3 == 32)
+        return launch_sa_small<16, 16, 32>(xyz, new_xyz, idx, B, N, M, nsample, weights, biases, out, ld_out, as_stream(s));
+    if (C1 == 32 && C2 == 32 && C3 == 64)
+        return launch_sa_small<32, 32, 64>(xyz, new_xyz, idx, B, N, M, nsample, weights, biases, out, ld_out, as_stream(s));
+    set_error("gp_sa_small_mlp: channel spec %d-%d-%d is not instantiated (16-16-32, 32-32-64)", C1, C2, C3);
+    return GP_ERR_UNSUPPORTED;
+}

@@ -162,6 +162,13 @@ class PointnetSAModuleMSG(nn.Module):
             out = torch.empty((B, M, sum(couts)), dtype=torch.float32, device=xyz.device)
             off = 0
             for i, mlp in enumerate(self.mlps):
+                spec = tuple(getattr(mlp, f"layer{j}").conv.out_channels for j in range(mlp.n_layers))
+                if (feat_cl is None and self.gemm_mode != "cublas" and self.nsamples[i] in (16, 32)
+                        and spec in ((16, 16, 32), (32, 32, 64))):
+                    # first level: the whole scale in one FP32 kernel (channels too narrow for tensor cores)
+                    pu.sa_small_mlp(xyz, new_xyz, bq[i], mlp._folded_layers(), out.view(B * M, -1)[:, off:off + couts[i]])
+                    off += couts[i]
+                    continue
                 rows = pu.group_rows(xyz, new_xyz, feat_cl, bq[i], pad_to=1 if self.gemm_mode == "cublas" else 4)
                 mlp.forward_rows_pooled(rows, B * M, self.nsamples[i], out.view(B * M, -1)[:, off:off + couts[i]],
                                         self.gemm_mode)

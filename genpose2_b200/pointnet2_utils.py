@@ -141,6 +141,23 @@ def maxpool_rows(h, groups, nsample, out=None):
     return out
 
 
+def sa_small_mlp(xyz, new_xyz, idx, layers, out):
+    """Fused first-level scale (no point features): grouping -> 3-layer SharedMLP -> max-pool, written into
+    `out` [B*M, >= C3] (may be a column slice).  `layers` = [(W [Cout,Cin], b [Cout])] x 3, BatchNorm folded."""
+    import ctypes
+    _lib.check_cuda(xyz, "xyz", torch.float32)
+    _lib.check_cuda(new_xyz, "new_xyz", torch.float32)
+    _lib.check_cuda(idx, "idx", torch.int32)
+    B, N, _ = xyz.size()
+    _, M, ns = idx.size()
+    ws = (ctypes.c_void_p * 3)(*[w.data_ptr() for w, _ in layers])
+    bs = (ctypes.c_void_p * 3)(*[b.data_ptr() for _, b in layers])
+    C1, C2, C3 = (w.shape[0] for w, _ in layers)
+    _lib.call("gp_sa_small_mlp", _lib.ptr(xyz), _lib.ptr(new_xyz), _lib.ptr(idx), B, N, M, ns, ws, bs, C1, C2, C3,
+              _lib.ptr(out), int(out.stride(-2)), device=xyz.device)
+    return out
+
+
 def gemm_pack(weight: torch.Tensor, npass: int) -> torch.Tensor:
     """Pack W [N, K] fp32 into the pre-swizzled bf16 (npass=1) / bf16 hi+lo (npass=3) chunk images the
     tcgen05 GEMM streams with TMA (gp_gemm_pack).  Do once per checkpoint."""

@@ -101,6 +101,16 @@ GP_API int gp_group_rows(const float *xyz, const float *new_xyz, const float *fe
  * (out has row stride ld_out so both MSG scales can land in one concatenated tensor). */
 GP_API int gp_maxpool_rows(const float *h, long long G, int nsample, int C, int ld_out, float *out, gp_stream_t s);
 
+/* A whole set-abstraction scale WITHOUT point features (the first level of Pointnet2ClsMSG(0)), fused:
+ * grouping (xyz[idx] - new_xyz, P2/pointnet2_utils.py:279-282) -> SharedMLP 3 -> C1 -> C2 -> C3
+ * (P2/pytorch_utils.py:5-33, BatchNorm folded by the caller: weights[i] is [Cout,Cin] row-major, biases[i]
+ * [Cout]) -> max over nsample (P2/pointnet2_modules.py:59-61).  out[(b*M + p) * ld_out + c], c < C3.
+ * FP32 FFMA (channels are too narrow for a tensor-core tile).  Instantiated specs: 16-16-32, 32-32-64;
+ * nsample 16 or 32. */
+GP_API int gp_sa_small_mlp(const float *xyz, const float *new_xyz, const int32_t *idx, int B, int N, int M,
+                    int nsample, const float *const *weights, const float *const *biases, int C1, int C2, int C3,
+                    float *out, int ld_out, gp_stream_t s);
+
 /* One SharedMLP layer (P2/pytorch_utils.py:5-33: conv1x1 + BatchNorm(eval) folded + ReLU) on channels-last
  * rows, on the tcgen05 tensor cores: Y = relu(X . W^T + bias), optionally fused with the max-pool over
  * `pool_ns` consecutive rows (P2/pointnet2_modules.py:59-61).
