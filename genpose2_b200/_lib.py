@@ -55,6 +55,11 @@ SIGNATURES = {
     "gp_gemm_pack": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gp_gemm_bias_relu": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                   c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "gp_gemm_linear": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
+                               c_void_p]),
+    "gp_gemm_gather_bias_relu": (c_int, [c_void_p, c_int, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_int,
+                                         c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                         c_void_p, c_int, c_void_p]),
     "gp_trunk_packed_bytes": (c_size_t, []),
     "gp_trunk_pack": (c_int, [ctypes.POINTER(TrunkParams), c_void_p, c_void_p]),
     "gp_trunk_project": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

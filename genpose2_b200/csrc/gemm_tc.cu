@@ -37,6 +37,13 @@ struct Args {
     float *pooled;         // [R / pool_ns, ld_pooled], zero-initialised by the caller
     int ld_pooled;
     int nchunks;           // ceil(K / 64)
+    // gather mode (first SharedMLP layer hoisted to the points, see gp_gemm_gather_bias_relu):
+    //   A[r][k] = relu(X[(r / rows_per_batch) * n_src + gidx[r]][k] - Q[r / q_ns][k])
+    const int *gidx;       // nullptr: plain mode
+    int rows_per_batch, n_src;
+    const float *Q;
+    int ldq, q_ns;
+    int linear;            // 1: epilogue writes X.W^T without bias / ReLU
 };
 
 __host__ __device__ inline int bn_of_tile(int N, int j) {  // columns of n-tile j, rounded up to 16
@@ -173,23 +180,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bias_relu_kernel(Args a) {
         const bool row_ok = grow < a.R;
         // register double buffering: the global loads of chunk c+1 are in flight while chunk c is converted
         // (the rows come from HBM; without this the loader is latency bound)
+        const bool gather = a.gidx != nullptr;
+        long long src[16];                                // source row of each of this thread's 16 passes (-1: none)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const long long lr = row0 + 32 * warp + 2 * i + sub;
+            if (lr >= a.R) src[i] = -1;
+            else src[i] = gather ? (lr / a.rows_per_batch) * (long long)a.n_src + __ldg(a.gidx + lr) : lr;
+        }
         auto load_chunk = [&](int c, float4 (&v)[16]) {
             const int k = c * KC + 4 * jv;
             const bool k_ok = k < a.ldx;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const long long lr = row0 + 32 * warp + 2 * i + sub;
-                v[i] = (k_ok && lr < a.R) ? __ldg(reinterpret_cast<const float4 *>(a.X + lr * (long long)a.ldx + k))
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int i = 0; i < 16; ++i)
+                v[i] = (k_ok && src[i] >= 0) ? __ldg(reinterpret_cast<const float4 *>(a.X + src[i] * (long long)a.ldx + k))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        auto convert_store = [&](int s, const float4 (&v)[16]) {
+        auto convert_store = [&](int s, int cc, const float4 (&v)[16]) {
             uint8_t *hi_img = a_img(s, 0), *lo_img = a_img(s, 1);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int rl = 32 * warp + 2 * i + sub;   // row inside the tile
                 const int off = rl * 128 + (((jv >> 1) ^ (rl & 7)) << 4) + ((jv & 1) << 3);
-                const float4 p = v[i];
+                float4 p = v[i];
+                if (gather) {  // hoisted first layer: relu(P[src] - Q[group]); Q rows hit L1 (shared by q_ns rows)
+                    const long long lr = row0 + rl;
+                    const int k = cc * KC + 4 * jv;
+                    if (lr < a.R && k < a.ldq) {
+                        const float4 q = __ldg(reinterpret_cast<const float4 *>(a.Q + (lr / a.q_ns) * (long long)a.ldq + k));
+                        p.x = fmaxf(p.x - q.x, 0.f); p.y = fmaxf(p.y - q.y, 0.f);
+                        p.z = fmaxf(p.z - q.z, 0.f); p.w = fmaxf(p.w - q.w, 0.f);
+                    } else {
+                        p = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
                 const __nv_bfloat162 h0 = __floats2bfloat162_rn(p.x, p.y), h1 = __floats2bfloat162_rn(p.z, p.w);
                 uint2 pk;
                 pk.x = *reinterpret_cast<const uint32_t *>(&h0); pk.y = *reinterpret_cast<const uint32_t *>(&h1);
@@ -211,7 +235,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bias_relu_kernel(Args a) {
             {
                 const int s = c % C::NS;
                 if (c >= C::NS) tc::mbar_wait(&empty[s], ((c / C::NS) + 1) & 1);
-                convert_store(s, va);
+                convert_store(s, c, va);
                 tc::fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&a_full[s]);
@@ -220,7 +244,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bias_relu_kernel(Args a) {
                 if (c + 2 < a.nchunks) load_chunk(c + 2, va);
                 const int c1 = c + 1, s = c1 % C::NS;
                 if (c1 >= C::NS) tc::mbar_wait(&empty[s], ((c1 / C::NS) + 1) & 1);
-                convert_store(s, vb);
+                convert_store(s, c1, vb);
                 tc::fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&a_full[s]);
@@ -238,8 +262,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bias_relu_kernel(Args a) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int n = n0 + g * 32 + j;
-                const float bv = n < a.N ? __ldg(a.bias + n) : 0.f;
-                out[j] = (n < a.N && row_ok) ? fmaxf(__uint_as_float(rv[j]) + bv, 0.f) : 0.f;
+                const float bv = (n < a.N && !a.linear) ? __ldg(a.bias + n) : 0.f;
+                const float acc = __uint_as_float(rv[j]) + bv;
+                out[j] = (n < a.N && row_ok) ? (a.linear ? acc : fmaxf(acc, 0.f)) : 0.f;
             }
             if (ns == 0) {
                 // transpose the warp's 32 x 32 block through shared memory (the operand stages are free once
@@ -362,5 +387,47 @@ extern "C" int gp_gemm_bias_relu(const float *X, long long R, int ldx, const voi
     a.X = X; a.R = R; a.ldx = ldx; a.Wp = (const uint8_t *)packed; a.bias = bias; a.N = N; a.K = K;
     a.Y = Y; a.ldy = ldy; a.pool_ns = pool_ns; a.pooled = pooled; a.ld_pooled = ld_pooled;
     a.nchunks = (K + gemm::KC - 1) / gemm::KC;
+    a.gidx = nullptr; a.rows_per_batch = 1; a.n_src = 0; a.Q = nullptr; a.ldq = 0; a.q_ns = 1; a.linear = 0;
+    return npass == 3 ? gemm::launch<3>(a, as_stream(s)) : gemm::launch<1>(a, as_stream(s));
+}
+
+extern "C" int gp_gemm_linear(const float *X, long long R, int ldx, const void *packed, int N, int K, int npass,
+                              float *Y, int ldy, gp_stream_t s) {
+    GP_REQUIRE(R >= 0 && N >= 1 && K >= 1 && (npass == 1 || npass == 3), "gp_gemm_linear: bad arguments");
+    if (R == 0) return GP_OK;
+    GP_REQUIRE(X && packed && Y, "gp_gemm_linear: null pointer");
+    GP_REQUIRE(ldx >= 4 && (ldx & 3) == 0 && ((uintptr_t)X & 15) == 0, "gp_gemm_linear: X rows must be 16-byte aligned");
+    GP_REQUIRE(ldy >= N && ldy <= ((N + 31) & ~31) && (ldy & 3) == 0 && ((uintptr_t)Y & 15) == 0, "gp_gemm_linear: bad Y / ldy");
+    gemm::Args a;
+    a.X = X; a.R = R; a.ldx = ldx; a.Wp = (const uint8_t *)packed; a.bias = nullptr; a.N = N; a.K = K;
+    a.Y = Y; a.ldy = ldy; a.pool_ns = 0; a.pooled = nullptr; a.ld_pooled = 0;
+    a.nchunks = (K + gemm::KC - 1) / gemm::KC;
+    a.gidx = nullptr; a.rows_per_batch = 1; a.n_src = 0; a.Q = nullptr; a.ldq = 0; a.q_ns = 1; a.linear = 1;
+    return npass == 3 ? gemm::launch<3>(a, as_stream(s)) : gemm::launch<1>(a, as_stream(s));
+}
+
+extern "C" int gp_gemm_gather_bias_relu(const float *P, int n_src, int ldp, const int32_t *gidx, long long R,
+                                        int rows_per_batch, const float *Q, int ldq, int q_ns, const void *packed,
+                                        const float *bias, int N, int K, int npass, float *Y, int ldy, int pool_ns,
+                                        float *pooled, int ld_pooled, gp_stream_t s) {
+    GP_REQUIRE(R >= 0 && N >= 1 && K >= 1 && (npass == 1 || npass == 3), "gp_gemm_gather_bias_relu: bad arguments");
+    if (R == 0) return GP_OK;
+    GP_REQUIRE(P && gidx && Q && packed && bias, "gp_gemm_gather_bias_relu: null pointer");
+    GP_REQUIRE(ldp >= 4 && (ldp & 3) == 0 && ((uintptr_t)P & 15) == 0 && ldq >= 4 && (ldq & 3) == 0 && ((uintptr_t)Q & 15) == 0,
+               "gp_gemm_gather_bias_relu: P / Q rows must be 16-byte aligned");
+    GP_REQUIRE(ldq >= K && ldp >= K, "gp_gemm_gather_bias_relu: ldp and ldq must cover K");
+    GP_REQUIRE(rows_per_batch >= 1 && n_src >= 1 && q_ns >= 1, "gp_gemm_gather_bias_relu: bad gather geometry");
+    if (pool_ns == 0) {
+        GP_REQUIRE(Y && ldy >= N && ldy <= ((N + 31) & ~31) && (ldy & 3) == 0 && ((uintptr_t)Y & 15) == 0,
+                   "gp_gemm_gather_bias_relu: bad Y / ldy");
+    } else {
+        GP_REQUIRE(pooled && ld_pooled >= N && R % pool_ns == 0 && (pool_ns == 8 || pool_ns == 16 || pool_ns % 32 == 0),
+                   "gp_gemm_gather_bias_relu: bad pooled output / pool_ns");
+    }
+    gemm::Args a;
+    a.X = P; a.R = R; a.ldx = ldp; a.Wp = (const uint8_t *)packed; a.bias = bias; a.N = N; a.K = K;
+    a.Y = Y; a.ldy = ldy; a.pool_ns = pool_ns; a.pooled = pooled; a.ld_pooled = ld_pooled;
+    a.nchunks = (K + gemm::KC - 1) / gemm::KC;
+    a.gidx = gidx; a.rows_per_batch = rows_per_batch; a.n_src = n_src; a.Q = Q; a.ldq = ldq; a.q_ns = q_ns; a.linear = 0;
     return npass == 3 ? gemm::launch<3>(a, as_stream(s)) : gemm::launch<1>(a, as_stream(s));
 }

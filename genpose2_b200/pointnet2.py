@@ -102,6 +102,40 @@ class SharedMLP(nn.Module):
             self._tc_key = key
         return self._tc
 
+    def _tc_hoisted(self, npass):
+        """Operands for the hoisted form of a 3-layer scale (see forward_hoisted), cached."""
+        fold = self._folded_layers()
+        key = (self._fold_key, npass, "hoisted")
+        if getattr(self, "_th_key", None) != key:
+            (w0, b0), (w1, b1), (w2, b2) = fold
+            w0p = torch.cat([w0[:, 3:], w0[:, :3]], dim=1).contiguous()  # feature columns first, xyz last
+            self._th = dict(p0=pu.gemm_pack(w0p, npass), k0=w0p.shape[1], c1=w0.shape[0],
+                            w0_xyz_t=w0[:, :3].t().contiguous(), b0=b0,
+                            p1=pu.gemm_pack(w1, npass), b1=b1, c2=w1.shape[0],
+                            p2=pu.gemm_pack(w2, npass), b2=b2, c3=w2.shape[0])
+            self._th_key = key
+        return self._th
+
+    def forward_hoisted(self, pts_rows, n_src, new_xyz, bq_idx, out, gemm_mode):
+        """A whole scale with point features on the tensor cores, first layer hoisted to the points.
+        The first 1x1 conv is linear before its ReLU, so
+            W0 . [xyz[idx] - new_xyz ; feat[idx]] + b0  =  (W0 . [xyz ; feat])[idx]  -  (W0_xyz . new_xyz - b0)
+        : it is evaluated once per POINT (nsample x fewer multiply-adds, exact algebra), and the gathered
+        (centre, sample) activation matrix of the reference (pointnet2_utils.py:279-296) never exists in HBM --
+        the second layer's operand loader gathers the per-point rows by ball-query index, subtracts the per-centre
+        term and applies the ReLU on the fly.  pts_rows = [feat | xyz | 0-pad] per point, [B*n_src, ld]."""
+        npass = {"bf16x3": 3, "bf16": 1}[gemm_mode]
+        t = self._tc_hoisted(npass)
+        B, M, ns = bq_idx.shape
+        P = pu.gemm_linear(pts_rows, t["p0"], t["c1"], t["k0"], npass)                 # [B*n_src, ldp]
+        Q = torch.zeros((B * M, P.shape[1]), dtype=torch.float32, device=P.device)
+        torch.addmm(-t["b0"], new_xyz.reshape(B * M, 3), t["w0_xyz_t"], out=Q[:, : t["c1"]])
+        h2 = pu.gemm_gather_bias_relu(P, n_src, bq_idx.reshape(-1), M * ns, Q, ns, t["p1"], t["b1"], t["c2"], t["c1"],
+                                      npass)
+        out.zero_()
+        pu.gemm_bias_relu(h2, t["p2"], t["b2"], t["c3"], t["c2"], npass, pool_ns=ns, pooled_out=out)
+        return out
+
     def forward_rows_pooled(self, rows, groups, nsample, out, gemm_mode):
         """rows (R, ld) -> SharedMLP -> max over `nsample` rows per group, written into `out` (groups, Cout).
         gemm_mode: "cublas" (fp32 library GEMM), "bf16x3" (tcgen05, split-bf16, fp32-class) or "bf16" (tcgen05)."""
@@ -161,7 +195,17 @@ class PointnetSAModuleMSG(nn.Module):
             M = self.npoint
             out = torch.empty((B, M, sum(couts)), dtype=torch.float32, device=xyz.device)
             off = 0
+            pts_rows = None
             for i, mlp in enumerate(self.mlps):
+                if feat_cl is not None and self.gemm_mode != "cublas" and mlp.n_layers == 3 and feat_cl.shape[2] % 4 == 0:
+                    if pts_rows is None:  # [feat | xyz | 0] per point, shared by both scales
+                        N = xyz.shape[1]
+                        pts_rows = torch.cat([feat_cl, xyz, torch.zeros((B, N, 1), dtype=torch.float32, device=xyz.device)],
+                                             dim=-1).reshape(B * N, -1)
+                    mlp.forward_hoisted(pts_rows, xyz.shape[1], new_xyz, bq[i], out.view(B * M, -1)[:, off:off + couts[i]],
+                                        self.gemm_mode)
+                    off += couts[i]
+                    continue
                 spec = tuple(getattr(mlp, f"layer{j}").conv.out_channels for j in range(mlp.n_layers))
                 if (feat_cl is None and self.gemm_mode != "cublas" and self.nsamples[i] in (16, 32)
                         and spec in ((16, 16, 32), (32, 32, 64))):

@@ -189,6 +189,36 @@ def gemm_bias_relu(x, packed, bias, N, K, npass, pool_ns=0, pooled_out=None):
     return y
 
 
+def gemm_linear(x, packed, N, K, npass):
+    """x @ W^T on the tensor cores, no bias / activation (gp_gemm_linear): [R, round_up(N, 32)]."""
+    _lib.check_cuda(x, "x", torch.float32)
+    R, ldx = x.shape
+    ldy = (N + 31) // 32 * 32
+    y = torch.empty((R, ldy), dtype=torch.float32, device=x.device)
+    _lib.call("gp_gemm_linear", _lib.ptr(x), R, ldx, _lib.ptr(packed), N, K, npass, _lib.ptr(y), ldy, device=x.device)
+    return y
+
+
+def gemm_gather_bias_relu(P, n_src, gidx, rows_per_batch, Q, q_ns, packed, bias, N, K, npass, pool_ns=0,
+                          pooled_out=None):
+    """relu(relu(P[batch * n_src + gidx] - Q[row // q_ns]) @ W^T + bias)  (gp_gemm_gather_bias_relu)."""
+    _lib.check_cuda(P, "P", torch.float32)
+    _lib.check_cuda(Q, "Q", torch.float32)
+    _lib.check_cuda(gidx, "gidx", torch.int32)
+    R = gidx.numel()
+    if pool_ns:
+        _lib.call("gp_gemm_gather_bias_relu", _lib.ptr(P), int(n_src), int(P.stride(0)), _lib.ptr(gidx), R,
+                  int(rows_per_batch), _lib.ptr(Q), int(Q.stride(0)), int(q_ns), _lib.ptr(packed), _lib.ptr(bias), N, K,
+                  npass, None, 0, int(pool_ns), _lib.ptr(pooled_out), int(pooled_out.stride(-2)), device=P.device)
+        return pooled_out
+    ldy = (N + 31) // 32 * 32
+    y = torch.empty((R, ldy), dtype=torch.float32, device=P.device)
+    _lib.call("gp_gemm_gather_bias_relu", _lib.ptr(P), int(n_src), int(P.stride(0)), _lib.ptr(gidx), R,
+              int(rows_per_batch), _lib.ptr(Q), int(Q.stride(0)), int(q_ns), _lib.ptr(packed), _lib.ptr(bias), N, K,
+              npass, _lib.ptr(y), ldy, 0, None, 0, device=P.device)
+    return y
+
+
 class QueryAndGroup(nn.Module):
     """pointnet2_utils.py:259-298."""
 

@@ -126,6 +126,23 @@ GP_API int gp_gemm_bias_relu(const float *X, long long R, int ldx, const void *p
                       int K, int npass, float *Y, int ldy, int pool_ns, float *pooled, int ld_pooled,
                       gp_stream_t s);
 
+/* Y = X . W^T (no bias, no activation), same engine and packing as gp_gemm_bias_relu.  Used to hoist the first
+ * SharedMLP layer of a scale from the (centre, sample) rows to the points: the layer is linear before its
+ * ReLU, so  W0 . [xyz[idx] - new_xyz ; feat[idx]]  =  (W0 . [xyz ; feat])[idx]  -  W0_xyz . new_xyz,
+ * nsample x fewer multiply-adds and no gathered activation matrix in HBM. */
+GP_API int gp_gemm_linear(const float *X, long long R, int ldx, const void *packed, int N, int K, int npass,
+                   float *Y, int ldy, gp_stream_t s);
+
+/* Second SharedMLP layer with the hoisted first layer applied on the fly in the operand loader:
+ *   A[r][k] = relu(P[(r / rows_per_batch) * n_src + gidx[r]][k] - Q[r / q_ns][k]),   Y = relu(A . W^T + bias)
+ * P [batches * n_src, ldp] = per-point first-layer pre-activations (gp_gemm_linear), gidx [R] = ball-query
+ * indices (row r = (batch, centre, sample)), Q [R / q_ns, ldq] = W0_xyz . new_xyz - b0 per centre.
+ * Output / pooling arguments as gp_gemm_bias_relu. */
+GP_API int gp_gemm_gather_bias_relu(const float *P, int n_src, int ldp, const int32_t *gidx, long long R,
+                             int rows_per_batch, const float *Q, int ldq, int q_ns, const void *packed,
+                             const float *bias, int N, int K, int npass, float *Y, int ldy, int pool_ns,
+                             float *pooled, int ld_pooled, gp_stream_t s);
+
 /* ---------------------------------------------------------------------------------------------
  * (2)(3) ScoreNet / EnergyNet trunk.  Raw parameters in the reference's state-dict layout
  * (SURVEY.md section 5): nn.Linear weights are [out,in] row-major.

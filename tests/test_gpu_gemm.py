@@ -52,3 +52,31 @@ def test_encoder_gemm_engines_vs_cpu_restatement(mode, tol):
     err = float((got.cpu() - want).abs().max() / want.abs().max())
     print(f"encoder {mode}: max rel err {err:.3e}")
     assert err < tol, err
+
+
+@pytest.mark.parametrize("npass,tol", [(3, 5e-5), (1, 3e-2)])
+def test_hoisted_scale_matches_direct_scale(npass, tol):
+    """the hoisted first layer + gather loader vs the direct (gather rows, 3 GEMMs) evaluation in float64"""
+    from genpose2_b200 import pointnet2_utils as pu
+    from genpose2_b200.pointnet2 import SharedMLP
+    B, N, M, ns, C = 3, 256, 128, 16, 96
+    g = torch.Generator().manual_seed(4)
+    pts, _ = synthetic.make_point_clouds(B, N, seed=21)
+    xyz = pts.cuda()
+    idx, new_xyz = pu.furthest_point_sample_gather(xyz, M)
+    bq = pu.ball_query(0.05, ns, xyz, new_xyz)
+    feat_cl = torch.randn(B, N, C, generator=g).cuda()
+    mlp = SharedMLP([C + 3, 64, 96, 128]).cuda().eval()
+    sd = {k: v for k, v in synthetic.random_encoder_state_dict(3, prefix="").items() if k.startswith("SA_modules.1.mlps.1.")}
+    mlp.load_state_dict({k[len("SA_modules.1.mlps.1."):]: v for k, v in sd.items()})
+    rows = pu.group_rows(xyz, new_xyz, feat_cl, bq).double()
+    h = rows
+    for w, b in mlp._folded_layers():
+        h = torch.relu(h @ w.double().t() + b.double())
+    want = h.view(B * M, ns, -1).amax(1)
+    out = torch.empty(B * M, 128, device="cuda")
+    pts_rows = torch.cat([feat_cl, xyz, torch.zeros(B, N, 1, device="cuda")], -1).reshape(B * N, -1)
+    mlp.forward_hoisted(pts_rows, N, new_xyz, bq, out, "bf16x3" if npass == 3 else "bf16")
+    err = float((out.double() - want).abs().max() / want.abs().max())
+    print("hoisted scale rel err", npass, err)
+    assert err < tol, err
