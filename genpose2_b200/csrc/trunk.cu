@@ -39,9 +39,9 @@ __global__ void pack_trunk_kernel(RawTrunk raw, float *__restrict__ P) {
             v = p.t_w[n * 128 + k];
         } else if (i < TrunkLayout::WHP) {
             v = p.t_b[i - TrunkLayout::BT];
-        } else if (i < TrunkLayout::WHT) {  // WHP[k][h*256+j] = head_w0[h][j][1152+k]
-            const size_t j = i - TrunkLayout::WHP, k = j / 768, n = j % 768;
-            v = p.head_w0[n / 256][(n % 256) * 1408 + 1152 + k];
+        } else if (i < TrunkLayout::WHT) {  // WHP[h][k][j] = head_w0[h][j][1152+k]
+            const size_t j = i - TrunkLayout::WHP, h = j / 65536, k = (j % 65536) / 256, n = j % 256;
+            v = p.head_w0[h][n * 1408 + 1152 + k];
         } else if (i < TrunkLayout::WHF) {  // WHT[k][h*256+j] = head_w0[h][j][1024+k]
             const size_t j = i - TrunkLayout::WHT, k = j / 768, n = j % 768;
             v = p.head_w0[n / 256][(n % 256) * 1408 + 1024 + k];
@@ -134,18 +134,17 @@ project_kernel(const float *__restrict__ P, const float *__restrict__ feat, int 
 template <int RPT>
 struct SimtEval {
     static constexpr int RT = 4 * RPT;
-    static constexpr int NT = 256;
+    static constexpr int NT = SIMT_THREADS;
     using Smem = TileSmem<RPT>;
-    struct Ctx {
-        float w1col[9];
-        float b1v;
-    };
-    static constexpr size_t smem_bytes() { return sizeof(Smem); }
-    static __device__ __forceinline__ Smem &smem(unsigned char *raw) { return *reinterpret_cast<Smem *>(raw); }
-    static __device__ __forceinline__ void setup(Smem &, Ctx &c, const float *P) { load_w1col(P, c.w1col, c.b1v); }
-    static __device__ __forceinline__ void teardown(Smem &, Ctx &) {}
+    using Ctx = SimtCtx;
+    static constexpr size_t smem_bytes() { return sizeof(Smem) + 16; }
+    static __device__ __forceinline__ Smem &smem(unsigned char *raw) {
+        return *reinterpret_cast<Smem *>(((uintptr_t)raw + 15) & ~(uintptr_t)15);
+    }
+    static __device__ __forceinline__ void setup(Smem &S, Ctx &c, const float *P) { simt_setup(S, c, P); }
+    static __device__ __forceinline__ void teardown(Smem &S, Ctx &c) { simt_teardown(S, c); }
     static __device__ __forceinline__ void forward(const float *P, const float *proj, Smem &S, Ctx &c, const float *tq) {
-        tile_forward<RPT>(P, proj, S, tq, c.w1col, c.b1v);
+        tile_forward<RPT>(P, proj, S, c, tq);
     }
 };
 
@@ -718,6 +717,19 @@ static int launch_ode(OdeArgs &a, cudaStream_t st) {
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// Rows per compute thread of the FFMA evaluator (tile = 4x that many rows): the choice that minimises the
+// per-CTA critical path  waves(tiles / SMs) x rows-per-tile; ties go to the larger tile (fewer weight streams).
+static int simt_rows_per_thread(int N, int sms) {
+    int best = 8;
+    long best_cost = -1;
+    for (int rpt = 8; rpt >= 2; rpt -= 2) {
+        const long tiles = (N + 4 * rpt - 1) / (4 * rpt);
+        const long cost = ((tiles + sms - 1) / sms) * rpt;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = rpt; }
+    }
+    return best;
+}
+
 }  // namespace gp
 
 using namespace gp;
@@ -826,9 +838,12 @@ extern "C" int gp_scorenet_ode(const void *packed, const float *proj, const doub
     cudaStream_t st = as_stream(s);
     const int sms = num_sms();
     if (mode == 1) return launch_ode<TcEval>(a, st);
-    if (N <= 8 * sms) return launch_ode<SimtEval<2>>(a, st);
-    if (N <= 16 * sms) return launch_ode<SimtEval<4>>(a, st);
-    return launch_ode<SimtEval<8>>(a, st);
+    switch (simt_rows_per_thread(N, sms)) {
+        case 2: return launch_ode<SimtEval<2>>(a, st);
+        case 4: return launch_ode<SimtEval<4>>(a, st);
+        case 6: return launch_ode<SimtEval<6>>(a, st);
+        default: return launch_ode<SimtEval<8>>(a, st);
+    }
 }
 
 extern "C" int gp_traj_finalize(const double *traj, const float *pts_center, int S, int N, double *xs, gp_stream_t s) {
@@ -882,7 +897,10 @@ extern "C" int gp_scorenet_pc(const void *packed, const float *proj, const float
     cudaStream_t st = as_stream(s);
     const int sms = num_sms();
     if (mode == 1) return launch_pc<TcEval>(a, st);
-    if (N <= 8 * sms) return launch_pc<SimtEval<2>>(a, st);
-    if (N <= 16 * sms) return launch_pc<SimtEval<4>>(a, st);
-    return launch_pc<SimtEval<8>>(a, st);
+    switch (simt_rows_per_thread(N, sms)) {
+        case 2: return launch_pc<SimtEval<2>>(a, st);
+        case 4: return launch_pc<SimtEval<4>>(a, st);
+        case 6: return launch_pc<SimtEval<6>>(a, st);
+        default: return launch_pc<SimtEval<8>>(a, st);
+    }
 }

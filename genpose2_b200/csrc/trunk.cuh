@@ -9,6 +9,7 @@
 // evaluated per row: 266 752 MAC instead of 1 167 872.
 #pragma once
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace gp {
 
@@ -21,7 +22,7 @@ struct TrunkLayout {
     static constexpr size_t FOUR = B2 + 256;                   // [64]
     static constexpr size_t WTT = FOUR + 64;                   // [128][128]  k-major
     static constexpr size_t BT = WTT + 128 * 128;              // [128]
-    static constexpr size_t WHP = BT + 128;                    // [256][768]  k-major, pose_feat cols
+    static constexpr size_t WHP = BT + 128;                    // [3 heads][256 k][256 n] k-major, pose_feat cols
     static constexpr size_t WHT = WHP + 256 * 768;             // [128][768]  k-major, t_feat cols
     static constexpr size_t WHF = WHT + 128 * 768;             // [768][1024] n-major, pts_feat cols
     static constexpr size_t BH = WHF + 768 * 1024;             // [768]
@@ -100,13 +101,23 @@ __device__ __forceinline__ void compute_tq(const float *__restrict__ P, const fl
 }
 
 // --------------------------------------------------------------------------------------------
-// FP32 tile evaluator: RT = 4*RPT rows per CTA of 256 threads.
-//   thread (ty = tid>>6, tx = tid&63) owns rows ty*RPT..+RPT-1 and columns 4*tx..4*tx+3 of each
-//   256-wide output chunk; weights stream from L2/L1 as float4, activations broadcast from smem.
+// FP32 tile evaluator: RT = 4*RPT rows per CTA, 8 compute warps + 1 TMA producer warp.
+//   compute thread (ty = tid>>6, tx = tid&63) owns rows ty*RPT..+RPT-1 and columns 4*tx..4*tx+3 of each
+//   256-wide output chunk.  The weights (1 MB of fp32 per evaluation, L2 resident) are streamed ONCE per
+//   CTA through a shared-memory ring of 32 KB chunks ([32 k][256 n]) with cp.async.bulk + mbarrier by the
+//   producer warp, which runs ahead across layers and evaluations; activations are broadcast from
+//   shared memory; every inner-loop operand comes from shared memory, so the loop is FFMA bound.
 // --------------------------------------------------------------------------------------------
+constexpr int W_NS = 3;                      // ring stages
+constexpr int W_CHUNK_FLOATS = 32 * 256;     // [32 k][256 n] fp32 = 32 KB
+constexpr int W_NCHUNK = 32;                 // 8 (pose_encoder.2) + 3 heads x 8
+constexpr int SIMT_COMPUTE_THREADS = 256;
+constexpr int SIMT_THREADS = 288;
+
 template <int RPT>
 struct TileSmem {
     static constexpr int RT = 4 * RPT;
+    float ring[W_NS][W_CHUNK_FLOATS];   // keep first: 16-byte aligned destination of the bulk copies
     float h1[RT * HS];
     float h2[RT * HS];
     float x[RT * 12];       // input poses, padded rows
@@ -117,150 +128,199 @@ struct TileSmem {
     float tfeat[6 * 128];
     float times[8];
     double red[16];
-    float trow[RT];
+    unsigned long long full[W_NS], empty[W_NS];
 };
 
-template <int RPT>
-__device__ __forceinline__ void gemm256(const float *__restrict__ Wt, int ldw, const float *s_h,
-                                        int row0, float (&acc)[RPT][4]) {
-    // weights for k..k+3 are fetched one iteration ahead (register double buffering): the L2/L1
-    // latency of the streamed weight rows is the dominant stall of this loop otherwise
-    float4 w0 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)0 * ldw));
-    float4 w1 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)1 * ldw));
-    float4 w2 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)2 * ldw));
-    float4 w3 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)3 * ldw));
+struct SimtCtx {
+    float w1col[9];
+    float b1v;
+    uint32_t loads = 0;      // producer lane: bulk copies issued
+    uint32_t consumed = 0;   // compute threads: chunks consumed
+};
+
+__device__ __forceinline__ const float *weight_chunk(const float *__restrict__ P, uint32_t q) {
+    return q < 8 ? P + TrunkLayout::W2T + (size_t)q * W_CHUNK_FLOATS
+                 : P + TrunkLayout::WHP + (size_t)(q - 8) * W_CHUNK_FLOATS;  // heads are stored [h][k][n]
+}
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// acc[i][0..3] += sum_k h[row0+i][k] * W[k][col..col+3] for the next 8 ring chunks (k = 0..255)
+template <int RPT, class SM>
+__device__ __forceinline__ void gemm256_ring(SM &sm, SimtCtx &ctx, const float *s_h, int row0, int col,
+                                             float (&acc)[RPT][4]) {
+    const int lane = threadIdx.x & 31;
+    for (int c = 0; c < 8; ++c) {
+        const uint32_t g = ctx.consumed;
+        const uint32_t st = g % W_NS;
+        tc::mbar_wait(&sm.full[st], (g / W_NS) & 1);
+        const float *w = &sm.ring[st][col];
+        const float *hrow = s_h + row0 * HS + c * 32;
 #pragma unroll 2
-    for (int k = 0; k < 256; k += 4) {
-        const int kn = (k + 4 < 256) ? k + 4 : k;
-        const float4 n0 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)(kn + 0) * ldw));
-        const float4 n1 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)(kn + 1) * ldw));
-        const float4 n2 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)(kn + 2) * ldw));
-        const float4 n3 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)(kn + 3) * ldw));
+        for (int k = 0; k < 32; k += 4) {
+            const float4 w0 = *reinterpret_cast<const float4 *>(w + (k + 0) * 256);
+            const float4 w1 = *reinterpret_cast<const float4 *>(w + (k + 1) * 256);
+            const float4 w2 = *reinterpret_cast<const float4 *>(w + (k + 2) * 256);
+            const float4 w3 = *reinterpret_cast<const float4 *>(w + (k + 3) * 256);
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-            const float4 a = *reinterpret_cast<const float4 *>(s_h + (row0 + i) * HS + k);
-            acc[i][0] = fmaf(a.x, w0.x, acc[i][0]);
-            acc[i][1] = fmaf(a.x, w0.y, acc[i][1]);
-            acc[i][2] = fmaf(a.x, w0.z, acc[i][2]);
-            acc[i][3] = fmaf(a.x, w0.w, acc[i][3]);
-            acc[i][0] = fmaf(a.y, w1.x, acc[i][0]);
-            acc[i][1] = fmaf(a.y, w1.y, acc[i][1]);
-            acc[i][2] = fmaf(a.y, w1.z, acc[i][2]);
-            acc[i][3] = fmaf(a.y, w1.w, acc[i][3]);
-            acc[i][0] = fmaf(a.z, w2.x, acc[i][0]);
-            acc[i][1] = fmaf(a.z, w2.y, acc[i][1]);
-            acc[i][2] = fmaf(a.z, w2.z, acc[i][2]);
-            acc[i][3] = fmaf(a.z, w2.w, acc[i][3]);
-            acc[i][0] = fmaf(a.w, w3.x, acc[i][0]);
-            acc[i][1] = fmaf(a.w, w3.y, acc[i][1]);
-            acc[i][2] = fmaf(a.w, w3.z, acc[i][2]);
-            acc[i][3] = fmaf(a.w, w3.w, acc[i][3]);
+            for (int i = 0; i < RPT; ++i) {
+                const float4 a = *reinterpret_cast<const float4 *>(hrow + i * HS + k);
+                acc[i][0] = fmaf(a.x, w0.x, acc[i][0]);
+                acc[i][1] = fmaf(a.x, w0.y, acc[i][1]);
+                acc[i][2] = fmaf(a.x, w0.z, acc[i][2]);
+                acc[i][3] = fmaf(a.x, w0.w, acc[i][3]);
+                acc[i][0] = fmaf(a.y, w1.x, acc[i][0]);
+                acc[i][1] = fmaf(a.y, w1.y, acc[i][1]);
+                acc[i][2] = fmaf(a.y, w1.z, acc[i][2]);
+                acc[i][3] = fmaf(a.y, w1.w, acc[i][3]);
+                acc[i][0] = fmaf(a.z, w2.x, acc[i][0]);
+                acc[i][1] = fmaf(a.z, w2.y, acc[i][1]);
+                acc[i][2] = fmaf(a.z, w2.z, acc[i][2]);
+                acc[i][3] = fmaf(a.z, w2.w, acc[i][3]);
+                acc[i][0] = fmaf(a.w, w3.x, acc[i][0]);
+                acc[i][1] = fmaf(a.w, w3.y, acc[i][1]);
+                acc[i][2] = fmaf(a.w, w3.z, acc[i][2]);
+                acc[i][3] = fmaf(a.w, w3.w, acc[i][3]);
+            }
         }
-        w0 = n0; w1 = n1; w2 = n2; w3 = n3;
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&sm.empty[st]);
+        ctx.consumed = g + 1;
     }
 }
 
-// Evaluates f_theta (un-normalised head outputs, 9 per row) for the RT rows whose inputs sit in
-// sm.x; result lands in sm.out[0][r*12 + c] (c < 9).  `w1col[9]`/`b1v` are this thread's column of
-// the first pose-encoder layer (kept in registers by the caller), `s_tq` this stage's t-branch.
-// Ends with a __syncthreads(); the caller may read sm.out[0] right after.
+template <class SM>
+__device__ __forceinline__ void simt_setup(SM &sm, SimtCtx &ctx, const float *__restrict__ P) {
+    const int tid = threadIdx.x;
+    if (tid < SIMT_COMPUTE_THREADS) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) ctx.w1col[k] = __ldg(P + TrunkLayout::W1T + k * 256 + tid);
+        ctx.b1v = __ldg(P + TrunkLayout::B1 + tid);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < W_NS; ++s) { tc::mbar_init(&sm.full[s], 1); tc::mbar_init(&sm.empty[s], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == SIMT_COMPUTE_THREADS) {  // producer lane: prefill the ring
+        for (int s = 0; s < W_NS; ++s) {
+            tc::mbar_arrive_expect_tx(&sm.full[s], W_CHUNK_FLOATS * 4);
+            tc::bulk_g2s(sm.ring[s], weight_chunk(P, s), W_CHUNK_FLOATS * 4, &sm.full[s]);
+        }
+        ctx.loads = W_NS;
+    }
+}
+
+template <class SM>
+__device__ __forceinline__ void simt_teardown(SM &sm, SimtCtx &ctx) {
+    if (threadIdx.x == 0) {  // the W_NS prefetched chunks are still in flight: let them land before exit
+        for (int i = 0; i < W_NS; ++i) {
+            const uint32_t g = ctx.consumed + i;
+            tc::mbar_wait(&sm.full[g % W_NS], (g / W_NS) & 1);
+        }
+    }
+    __syncthreads();
+}
+
+// Evaluates f_theta (un-normalised head outputs, 9 per row) for the RT rows whose inputs sit in sm.x;
+// result lands in sm.out[0][r*12 + c] (c < 9).  `s_tq` is this stage's t-branch.  All 288 threads call;
+// ends with a __syncthreads().
 template <int RPT>
 __device__ __forceinline__ void tile_forward(const float *__restrict__ P, const float *__restrict__ proj,
-                                             TileSmem<RPT> &sm, const float *s_tq,
-                                             const float (&w1col)[9], float b1v) {
+                                             TileSmem<RPT> &sm, SimtCtx &ctx, const float *s_tq) {
     constexpr int RT = 4 * RPT;
     const int tid = threadIdx.x;
-    const int tx = tid & 63, ty = tid >> 6;
-    const int row0 = ty * RPT, col = 4 * tx;
+    if (tid >= SIMT_COMPUTE_THREADS) {
+        // ---------------- TMA producer: 32 chunks per evaluation, running W_NS chunks ahead ----------------
+        if (tid == SIMT_COMPUTE_THREADS) {
+            for (int i = 0; i < W_NCHUNK; ++i) {
+                const uint32_t L = ctx.loads;
+                const uint32_t st = L % W_NS;
+                tc::mbar_wait(&sm.empty[st], ((L / W_NS) + 1) & 1);
+                tc::mbar_arrive_expect_tx(&sm.full[st], W_CHUNK_FLOATS * 4);
+                tc::bulk_g2s(sm.ring[st], weight_chunk(P, L % W_NCHUNK), W_CHUNK_FLOATS * 4, &sm.full[st]);
+                ctx.loads = L + 1;
+            }
+        }
+        __syncwarp();
+    } else {
+        const int tx = tid & 63, ty = tid >> 6;
+        const int row0 = ty * RPT, col = 4 * tx;
 
-    // layer 1: thread n = tid computes column n for every row
-    for (int r = 0; r < RT; ++r) {
-        const float4 xa = *reinterpret_cast<const float4 *>(sm.x + r * 12);
-        const float4 xb = *reinterpret_cast<const float4 *>(sm.x + r * 12 + 4);
-        const float xc = sm.x[r * 12 + 8];
-        float a = b1v;
-        a = fmaf(xa.x, w1col[0], a); a = fmaf(xa.y, w1col[1], a); a = fmaf(xa.z, w1col[2], a);
-        a = fmaf(xa.w, w1col[3], a); a = fmaf(xb.x, w1col[4], a); a = fmaf(xb.y, w1col[5], a);
-        a = fmaf(xb.z, w1col[6], a); a = fmaf(xb.w, w1col[7], a); a = fmaf(xc, w1col[8], a);
-        sm.h1[r * HS + tid] = fmaxf(a, 0.f);
-    }
-    __syncthreads();
+        // layer 1: thread n = tid computes column n for every row
+        for (int r = 0; r < RT; ++r) {
+            const float4 xa = *reinterpret_cast<const float4 *>(sm.x + r * 12);
+            const float4 xb = *reinterpret_cast<const float4 *>(sm.x + r * 12 + 4);
+            const float xc = sm.x[r * 12 + 8];
+            float a = ctx.b1v;
+            a = fmaf(xa.x, ctx.w1col[0], a); a = fmaf(xa.y, ctx.w1col[1], a); a = fmaf(xa.z, ctx.w1col[2], a);
+            a = fmaf(xa.w, ctx.w1col[3], a); a = fmaf(xb.x, ctx.w1col[4], a); a = fmaf(xb.y, ctx.w1col[5], a);
+            a = fmaf(xb.z, ctx.w1col[6], a); a = fmaf(xb.w, ctx.w1col[7], a); a = fmaf(xc, ctx.w1col[8], a);
+            sm.h1[r * HS + tid] = fmaxf(a, 0.f);
+        }
+        bar_compute();
 
-    // layer 2: h2 = relu(h1 @ W2^T + b2)
-    {
-        float acc[RPT][4];
-        const float4 bb = __ldg(reinterpret_cast<const float4 *>(P + TrunkLayout::B2 + col));
+        // layer 2: h2 = relu(h1 @ W2^T + b2)
+        {
+            float acc[RPT][4];
+            const float4 bb = __ldg(reinterpret_cast<const float4 *>(P + TrunkLayout::B2 + col));
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
-        gemm256<RPT>(P + TrunkLayout::W2T + col, 256, sm.h1, row0, acc);
+            for (int i = 0; i < RPT; ++i) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
+            gemm256_ring<RPT>(sm, ctx, sm.h1, row0, col, acc);
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-            float4 v = make_float4(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f), fmaxf(acc[i][2], 0.f), fmaxf(acc[i][3], 0.f));
-            *reinterpret_cast<float4 *>(sm.h2 + (row0 + i) * HS + col) = v;
+            for (int i = 0; i < RPT; ++i) {
+                float4 v = make_float4(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f), fmaxf(acc[i][2], 0.f), fmaxf(acc[i][3], 0.f));
+                *reinterpret_cast<float4 *>(sm.h2 + (row0 + i) * HS + col) = v;
+            }
+        }
+        bar_compute();
+
+        // heads: z = relu(h2 @ Whp^T + proj[obj] + tq);  out = z @ Wo^T
+        const int lane = tid & 31, half = (tid >> 5) & 1;
+#pragma unroll 1
+        for (int h = 0; h < 3; ++h) {
+            float acc[RPT][4];
+            const float4 tq = *reinterpret_cast<const float4 *>(s_tq + h * 256 + col);
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                const int o = sm.obj[row0 + i];
+                float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (o >= 0) pj = __ldg(reinterpret_cast<const float4 *>(proj + (size_t)o * 768 + h * 256 + col));
+                acc[i][0] = pj.x + tq.x; acc[i][1] = pj.y + tq.y; acc[i][2] = pj.z + tq.z; acc[i][3] = pj.w + tq.w;
+            }
+            gemm256_ring<RPT>(sm, ctx, sm.h2, row0, col, acc);
+            // output layer of this head: 3 dot products over this thread's 4 columns, then the 64 column-threads
+            // of the row group are reduced: 32 lanes by shuffle, the 2 warps through shared memory
+            const float4 wo0 = __ldg(reinterpret_cast<const float4 *>(P + TrunkLayout::WO + (size_t)(h * 256 + col + 0) * 4));
+            const float4 wo1 = __ldg(reinterpret_cast<const float4 *>(P + TrunkLayout::WO + (size_t)(h * 256 + col + 1) * 4));
+            const float4 wo2 = __ldg(reinterpret_cast<const float4 *>(P + TrunkLayout::WO + (size_t)(h * 256 + col + 2) * 4));
+            const float4 wo3 = __ldg(reinterpret_cast<const float4 *>(P + TrunkLayout::WO + (size_t)(h * 256 + col + 3) * 4));
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                const float z0 = fmaxf(acc[i][0], 0.f), z1 = fmaxf(acc[i][1], 0.f);
+                const float z2 = fmaxf(acc[i][2], 0.f), z3 = fmaxf(acc[i][3], 0.f);
+                float p3[3];
+                p3[0] = fmaf(z3, wo3.x, fmaf(z2, wo2.x, fmaf(z1, wo1.x, z0 * wo0.x)));
+                p3[1] = fmaf(z3, wo3.y, fmaf(z2, wo2.y, fmaf(z1, wo1.y, z0 * wo0.y)));
+                p3[2] = fmaf(z3, wo3.z, fmaf(z2, wo2.z, fmaf(z1, wo1.z, z0 * wo0.z)));
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float v = p3[c];
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    if (lane == 0) sm.out[half][(row0 + i) * 12 + h * 3 + c] = v;
+                }
+            }
+        }
+        bar_compute();
+        for (int i = tid; i < RT * 9; i += SIMT_COMPUTE_THREADS) {
+            const int r = i / 9, c = i - 9 * r;
+            sm.out[0][r * 12 + c] = (sm.out[0][r * 12 + c] + sm.out[1][r * 12 + c]) + __ldg(P + TrunkLayout::BO + c);
         }
     }
     __syncthreads();
-
-    // heads: z = relu(h2 @ Whp^T + proj[obj] + tq);  out = z @ Wo^T (+ bo added by the caller side)
-    float part[RPT][9];
-#pragma unroll
-    for (int i = 0; i < RPT; ++i)
-#pragma unroll
-        for (int c = 0; c < 9; ++c) part[i][c] = 0.f;
-#pragma unroll
-    for (int h = 0; h < 3; ++h) {
-        float acc[RPT][4];
-        const float4 tq = *reinterpret_cast<const float4 *>(s_tq + h * 256 + col);
-#pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-            const int o = sm.obj[row0 + i];
-            float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (o >= 0) pj = __ldg(reinterpret_cast<const float4 *>(proj + (size_t)o * 768 + h * 256 + col));
-            acc[i][0] = pj.x + tq.x; acc[i][1] = pj.y + tq.y; acc[i][2] = pj.z + tq.z; acc[i][3] = pj.w + tq.w;
-        }
-        gemm256<RPT>(P + TrunkLayout::WHP + h * 256 + col, 768, sm.h2, row0, acc);
-        // output layer of this head: 3 dot products over this thread's 4 columns
-        const float4 wo0 = __ldg(reinterpret_cast<const float4 *>(P + TrunkLayout::WO + (size_t)(h * 256 + col + 0) * 4));
-        const float4 wo1 = __ldg(reinterpret_cast<const float4 *>(P + TrunkLayout::WO + (size_t)(h * 256 + col + 1) * 4));
-        const float4 wo2 = __ldg(reinterpret_cast<const float4 *>(P + TrunkLayout::WO + (size_t)(h * 256 + col + 2) * 4));
-        const float4 wo3 = __ldg(reinterpret_cast<const float4 *>(P + TrunkLayout::WO + (size_t)(h * 256 + col + 3) * 4));
-#pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-            const float z0 = fmaxf(acc[i][0], 0.f), z1 = fmaxf(acc[i][1], 0.f);
-            const float z2 = fmaxf(acc[i][2], 0.f), z3 = fmaxf(acc[i][3], 0.f);
-            part[i][h * 3 + 0] = fmaf(z3, wo3.x, fmaf(z2, wo2.x, fmaf(z1, wo1.x, z0 * wo0.x)));
-            part[i][h * 3 + 1] = fmaf(z3, wo3.y, fmaf(z2, wo2.y, fmaf(z1, wo1.y, z0 * wo0.y)));
-            part[i][h * 3 + 2] = fmaf(z3, wo3.z, fmaf(z2, wo2.z, fmaf(z1, wo1.z, z0 * wo0.z)));
-        }
-    }
-    // reduce the 64 column-threads of each row group: 32 lanes by shuffle, 2 warps through smem
-    const int lane = tid & 31, half = (tid >> 5) & 1;
-#pragma unroll
-    for (int i = 0; i < RPT; ++i)
-#pragma unroll
-        for (int c = 0; c < 9; ++c) {
-            float v = part[i][c];
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            if (lane == 0) sm.out[half][(row0 + i) * 12 + c] = v;
-        }
-    __syncthreads();
-    for (int i = tid; i < RT * 9; i += blockDim.x) {
-        const int r = i / 9, c = i - 9 * r;
-        sm.out[0][r * 12 + c] = (sm.out[0][r * 12 + c] + sm.out[1][r * 12 + c]) + __ldg(P + TrunkLayout::BO + c);
-    }
-    __syncthreads();
-}
-
-// loads this thread's column of W1 (layer 1) into registers
-__device__ __forceinline__ void load_w1col(const float *__restrict__ P, float (&w1col)[9], float &b1v) {
-    const int n = threadIdx.x;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) w1col[k] = __ldg(P + TrunkLayout::W1T + k * 256 + n);
-    b1v = __ldg(P + TrunkLayout::B1 + n);
 }
 
 // deterministic block-wide sum of one double per thread (<= 16 warps); result valid in all threads
