@@ -138,7 +138,8 @@ template <int NPASS>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_bias_relu_kernel(Args a) {
     using C = Cfg<NPASS>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // pointer arithmetic on the __shared__ array keeps the shared address space (LDS/STS, not generic LD/ST)
+    uint8_t *base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     // stage s: [A_hi | A_lo | B_hi | B_lo]
     auto a_img = [&](int s, int which) { return base + (size_t)s * C::STAGE_BYTES + (size_t)which * A_TILE; };
     auto b_img = [&](int s, int which) { return base + (size_t)s * C::STAGE_BYTES + (size_t)C::IMAGES * A_TILE + (size_t)which * B_TILE_MAX; };

@@ -139,7 +139,8 @@ struct SimtEval {
     using Ctx = SimtCtx;
     static constexpr size_t smem_bytes() { return sizeof(Smem) + 16; }
     static __device__ __forceinline__ Smem &smem(unsigned char *raw) {
-        return *reinterpret_cast<Smem *>(((uintptr_t)raw + 15) & ~(uintptr_t)15);
+        // pointer arithmetic on the __shared__ array keeps the shared address space (LDS/STS, not generic LD/ST)
+        return *reinterpret_cast<Smem *>(raw + ((16u - (tc::smem_u32(raw) & 15u)) & 15u));
     }
     static __device__ __forceinline__ void setup(Smem &S, Ctx &c, const float *P) { simt_setup(S, c, P); }
     static __device__ __forceinline__ void teardown(Smem &S, Ctx &c) { simt_teardown(S, c); }
@@ -155,7 +156,7 @@ struct TcEval {
     using Ctx = tc::State;
     static constexpr size_t smem_bytes() { return sizeof(Smem) + 1024; }
     static __device__ __forceinline__ Smem &smem(unsigned char *raw) {
-        return *reinterpret_cast<Smem *>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+        return *reinterpret_cast<Smem *>(raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u));
     }
     static __device__ __forceinline__ void setup(Smem &S, Ctx &c, const float *P) { tc::setup(S, c, P); }
     static __device__ __forceinline__ void teardown(Smem &S, Ctx &c) { tc::teardown(S, c); }
