@@ -156,7 +156,7 @@ struct TcEval {
     using Ctx = tc::State;
     static constexpr size_t smem_bytes() { return sizeof(Smem) + 1024; }
     static __device__ __forceinline__ Smem &smem(unsigned char *raw) {
-        return *reinterpret_cast<Smem *>(raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u));
+        return *reinterpret_cast<Smem *>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     }
     static __device__ __forceinline__ void setup(Smem &S, Ctx &c, const float *P) { tc::setup(S, c, P); }
     static __device__ __forceinline__ void teardown(Smem &S, Ctx &c) { tc::teardown(S, c); }
