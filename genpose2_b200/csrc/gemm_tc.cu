@@ -182,19 +182,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bias_relu_kernel(Args a) {
         // register double buffering: the global loads of chunk c+1 are in flight while chunk c is converted
         // (the rows come from HBM; without this the loader is latency bound)
         const bool gather = a.gidx != nullptr;
-        long long src[16];                                // source row of each of this thread's 16 passes (-1: none)
+        // per pass: element offset of the source row in X (-1: no row) and of the group's row in Q, computed once
+        // per tile with 32-bit divisions (the host checks that the offsets fit)
+        long long src[16];
+        int qoff[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const long long lr = row0 + 32 * warp + 2 * i + sub;
-            if (lr >= a.R) src[i] = -1;
-            else src[i] = gather ? (lr / a.rows_per_batch) * (long long)a.n_src + __ldg(a.gidx + lr) : lr;
+            src[i] = -1;
+            qoff[i] = -1;
+            if (lr < a.R) {
+                const int lr32 = (int)lr;
+                const long long srow = gather ? (long long)(lr32 / a.rows_per_batch) * a.n_src + __ldg(a.gidx + lr) : lr;
+                src[i] = srow * a.ldx;
+                if (gather) qoff[i] = (lr32 / a.q_ns) * a.ldq;
+            }
         }
         auto load_chunk = [&](int c, float4 (&v)[16]) {
             const int k = c * KC + 4 * jv;
             const bool k_ok = k < a.ldx;
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-                v[i] = (k_ok && src[i] >= 0) ? __ldg(reinterpret_cast<const float4 *>(a.X + src[i] * (long long)a.ldx + k))
+                v[i] = (k_ok && src[i] >= 0) ? __ldg(reinterpret_cast<const float4 *>(a.X + src[i] + k))
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         auto convert_store = [&](int s, int cc, const float4 (&v)[16]) {
@@ -205,10 +214,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bias_relu_kernel(Args a) {
                 const int off = rl * 128 + (((jv >> 1) ^ (rl & 7)) << 4) + ((jv & 1) << 3);
                 float4 p = v[i];
                 if (gather) {  // hoisted first layer: relu(P[src] - Q[group]); Q rows hit L1 (shared by q_ns rows)
-                    const long long lr = row0 + rl;
                     const int k = cc * KC + 4 * jv;
-                    if (lr < a.R && k < a.ldq) {
-                        const float4 q = __ldg(reinterpret_cast<const float4 *>(a.Q + (lr / a.q_ns) * (long long)a.ldq + k));
+                    if (qoff[i] >= 0 && k < a.ldq) {
+                        const float4 q = __ldg(reinterpret_cast<const float4 *>(a.Q + qoff[i] + k));
                         p.x = fmaxf(p.x - q.x, 0.f); p.y = fmaxf(p.y - q.y, 0.f);
                         p.z = fmaxf(p.z - q.z, 0.f); p.w = fmaxf(p.w - q.w, 0.f);
                     } else {
@@ -418,6 +426,7 @@ extern "C" int gp_gemm_gather_bias_relu(const float *P, int n_src, int ldp, cons
                "gp_gemm_gather_bias_relu: P / Q rows must be 16-byte aligned");
     GP_REQUIRE(ldq >= K && ldp >= K, "gp_gemm_gather_bias_relu: ldp and ldq must cover K");
     GP_REQUIRE(rows_per_batch >= 1 && n_src >= 1 && q_ns >= 1, "gp_gemm_gather_bias_relu: bad gather geometry");
+    GP_REQUIRE(R < 2147483647LL && (R / q_ns + 1) * (long long)ldq < 2147483647LL, "gp_gemm_gather_bias_relu: too many rows");
     if (pool_ns == 0) {
         GP_REQUIRE(Y && ldy >= N && ldy <= ((N + 31) & ~31) && (ldy & 3) == 0 && ((uintptr_t)Y & 15) == 0,
                    "gp_gemm_gather_bias_relu: bad Y / ldy");
