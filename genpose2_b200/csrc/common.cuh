@@ -56,6 +56,13 @@ __device__ __forceinline__ unsigned warp_max_u32(unsigned v) {
     return __reduce_max_sync(0xffffffffu, v);
 }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+// redux.sync with a register member mask (sub-warp groups): the CUDA intrinsic wraps partial masks in a
+// branchy helper loop, the instruction itself takes the mask directly
+__device__ __forceinline__ unsigned redux_max_u32(unsigned mask, unsigned v) {
+    unsigned r;
+    asm volatile("redux.sync.max.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(mask));
+    return r;
+}
 #endif
 
 }  // namespace gp

@@ -109,7 +109,7 @@ __device__ __forceinline__ void pool_store(const float (&out)[32], int lane, boo
     for (int q = 0; q < PER_LANE; ++q) keep[q] = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        const unsigned m = __reduce_max_sync(mask, __float_as_uint(out[j]));
+        const unsigned m = redux_max_u32(mask, __float_as_uint(out[j]));
         if ((lane % GL) == (j % GL)) keep[j / GL] = __uint_as_float(m);
     }
     if (row_ok) {

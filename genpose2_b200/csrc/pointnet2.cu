@@ -606,7 +606,7 @@ sa_small_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz
     float keep[C3 / GL > 0 ? C3 / GL : 1];
 #pragma unroll
     for (int n = 0; n < C3; ++n) {
-        const unsigned m = __reduce_max_sync(mask, ok ? __float_as_uint(h3[n]) : 0u);
+        const unsigned m = redux_max_u32(mask, ok ? __float_as_uint(h3[n]) : 0u);
         if ((lane % GL) == (n % GL)) keep[n / GL] = __uint_as_float(m);
     }
     if (ok) {
