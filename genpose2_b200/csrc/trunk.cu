@@ -60,20 +60,22 @@ __global__ void pack_trunk_kernel(RawTrunk raw, float *__restrict__ P) {
         } else if (i < TrunkLayout::W_TC) {
             v = 0.f;  // alignment padding
         } else {
-            // destination float slot -> byte offset inside chunk c -> (row n, 16-byte chunk, element pair)
+            // destination float slot -> (chunk q, image hi/lo, row n, 16-byte unit, element pair)
             const size_t f = i - TrunkLayout::W_TC;
-            const size_t c = f / (256 * 64 / 2), o = (f % (256 * 64 / 2)) * 4;
-            const size_t n = o / 128, wb = o % 128;
-            const size_t logical16 = (wb / 16) ^ (n & 7);      // undo the SWIZZLE_128B XOR
-            const size_t kk = logical16 * 8 + (wb % 16) / 2;    // k inside the 64-wide atom
-            const float *src;
-            if (c < 4) {
-                src = p.pose_w1 + n * 256 + c * 64 + kk;       // W2[n][k]
-            } else {
-                const size_t h = (c - 4) / 4, a = (c - 4) % 4;
-                src = p.head_w0[h] + n * 1408 + 1152 + a * 64 + kk;  // head h, pose_feat columns
+            const size_t per_img = 128 * 64 / 2;
+            const size_t q = f / (2 * per_img), which = (f / per_img) % 2, o = (f % per_img) * 4;
+            const size_t gm = q / 8, kc = (q % 8) / 2, nh = q % 2;
+            const size_t nl = o / 128, wb = o % 128;
+            const size_t logical16 = (wb / 16) ^ (nl & 7);      // undo the SWIZZLE_128B XOR
+            const size_t k = kc * 64 + logical16 * 8 + (wb % 16) / 2;
+            const size_t n = nh * 128 + nl;
+            const float *src = gm == 0 ? p.pose_w1 + n * 256 + k : p.head_w0[gm - 1] + n * 1408 + 1152 + k;
+            float e[2];
+            for (int t = 0; t < 2; ++t) {
+                const float hi = __bfloat162float(__float2bfloat16_rn(src[t]));
+                e[t] = which == 0 ? hi : src[t] - hi;
             }
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(src[0], src[1]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(e[0], e[1]);
             v = *reinterpret_cast<float *>(&h2);
         }
         P[i] = v;
@@ -135,6 +137,7 @@ template <int RPT>
 struct SimtEval {
     static constexpr int RT = 4 * RPT;
     static constexpr int NT = SIMT_THREADS;
+    static constexpr int TQ_STAGES = 6;   // t-branch stage slots held in shared memory
     using Smem = TileSmem<RPT>;
     using Ctx = SimtCtx;
     static constexpr size_t smem_bytes() { return sizeof(Smem) + 16; }
@@ -142,6 +145,11 @@ struct SimtEval {
         // pointer arithmetic on the __shared__ array keeps the shared address space (LDS/STS, not generic LD/ST)
         return *reinterpret_cast<Smem *>(raw + ((16u - (tc::smem_u32(raw) & 15u)) & 15u));
     }
+    static __device__ __forceinline__ float *xin(Smem &S) { return S.x; }
+    static __device__ __forceinline__ float *outp(Smem &S) { return S.out[0]; }
+    static __device__ __forceinline__ float *tq(Smem &S) { return S.tq; }
+    static __device__ __forceinline__ float *four(Smem &S) { return S.four; }
+    static __device__ __forceinline__ float *tfeat(Smem &S) { return S.tfeat; }
     static __device__ __forceinline__ void setup(Smem &S, Ctx &c, const float *P) { simt_setup(S, c, P); }
     static __device__ __forceinline__ void teardown(Smem &S, Ctx &c) { simt_teardown(S, c); }
     static __device__ __forceinline__ void forward(const float *P, const float *proj, Smem &S, Ctx &c, const float *tq) {
@@ -149,21 +157,30 @@ struct SimtEval {
     }
 };
 
+template <int NPASS>
 struct TcEval {
     static constexpr int RT = tc::RT;
     static constexpr int NT = tc::NTHREADS;
-    using Smem = tc::Smem;
+    static constexpr int TQ_STAGES = 1;   // one slot in shared memory; the integrator keeps its 6 in global
+    using Smem = tc::Smem<NPASS>;
     using Ctx = tc::State;
     static constexpr size_t smem_bytes() { return sizeof(Smem) + 1024; }
     static __device__ __forceinline__ Smem &smem(unsigned char *raw) {
         return *reinterpret_cast<Smem *>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     }
-    static __device__ __forceinline__ void setup(Smem &S, Ctx &c, const float *P) { tc::setup(S, c, P); }
-    static __device__ __forceinline__ void teardown(Smem &S, Ctx &c) { tc::teardown(S, c); }
+    static __device__ __forceinline__ float *xin(Smem &S) { return S.x; }
+    static __device__ __forceinline__ float *outp(Smem &S) { return S.x; }   // out aliases the (dead) inputs
+    static __device__ __forceinline__ float *tq(Smem &S) { return S.tq; }
+    static __device__ __forceinline__ float *four(Smem &S) { return S.E; }   // scratch between evaluations
+    static __device__ __forceinline__ float *tfeat(Smem &S) { return S.E + 768; }
+    static __device__ __forceinline__ void setup(Smem &S, Ctx &c, const float *P) { tc::setup<NPASS>(S, c, P); }
+    static __device__ __forceinline__ void teardown(Smem &S, Ctx &c) { tc::teardown<NPASS>(S, c); }
     static __device__ __forceinline__ void forward(const float *P, const float *proj, Smem &S, Ctx &c, const float *tq) {
-        tc::forward(P, proj, S, c, tq);
+        tc::forward<NPASS>(P, proj, S, c, tq);
     }
 };
+static_assert(sizeof(tc::Smem<3>) + 1024 <= 227 * 1024, "TC evaluator shared memory exceeds 227 KB");
+static_assert(sizeof(tc::Smem<1>) + 1024 <= 227 * 1024, "TC evaluator shared memory exceeds 227 KB");
 
 // ------------------------------------------------------------------------------------------
 // single evaluation / energy: one CTA per tile; rows may carry different t (handled by runs)
@@ -182,20 +199,6 @@ eval_kernel(const float *__restrict__ P, const float *__restrict__ proj, const f
     const int r0 = blockIdx.x * RT;
     EV::setup(S, ctx, P);
     __shared__ float s_trow[EV::RT];
-    for (int i = tid; i < RT * 12; i += NT) {
-        const int r = i / 12, c = i - 12 * r;
-        float v = 0.f;
-        if (r0 + r < N && c < 9) {
-            if (MODE == 0) {
-                v = x[(size_t)(r0 + r) * 9 + c];
-            } else {
-                // pose_samples.type_as(f32) then [:, -3:] -= pts_center (posenet_agent.py:668-694)
-                v = (float)poses[(size_t)(r0 + r) * 9 + c];
-                if (c >= 6) v = v - center[(size_t)(r0 + r) * 3 + (c - 6)];
-            }
-        }
-        S.x[i] = v;
-    }
     for (int r = tid; r < RT; r += NT) {
         S.obj[r] = (r0 + r < N) ? (r0 + r) / rpo : -1;
         s_trow[r] = (r0 + r < N) ? t[r0 + r] : 0.f;
@@ -207,23 +210,47 @@ eval_kernel(const float *__restrict__ P, const float *__restrict__ proj, const f
         const float tv = s_trow[run0];
         int run1 = run0 + 1;
         while (run1 < nrows && s_trow[run1] == tv) ++run1;
+        // (re)load the inputs: the evaluator may reuse the input buffer for its outputs
+        float *xin = EV::xin(S);
+        for (int i = tid; i < RT * 12; i += NT) {
+            const int r = i / 12, c = i - 12 * r;
+            float v = 0.f;
+            if (r0 + r < N && c < 9) {
+                if (MODE == 0) {
+                    v = x[(size_t)(r0 + r) * 9 + c];
+                } else {
+                    // pose_samples.type_as(f32) then [:, -3:] -= pts_center (posenet_agent.py:668-694)
+                    v = (float)poses[(size_t)(r0 + r) * 9 + c];
+                    if (c >= 6) v = v - center[(size_t)(r0 + r) * 3 + (c - 6)];
+                }
+            }
+            xin[i] = v;
+        }
         if (tid == 0) S.times[0] = tv;
         __syncthreads();
-        compute_tq(P, S.times, 1, S.four, S.tfeat, S.tq);
-        EV::forward(P, proj, S, ctx, S.tq);
+        float xr[9];  // this thread's row for the energy inner products (kept across the evaluation)
+        if (MODE == 1) {
+#pragma unroll
+            for (int c = 0; c < 9; ++c) xr[c] = (run0 + tid < run1) ? xin[(run0 + tid) * 12 + c] : 0.f;
+        }
+        compute_tq(P, S.times, 1, EV::four(S), EV::tfeat(S), EV::tq(S));
+        EV::forward(P, proj, S, ctx, EV::tq(S));
+        const float *fo = EV::outp(S);
         const float std = sigma_f32(tv);
         if (MODE == 0) {
             for (int i = tid; i < (run1 - run0) * 9; i += NT) {
                 const int r = run0 + i / 9, c = i % 9;
-                out[(size_t)(r0 + r) * 9 + c] = S.out[0][r * 12 + c] / (std + 1e-7f);
+                out[(size_t)(r0 + r) * 9 + c] = fo[r * 12 + c] / (std + 1e-7f);
             }
         } else {
-            for (int r = run0 + tid; r < run1; r += NT) {
+            static_assert(EV::RT <= EV::NT, "one thread per row");
+            const int r = run0 + tid;
+            if (r < run1) {
                 float er = 0.f, et = 0.f;
 #pragma unroll
-                for (int c = 0; c < 6; ++c) er += S.x[r * 12 + c] * (S.out[0][r * 12 + c] / std);
+                for (int c = 0; c < 6; ++c) er += xr[c] * (fo[r * 12 + c] / std);
 #pragma unroll
-                for (int c = 6; c < 9; ++c) et += S.x[r * 12 + c] * (S.out[0][r * 12 + c] / std);
+                for (int c = 6; c < 9; ++c) et += xr[c] * (fo[r * 12 + c] / std);
                 out[(size_t)(r0 + r) * 2 + 0] = er;
                 out[(size_t)(r0 + r) * 2 + 1] = et;
             }
@@ -264,6 +291,7 @@ struct OdeArgs {
     double *y[2];     // current / candidate state   [N][9]
     double *K[7];     // stage derivatives K[0..6]    [N][9]
     double *part;     // [2][3][ntiles] partial sums
+    float *tq_ws;     // [grid][6][768] t-branch table for evaluators that keep only one stage in shared memory
     int ntiles;
 };
 
@@ -286,6 +314,9 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
     const int N = a.N;
     const double n_total = (double)N * 9.0;
     EV::setup(S, ctx, P);
+    float *const tqtab = (EV::TQ_STAGES >= 6) ? EV::tq(S) : a.tq_ws + (size_t)blockIdx.x * 6 * 768;
+    float *const xin = EV::xin(S);
+    const float *const fo = EV::outp(S);
 
     const double direction = (a.eps > a.T) ? 1.0 : ((a.eps < a.T) ? -1.0 : 1.0);
     const double t_bound = a.eps;
@@ -297,7 +328,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
 
     // RHS of the rows whose float32 inputs sit in S.x -> K[kdst] (float64), scipy's `fun`
     auto stage_eval = [&](int tile, int tq_slot, double t_stage, int kdst) {
-        EV::forward(P, a.proj, S, ctx, S.tq + tq_slot * 768);
+        EV::forward(P, a.proj, S, ctx, tqtab + tq_slot * 768);
         const float tf = (float)t_stage;
         const float std = sigma_f32(tf);
         const double g = diffusion_f64(t_stage);
@@ -307,7 +338,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
         for (int i = tid; i < RT * 9; i += NT) {
             const int r = i / 9, c = i - 9 * r;
             if (r0 + r < N) {
-                const float sc = S.out[0][r * 12 + c] / (std + 1e-7f);  // scorenet.py:262-264
+                const float sc = fo[r * 12 + c] / (std + 1e-7f);  // scorenet.py:262-264
                 Kd[(size_t)(r0 + r) * 9 + c] = 0.0 - coef * (double)sc;  // samplers.py:219
             }
         }
@@ -322,7 +353,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
     double t = a.T;
     if (tid == 0) S.times[0] = (float)t;
     __syncthreads();
-    compute_tq(P, S.times, 1, S.four, S.tfeat, S.tq);
+    compute_tq(P, S.times, 1, EV::four(S), EV::tfeat(S), tqtab);
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const int r0 = tile * RT;
         set_obj(tile);
@@ -335,7 +366,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
                 if (a.traj) a.traj[(size_t)(r0 + r) * 9 + c] = yv;
                 v = (float)yv;
             }
-            S.x[i] = v;
+            xin[i] = v;
         }
         __syncthreads();
         stage_eval(tile, 0, t, kidx[0]);
@@ -371,7 +402,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
         const double t1 = t + h0 * direction;
         if (tid == 0) S.times[0] = (float)t1;
         __syncthreads();
-        compute_tq(P, S.times, 1, S.four, S.tfeat, S.tq);
+        compute_tq(P, S.times, 1, EV::four(S), EV::tfeat(S), tqtab);
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             const int r0 = tile * RT;
             set_obj(tile);
@@ -382,7 +413,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
                     const size_t g = (size_t)(r0 + r) * 9 + c;
                     v = (float)(ycur[g] + h0 * direction * a.K[kidx[0]][g]);
                 }
-                S.x[i] = v;
+                xin[i] = v;
             }
             __syncthreads();
             stage_eval(tile, 0, t1, kidx[1]);
@@ -429,7 +460,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
             if (tid < 5) S.times[tid] = (float)(t + c_C[tid + 1] * h);
             if (tid == 5) S.times[5] = (float)(t + h);
             __syncthreads();
-            compute_tq(P, S.times, 6, S.four, S.tfeat, S.tq);
+            compute_tq(P, S.times, 6, EV::four(S), EV::tfeat(S), tqtab);
 
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 const int r0 = tile * RT;
@@ -452,7 +483,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
                                 v = (float)yn;
                             }
                         }
-                        S.x[i] = v;
+                        xin[i] = v;
                     }
                     __syncthreads();
                     const double ts = (s < 6) ? t + c_C[s] * h : t + h;
@@ -507,7 +538,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
         if (a.denoise) {
             if (tid == 0) S.times[0] = eps_f;
             __syncthreads();
-            compute_tq(P, S.times, 1, S.four, S.tfeat, S.tq);
+            compute_tq(P, S.times, 1, EV::four(S), EV::tfeat(S), tqtab);
         }
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             const int r0 = tile * RT;
@@ -517,10 +548,10 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
                     const int r = i / 12, c = i - 12 * r;
                     float v = 0.f;
                     if (r0 + r < N && c < 9) v = (float)ycur[(size_t)(r0 + r) * 9 + c];
-                    S.x[i] = v;
+                    xin[i] = v;
                 }
                 __syncthreads();
-                EV::forward(P, a.proj, S, ctx, S.tq);
+                EV::forward(P, a.proj, S, ctx, tqtab);
             }
             for (int r = tid; r < RT; r += NT) {
                 if (r0 + r >= N) continue;
@@ -533,7 +564,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
                     const float step = (float)((1.0 - a.eps) / 1000.0);
 #pragma unroll
                     for (int c = 0; c < 9; ++c) {
-                        const float grad = S.out[0][r * 12 + c] / (std + 1e-7f);
+                        const float grad = fo[r * 12 + c] / (std + 1e-7f);
                         const float drift = 0.f - (dif * dif) * grad;
                         v[c] = v[c] + (double)(drift * step);
                     }
@@ -598,6 +629,8 @@ __global__ void __launch_bounds__(EV::NT, 1) pc_kernel(PcArgs a) {
     const int tid = threadIdx.x, N = a.N;
     const float *P = a.P;
     EV::setup(S, ctx, P);
+    float *const xin = EV::xin(S);
+    const float *const fo = EV::outp(S);
     // grad of this CTA's tiles stays in global scratch between the two halves of a step: reuse
     // mean_x as scratch for grad (it is overwritten with the real mean_x at the end of each step).
     float *grad = a.mean_x;
@@ -608,7 +641,7 @@ __global__ void __launch_bounds__(EV::NT, 1) pc_kernel(PcArgs a) {
         const float tv = a.time_steps[it];
         if (tid == 0) S.times[0] = tv;
         __syncthreads();
-        compute_tq(P, S.times, 1, S.four, S.tfeat, S.tq);
+        compute_tq(P, S.times, 1, EV::four(S), EV::tfeat(S), EV::tq(S));
         const float std = sigma_f32(tv);
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             const int r0 = tile * RT;
@@ -617,17 +650,17 @@ __global__ void __launch_bounds__(EV::NT, 1) pc_kernel(PcArgs a) {
                 const int r = i / 12, c = i - 12 * r;
                 float v = 0.f;
                 if (r0 + r < N && c < 9) v = (it == 0 ? a.x0 : a.x)[(size_t)(r0 + r) * 9 + c];
-                S.x[i] = v;
+                xin[i] = v;
             }
             __syncthreads();
-            EV::forward(P, a.proj, S, ctx, S.tq);
+            EV::forward(P, a.proj, S, ctx, EV::tq(S));
             double sn = 0.0;
             for (int r = tid; r < RT; r += NT) {
                 if (r0 + r >= N) continue;
                 float ss = 0.f;
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {
-                    const float gv = S.out[0][r * 12 + c] / (std + 1e-7f);
+                    const float gv = fo[r * 12 + c] / (std + 1e-7f);
                     grad[(size_t)(r0 + r) * 9 + c] = gv;
                     ss += gv * gv;
                 }
@@ -709,6 +742,7 @@ static int launch_ode(OdeArgs &a, cudaStream_t st) {
     GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int limit = coop_grid_limit((const void *)kern, EV::NT, smem);
     if (limit <= 0) { set_error("gp_scorenet_ode: kernel cannot be made resident"); return GP_ERR_LAUNCH; }
+    if (limit > 2 * num_sms() + 8) limit = 2 * num_sms() + 8;  // size of the per-CTA t-branch table
     int grid = a.ntiles < limit ? a.ntiles : limit;
     void *params[] = {&a};
     GP_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(EV::NT), params, smem, st));
@@ -778,7 +812,8 @@ static int launch_eval(const void *packed, const float *proj, const float *x, co
                        cudaStream_t st, const char *name) {
     if (N == 0) return GP_OK;
     int rc;
-    if (mode == 1) rc = launch_eval_ev<TcEval, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
+    if (mode == 1) rc = launch_eval_ev<TcEval<1>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
+    else if (mode == 2) rc = launch_eval_ev<TcEval<3>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
     else if (N <= 16 * num_sms()) rc = launch_eval_ev<SimtEval<4>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
     else rc = launch_eval_ev<SimtEval<8>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
     if (rc != GP_OK) return rc;
@@ -791,7 +826,7 @@ extern "C" int gp_scorenet_eval(const void *packed, const float *proj, const flo
     GP_REQUIRE(N >= 0 && rows_per_object >= 1, "gp_scorenet_eval: bad sizes");
     if (N == 0) return GP_OK;
     GP_REQUIRE(packed && proj && x && t && score, "gp_scorenet_eval: null pointer");
-    GP_REQUIRE(mode == 0 || mode == 1, "gp_scorenet_eval: mode must be 0 (fp32) or 1 (bf16 tensor cores)");
+    GP_REQUIRE(mode >= 0 && mode <= 2, "gp_scorenet_eval: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05)");
     return launch_eval<0>(packed, proj, x, nullptr, nullptr, t, N, rows_per_object, score, mode, as_stream(s), "gp_scorenet_eval");
 }
 
@@ -800,15 +835,17 @@ extern "C" int gp_energy(const void *packed, const float *proj, const double *po
     GP_REQUIRE(N >= 0 && rows_per_object >= 1, "gp_energy: bad sizes");
     if (N == 0) return GP_OK;
     GP_REQUIRE(packed && proj && poses && pts_center && t_rows && energy, "gp_energy: null pointer");
-    GP_REQUIRE(mode == 0 || mode == 1, "gp_energy: mode must be 0 (fp32) or 1 (bf16 tensor cores)");
+    GP_REQUIRE(mode >= 0 && mode <= 2, "gp_energy: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05)");
     return launch_eval<1>(packed, proj, nullptr, poses, pts_center, t_rows, N, rows_per_object, energy, mode, as_stream(s), "gp_energy");
 }
+
+static size_t tq_table_bytes() { return (size_t)(2 * num_sms() + 8) * 6 * 768 * sizeof(float); }
 
 extern "C" size_t gp_scorenet_ode_workspace_bytes(int N) {
     if (N < 0) return 0;
     const size_t state = align256((size_t)N * 9 * sizeof(double));
     const size_t ntiles_max = (size_t)(N + 7) / 8 + 1;
-    return state * 9 + align256(2 * 3 * ntiles_max * sizeof(double)) + 256;
+    return state * 9 + align256(2 * 3 * ntiles_max * sizeof(double)) + align256(tq_table_bytes()) + 256;
 }
 
 extern "C" int gp_scorenet_ode(const void *packed, const float *proj, const double *x0, const float *pts_center,
@@ -819,7 +856,7 @@ extern "C" int gp_scorenet_ode(const void *packed, const float *proj, const doub
     GP_REQUIRE(N >= 1 && rows_per_object >= 1, "gp_scorenet_ode: bad sizes N=%d rows_per_object=%d", N, rows_per_object);
     GP_REQUIRE(rtol > 0 && atol > 0, "gp_scorenet_ode: tolerances must be positive");
     GP_REQUIRE(traj == nullptr || max_traj >= 1, "gp_scorenet_ode: max_traj < 1");
-    GP_REQUIRE(mode == 0 || mode == 1, "gp_scorenet_ode: mode must be 0 (fp32) or 1 (bf16 tensor cores)");
+    GP_REQUIRE(mode >= 0 && mode <= 2, "gp_scorenet_ode: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05)");
     if (workspace_bytes < gp_scorenet_ode_workspace_bytes(N)) {
         set_error("gp_scorenet_ode: workspace too small (%zu < %zu)", workspace_bytes, gp_scorenet_ode_workspace_bytes(N));
         return GP_ERR_WORKSPACE;
@@ -835,10 +872,12 @@ extern "C" int gp_scorenet_ode(const void *packed, const float *proj, const doub
     a.y[0] = (double *)w; w += state;
     a.y[1] = (double *)w; w += state;
     for (int k = 0; k < 7; ++k) { a.K[k] = (double *)w; w += state; }
-    a.part = (double *)w;
+    a.part = (double *)w; w += align256(2 * 3 * ((size_t)(N + 7) / 8 + 1) * sizeof(double));
+    a.tq_ws = (float *)w;
     cudaStream_t st = as_stream(s);
     const int sms = num_sms();
-    if (mode == 1) return launch_ode<TcEval>(a, st);
+    if (mode == 1) return launch_ode<TcEval<1>>(a, st);
+    if (mode == 2) return launch_ode<TcEval<3>>(a, st);
     switch (simt_rows_per_thread(N, sms)) {
         case 2: return launch_ode<SimtEval<2>>(a, st);
         case 4: return launch_ode<SimtEval<4>>(a, st);
@@ -883,7 +922,7 @@ extern "C" int gp_scorenet_pc(const void *packed, const float *proj, const float
                               size_t workspace_bytes, int mode, gp_stream_t s) {
     GP_REQUIRE(packed && proj && x0 && noise && pts_center && time_steps && mean_x && workspace, "gp_scorenet_pc: null pointer");
     GP_REQUIRE(N >= 1 && rows_per_object >= 1 && num_steps >= 2, "gp_scorenet_pc: bad sizes");
-    GP_REQUIRE(mode == 0 || mode == 1, "gp_scorenet_pc: mode must be 0 (fp32) or 1 (bf16 tensor cores)");
+    GP_REQUIRE(mode >= 0 && mode <= 2, "gp_scorenet_pc: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05)");
     if (workspace_bytes < gp_scorenet_pc_workspace_bytes(N)) {
         set_error("gp_scorenet_pc: workspace too small");
         return GP_ERR_WORKSPACE;
@@ -897,7 +936,8 @@ extern "C" int gp_scorenet_pc(const void *packed, const float *proj, const float
     a.part = (double *)w;
     cudaStream_t st = as_stream(s);
     const int sms = num_sms();
-    if (mode == 1) return launch_pc<TcEval>(a, st);
+    if (mode == 1) return launch_pc<TcEval<1>>(a, st);
+    if (mode == 2) return launch_pc<TcEval<3>>(a, st);
     switch (simt_rows_per_thread(N, sms)) {
         case 2: return launch_pc<SimtEval<2>>(a, st);
         case 4: return launch_pc<SimtEval<4>>(a, st);

@@ -29,11 +29,12 @@ struct TrunkLayout {
     static constexpr size_t WO = BH + 768;                     // [768][4]    (3 used) out weights
     static constexpr size_t BO = WO + 768 * 4;                 // [12]        (9 used)
     static constexpr size_t F32_END = BO + 12;
-    // bf16 B operands for the tensor-core path (tcgen05), as 16 ready-to-copy shared-memory images of
-    // [256 n][64 k] bf16 in the canonical K-major SWIZZLE_128B layout (32 KB each): chunks 0-3 = W2
-    // k-atoms, chunks 4+4h+a = head h k-atom a.  Offsets counted in floats; 1024-byte aligned.
+    // bf16 B operands for the tensor-core path (tcgen05): 32 chunks x {hi, lo} ready-to-copy shared-memory
+    // images of [128 n][64 k] bf16 in the canonical K-major SWIZZLE_128B layout (16 KB each).  Chunk
+    // q = gemm*8 + k_atom*2 + n_half with gemm 0 = pose_encoder.2, 1..3 = heads (pose_feat columns);
+    // lo = bf16(w - hi) for the split-bf16 (fp32-class) mode.  Offsets counted in floats; 1024-byte aligned.
     static constexpr size_t W_TC = (F32_END + 255) / 256 * 256;
-    static constexpr size_t END = W_TC + 16 * (256 * 64 / 2);
+    static constexpr size_t END = W_TC + 32 * 2 * (128 * 64 / 2);
 };
 
 constexpr float kFloatPi = 3.14159265358979323846f;  // np.pi cast to float32 by torch

@@ -15,7 +15,13 @@ import torch.nn as nn
 from . import _lib
 
 
-MLP_MODES = {"fp32": 0, "bf16": 1}
+# numerical mode of the fused MLP kernels:
+#   "fp32"      split-bf16 x3 on the tcgen05 tensor cores (every operand = hi + lo bf16, products accumulated
+#               as hi*hi + lo*hi + hi*lo in fp32): fp32-class results (same distance to the reference as a
+#               different fp32 summation order)
+#   "fp32_ffma" plain FP32 FFMA on the CUDA cores
+#   "bf16"      bf16 operands on the tensor cores, fp32 accumulation (stated looser bound)
+MLP_MODES = {"fp32_ffma": 0, "bf16": 1, "fp32": 2}
 
 
 def zero_module(module):
@@ -54,7 +60,7 @@ class _Trunk(nn.Module):
             setattr(self, f"fusion_tail_{name}",
                     nn.Sequential(nn.Linear(128 + 256 + 1024, 256), self.act, zero_module(nn.Linear(256, 3))))
         self.marginal_prob_func = marginal_prob_func
-        self.mlp_mode = "fp32"  # "fp32": FFMA MLP; "bf16": tcgen05 tensor-core MLP (set by GFObjectPose from cfg.mlp_mode)
+        self.mlp_mode = "fp32"  # see MLP_MODES (set by GFObjectPose from cfg.mlp_mode)
         self._packed = None
         self._packed_key = None
 

@@ -17,19 +17,21 @@ ROT_TOL = 1e-3   # rad
 TRANS_TOL = 1e-4
 
 
-def make_net(seed, agent_type="score"):
+def make_net(seed, agent_type="score", mlp_mode="fp32"):
     from genpose2_b200.config import get_config
     from genpose2_b200.posenet import GFObjectPose
     from genpose2_b200.sde import init_sde
     cfg = get_config()
     cfg.agent_type = agent_type
+    cfg.mlp_mode = mlp_mode
     net = GFObjectPose(cfg, *init_sde("ve")).cuda().eval()
     net.load_state_dict(synthetic.random_gfobjectpose_state_dict(seed))
     return net
 
 
-def test_scorenet_eval_matches_oracle():
-    net = make_net(100)
+@pytest.mark.parametrize("mlp_mode", ["fp32", "fp32_ffma"])
+def test_scorenet_eval_matches_oracle(mlp_mode):
+    net = make_net(100, mlp_mode=mlp_mode)
     trunk = po.Trunk(synthetic.random_gfobjectpose_state_dict(100))
     g = torch.Generator().manual_seed(0)
     B, R = 5, 50
@@ -40,6 +42,7 @@ def test_scorenet_eval_matches_oracle():
         want = trunk.score(rep(feat, R), x, t)
         got = net({"pts_feat": rep(feat, R).cuda(), "sampled_pose": x.cuda(), "t": t.cuda()}, mode="score").cpu()
         scale = want.abs().max()
+        print(mlp_mode, "eval rel err", tval, float((got - want).abs().max() / scale))
         assert (got - want).abs().max() <= 2e-5 * scale, (tval, float((got - want).abs().max()), float(scale))
         # hoisted per-object path gives the same numbers as one-object-per-row
         got2 = net({"_gp_pts_feat_obj": feat.cuda(), "_gp_rows_per_object": R, "pts_feat": None,
@@ -52,11 +55,12 @@ def test_scorenet_eval_matches_oracle():
     assert ((got - want).abs() <= 2e-5 * want.abs().max()).all()
 
 
+@pytest.mark.parametrize("mlp_mode", ["fp32", "fp32_ffma"])
 @pytest.mark.parametrize("name", ["ode_c1_T1", "ode_b4_T055", "ode_track_T025"])
-def test_ode_sampler_matches_reference_golden(name):
+def test_ode_sampler_matches_reference_golden(name, mlp_mode):
     from genpose2_b200 import samplers
     g = load_golden(name)
-    net = make_net(int(g["score_seed"]))
+    net = make_net(int(g["score_seed"]), mlp_mode=mlp_mode)
     R, B = int(g["R"]), int(g["B"])
     feat, center = torch.from_numpy(g["feat"]).cuda(), torch.from_numpy(g["center"]).cuda()
     noise = torch.from_numpy(g["noise"])
@@ -93,10 +97,12 @@ def test_ode_sampler_matches_reference_golden(name):
     assert torch.equal(x, x2)
 
 
-def test_ode_sampler_vs_oracle_ragged_batch():
-    """a batch size that is not a multiple of the tile, rows_per_object = 7"""
+@pytest.mark.parametrize("mlp_mode", ["fp32", "fp32_ffma"])
+def test_ode_sampler_vs_oracle_ragged_batch(mlp_mode):
+    """a batch size that is not a multiple of the tile, rows_per_object = 7 (more objects per tile than the
+    tensor-core evaluator's shared-memory (proj + tq) table holds: exercises its global fallback)"""
     from genpose2_b200 import samplers
-    net = make_net(100)
+    net = make_net(100, mlp_mode=mlp_mode)
     trunk = po.Trunk(synthetic.random_gfobjectpose_state_dict(100))
     g = torch.Generator().manual_seed(5)
     B, R = 13, 7
@@ -114,10 +120,11 @@ def test_ode_sampler_vs_oracle_ragged_batch():
     assert rot <= ROT_TOL and trans <= TRANS_TOL, (rot, trans)
 
 
-def test_pc_sampler_matches_reference_golden():
+@pytest.mark.parametrize("mlp_mode", ["fp32", "fp32_ffma"])
+def test_pc_sampler_matches_reference_golden(mlp_mode):
     from genpose2_b200 import samplers
     g = load_golden("pc_b2")
-    net = make_net(int(g["score_seed"]))
+    net = make_net(int(g["score_seed"]), mlp_mode=mlp_mode)
     R, B, steps = int(g["R"]), int(g["B"]), int(g["steps"])
     feat, center = torch.from_numpy(g["feat"]).cuda(), torch.from_numpy(g["center"]).cuda()
     data = {"pts": torch.zeros(B * R, 1, 3), "pts_center": rep(center, R), "_gp_pts_feat_obj": feat,
@@ -161,13 +168,11 @@ BF16_TRANS_TOL = 2e-3
 
 
 def make_net_mode(seed, mode):
-    net = make_net(seed)
-    net.pose_score_net.mlp_mode = mode
-    return net
+    return make_net(seed, mlp_mode=mode)
 
 
 def test_bf16_scorenet_eval_close_to_fp32():
-    net32, net16 = make_net_mode(100, "fp32"), make_net_mode(100, "bf16")
+    net32, net16 = make_net_mode(100, "fp32_ffma"), make_net_mode(100, "bf16")
     g = torch.Generator().manual_seed(3)
     B, R = 7, 50   # 350 rows: 2 full tiles + a ragged one
     feat = torch.relu(torch.randn(B, 1024, generator=g)).cuda()
