@@ -79,20 +79,30 @@ __device__ __forceinline__ void compute_tq(const float *__restrict__ P, const fl
         float acc = __ldg(P + TrunkLayout::BT + j);
         const float *w = P + TrunkLayout::WTT + j;
         const float *f = s_four + s * 128;
-#pragma unroll 8
-        for (int k = 0; k < 128; ++k) acc = fmaf(f[k], __ldg(w + k * 128), acc);
+        // the weight column is strided through L2: fetch 16 values at a time so the loads overlap
+        for (int k0 = 0; k0 < 128; k0 += 16) {
+            float wv[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) wv[u] = __ldg(w + (k0 + u) * 128);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc = fmaf(f[k0 + u], wv[u], acc);
+        }
         s_tfeat[i] = fmaxf(acc, 0.f);
     }
     __syncthreads();
     for (int n = tid; n < 768; n += nt) {
         float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         const float *w = P + TrunkLayout::WHT + n;
-#pragma unroll 4
-        for (int k = 0; k < 128; ++k) {
-            const float wv = __ldg(w + k * 768);
+        for (int k0 = 0; k0 < 128; k0 += 16) {
+            float wv[16];
 #pragma unroll
-            for (int s = 0; s < 6; ++s)
-                if (s < ns) acc[s] = fmaf(s_tfeat[s * 128 + k], wv, acc[s]);
+            for (int u = 0; u < 16; ++u) wv[u] = __ldg(w + (k0 + u) * 768);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+#pragma unroll
+                for (int s = 0; s < 6; ++s)
+                    if (s < ns) acc[s] = fmaf(s_tfeat[s * 128 + k0 + u], wv[u], acc[s]);
+            }
         }
 #pragma unroll
         for (int s = 0; s < 6; ++s)

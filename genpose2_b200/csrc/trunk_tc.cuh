@@ -224,24 +224,28 @@ __device__ __forceinline__ void forward(const float *__restrict__ P, const float
         const int half = e >> 2;                  // column half 0 / 1
         const int c0 = half * 128;
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-        uint8_t *A_hi = &S.abuf[0][0][0];
-        uint8_t *A_lo = &S.abuf[NPASS == 3 ? 1 : 0][0][0];
+        const uint32_t A_hi = smem_u32(&S.abuf[0][0][0]);
+        const uint32_t A_lo = smem_u32(&S.abuf[NPASS == 3 ? 1 : 0][0][0]);
+        const uint32_t sx = smem_u32(S.x), sb2 = smem_u32(S.b2);
         // layer 1 (9 -> 256): this thread owns output column c for all 128 rows (weights in registers)
         {
             const int c = tid - 64;
+            // (row-independent part of the swizzled offset of column c)
+            const int c_atom = (c >> 6) * ATOM_BYTES, c_unit = (c & 63) >> 3, c_byte = (c & 7) << 1;
+#pragma unroll 4
             for (int r = 0; r < RT; ++r) {
-                const float4 xa = *reinterpret_cast<const float4 *>(S.x + r * 12);
-                const float4 xb = *reinterpret_cast<const float4 *>(S.x + r * 12 + 4);
-                const float xc = S.x[r * 12 + 8];
+                const float4 xa = lds_f4(sx + r * 48);
+                const float4 xb = lds_f4(sx + r * 48 + 16);
+                const float xc = lds_f(sx + r * 48 + 32);
                 float a = st.b1v;
                 a = fmaf(xa.x, st.w1col[0], a); a = fmaf(xa.y, st.w1col[1], a); a = fmaf(xa.z, st.w1col[2], a);
                 a = fmaf(xa.w, st.w1col[3], a); a = fmaf(xb.x, st.w1col[4], a); a = fmaf(xb.y, st.w1col[5], a);
                 a = fmaf(xb.z, st.w1col[6], a); a = fmaf(xb.w, st.w1col[7], a); a = fmaf(xc, st.w1col[8], a);
                 a = fmaxf(a, 0.f);
                 const __nv_bfloat16 hi = __float2bfloat16_rn(a);
-                const int off = a_offset(r, c);
-                *reinterpret_cast<__nv_bfloat16 *>(A_hi + off) = hi;
-                if (NPASS == 3) *reinterpret_cast<__nv_bfloat16 *>(A_lo + off) = __float2bfloat16_rn(a - __bfloat162float(hi));
+                const int off = c_atom + r * 128 + ((c_unit ^ (r & 7)) << 4) + c_byte;
+                sts_u16(A_hi + off, __bfloat16_as_ushort(hi));
+                if (NPASS == 3) sts_u16(A_lo + off, __bfloat16_as_ushort(__float2bfloat16_rn(a - __bfloat162float(hi))));
             }
             fence_proxy_async();
             // every epilogue thread has now read the inputs: S.x may be reused as the output buffer
@@ -260,14 +264,17 @@ __device__ __forceinline__ void forward(const float *__restrict__ P, const float
                     const int n0 = c0 + g * 32 + j8 * 8;
                     float v[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r[j8 * 8 + j]) + S.b2[n0 + j], 0.f);
+                    const float4 ba = lds_f4(sb2 + n0 * 4), bb = lds_f4(sb2 + n0 * 4 + 16);
+                    const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r[j8 * 8 + j]) + bv[j], 0.f);
                     const __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
                     const __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
                     uint4 pk;
                     pk.x = *reinterpret_cast<const uint32_t *>(&p0); pk.y = *reinterpret_cast<const uint32_t *>(&p1);
                     pk.z = *reinterpret_cast<const uint32_t *>(&p2); pk.w = *reinterpret_cast<const uint32_t *>(&p3);
                     const int off = a_offset(row, n0);
-                    *reinterpret_cast<uint4 *>(A_hi + off) = pk;
+                    sts_u4(A_hi + off, pk);
                     if (NPASS == 3) {
                         const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
                         const float2 f2 = __bfloat1622float2(p2), f3 = __bfloat1622float2(p3);
@@ -276,7 +283,7 @@ __device__ __forceinline__ void forward(const float *__restrict__ P, const float
                         uint4 pl;
                         pl.x = *reinterpret_cast<const uint32_t *>(&l0); pl.y = *reinterpret_cast<const uint32_t *>(&l1);
                         pl.z = *reinterpret_cast<const uint32_t *>(&l2); pl.w = *reinterpret_cast<const uint32_t *>(&l3);
-                        *reinterpret_cast<uint4 *>(A_lo + off) = pl;
+                        sts_u4(A_lo + off, pl);
                     }
                 }
             }
@@ -290,7 +297,7 @@ __device__ __forceinline__ void forward(const float *__restrict__ P, const float
 #pragma unroll
         for (int c = 0; c < 9; ++c) acc[c] = 0.f;
         const int o = S.obj[row];
-        const float *erow = S.E + (use_E && o >= 0 ? o - slot_base : 0) * 768;
+        const uint32_t erow = smem_u32(S.E + (use_E && o >= 0 ? o - slot_base : 0) * 768);
         const float *prow = proj + (size_t)(o < 0 ? 0 : o) * 768;
 #pragma unroll 1
         for (int h = 0; h < 3; ++h) {
@@ -311,8 +318,8 @@ __device__ __forceinline__ void forward(const float *__restrict__ P, const float
                     for (int j = 0; j < 8; ++j) w[j] = __ldg(reinterpret_cast<const float4 *>(P + TrunkLayout::WO + (size_t)(nb + j8 * 8 + j) * 4));
                     float ev[8];
                     if (use_E) {
-                        const float4 ea = *reinterpret_cast<const float4 *>(erow + nb + j8 * 8);
-                        const float4 eb = *reinterpret_cast<const float4 *>(erow + nb + j8 * 8 + 4);
+                        const float4 ea = lds_f4(erow + (nb + j8 * 8) * 4);
+                        const float4 eb = lds_f4(erow + (nb + j8 * 8) * 4 + 16);
                         ev[0] = ea.x; ev[1] = ea.y; ev[2] = ea.z; ev[3] = ea.w; ev[4] = eb.x; ev[5] = eb.y; ev[6] = eb.z; ev[7] = eb.w;
                     } else {
 #pragma unroll
