@@ -96,10 +96,12 @@ __device__ __forceinline__ float lds_f(uint32_t addr) {
     return v;
 }
 __device__ __forceinline__ void sts_u4(uint32_t addr, const uint4 &v) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    // volatile (ordered against the fences / mbarrier arrives, which are volatile too) but no "memory" clobber:
+    // ordinary loads of the surrounding loop may be scheduled across the store
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
 __device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
-    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v));
 }
 __device__ __forceinline__ void sts_f(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");

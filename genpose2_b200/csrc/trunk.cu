@@ -155,6 +155,7 @@ struct SimtEval {
     static __device__ __forceinline__ void forward(const float *P, const float *proj, Smem &S, Ctx &c, const float *tq) {
         tile_forward<RPT>(P, proj, S, c, tq);
     }
+    static __device__ __forceinline__ void report(Ctx &, double *) {}
 };
 
 template <int NPASS>
@@ -177,6 +178,13 @@ struct TcEval {
     static __device__ __forceinline__ void teardown(Smem &S, Ctx &c) { tc::teardown<NPASS>(S, c); }
     static __device__ __forceinline__ void forward(const float *P, const float *proj, Smem &S, Ctx &c, const float *tq) {
         tc::forward<NPASS>(P, proj, S, c, tq);
+    }
+    // phase cycle counters of epilogue thread 0 of CTA 0 (profiling aid, stats[8..13]; stats[14] = whole kernel)
+    static __device__ __forceinline__ void report(Ctx &c, double *stats) {
+        if (blockIdx.x == 0 && threadIdx.x == 64) {
+            stats[8] = (double)c.cyc_fwd; stats[9] = (double)c.cyc_l1; stats[10] = (double)c.cyc_wait1;
+            stats[11] = (double)c.cyc_epi1; stats[12] = (double)c.cyc_waith; stats[13] = (double)c.cyc_epi2;
+        }
     }
 };
 static_assert(sizeof(tc::Smem<3>) + 1024 <= 227 * 1024, "TC evaluator shared memory exceeds 227 KB");
@@ -313,6 +321,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
     const float *P = a.P;
     const int N = a.N;
     const double n_total = (double)N * 9.0;
+    const long long t_kernel0 = clock64();
     EV::setup(S, ctx, P);
     float *const tqtab = (EV::TQ_STAGES >= 6) ? EV::tq(S) : a.tq_ws + (size_t)blockIdx.x * 6 * 768;
     float *const xin = EV::xin(S);
@@ -586,7 +595,9 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
         a.stats[GP_STAT_T_FINAL] = t;
         a.stats[GP_STAT_H_INITIAL] = h_initial;
         a.stats[GP_STAT_H_LAST] = h_last;
+        a.stats[14] = (double)(clock64() - t_kernel0);
     }
+    EV::report(ctx, a.stats);
     EV::teardown(S, ctx);
 }
 

@@ -65,6 +65,8 @@ struct State {
     uint32_t dfull_phase[2] = {0, 0};  // epilogue: parity of the next d_full[i] completion
     float w1col[9];          // epilogue thread c: column c of the first pose-encoder layer
     float b1v;
+    // cycle counters of one epilogue thread (phase breakdown of an evaluation, reported through `stats`)
+    long long cyc_l1 = 0, cyc_wait1 = 0, cyc_epi1 = 0, cyc_waith = 0, cyc_epi2 = 0, cyc_fwd = 0;
 };
 
 __device__ __forceinline__ const uint8_t *chunk_src(const float *__restrict__ P, uint32_t q, int which) {
@@ -138,6 +140,7 @@ __device__ __forceinline__ void forward(const float *__restrict__ P, const float
     constexpr int NST = Smem<NPASS>::NSTAGE;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t tmem = S.tmem_base;
+    const long long t_begin = clock64();
 
     // ---- (proj + tq) table for the objects this tile spans (rows of an object are contiguous) ----
     if (tid == 0) {
@@ -226,26 +229,56 @@ __device__ __forceinline__ void forward(const float *__restrict__ P, const float
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
         const uint32_t A_hi = smem_u32(&S.abuf[0][0][0]);
         const uint32_t A_lo = smem_u32(&S.abuf[NPASS == 3 ? 1 : 0][0][0]);
-        const uint32_t sx = smem_u32(S.x), sb2 = smem_u32(S.b2);
+        // Views of S.x / S.b2 / S.E derived from the dynamic shared array itself: the compiler then knows the
+        // address space (LDS, freely schedulable) although S is only reachable through a generic pointer.
+        extern __shared__ __align__(16) unsigned char gp_dyn_smem[];
+        const uint32_t dyn0 = smem_u32(gp_dyn_smem);
+        const float *sx = reinterpret_cast<const float *>(gp_dyn_smem + (smem_u32(S.x) - dyn0));
+        const float *sb2 = reinterpret_cast<const float *>(gp_dyn_smem + (smem_u32(S.b2) - dyn0));
+        const float *sE = reinterpret_cast<const float *>(gp_dyn_smem + (smem_u32(S.E) - dyn0));
         // layer 1 (9 -> 256): this thread owns output column c for all 128 rows (weights in registers)
+        long long t0 = clock64();
         {
             const int c = tid - 64;
             // (row-independent part of the swizzled offset of column c)
             const int c_atom = (c >> 6) * ATOM_BYTES, c_unit = (c & 63) >> 3, c_byte = (c & 7) << 1;
-#pragma unroll 4
-            for (int r = 0; r < RT; ++r) {
-                const float4 xa = lds_f4(sx + r * 48);
-                const float4 xb = lds_f4(sx + r * 48 + 16);
-                const float xc = lds_f(sx + r * 48 + 32);
-                float a = st.b1v;
-                a = fmaf(xa.x, st.w1col[0], a); a = fmaf(xa.y, st.w1col[1], a); a = fmaf(xa.z, st.w1col[2], a);
-                a = fmaf(xa.w, st.w1col[3], a); a = fmaf(xb.x, st.w1col[4], a); a = fmaf(xb.y, st.w1col[5], a);
-                a = fmaf(xb.z, st.w1col[6], a); a = fmaf(xb.w, st.w1col[7], a); a = fmaf(xc, st.w1col[8], a);
-                a = fmaxf(a, 0.f);
-                const __nv_bfloat16 hi = __float2bfloat16_rn(a);
-                const int off = c_atom + r * 128 + ((c_unit ^ (r & 7)) << 4) + c_byte;
-                sts_u16(A_hi + off, __bfloat16_as_ushort(hi));
-                if (NPASS == 3) sts_u16(A_lo + off, __bfloat16_as_ushort(__float2bfloat16_rn(a - __bfloat162float(hi))));
+            for (int r0 = 0; r0 < RT; r0 += 4) {
+                // four rows at a time: four independent FMA chains instead of one 9-deep dependent chain per row
+                float4 xa[4], xb[4];
+                float xc[4], a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    xa[u] = *reinterpret_cast<const float4 *>(sx + (r0 + u) * 12);
+                    xb[u] = *reinterpret_cast<const float4 *>(sx + (r0 + u) * 12 + 4);
+                    xc[u] = sx[(r0 + u) * 12 + 8];
+                    a[u] = st.b1v;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = fmaf(xa[u].x, st.w1col[0], a[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = fmaf(xa[u].y, st.w1col[1], a[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = fmaf(xa[u].z, st.w1col[2], a[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = fmaf(xa[u].w, st.w1col[3], a[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = fmaf(xb[u].x, st.w1col[4], a[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = fmaf(xb[u].y, st.w1col[5], a[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = fmaf(xb[u].z, st.w1col[6], a[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = fmaf(xb[u].w, st.w1col[7], a[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = fmaxf(fmaf(xc[u], st.w1col[8], a[u]), 0.f);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = r0 + u;
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(a[u]);
+                    const int off = c_atom + r * 128 + ((c_unit ^ (r & 7)) << 4) + c_byte;
+                    sts_u16(A_hi + off, __bfloat16_as_ushort(hi));
+                    if (NPASS == 3) sts_u16(A_lo + off, __bfloat16_as_ushort(__float2bfloat16_rn(a[u] - __bfloat162float(hi))));
+                }
             }
             fence_proxy_async();
             // every epilogue thread has now read the inputs: S.x may be reused as the output buffer
@@ -254,8 +287,12 @@ __device__ __forceinline__ void forward(const float *__restrict__ P, const float
         }
         // layer 2 epilogue: h2 = relu(D1 + b2) -> A buffers
         {
+            long long t1 = clock64();
+            st.cyc_l1 += t1 - t0;
             mbar_wait(&S.d_full[0], st.dfull_phase[0]); st.dfull_phase[0] ^= 1;
             tc_fence_after();
+            t0 = clock64();
+            st.cyc_wait1 += t0 - t1;
             for (int g = 0; g < 4; ++g) {
                 uint32_t r[32];
                 tmem_ld32(lane_addr + c0 + g * 32, r);
@@ -264,7 +301,7 @@ __device__ __forceinline__ void forward(const float *__restrict__ P, const float
                     const int n0 = c0 + g * 32 + j8 * 8;
                     float v[8];
 #pragma unroll
-                    const float4 ba = lds_f4(sb2 + n0 * 4), bb = lds_f4(sb2 + n0 * 4 + 16);
+                    const float4 ba = *reinterpret_cast<const float4 *>(sb2 + n0), bb = *reinterpret_cast<const float4 *>(sb2 + n0 + 4);
                     const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r[j8 * 8 + j]) + bv[j], 0.f);
@@ -293,17 +330,27 @@ __device__ __forceinline__ void forward(const float *__restrict__ P, const float
             if (lane == 0) mbar_arrive(&S.a_ready);
         }
         // heads: z = relu(D + proj + tq), out = z . Wo^T over this thread's 128 columns
+        {
+            const long long t1 = clock64();
+            st.cyc_epi1 += t1 - t0;
+            t0 = t1;
+        }
         float acc[9];
 #pragma unroll
         for (int c = 0; c < 9; ++c) acc[c] = 0.f;
         const int o = S.obj[row];
-        const uint32_t erow = smem_u32(S.E + (use_E && o >= 0 ? o - slot_base : 0) * 768);
+        const float *erow = sE + (use_E && o >= 0 ? o - slot_base : 0) * 768;
         const float *prow = proj + (size_t)(o < 0 ? 0 : o) * 768;
 #pragma unroll 1
         for (int h = 0; h < 3; ++h) {
             const int buf = (h == 1) ? 0 : 1;
             mbar_wait(&S.d_full[buf], st.dfull_phase[buf]); st.dfull_phase[buf] ^= 1;
             tc_fence_after();
+            {
+                const long long t1 = clock64();
+                st.cyc_waith += t1 - t0;
+                t0 = t1;
+            }
             float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll 1
             for (int g = 0; g < 4; ++g) {
@@ -315,11 +362,11 @@ __device__ __forceinline__ void forward(const float *__restrict__ P, const float
                     // output-layer weights of 8 columns (L1 broadcast hits, independent of the accumulator)
                     float4 w[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) w[j] = __ldg(reinterpret_cast<const float4 *>(P + TrunkLayout::WO + (size_t)(nb + j8 * 8 + j) * 4));
+                    for (int j = 0; j < 8; ++j) w[j] = *reinterpret_cast<const float4 *>(P + TrunkLayout::WO + (size_t)(nb + j8 * 8 + j) * 4);
                     float ev[8];
                     if (use_E) {
-                        const float4 ea = lds_f4(erow + (nb + j8 * 8) * 4);
-                        const float4 eb = lds_f4(erow + (nb + j8 * 8) * 4 + 16);
+                        const float4 ea = *reinterpret_cast<const float4 *>(erow + nb + j8 * 8);
+                        const float4 eb = *reinterpret_cast<const float4 *>(erow + nb + j8 * 8 + 4);
                         ev[0] = ea.x; ev[1] = ea.y; ev[2] = ea.z; ev[3] = ea.w; ev[4] = eb.x; ev[5] = eb.y; ev[6] = eb.z; ev[7] = eb.w;
                     } else {
 #pragma unroll
@@ -333,6 +380,11 @@ __device__ __forceinline__ void forward(const float *__restrict__ P, const float
                 }
             }
             acc[h * 3 + 0] = a0; acc[h * 3 + 1] = a1; acc[h * 3 + 2] = a2;
+            {
+                const long long t1 = clock64();
+                st.cyc_epi2 += t1 - t0;
+                t0 = t1;
+            }
             if (h == 0) {  // cols 256..511 may now be overwritten by head 2
                 tc_fence_before();
                 __syncwarp();
@@ -351,6 +403,7 @@ __device__ __forceinline__ void forward(const float *__restrict__ P, const float
         }
     }
     __syncthreads();
+    st.cyc_fwd += clock64() - t_begin;
 }
 
 }  // namespace tc
