@@ -64,12 +64,22 @@ __global__ void pack_trunk_kernel(RawTrunk raw, float *__restrict__ P) {
             const size_t f = i - TrunkLayout::W_TC;
             const size_t per_img = 128 * 64 / 2;
             const size_t q = f / (2 * per_img), which = (f / per_img) % 2, o = (f % per_img) * 4;
-            const size_t gm = q / 8, kc = (q % 8) / 2, nh = q % 2;
             const size_t nl = o / 128, wb = o % 128;
             const size_t logical16 = (wb / 16) ^ (nl & 7);      // undo the SWIZZLE_128B XOR
-            const size_t k = kc * 64 + logical16 * 8 + (wb % 16) / 2;
-            const size_t n = nh * 128 + nl;
-            const float *src = gm == 0 ? p.pose_w1 + n * 256 + k : p.head_w0[gm - 1] + n * 1408 + 1152 + k;
+            const size_t kl = logical16 * 8 + (wb % 16) / 2;    // k inside the 64-wide atom (even)
+            float src[2] = {0.f, 0.f};
+            if (q < 2) {                 // pose_encoder.0: [256][9], zero-padded to k = 64
+                const size_t n = q * 128 + nl;
+                for (int t = 0; t < 2; ++t)
+                    if (kl + t < 9) src[t] = p.pose_w0[n * 9 + kl + t];
+            } else if (q < 10) {         // pose_encoder.2
+                const size_t kc = (q - 2) / 2, nh = (q - 2) % 2, n = nh * 128 + nl, k = kc * 64 + kl;
+                for (int t = 0; t < 2; ++t) src[t] = p.pose_w1[n * 256 + k + t];
+            } else {                     // head columns of one cluster rank, two k-atoms per image
+                const size_t r = (q - 10) / 6, hh = ((q - 10) % 6) / 2, j = (q - 10) % 2;
+                const size_t kc = 2 * j + nl / 64, n = 64 * r + nl % 64, k = kc * 64 + kl;
+                for (int t = 0; t < 2; ++t) src[t] = p.head_w0[hh][n * 1408 + 1152 + k + t];
+            }
             float e[2];
             for (int t = 0; t < 2; ++t) {
                 const float hi = __bfloat162float(__float2bfloat16_rn(src[t]));
@@ -137,7 +147,9 @@ template <int RPT>
 struct SimtEval {
     static constexpr int RT = 4 * RPT;
     static constexpr int NT = SIMT_THREADS;
-    static constexpr int TQ_STAGES = 6;   // t-branch stage slots held in shared memory
+    static constexpr int XS = 12;         // row stride of the input / output tile
+    static constexpr int TQW = 768;       // t-branch columns held per stage
+    static constexpr int CLUSTER = 1;     // CTAs that share a tile
     using Smem = TileSmem<RPT>;
     using Ctx = SimtCtx;
     static constexpr size_t smem_bytes() { return sizeof(Smem) + 16; }
@@ -145,13 +157,22 @@ struct SimtEval {
         // pointer arithmetic on the __shared__ array keeps the shared address space (LDS/STS, not generic LD/ST)
         return *reinterpret_cast<Smem *>(raw + ((16u - (tc::smem_u32(raw) & 15u)) & 15u));
     }
+    static __device__ __forceinline__ int tile_first() { return blockIdx.x; }
+    static __device__ __forceinline__ int tile_step() { return gridDim.x; }
+    static __device__ __forceinline__ bool writer(const Ctx &) { return true; }
+    static __device__ __forceinline__ void tile_sync() {}
     static __device__ __forceinline__ float *xin(Smem &S) { return S.x; }
     static __device__ __forceinline__ float *outp(Smem &S) { return S.out[0]; }
     static __device__ __forceinline__ float *tq(Smem &S) { return S.tq; }
-    static __device__ __forceinline__ float *four(Smem &S) { return S.four; }
-    static __device__ __forceinline__ float *tfeat(Smem &S) { return S.tfeat; }
     static __device__ __forceinline__ void setup(Smem &S, Ctx &c, const float *P) { simt_setup(S, c, P); }
     static __device__ __forceinline__ void teardown(Smem &S, Ctx &c) { simt_teardown(S, c); }
+    // t-branch of the ns stage times in S.times -> S.tq[ns][TQW]
+    static __device__ __forceinline__ void stage_tq(const float *P, Smem &S, Ctx &, int ns) {
+        compute_tq(P, S.times, ns, S.four, S.tfeat, S.tq);
+    }
+    static __device__ __forceinline__ void begin_tile(Smem &S, Ctx &, const float *, int r0, int N, int rpo) {
+        for (int r = threadIdx.x; r < RT; r += NT) S.obj[r] = (r0 + r < N) ? (r0 + r) / rpo : -1;
+    }
     static __device__ __forceinline__ void forward(const float *P, const float *proj, Smem &S, Ctx &c, const float *tq) {
         tile_forward<RPT>(P, proj, S, c, tq);
     }
@@ -162,20 +183,29 @@ template <int NPASS>
 struct TcEval {
     static constexpr int RT = tc::RT;
     static constexpr int NT = tc::NTHREADS;
-    static constexpr int TQ_STAGES = 1;   // one slot in shared memory; the integrator keeps its 6 in global
+    static constexpr int XS = tc::XS;
+    static constexpr int TQW = tc::NHC;   // only the head columns this cluster rank owns
+    static constexpr int CLUSTER = tc::CL;
     using Smem = tc::Smem<NPASS>;
     using Ctx = tc::State;
     static constexpr size_t smem_bytes() { return sizeof(Smem) + 1024; }
     static __device__ __forceinline__ Smem &smem(unsigned char *raw) {
         return *reinterpret_cast<Smem *>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     }
+    // the CTAs of a cluster work on the same tile and run the code around forward() replicated
+    static __device__ __forceinline__ int tile_first() { return (int)tc::cluster_id_x(); }
+    static __device__ __forceinline__ int tile_step() { return (int)tc::cluster_count_x(); }
+    static __device__ __forceinline__ bool writer(const Ctx &c) { return c.rank == 0; }
+    static __device__ __forceinline__ void tile_sync() { tc::cluster_arrive(); tc::cluster_wait(); }
     static __device__ __forceinline__ float *xin(Smem &S) { return S.x; }
-    static __device__ __forceinline__ float *outp(Smem &S) { return S.x; }   // out aliases the (dead) inputs
+    static __device__ __forceinline__ float *outp(Smem &S) { return S.x; }   // forward() overwrites its inputs
     static __device__ __forceinline__ float *tq(Smem &S) { return S.tq; }
-    static __device__ __forceinline__ float *four(Smem &S) { return S.E; }   // scratch between evaluations
-    static __device__ __forceinline__ float *tfeat(Smem &S) { return S.E + 768; }
     static __device__ __forceinline__ void setup(Smem &S, Ctx &c, const float *P) { tc::setup<NPASS>(S, c, P); }
     static __device__ __forceinline__ void teardown(Smem &S, Ctx &c) { tc::teardown<NPASS>(S, c); }
+    static __device__ __forceinline__ void stage_tq(const float *P, Smem &S, Ctx &c, int ns) { tc::compute_tq_rank<NPASS>(P, S, c, ns); }
+    static __device__ __forceinline__ void begin_tile(Smem &S, Ctx &c, const float *proj, int r0, int N, int rpo) {
+        tc::begin_tile<NPASS>(S, c, proj, r0, N, rpo);
+    }
     static __device__ __forceinline__ void forward(const float *P, const float *proj, Smem &S, Ctx &c, const float *tq) {
         tc::forward<NPASS>(P, proj, S, c, tq);
     }
@@ -194,23 +224,31 @@ static_assert(sizeof(tc::Smem<1>) + 1024 <= 227 * 1024, "TC evaluator shared mem
 // single evaluation / energy: one CTA per tile; rows may carry different t (handled by runs)
 // MODE 0: score = f/(std+1e-7) -> out [N,9];  MODE 1: energy [N,2] from f64 poses
 // ------------------------------------------------------------------------------------------
+struct EvalArgs {
+    const float *P, *proj, *x;
+    const double *poses;
+    const float *center, *t;
+    int N, rpo;
+    float *out;
+};
+
 template <class EV, int MODE>
-__global__ void __launch_bounds__(EV::NT, 1)
-eval_kernel(const float *__restrict__ P, const float *__restrict__ proj, const float *__restrict__ x,
-            const double *__restrict__ poses, const float *__restrict__ center,
-            const float *__restrict__ t, int N, int rpo, float *__restrict__ out) {
-    constexpr int RT = EV::RT, NT = EV::NT;
+__global__ void __launch_bounds__(EV::NT, 1) eval_kernel(EvalArgs a) {
+    const float *__restrict__ P = a.P, *__restrict__ proj = a.proj, *__restrict__ x = a.x;
+    const double *__restrict__ poses = a.poses;
+    const float *__restrict__ center = a.center, *__restrict__ t = a.t;
+    const int N = a.N, rpo = a.rpo;
+    float *__restrict__ out = a.out;
+    constexpr int RT = EV::RT, NT = EV::NT, XS = EV::XS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename EV::Smem &S = EV::smem(smem_raw);
     typename EV::Ctx ctx;
     const int tid = threadIdx.x;
-    const int r0 = blockIdx.x * RT;
+    const int r0 = EV::tile_first() * RT;
     EV::setup(S, ctx, P);
     __shared__ float s_trow[EV::RT];
-    for (int r = tid; r < RT; r += NT) {
-        S.obj[r] = (r0 + r < N) ? (r0 + r) / rpo : -1;
-        s_trow[r] = (r0 + r < N) ? t[r0 + r] : 0.f;
-    }
+    EV::begin_tile(S, ctx, proj, r0, N, rpo);
+    for (int r = tid; r < RT; r += NT) s_trow[r] = (r0 + r < N) ? t[r0 + r] : 0.f;
     __syncthreads();
     const int nrows = min(RT, N - r0);
     int run0 = 0;
@@ -220,8 +258,8 @@ eval_kernel(const float *__restrict__ P, const float *__restrict__ proj, const f
         while (run1 < nrows && s_trow[run1] == tv) ++run1;
         // (re)load the inputs: the evaluator may reuse the input buffer for its outputs
         float *xin = EV::xin(S);
-        for (int i = tid; i < RT * 12; i += NT) {
-            const int r = i / 12, c = i - 12 * r;
+        for (int i = tid; i < RT * XS; i += NT) {
+            const int r = i / XS, c = i - XS * r;
             float v = 0.f;
             if (r0 + r < N && c < 9) {
                 if (MODE == 0) {
@@ -239,16 +277,18 @@ eval_kernel(const float *__restrict__ P, const float *__restrict__ proj, const f
         float xr[9];  // this thread's row for the energy inner products (kept across the evaluation)
         if (MODE == 1) {
 #pragma unroll
-            for (int c = 0; c < 9; ++c) xr[c] = (run0 + tid < run1) ? xin[(run0 + tid) * 12 + c] : 0.f;
+            for (int c = 0; c < 9; ++c) xr[c] = (run0 + tid < run1) ? xin[(run0 + tid) * XS + c] : 0.f;
         }
-        compute_tq(P, S.times, 1, EV::four(S), EV::tfeat(S), EV::tq(S));
+        EV::stage_tq(P, S, ctx, 1);
         EV::forward(P, proj, S, ctx, EV::tq(S));
         const float *fo = EV::outp(S);
         const float std = sigma_f32(tv);
-        if (MODE == 0) {
+        if (!EV::writer(ctx)) {
+            // replicated CTAs of a cluster hold the same result; one of them stores it
+        } else if (MODE == 0) {
             for (int i = tid; i < (run1 - run0) * 9; i += NT) {
                 const int r = run0 + i / 9, c = i % 9;
-                out[(size_t)(r0 + r) * 9 + c] = fo[r * 12 + c] / (std + 1e-7f);
+                out[(size_t)(r0 + r) * 9 + c] = fo[r * XS + c] / (std + 1e-7f);
             }
         } else {
             static_assert(EV::RT <= EV::NT, "one thread per row");
@@ -256,9 +296,9 @@ eval_kernel(const float *__restrict__ P, const float *__restrict__ proj, const f
             if (r < run1) {
                 float er = 0.f, et = 0.f;
 #pragma unroll
-                for (int c = 0; c < 6; ++c) er += xr[c] * (fo[r * 12 + c] / std);
+                for (int c = 0; c < 6; ++c) er += xr[c] * (fo[r * XS + c] / std);
 #pragma unroll
-                for (int c = 6; c < 9; ++c) et += xr[c] * (fo[r * 12 + c] / std);
+                for (int c = 6; c < 9; ++c) et += xr[c] * (fo[r * XS + c] / std);
                 out[(size_t)(r0 + r) * 2 + 0] = er;
                 out[(size_t)(r0 + r) * 2 + 1] = et;
             }
@@ -312,7 +352,7 @@ __device__ __forceinline__ double grid_total(const double *part, int ntiles, dou
 
 template <class EV>
 __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
-    constexpr int RT = EV::RT, NT = EV::NT;
+    constexpr int RT = EV::RT, NT = EV::NT, XS = EV::XS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename EV::Smem &S = EV::smem(smem_raw);
     typename EV::Ctx ctx;
@@ -323,7 +363,8 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
     const double n_total = (double)N * 9.0;
     const long long t_kernel0 = clock64();
     EV::setup(S, ctx, P);
-    float *const tqtab = (EV::TQ_STAGES >= 6) ? EV::tq(S) : a.tq_ws + (size_t)blockIdx.x * 6 * 768;
+    const int tile0 = EV::tile_first(), tile_step = EV::tile_step();
+    float *const tqtab = EV::tq(S);
     float *const xin = EV::xin(S);
     const float *const fo = EV::outp(S);
 
@@ -337,7 +378,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
 
     // RHS of the rows whose float32 inputs sit in S.x -> K[kdst] (float64), scipy's `fun`
     auto stage_eval = [&](int tile, int tq_slot, double t_stage, int kdst) {
-        EV::forward(P, a.proj, S, ctx, tqtab + tq_slot * 768);
+        EV::forward(P, a.proj, S, ctx, tqtab + tq_slot * EV::TQW);
         const float tf = (float)t_stage;
         const float std = sigma_f32(tf);
         const double g = diffusion_f64(t_stage);
@@ -347,27 +388,24 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
         for (int i = tid; i < RT * 9; i += NT) {
             const int r = i / 9, c = i - 9 * r;
             if (r0 + r < N) {
-                const float sc = fo[r * 12 + c] / (std + 1e-7f);  // scorenet.py:262-264
+                const float sc = fo[r * XS + c] / (std + 1e-7f);  // scorenet.py:262-264
                 Kd[(size_t)(r0 + r) * 9 + c] = 0.0 - coef * (double)sc;  // samplers.py:219
             }
         }
         __syncthreads();
     };
-    auto set_obj = [&](int tile) {
-        const int r0 = tile * RT;
-        for (int r = tid; r < RT; r += NT) S.obj[r] = (r0 + r < N) ? (r0 + r) / a.rpo : -1;
-    };
+    auto set_obj = [&](int tile) { EV::begin_tile(S, ctx, a.proj, tile * RT, N, a.rpo); };
 
     // ---- f0 = fun(T, y0), d0, d1 (select_initial_step, common.py:68-134) ----
     double t = a.T;
     if (tid == 0) S.times[0] = (float)t;
     __syncthreads();
-    compute_tq(P, S.times, 1, EV::four(S), EV::tfeat(S), tqtab);
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    EV::stage_tq(P, S, ctx, 1);
+    for (int tile = tile0; tile < a.ntiles; tile += tile_step) {
         const int r0 = tile * RT;
         set_obj(tile);
-        for (int i = tid; i < RT * 12; i += NT) {
-            const int r = i / 12, c = i - 12 * r;
+        for (int i = tid; i < RT * XS; i += NT) {
+            const int r = i / XS, c = i - XS * r;
             float v = 0.f;
             if (r0 + r < N && c < 9) {
                 const double yv = a.x0[(size_t)(r0 + r) * 9 + c];
@@ -411,12 +449,12 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
         const double t1 = t + h0 * direction;
         if (tid == 0) S.times[0] = (float)t1;
         __syncthreads();
-        compute_tq(P, S.times, 1, EV::four(S), EV::tfeat(S), tqtab);
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        EV::stage_tq(P, S, ctx, 1);
+        for (int tile = tile0; tile < a.ntiles; tile += tile_step) {
             const int r0 = tile * RT;
             set_obj(tile);
-            for (int i = tid; i < RT * 12; i += NT) {
-                const int r = i / 12, c = i - 12 * r;
+            for (int i = tid; i < RT * XS; i += NT) {
+                const int r = i / XS, c = i - XS * r;
                 float v = 0.f;
                 if (r0 + r < N && c < 9) {
                     const size_t g = (size_t)(r0 + r) * 9 + c;
@@ -469,15 +507,15 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
             if (tid < 5) S.times[tid] = (float)(t + c_C[tid + 1] * h);
             if (tid == 5) S.times[5] = (float)(t + h);
             __syncthreads();
-            compute_tq(P, S.times, 6, EV::four(S), EV::tfeat(S), tqtab);
+            EV::stage_tq(P, S, ctx, 6);
 
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < a.ntiles; tile += tile_step) {
                 const int r0 = tile * RT;
                 set_obj(tile);
                 // rk_step (rk.py:14-78)
                 for (int s = 1; s <= 6; ++s) {
-                    for (int i = tid; i < RT * 12; i += NT) {
-                        const int r = i / 12, c = i - 12 * r;
+                    for (int i = tid; i < RT * XS; i += NT) {
+                        const int r = i / XS, c = i - XS * r;
                         float v = 0.f;
                         if (r0 + r < N && c < 9) {
                             const size_t g = (size_t)(r0 + r) * 9 + c;
@@ -547,14 +585,14 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
         if (a.denoise) {
             if (tid == 0) S.times[0] = eps_f;
             __syncthreads();
-            compute_tq(P, S.times, 1, EV::four(S), EV::tfeat(S), tqtab);
+            EV::stage_tq(P, S, ctx, 1);
         }
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < a.ntiles; tile += tile_step) {
             const int r0 = tile * RT;
             if (a.denoise) {
                 set_obj(tile);
-                for (int i = tid; i < RT * 12; i += NT) {
-                    const int r = i / 12, c = i - 12 * r;
+                for (int i = tid; i < RT * XS; i += NT) {
+                    const int r = i / XS, c = i - XS * r;
                     float v = 0.f;
                     if (r0 + r < N && c < 9) v = (float)ycur[(size_t)(r0 + r) * 9 + c];
                     xin[i] = v;
@@ -573,7 +611,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
                     const float step = (float)((1.0 - a.eps) / 1000.0);
 #pragma unroll
                     for (int c = 0; c < 9; ++c) {
-                        const float grad = fo[r * 12 + c] / (std + 1e-7f);
+                        const float grad = fo[r * XS + c] / (std + 1e-7f);
                         const float drift = 0.f - (dif * dif) * grad;
                         v[c] = v[c] + (double)(drift * step);
                     }
@@ -632,7 +670,7 @@ struct PcArgs {
 
 template <class EV>
 __global__ void __launch_bounds__(EV::NT, 1) pc_kernel(PcArgs a) {
-    constexpr int RT = EV::RT, NT = EV::NT;
+    constexpr int RT = EV::RT, NT = EV::NT, XS = EV::XS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename EV::Smem &S = EV::smem(smem_raw);
     typename EV::Ctx ctx;
@@ -640,6 +678,7 @@ __global__ void __launch_bounds__(EV::NT, 1) pc_kernel(PcArgs a) {
     const int tid = threadIdx.x, N = a.N;
     const float *P = a.P;
     EV::setup(S, ctx, P);
+    const int tile0 = EV::tile_first(), tile_step = EV::tile_step();
     float *const xin = EV::xin(S);
     const float *const fo = EV::outp(S);
     // grad of this CTA's tiles stays in global scratch between the two halves of a step: reuse
@@ -652,15 +691,16 @@ __global__ void __launch_bounds__(EV::NT, 1) pc_kernel(PcArgs a) {
         const float tv = a.time_steps[it];
         if (tid == 0) S.times[0] = tv;
         __syncthreads();
-        compute_tq(P, S.times, 1, EV::four(S), EV::tfeat(S), EV::tq(S));
+        EV::stage_tq(P, S, ctx, 1);
         const float std = sigma_f32(tv);
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < a.ntiles; tile += tile_step) {
             const int r0 = tile * RT;
-            for (int r = tid; r < RT; r += NT) S.obj[r] = (r0 + r < N) ? (r0 + r) / a.rpo : -1;
-            for (int i = tid; i < RT * 12; i += NT) {
-                const int r = i / 12, c = i - 12 * r;
+            EV::begin_tile(S, ctx, a.proj, r0, N, a.rpo);
+            for (int i = tid; i < RT * XS; i += NT) {
+                const int r = i / XS, c = i - XS * r;
                 float v = 0.f;
-                if (r0 + r < N && c < 9) v = (it == 0 ? a.x0 : a.x)[(size_t)(r0 + r) * 9 + c];
+                // the state is written by one CTA of the tile's cluster and read by all of them: L2 loads
+                if (r0 + r < N && c < 9) v = __ldcg((it == 0 ? a.x0 : a.x) + (size_t)(r0 + r) * 9 + c);
                 xin[i] = v;
             }
             __syncthreads();
@@ -671,7 +711,7 @@ __global__ void __launch_bounds__(EV::NT, 1) pc_kernel(PcArgs a) {
                 float ss = 0.f;
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {
-                    const float gv = fo[r * 12 + c] / (std + 1e-7f);
+                    const float gv = fo[r * XS + c] / (std + 1e-7f);
                     grad[(size_t)(r0 + r) * 9 + c] = gv;
                     ss += gv * gv;
                 }
@@ -692,9 +732,10 @@ __global__ void __launch_bounds__(EV::NT, 1) pc_kernel(PcArgs a) {
         const float dif = diffusion_f32(tv);
         const float *z1 = a.noise + ((size_t)it * 2 + 0) * N * 9;
         const float *z2 = a.noise + ((size_t)it * 2 + 1) * N * 9;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < a.ntiles; tile += tile_step) {
             const int r0 = tile * RT;
-            for (int r = tid; r < RT; r += NT) {
+            // the update overwrites what it reads (state, and grad kept in mean_x): one CTA per tile does it
+            for (int r = tid; r < RT && EV::writer(ctx); r += NT) {
                 if (r0 + r >= N) continue;
                 const size_t g = (size_t)(r0 + r) * 9;
                 float x[9], gr[9], m[9];
@@ -732,6 +773,7 @@ __global__ void __launch_bounds__(EV::NT, 1) pc_kernel(PcArgs a) {
             }
         }
         __syncthreads();
+        EV::tile_sync();
     }
     EV::teardown(S, ctx);
 }
@@ -739,26 +781,53 @@ __global__ void __launch_bounds__(EV::NT, 1) pc_kernel(PcArgs a) {
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static int coop_grid_limit(const void *kern, int threads, size_t smem) {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess) return 0;
-    return per_sm * num_sms();
+// Launch `kern` over tiles: `tiles` CTAs (evaluators without clusters) or `tiles` clusters of EV::CLUSTER CTAs.
+// Cooperative launches are clamped to what can be co-resident (tiles are then strided); returns the error code.
+template <class EV, class Kern, class Args>
+static int launch_tiles(Kern kern, int tiles, bool cooperative, Args &args, cudaStream_t st, const char *name) {
+    const size_t smem = EV::smem_bytes();
+    GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(EV::NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (EV::CLUSTER > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = EV::CLUSTER; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (cooperative) {
+        at[na].id = cudaLaunchAttributeCooperative;
+        at[na].val.cooperative = 1;
+        ++na;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = na;
+    int units = tiles;
+    if (cooperative) {
+        int limit = 0;
+        if (EV::CLUSTER > 1) {
+            cfg.gridDim = dim3(EV::CLUSTER * tiles);
+            if (cudaOccupancyMaxActiveClusters(&limit, kern, &cfg) != cudaSuccess) limit = 0;
+        } else {
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EV::NT, smem) == cudaSuccess) limit = per_sm * num_sms();
+        }
+        if (limit <= 0) { set_error("%s: kernel cannot be made resident", name); return GP_ERR_LAUNCH; }
+        if (units > limit) units = limit;
+    }
+    cfg.gridDim = dim3(EV::CLUSTER * units);
+    GP_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
+    count_launch();
+    return GP_OK;
 }
 
 template <class EV>
 static int launch_ode(OdeArgs &a, cudaStream_t st) {
     a.ntiles = (a.N + EV::RT - 1) / EV::RT;
-    const size_t smem = EV::smem_bytes();
-    auto kern = ode_rk45_kernel<EV>;
-    GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int limit = coop_grid_limit((const void *)kern, EV::NT, smem);
-    if (limit <= 0) { set_error("gp_scorenet_ode: kernel cannot be made resident"); return GP_ERR_LAUNCH; }
-    if (limit > 2 * num_sms() + 8) limit = 2 * num_sms() + 8;  // size of the per-CTA t-branch table
-    int grid = a.ntiles < limit ? a.ntiles : limit;
-    void *params[] = {&a};
-    GP_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(EV::NT), params, smem, st));
-    count_launch();
-    return GP_OK;
+    return launch_tiles<EV>(ode_rk45_kernel<EV>, a.ntiles, true, a, st, "gp_scorenet_ode");
 }
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -810,11 +879,10 @@ extern "C" int gp_trunk_project(const void *packed, const float *pts_feat, int B
 template <class EV, int MODE>
 static int launch_eval_ev(const void *packed, const float *proj, const float *x, const double *poses,
                           const float *center, const float *t, int N, int rpo, float *out, cudaStream_t st) {
-    const size_t smem = EV::smem_bytes();
-    auto kern = eval_kernel<EV, MODE>;
-    GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(N + EV::RT - 1) / EV::RT, EV::NT, smem, st>>>((const float *)packed, proj, x, poses, center, t, N, rpo, out);
-    return GP_OK;
+    EvalArgs a;
+    a.P = (const float *)packed; a.proj = proj; a.x = x; a.poses = poses; a.center = center; a.t = t;
+    a.N = N; a.rpo = rpo; a.out = out;
+    return launch_tiles<EV>(eval_kernel<EV, MODE>, (N + EV::RT - 1) / EV::RT, false, a, st, "gp_scorenet_eval");
 }
 
 template <int MODE>
@@ -827,9 +895,8 @@ static int launch_eval(const void *packed, const float *proj, const float *x, co
     else if (mode == 2) rc = launch_eval_ev<TcEval<3>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
     else if (N <= 16 * num_sms()) rc = launch_eval_ev<SimtEval<4>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
     else rc = launch_eval_ev<SimtEval<8>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
-    if (rc != GP_OK) return rc;
-    GP_CHECK_LAUNCH(name);
-    return GP_OK;
+    (void)name;
+    return rc;
 }
 
 extern "C" int gp_scorenet_eval(const void *packed, const float *proj, const float *x, const float *t,
@@ -915,16 +982,7 @@ extern "C" size_t gp_scorenet_pc_workspace_bytes(int N) {
 template <class EV>
 static int launch_pc(PcArgs &a, cudaStream_t st) {
     a.ntiles = (a.N + EV::RT - 1) / EV::RT;
-    const size_t smem = EV::smem_bytes();
-    auto kern = pc_kernel<EV>;
-    GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int limit = coop_grid_limit((const void *)kern, EV::NT, smem);
-    if (limit <= 0) { set_error("gp_scorenet_pc: kernel cannot be made resident"); return GP_ERR_LAUNCH; }
-    int grid = a.ntiles < limit ? a.ntiles : limit;
-    void *params[] = {&a};
-    GP_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(EV::NT), params, smem, st));
-    count_launch();
-    return GP_OK;
+    return launch_tiles<EV>(pc_kernel<EV>, a.ntiles, true, a, st, "gp_scorenet_pc");
 }
 
 extern "C" int gp_scorenet_pc(const void *packed, const float *proj, const float *x0, const float *noise,

@@ -29,12 +29,16 @@ struct TrunkLayout {
     static constexpr size_t WO = BH + 768;                     // [768][4]    (3 used) out weights
     static constexpr size_t BO = WO + 768 * 4;                 // [12]        (9 used)
     static constexpr size_t F32_END = BO + 12;
-    // bf16 B operands for the tensor-core path (tcgen05): 32 chunks x {hi, lo} ready-to-copy shared-memory
-    // images of [128 n][64 k] bf16 in the canonical K-major SWIZZLE_128B layout (16 KB each).  Chunk
-    // q = gemm*8 + k_atom*2 + n_half with gemm 0 = pose_encoder.2, 1..3 = heads (pose_feat columns);
+    // bf16 B operands for the tensor-core path (tcgen05): 34 chunks x {hi, lo} ready-to-copy shared-memory
+    // images of [128 rows][64 k] bf16 in the canonical K-major SWIZZLE_128B layout (16 KB each):
+    //   q = 0, 1          pose_encoder.0, n-half q (k < 9 populated)
+    //   q = 2 + 2*kc + nh pose_encoder.2, k-atom kc, n-half nh
+    //   q = 10 + 6*r + 2*h + j   head h, the 64 output columns owned by cluster rank r, rows 0..63 = k-atom 2j,
+    //                            rows 64..127 = k-atom 2j+1 (pose_feat columns of the first head layer)
     // lo = bf16(w - hi) for the split-bf16 (fp32-class) mode.  Offsets counted in floats; 1024-byte aligned.
+    static constexpr size_t TC_CHUNKS = 34;
     static constexpr size_t W_TC = (F32_END + 255) / 256 * 256;
-    static constexpr size_t END = W_TC + 32 * 2 * (128 * 64 / 2);
+    static constexpr size_t END = W_TC + TC_CHUNKS * 2 * (128 * 64 / 2);
 };
 
 constexpr float kFloatPi = 3.14159265358979323846f;  // np.pi cast to float32 by torch
@@ -61,8 +65,11 @@ __device__ __forceinline__ float diffusion_f32(float t) {
 // t-branch: tq[s][n] = Wh[:, 1024:1152] @ relu(Wt @ [sin, cos](t_s * W * 2pi) + bt), n < 768.
 // Whole block cooperates; ns <= 6 stage times; s_four/s_tfeat are [6][128] scratch.
 // --------------------------------------------------------------------------------------------
-__device__ __forceinline__ void compute_tq(const float *__restrict__ P, const float *s_times, int ns,
-                                           float *s_four, float *s_tfeat, float *s_tq) {
+// `ncols` head columns are produced; local column i is global column colmap(i) (a CTA of the tensor-core
+// cluster evaluator only needs the 3 x 64 columns it owns).  s_tq is [ns][ncols].
+template <class ColMap>
+__device__ __forceinline__ void compute_tq_cols(const float *__restrict__ P, const float *s_times, int ns,
+                                                float *s_four, float *s_tfeat, float *s_tq, int ncols, ColMap colmap) {
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < ns * 64; i += nt) {
         const int s = i >> 6, j = i & 63;
@@ -90,9 +97,9 @@ __device__ __forceinline__ void compute_tq(const float *__restrict__ P, const fl
         s_tfeat[i] = fmaxf(acc, 0.f);
     }
     __syncthreads();
-    for (int n = tid; n < 768; n += nt) {
+    for (int n = tid; n < ncols; n += nt) {
         float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        const float *w = P + TrunkLayout::WHT + n;
+        const float *w = P + TrunkLayout::WHT + colmap(n);
         for (int k0 = 0; k0 < 128; k0 += 16) {
             float wv[16];
 #pragma unroll
@@ -106,9 +113,13 @@ __device__ __forceinline__ void compute_tq(const float *__restrict__ P, const fl
         }
 #pragma unroll
         for (int s = 0; s < 6; ++s)
-            if (s < ns) s_tq[s * 768 + n] = acc[s];
+            if (s < ns) s_tq[s * ncols + n] = acc[s];
     }
     __syncthreads();
+}
+__device__ __forceinline__ void compute_tq(const float *__restrict__ P, const float *s_times, int ns,
+                                           float *s_four, float *s_tfeat, float *s_tq) {
+    compute_tq_cols(P, s_times, ns, s_four, s_tfeat, s_tq, 768, [](int n) { return n; });
 }
 
 // --------------------------------------------------------------------------------------------
