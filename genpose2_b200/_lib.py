@@ -79,7 +79,7 @@ SIGNATURES = {
                             c_void_p, c_void_p]),
 }
 
-GP_STAT_COUNT = 16
+GP_STAT_COUNT = 32
 STAT_NFEV, STAT_ACCEPTED, STAT_REJECTED, STAT_STATUS, STAT_T_FINAL, STAT_H_INITIAL, STAT_H_LAST = range(7)
 
 _lib = None

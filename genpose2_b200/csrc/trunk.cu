@@ -4,6 +4,8 @@
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "trunk_tc.cuh"
 
 namespace cg = cooperative_groups;
@@ -160,6 +162,7 @@ struct SimtEval {
     static __device__ __forceinline__ int tile_first() { return blockIdx.x; }
     static __device__ __forceinline__ int tile_step() { return gridDim.x; }
     static __device__ __forceinline__ bool writer(const Ctx &) { return true; }
+    static __device__ __forceinline__ size_t replica_index(const Ctx &) { return 0; }
     static __device__ __forceinline__ void tile_sync() {}
     static __device__ __forceinline__ float *xin(Smem &S) { return S.x; }
     static __device__ __forceinline__ float *outp(Smem &S) { return S.out[0]; }
@@ -168,7 +171,7 @@ struct SimtEval {
     static __device__ __forceinline__ void teardown(Smem &S, Ctx &c) { simt_teardown(S, c); }
     // t-branch of the ns stage times in S.times -> S.tq[ns][TQW]
     static __device__ __forceinline__ void stage_tq(const float *P, Smem &S, Ctx &, int ns) {
-        compute_tq(P, S.times, ns, S.four, S.tfeat, S.tq);
+        compute_tq(P, S.times, ns, S.tqs, S.tq);
     }
     static __device__ __forceinline__ void begin_tile(Smem &S, Ctx &, const float *, int r0, int N, int rpo) {
         for (int r = threadIdx.x; r < RT; r += NT) S.obj[r] = (r0 + r < N) ? (r0 + r) / rpo : -1;
@@ -196,6 +199,7 @@ struct TcEval {
     static __device__ __forceinline__ int tile_first() { return (int)tc::cluster_id_x(); }
     static __device__ __forceinline__ int tile_step() { return (int)tc::cluster_count_x(); }
     static __device__ __forceinline__ bool writer(const Ctx &c) { return c.rank == 0; }
+    static __device__ __forceinline__ size_t replica_index(const Ctx &c) { return c.rank; }
     static __device__ __forceinline__ void tile_sync() { tc::cluster_arrive(); tc::cluster_wait(); }
     static __device__ __forceinline__ float *xin(Smem &S) { return S.x; }
     static __device__ __forceinline__ float *outp(Smem &S) { return S.x; }   // forward() overwrites its inputs
@@ -338,8 +342,8 @@ struct OdeArgs {
     // workspace
     double *y[2];     // current / candidate state   [N][9]
     double *K[7];     // stage derivatives K[0..6]    [N][9]
+    size_t replica;   // doubles between the private copies of y / K of the CTAs that share a tile (cluster evaluator)
     double *part;     // [2][3][ntiles] partial sums
-    float *tq_ws;     // [grid][6][768] t-branch table for evaluators that keep only one stage in shared memory
     int ntiles;
 };
 
@@ -348,6 +352,116 @@ __device__ __forceinline__ double grid_total(const double *part, int ntiles, dou
     double v = 0.0;
     for (int i = threadIdx.x; i < ntiles; i += blockDim.x) v += __ldcg(part + i);
     return block_sum(v, s_red);
+}
+
+// The pieces of a Runge-Kutta step that touch the float64 state.  They are separate (not inlined) functions:
+// each gets its own register allocation (the integrator around them keeps ~100 live values) and the kernel's
+// code stays small -- it runs once per step, so instruction fetch matters.
+// inputs of stage S (1..5: y + h * sum_j a_Sj K_j; 6: y_new, also stored) for one tile -> xin (float32).
+// All loads of a thread are issued before any use: one memory round trip per stage.
+// 4 consecutive float64 values (32-byte aligned)
+struct D4 { double v[4]; };
+__device__ __forceinline__ D4 ld_d4(const double *p) {
+    const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
+    return D4{{a.x, a.y, b.x, b.y}};
+}
+
+// inputs of stage S (1..5: y + h * sum_j a_Sj K_j; 6: y_new, also stored) for one tile -> xin (float32).
+// Thread t owns elements 4t..4t+3 of the tile; its loads are unconditional (the buffers are padded to whole
+// tiles) and all issued before the first use: one memory round trip per stage.
+template <class EV, int S>
+__device__ __noinline__ void ode_stage_input(const double *y, double *ynew, const double *k0, const double *k1,
+                                             const double *k2, const double *k3, const double *k4, const double *k5,
+                                             float *xin, int tile, int N, double h) {
+    constexpr int RT = EV::RT, XS = EV::XS;
+    constexpr int NK = S < 6 ? S : 6;
+    static_assert(RT * 9 / 4 <= EV::NT && (RT * 9) % 4 == 0, "one quad per thread");
+    const int q = threadIdx.x;
+    if (q < RT * 9 / 4) {
+        const size_t g = (size_t)tile * RT * 9 + 4 * q;
+        const int nvalid = min(RT, N - tile * RT) * 9;
+        const double *const ks[6] = {k0, k1, k2, k3, k4, k5};
+        D4 kv[NK];
+        const D4 yv = ld_d4(y + g);
+#pragma unroll
+        for (int j = 0; j < NK; ++j) kv[j] = ld_d4(ks[j] + g);
+        float v[4];
+        D4 yn;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            double acc = 0.0;
+            if (S < 6) {
+#pragma unroll
+                for (int j = 0; j < NK; ++j) acc += kv[j].v[e] * c_A[S][j];
+                yn.v[e] = yv.v[e] + acc * h;  // dy = dot(K[:s].T, a[:s]) * h
+            } else {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) acc += kv[j].v[e] * c_B[j];
+                yn.v[e] = yv.v[e] + h * acc;  // y_new = y + h * dot(K[:-1].T, B)
+            }
+            v[e] = 4 * q + e < nvalid ? (float)yn.v[e] : 0.f;
+        }
+        if (S == 6) {
+            *reinterpret_cast<double2 *>(ynew + g) = make_double2(yn.v[0], yn.v[1]);
+            *reinterpret_cast<double2 *>(ynew + g + 2) = make_double2(yn.v[2], yn.v[3]);
+        }
+        if (XS == 9) {
+            *reinterpret_cast<float4 *>(xin + 4 * q) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) xin[((4 * q + e) / 9) * XS + (4 * q + e) % 9] = v[e];  // padding columns stay zero
+        }
+    }
+    __syncthreads();
+}
+
+// K_dst = -0.5 g(t)^2 * score for one tile (scipy's `fun`): score = f_theta / (std + 1e-7) (scorenet.py:262-264),
+// samplers.py:219
+template <class EV>
+__device__ __noinline__ void ode_store_k(const float *fo, double *Kd, int tile, int N, float std, double coef) {
+    constexpr int RT = EV::RT, NT = EV::NT, XS = EV::XS;
+    const int r0 = tile * RT;
+    for (int i = threadIdx.x; i < RT * 9; i += NT) {
+        const int r = i / 9, c = i - 9 * r;
+        if (r0 + r < N) {
+            const float sc = fo[r * XS + c] / (std + 1e-7f);
+            Kd[(size_t)(r0 + r) * 9 + c] = 0.0 - coef * (double)sc;
+        }
+    }
+    __syncthreads();
+}
+
+// this thread's share of sum((h * K^T E / scale)^2) over one tile (rk.py:139-147); candidate state -> traj_slot
+template <class EV>
+__device__ __noinline__ double ode_error_part(const double *y, const double *ynew, const double *k0, const double *k1,
+                                              const double *k2, const double *k3, const double *k4, const double *k5,
+                                              const double *k6, int tile, int N, double h, double atol, double rtol,
+                                              double *traj_slot) {
+    constexpr int RT = EV::RT;
+    const int q = threadIdx.x;
+    double se = 0.0;
+    if (q < RT * 9 / 4) {
+        const size_t g = (size_t)tile * RT * 9 + 4 * q;
+        const int nvalid = min(RT, N - tile * RT) * 9;
+        const double *const ks[7] = {k0, k1, k2, k3, k4, k5, k6};
+        D4 kv[7];
+        const D4 y0 = ld_d4(y + g), y1 = ld_d4(ynew + g);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) kv[j] = ld_d4(ks[j] + g);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            double ev = 0.0;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) ev += kv[j].v[e] * c_E[j];
+            ev *= h;
+            const double sc = atol + fmax(fabs(y0.v[e]), fabs(y1.v[e])) * rtol;
+            if (4 * q + e < nvalid) {
+                se += (ev / sc) * (ev / sc);
+                if (traj_slot) traj_slot[g + e] = y1.v[e];  // speculative: kept only if the step is accepted
+            }
+        }
+    }
+    return se;
 }
 
 template <class EV>
@@ -370,29 +484,31 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
 
     const double direction = (a.eps > a.T) ? 1.0 : ((a.eps < a.T) ? -1.0 : 1.0);
     const double t_bound = a.eps;
-    double *ycur = a.y[0], *ynew = a.y[1];
-    int kidx[7] = {0, 1, 2, 3, 4, 5, 6};  // K buffers: kidx[0] holds f(t, y) (FSAL)
+    // the CTAs of a cluster integrate the same tile redundantly, each on its own copy of the state
+    const size_t roff = EV::replica_index(ctx) * a.replica;
+    double *ycur = a.y[0] + roff, *ynew = a.y[1] + roff;
+    // stage derivatives: K0 holds f(t, y); K0 and K6 trade places when a step is accepted (FSAL)
+    double *K0 = a.K[0] + roff, *K6 = a.K[6] + roff;
+    double *const K1 = a.K[1] + roff, *const K2 = a.K[2] + roff, *const K3 = a.K[3] + roff, *const K4 = a.K[4] + roff,
+                 *const K5 = a.K[5] + roff;
+    __shared__ double s_coef[8];  // per stage of the current step: 0.5 g(t_s)^2 ...
+    __shared__ float s_std[8];    // ... and sigma(t_s) as the network sees it
+    long long cyc_tq = 0, cyc_x = 0, cyc_k = 0, cyc_err = 0;
     double nfev = 0, n_acc = 0, n_rej = 0;
     int status = 0;
     int pbuf = 0;
 
     // RHS of the rows whose float32 inputs sit in S.x -> K[kdst] (float64), scipy's `fun`
-    auto stage_eval = [&](int tile, int tq_slot, double t_stage, int kdst) {
+    // RHS of the rows whose float32 inputs sit in S.x -> Kd (float64), scipy's `fun`
+    auto stage_eval_c = [&](int tile, int tq_slot, float std, double coef, double *Kd) {
         EV::forward(P, a.proj, S, ctx, tqtab + tq_slot * EV::TQW);
-        const float tf = (float)t_stage;
-        const float std = sigma_f32(tf);
+        const long long tk0 = clock64();
+        ode_store_k<EV>(fo, Kd, tile, N, std, coef);
+        cyc_k += clock64() - tk0;
+    };
+    auto stage_eval = [&](int tile, int tq_slot, double t_stage, double *Kd) {
         const double g = diffusion_f64(t_stage);
-        const double coef = 0.5 * (g * g);
-        const int r0 = tile * RT;
-        double *Kd = a.K[kdst];
-        for (int i = tid; i < RT * 9; i += NT) {
-            const int r = i / 9, c = i - 9 * r;
-            if (r0 + r < N) {
-                const float sc = fo[r * XS + c] / (std + 1e-7f);  // scorenet.py:262-264
-                Kd[(size_t)(r0 + r) * 9 + c] = 0.0 - coef * (double)sc;  // samplers.py:219
-            }
-        }
-        __syncthreads();
+        stage_eval_c(tile, tq_slot, sigma_f32((float)t_stage), 0.5 * (g * g), Kd);
     };
     auto set_obj = [&](int tile) { EV::begin_tile(S, ctx, a.proj, tile * RT, N, a.rpo); };
 
@@ -416,13 +532,13 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
             xin[i] = v;
         }
         __syncthreads();
-        stage_eval(tile, 0, t, kidx[0]);
+        stage_eval(tile, 0, t, K0);
         double s0 = 0.0, s1 = 0.0;
         for (int i = tid; i < RT * 9; i += NT) {
             const int r = i / 9;
             if (r0 + r < N) {
                 const size_t g = (size_t)r0 * 9 + i;
-                const double yv = ycur[g], fv = a.K[kidx[0]][g];
+                const double yv = ycur[g], fv = K0[g];
                 const double sc = a.atol + fabs(yv) * a.rtol;
                 s0 += (yv / sc) * (yv / sc);
                 s1 += (fv / sc) * (fv / sc);
@@ -458,19 +574,19 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
                 float v = 0.f;
                 if (r0 + r < N && c < 9) {
                     const size_t g = (size_t)(r0 + r) * 9 + c;
-                    v = (float)(ycur[g] + h0 * direction * a.K[kidx[0]][g]);
+                    v = (float)(ycur[g] + h0 * direction * K0[g]);
                 }
                 xin[i] = v;
             }
             __syncthreads();
-            stage_eval(tile, 0, t1, kidx[1]);
+            stage_eval(tile, 0, t1, K1);
             double s2 = 0.0;
             for (int i = tid; i < RT * 9; i += NT) {
                 const int r = i / 9;
                 if (r0 + r < N) {
                     const size_t g = (size_t)r0 * 9 + i;
                     const double sc = a.atol + fabs(ycur[g]) * a.rtol;
-                    const double d = (a.K[kidx[1]][g] - a.K[kidx[0]][g]) / sc;
+                    const double d = (K1[g] - K0[g]) / sc;
                     s2 += d * d;
                 }
             }
@@ -504,67 +620,72 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
             h = t_new - t;
             h_abs = fabs(h);
 
-            if (tid < 5) S.times[tid] = (float)(t + c_C[tid + 1] * h);
-            if (tid == 5) S.times[5] = (float)(t + h);
+            const long long tq0 = clock64();
+            if (tid < 6) {
+                const double ts = tid < 5 ? t + c_C[tid + 1] * h : t + h;
+                S.times[tid] = (float)ts;
+            } else if (tid >= 32 && tid < 38) {   // the stage constants, one thread each (pow() is a long chain)
+                const int sI = tid - 32;
+                const double ts = sI < 5 ? t + c_C[sI + 1] * h : t + h;
+                s_std[sI] = sigma_f32((float)ts);
+            } else if (tid >= 64 && tid < 70) {
+                const int sI = tid - 64;
+                const double ts = sI < 5 ? t + c_C[sI + 1] * h : t + h;
+                const double g = diffusion_f64(ts);
+                s_coef[sI] = 0.5 * (g * g);
+            }
             __syncthreads();
             EV::stage_tq(P, S, ctx, 6);
+            cyc_tq += clock64() - tq0;
 
             for (int tile = tile0; tile < a.ntiles; tile += tile_step) {
-                const int r0 = tile * RT;
                 set_obj(tile);
                 // rk_step (rk.py:14-78)
-                for (int s = 1; s <= 6; ++s) {
-                    for (int i = tid; i < RT * XS; i += NT) {
-                        const int r = i / XS, c = i - XS * r;
-                        float v = 0.f;
-                        if (r0 + r < N && c < 9) {
-                            const size_t g = (size_t)(r0 + r) * 9 + c;
-                            double acc = 0.0;
-                            if (s < 6) {
-                                for (int j = 0; j < s; ++j) acc += a.K[kidx[j]][g] * c_A[s][j];
-                                v = (float)(ycur[g] + acc * h);  // dy = dot(K[:s].T, a[:s]) * h
-                            } else {
-                                for (int j = 0; j < 6; ++j) acc += a.K[kidx[j]][g] * c_B[j];
-                                const double yn = ycur[g] + h * acc;  // y_new = y + h * dot(K[:-1].T, B)
-                                ynew[g] = yn;
-                                v = (float)yn;
-                            }
-                        }
-                        xin[i] = v;
-                    }
-                    __syncthreads();
-                    const double ts = (s < 6) ? t + c_C[s] * h : t + h;
-                    stage_eval(tile, s - 1, ts, kidx[s]);
-                }
+                long long tx0 = clock64();
+                ode_stage_input<EV, 1>(ycur, ynew, K0, K1, K2, K3, K4, K5, xin, tile, N, h);
+                cyc_x += clock64() - tx0;
+                stage_eval_c(tile, 0, s_std[0], s_coef[0], K1);
+                tx0 = clock64();
+                ode_stage_input<EV, 2>(ycur, ynew, K0, K1, K2, K3, K4, K5, xin, tile, N, h);
+                cyc_x += clock64() - tx0;
+                stage_eval_c(tile, 1, s_std[1], s_coef[1], K2);
+                tx0 = clock64();
+                ode_stage_input<EV, 3>(ycur, ynew, K0, K1, K2, K3, K4, K5, xin, tile, N, h);
+                cyc_x += clock64() - tx0;
+                stage_eval_c(tile, 2, s_std[2], s_coef[2], K3);
+                tx0 = clock64();
+                ode_stage_input<EV, 4>(ycur, ynew, K0, K1, K2, K3, K4, K5, xin, tile, N, h);
+                cyc_x += clock64() - tx0;
+                stage_eval_c(tile, 3, s_std[3], s_coef[3], K4);
+                tx0 = clock64();
+                ode_stage_input<EV, 5>(ycur, ynew, K0, K1, K2, K3, K4, K5, xin, tile, N, h);
+                cyc_x += clock64() - tx0;
+                stage_eval_c(tile, 4, s_std[4], s_coef[4], K5);
+                tx0 = clock64();
+                ode_stage_input<EV, 6>(ycur, ynew, K0, K1, K2, K3, K4, K5, xin, tile, N, h);
+                cyc_x += clock64() - tx0;
+                stage_eval_c(tile, 5, s_std[5], s_coef[5], K6);
                 // error estimate (rk.py:139-147)
-                double se = 0.0;
-                for (int i = tid; i < RT * 9; i += NT) {
-                    const int r = i / 9;
-                    if (r0 + r < N) {
-                        const size_t g = (size_t)r0 * 9 + i;
-                        double e = 0.0;
-                        for (int j = 0; j < 7; ++j) e += a.K[kidx[j]][g] * c_E[j];
-                        e *= h;
-                        const double sc = a.atol + fmax(fabs(ycur[g]), fabs(ynew[g])) * a.rtol;
-                        se += (e / sc) * (e / sc);
-                        if (a.traj && (int)n_acc + 1 < a.max_traj)  // speculative: kept only if accepted
-                            a.traj[((size_t)((int)n_acc + 1) * N) * 9 + g] = ynew[g];
-                    }
-                }
+                const long long te0 = clock64();
+                double *traj_slot = (a.traj && (int)n_acc + 1 < a.max_traj) ? a.traj + ((size_t)((int)n_acc + 1) * N) * 9 : nullptr;
+                double se = ode_error_part<EV>(ycur, ynew, K0, K1, K2, K3, K4, K5, K6, tile, N, h, a.atol, a.rtol, traj_slot);
                 se = block_sum(se, S.red);
                 if (tid == 0) a.part[(pbuf * 3 + 0) * a.ntiles + tile] = se;
+                cyc_err += clock64() - te0;
             }
             nfev += 6;
+            const long long tg0 = clock64();
             grid.sync();
             const double error_norm = sqrt(grid_total(a.part + (pbuf * 3 + 0) * a.ntiles, a.ntiles, S.red) / n_total);
             pbuf ^= 1;
+            cyc_err += clock64() - tg0;
             if (error_norm < 1.0) {
                 double factor = (error_norm == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(error_norm, -0.2));
                 if (step_rejected) factor = fmin(1.0, factor);
                 h_abs *= factor;
                 // accept: y <- y_new, f <- f_new (FSAL: K[6] becomes K[0]); pointer rotation only
                 double *ty = ycur; ycur = ynew; ynew = ty;
-                const int k0 = kidx[0]; kidx[0] = kidx[6]; kidx[6] = k0;
+                double *tk = K0; K0 = K6; K6 = tk;
                 t = t_new;
                 h_last = h;
                 n_acc += 1;
@@ -634,6 +755,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
         a.stats[GP_STAT_H_INITIAL] = h_initial;
         a.stats[GP_STAT_H_LAST] = h_last;
         a.stats[14] = (double)(clock64() - t_kernel0);
+        a.stats[16] = (double)cyc_tq; a.stats[17] = (double)cyc_x; a.stats[18] = (double)cyc_k; a.stats[19] = (double)cyc_err;
     }
     EV::report(ctx, a.stats);
     EV::teardown(S, ctx);
@@ -917,13 +1039,14 @@ extern "C" int gp_energy(const void *packed, const float *proj, const double *po
     return launch_eval<1>(packed, proj, nullptr, poses, pts_center, t_rows, N, rows_per_object, energy, mode, as_stream(s), "gp_energy");
 }
 
-static size_t tq_table_bytes() { return (size_t)(2 * num_sms() + 8) * 6 * 768 * sizeof(float); }
+// one [N][9] float64 array, padded to whole 128-row tiles (the per-tile vector loads are unconditional)
+static size_t ode_state_bytes(int N) { return align256(((size_t)N + 127) / 128 * 128 * 9 * sizeof(double)); }
 
 extern "C" size_t gp_scorenet_ode_workspace_bytes(int N) {
     if (N < 0) return 0;
-    const size_t state = align256((size_t)N * 9 * sizeof(double));
+    const size_t state = ode_state_bytes(N);
     const size_t ntiles_max = (size_t)(N + 7) / 8 + 1;
-    return state * 9 + align256(2 * 3 * ntiles_max * sizeof(double)) + align256(tq_table_bytes()) + 256;
+    return state * 9 * tc::CL + align256(2 * 3 * ntiles_max * sizeof(double)) + 256;
 }
 
 extern "C" int gp_scorenet_ode(const void *packed, const float *proj, const double *x0, const float *pts_center,
@@ -946,12 +1069,13 @@ extern "C" int gp_scorenet_ode(const void *packed, const float *proj, const doub
     a.N = N; a.rpo = rows_per_object; a.T = T; a.eps = eps; a.rtol = rtol; a.atol = atol;
     a.denoise = denoise; a.x_out = x_out; a.traj = traj; a.max_traj = max_traj; a.stats = stats;
     unsigned char *w = (unsigned char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    const size_t state = align256((size_t)N * 9 * sizeof(double));
+    const size_t state = ode_state_bytes(N);
     a.y[0] = (double *)w; w += state;
     a.y[1] = (double *)w; w += state;
     for (int k = 0; k < 7; ++k) { a.K[k] = (double *)w; w += state; }
-    a.part = (double *)w; w += align256(2 * 3 * ((size_t)(N + 7) / 8 + 1) * sizeof(double));
-    a.tq_ws = (float *)w;
+    a.replica = 9 * state / sizeof(double);
+    w += (tc::CL - 1) * 9 * state;
+    a.part = (double *)w;
     cudaStream_t st = as_stream(s);
     const int sms = num_sms();
     if (mode == 1) return launch_ode<TcEval<1>>(a, st);

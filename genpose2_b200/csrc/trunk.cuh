@@ -63,52 +63,73 @@ __device__ __forceinline__ float diffusion_f32(float t) {
 
 // --------------------------------------------------------------------------------------------
 // t-branch: tq[s][n] = Wh[:, 1024:1152] @ relu(Wt @ [sin, cos](t_s * W * 2pi) + bt), n < 768.
-// Whole block cooperates; ns <= 6 stage times; s_four/s_tfeat are [6][128] scratch.
+// Whole block cooperates; ns <= 6 stage times.
 // --------------------------------------------------------------------------------------------
 // `ncols` head columns are produced; local column i is global column colmap(i) (a CTA of the tensor-core
-// cluster evaluator only needs the 3 x 64 columns it owns).  s_tq is [ns][ncols].
+// cluster evaluator only needs the 3 x 64 columns it owns).  s_tq is [ns][ncols]; `scratch` holds 2048 floats.
+// Runs once per step between evaluations, so it is written for latency: every thread keeps 32 independent
+// weight loads in flight, the stage values of one k sit in one 32-byte shared-memory row (two broadcast loads
+// feed six FMAs), and the loops stay rolled so the code is fetched once.
 template <class ColMap>
-__device__ __forceinline__ void compute_tq_cols(const float *__restrict__ P, const float *s_times, int ns,
-                                                float *s_four, float *s_tfeat, float *s_tq, int ncols, ColMap colmap) {
+__device__ __noinline__ void compute_tq_cols(const float *__restrict__ P, const float *s_times, int ns,
+                                             float *scratch, float *s_tq, int ncols, ColMap colmap) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int i = tid; i < ns * 64; i += nt) {
+    float *four8 = scratch, *tfeat8 = scratch + 1024;  // [128 k][8 stages]
+    const uint32_t four_a = tc::smem_u32(four8), tfeat_a = tc::smem_u32(tfeat8);
+    for (int i = tid; i < 8 * 64; i += nt) {
         const int s = i >> 6, j = i & 63;
-        // x[:, None] * W[None, :] * 2 * np.pi, left to right in float32 (scorenet.py:87)
-        const float arg = __fmul_rn(__fmul_rn(__fmul_rn(s_times[s], __ldg(P + TrunkLayout::FOUR + j)), 2.0f), kFloatPi);
-        float sn, cs;
-        sincosf(arg, &sn, &cs);
-        s_four[s * 128 + j] = sn;
-        s_four[s * 128 + 64 + j] = cs;
+        float sn = 0.f, cs = 0.f;
+        if (s < ns) {
+            // x[:, None] * W[None, :] * 2 * np.pi, left to right in float32 (scorenet.py:87)
+            const float arg = __fmul_rn(__fmul_rn(__fmul_rn(s_times[s], __ldg(P + TrunkLayout::FOUR + j)), 2.0f), kFloatPi);
+            sincosf(arg, &sn, &cs);
+        }
+        four8[j * 8 + s] = sn;
+        four8[(64 + j) * 8 + s] = cs;
     }
     __syncthreads();
-    for (int i = tid; i < ns * 128; i += nt) {
-        const int s = i >> 7, j = i & 127;
-        float acc = __ldg(P + TrunkLayout::BT + j);
-        const float *w = P + TrunkLayout::WTT + j;
-        const float *f = s_four + s * 128;
-        // the weight column is strided through L2: fetch 16 values at a time so the loads overlap
-        for (int k0 = 0; k0 < 128; k0 += 16) {
-            float wv[16];
+    // t_feat = relu(Wt . [sin, cos] + bt): thread pair (2j, 2j+1) splits k, all stages at once
+    if (tid < 256) {
+        const int j = tid >> 1, kp = tid & 1;
+        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const float *w = P + TrunkLayout::WTT + j + (size_t)(64 * kp) * 128;
+#pragma unroll 1
+        for (int b = 0; b < 2; ++b) {
+            float wv[32];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) wv[u] = __ldg(w + (k0 + u) * 128);
+            for (int u = 0; u < 32; ++u) wv[u] = __ldg(w + (b * 32 + u) * 128);
 #pragma unroll
-            for (int u = 0; u < 16; ++u) acc = fmaf(f[k0 + u], wv[u], acc);
+            for (int u = 0; u < 32; ++u) {
+                const uint32_t fa = four_a + (uint32_t)(64 * kp + b * 32 + u) * 32;
+                const float4 f0 = tc::lds_f4_sync(fa);
+                const float2 f1 = tc::lds_f2_sync(fa + 16);
+                acc[0] = fmaf(f0.x, wv[u], acc[0]); acc[1] = fmaf(f0.y, wv[u], acc[1]); acc[2] = fmaf(f0.z, wv[u], acc[2]);
+                acc[3] = fmaf(f0.w, wv[u], acc[3]); acc[4] = fmaf(f1.x, wv[u], acc[4]); acc[5] = fmaf(f1.y, wv[u], acc[5]);
+            }
         }
-        s_tfeat[i] = fmaxf(acc, 0.f);
+        const float bt = __ldg(P + TrunkLayout::BT + j);
+#pragma unroll
+        for (int s = 0; s < 6; ++s) {
+            const float v = acc[s] + __shfl_xor_sync(0xffffffffu, acc[s], 1);
+            if (kp == 0) tfeat8[j * 8 + s] = fmaxf(v + bt, 0.f);
+        }
     }
     __syncthreads();
     for (int n = tid; n < ncols; n += nt) {
         float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         const float *w = P + TrunkLayout::WHT + colmap(n);
-        for (int k0 = 0; k0 < 128; k0 += 16) {
-            float wv[16];
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {
+            float wv[32];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) wv[u] = __ldg(w + (k0 + u) * 768);
+            for (int u = 0; u < 32; ++u) wv[u] = __ldg(w + (b * 32 + u) * 768);
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-#pragma unroll
-                for (int s = 0; s < 6; ++s)
-                    if (s < ns) acc[s] = fmaf(s_tfeat[s * 128 + k0 + u], wv[u], acc[s]);
+            for (int u = 0; u < 32; ++u) {
+                const uint32_t fa = tfeat_a + (uint32_t)(b * 32 + u) * 32;
+                const float4 f0 = tc::lds_f4_sync(fa);
+                const float2 f1 = tc::lds_f2_sync(fa + 16);
+                acc[0] = fmaf(f0.x, wv[u], acc[0]); acc[1] = fmaf(f0.y, wv[u], acc[1]); acc[2] = fmaf(f0.z, wv[u], acc[2]);
+                acc[3] = fmaf(f0.w, wv[u], acc[3]); acc[4] = fmaf(f1.x, wv[u], acc[4]); acc[5] = fmaf(f1.y, wv[u], acc[5]);
             }
         }
 #pragma unroll
@@ -118,8 +139,8 @@ __device__ __forceinline__ void compute_tq_cols(const float *__restrict__ P, con
     __syncthreads();
 }
 __device__ __forceinline__ void compute_tq(const float *__restrict__ P, const float *s_times, int ns,
-                                           float *s_four, float *s_tfeat, float *s_tq) {
-    compute_tq_cols(P, s_times, ns, s_four, s_tfeat, s_tq, 768, [](int n) { return n; });
+                                           float *scratch, float *s_tq) {
+    compute_tq_cols(P, s_times, ns, scratch, s_tq, 768, [](int n) { return n; });
 }
 
 // --------------------------------------------------------------------------------------------
@@ -146,8 +167,7 @@ struct TileSmem {
     float out[2][RT * 12];  // per-half-warp-pair partial head outputs
     int obj[RT];            // object index of each row (-1: padding row)
     float tq[6 * 768];      // t-branch of up to 6 stage times
-    float four[6 * 128];
-    float tfeat[6 * 128];
+    float tqs[2048];        // compute_tq scratch
     float times[8];
     double red[16];
     unsigned long long full[W_NS], empty[W_NS];

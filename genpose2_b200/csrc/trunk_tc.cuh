@@ -61,12 +61,14 @@ struct Smem {
     static constexpr int NSTAGE = NPASS == 3 ? 2 : 4;
     uint8_t ring[NSTAGE][IMAGES][IMG_BYTES];  // 64 KB; the struct sits on a 1024-byte boundary
     uint8_t abuf[IMAGES][4][ATOM_BYTES];      // x / h1 / h2 as A operand (hi, lo), 4 k-atoms each
-    float part[CL][9 * RT];                   // [source rank][c][row] partial outputs, written by the whole cluster;
+    float part[CL - 1][9 * RT];               // [peer][c][row] partial outputs, written by the other CTAs of the cluster;
                                               // compute_tq scratch between evaluations
+    float4 wo[NHC];                           // output-layer weights of this rank's head columns
     float x[RT * XS];                         // inputs [RT][9]; overwritten with f_theta [RT][9] by forward()
     float pj[MAX_SLOTS * NHC];                // proj[obj][this rank's columns] for the objects of the tile
     float tq[6 * NHC];                        // t-branch, up to 6 stages x this rank's columns
     float b1[256], b2[256];
+    float bo[12];
     float times[8];
     double red[16];
     int obj[RT];
@@ -86,6 +88,9 @@ struct State {
     // cycle counters of one epilogue thread (phase breakdown of an evaluation, reported through `stats`)
     long long cyc_l1 = 0, cyc_wait1 = 0, cyc_epi1 = 0, cyc_waith = 0, cyc_epi2 = 0, cyc_fwd = 0;
 };
+
+// global head column (0..767) of this rank's local column i (0..191)
+__device__ __forceinline__ int head_col(uint32_t rank, int i) { return (i / HC) * 256 + HC * (int)rank + (i % HC); }
 
 __device__ __forceinline__ const uint8_t *chunk_src(const float *__restrict__ P, uint32_t q, int which) {
     return reinterpret_cast<const uint8_t *>(P + TrunkLayout::W_TC) + ((size_t)q * 2 + which) * IMG_BYTES;
@@ -117,6 +122,9 @@ __device__ __forceinline__ void setup(Smem<NPASS> &S, State &st, const float *__
         S.b1[i] = __ldg(P + TrunkLayout::B1 + i);
         S.b2[i] = __ldg(P + TrunkLayout::B2 + i);
     }
+    for (int i = tid; i < NHC; i += NTHREADS)
+        S.wo[i] = __ldg(reinterpret_cast<const float4 *>(P + TrunkLayout::WO) + head_col(st.rank, i));
+    if (tid < 12) S.bo[tid] = __ldg(P + TrunkLayout::BO + tid);
     __syncthreads();
     if (warp == 1) tmem_alloc(&S.tmem_base, TMEM_COLS);
     tc_fence_before();
@@ -156,15 +164,12 @@ __device__ __forceinline__ int a_offset(int row, int n) {
     return (n >> 6) * ATOM_BYTES + row * 128 + ((((n & 63) >> 3) ^ (row & 7)) << 4) + ((n & 7) << 1);
 }
 
-// global head column (0..767) of this rank's local column i (0..191)
-__device__ __forceinline__ int head_col(uint32_t rank, int i) { return (i / HC) * 256 + HC * (int)rank + (i % HC); }
-
 // t-branch of `ns` stage times into S.tq[ns][NHC] (this rank's columns only); whole block; scratch = S.part
 template <int NPASS>
 __device__ __forceinline__ void compute_tq_rank(const float *__restrict__ P, Smem<NPASS> &S, const State &st, int ns) {
     const uint32_t rank = st.rank;
-    float *scratch = &S.part[0][0];
-    compute_tq_cols(P, S.times, ns, scratch, scratch + 6 * 128, S.tq, NHC, [rank](int n) { return head_col(rank, n); });
+    static_assert(sizeof(S.part) >= 2048 * sizeof(float), "compute_tq scratch");
+    compute_tq_cols(P, S.times, ns, &S.part[0][0], S.tq, NHC, [rank](int n) { return head_col(rank, n); });
 }
 
 // rows r0.. of the batch become the current tile: object of every row and the proj columns this rank needs.
@@ -225,13 +230,14 @@ __device__ __forceinline__ void epi_hidden(uint32_t taddr, const float *sbias, i
 // f_theta for the 128 rows in S.x -> S.x [r*9 + c]; `tq` is this stage's t-branch (NHC floats in shared memory,
 // this rank's columns).  All 320 threads of all CL CTAs of the cluster call; ends with __syncthreads().
 template <int NPASS>
-__device__ __forceinline__ void forward(const float *__restrict__ P, const float *__restrict__ proj, Smem<NPASS> &S,
-                                        State &st, const float *tq) {
+__device__ __noinline__ void forward(const float *__restrict__ P, const float *__restrict__ proj, Smem<NPASS> &S,
+                                     State &st, const float *tq) {
     constexpr int NST = Smem<NPASS>::NSTAGE;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t tmem = S.tmem_base;
     const uint32_t rank = st.rank;
     const long long t_begin = clock64();
+    float acc[9];   // epilogue threads: this row's partial output over the thread's columns
 
     // cluster barrier A (arrive here, wait before the partial results are scattered): this CTA has consumed the
     // previous evaluation's partials and is done using S.part as scratch
@@ -333,7 +339,8 @@ __device__ __forceinline__ void forward(const float *__restrict__ P, const float
         const float *sb2 = reinterpret_cast<const float *>(gp_dyn_smem + (smem_u32(S.b2) - dyn0));
         const float *spj = reinterpret_cast<const float *>(gp_dyn_smem + (smem_u32(S.pj) - dyn0));
         const float *stq = reinterpret_cast<const float *>(gp_dyn_smem + (smem_u32(tq) - dyn0));
-        float *spart = reinterpret_cast<float *>(gp_dyn_smem + (smem_u32(&S.part[rank][0]) - dyn0));
+        const float4 *swo = reinterpret_cast<const float4 *>(gp_dyn_smem + (smem_u32(S.wo) - dyn0));
+        float *sxw = reinterpret_cast<float *>(gp_dyn_smem + (smem_u32(S.x) - dyn0));
 
         long long t0 = clock64();
         // inputs -> A operand: k 0..8 of atom 0 (k 9..15 zero), one row per thread of the first four warps
@@ -396,7 +403,6 @@ __device__ __forceinline__ void forward(const float *__restrict__ P, const float
         }
 
         // heads: z = relu(D + proj + tq), partial out = z . Wo^T over this thread's 32 columns of each head
-        float acc[9];
         const int o = S.obj[row];
         const bool use_pj = st.nslots <= MAX_SLOTS;
         const float *pjrow = spj + (use_pj && o >= 0 ? o - st.slot_base : 0) * NHC;
@@ -417,10 +423,10 @@ __device__ __forceinline__ void forward(const float *__restrict__ P, const float
             float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
-                // output-layer weights of 8 columns (L1 broadcast hits, independent of the accumulator)
+                // output-layer weights of 8 columns (shared-memory broadcasts)
                 float4 w[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) w[j] = *reinterpret_cast<const float4 *>(P + TrunkLayout::WO + (size_t)(gcol + j8 * 8 + j) * 4);
+                for (int j = 0; j < 8; ++j) w[j] = swo[cb + j8 * 8 + j];
                 float ev[8];
                 const float4 ta = *reinterpret_cast<const float4 *>(stq + cb + j8 * 8);
                 const float4 tb = *reinterpret_cast<const float4 *>(stq + cb + j8 * 8 + 4);
@@ -448,20 +454,23 @@ __device__ __forceinline__ void forward(const float *__restrict__ P, const float
             }
         }
         tc_fence_before();
-        // the two column halves of a row meet in this CTA's own slot, then the row's partial goes to every CTA
+        // the two column halves of a row meet through S.x (dead since the inputs were converted), then the row's
+        // partial goes to the three peers
         if (half == 1) {
 #pragma unroll
-            for (int c = 0; c < 9; ++c) spart[c * RT + row] = acc[c];
+            for (int c = 0; c < 9; ++c) sxw[c * RT + row] = acc[c];
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+        if (half == 0) {
+#pragma unroll
+            for (int c = 0; c < 9; ++c) acc[c] += sxw[c * RT + row];
+        }
         cluster_wait();                                 // barrier A: every CTA has consumed the previous partials
         if (half == 0) {
 #pragma unroll
-            for (int c = 0; c < 9; ++c) acc[c] += spart[c * RT + row];
-            const uint32_t base = smem_u32(&S.part[rank][row]);
-#pragma unroll
             for (uint32_t d = 0; d < (uint32_t)CL; ++d) {
-                const uint32_t ra = mapa(base, d);
+                if (d == rank) continue;
+                const uint32_t ra = mapa(smem_u32(&S.part[rank < d ? rank : rank - 1][row]), d);
 #pragma unroll
                 for (int c = 0; c < 9; ++c) st_cluster_f32(ra + c * RT * 4, acc[c]);
             }
@@ -470,10 +479,16 @@ __device__ __forceinline__ void forward(const float *__restrict__ P, const float
     // cluster barrier B: all partials of this evaluation have landed everywhere
     cluster_arrive();
     cluster_wait();
-    for (int i = tid; i < 9 * RT; i += NTHREADS) {
-        const int c = i >> 7, r = i & (RT - 1);
-        const float v = (S.part[0][i] + S.part[1][i]) + (S.part[2][i] + S.part[3][i]);
-        S.x[r * XS + c] = v + __ldg(P + TrunkLayout::BO + c);
+    if (warp >= 2 && warp < 6) {
+        // every CTA adds the four partials in rank order: bit-identical f_theta in the whole cluster
+        const int row = 32 * (warp & 3) + lane;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+            float p[CL];
+#pragma unroll
+            for (uint32_t s = 0; s < (uint32_t)CL; ++s) p[s] = s == rank ? acc[c] : S.part[s < rank ? s : s - 1][c * RT + row];
+            S.x[row * XS + c] = ((p[0] + p[1]) + (p[2] + p[3])) + S.bo[c];
+        }
     }
     __syncthreads();
     st.cyc_fwd += clock64() - t_begin;

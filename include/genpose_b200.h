@@ -187,7 +187,7 @@ enum gp_ode_stat {
     GP_STAT_T_FINAL = 4,
     GP_STAT_H_INITIAL = 5,
     GP_STAT_H_LAST = 6,
-    GP_STAT_COUNT = 16
+    GP_STAT_COUNT = 32
 };
 
 /* Bytes of device workspace gp_scorenet_ode needs for N rows. */
