@@ -109,6 +109,22 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
 }
 // split cluster barrier: every thread of every CTA in the cluster arrives / waits (warp-convergent)
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// bulk copy from this CTA's shared memory into a peer's (addresses from mapa), completing on the peer's mbarrier
+__device__ __forceinline__ void bulk_s2peer(uint32_t dst_cluster_addr, const void *src, uint32_t bytes, uint32_t bar_cluster_addr) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster_addr), "r"(smem_u32(src)), "r"(bytes), "r"(bar_cluster_addr) : "memory");
+}
+// the issuing thread blocks until the bulk copies it issued so far have read their sources
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// arrive on a peer's mbarrier without a memory fence (a credit: "your data has been consumed")
+__device__ __forceinline__ void mbar_arrive_peer_relaxed(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// arrival without a memory fence: for threads that published nothing the peers will read
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 // explicit shared-state-space accesses (32-bit shared addresses): used where a structure is only reachable

@@ -218,6 +218,7 @@ struct TcEval {
         if (blockIdx.x == 0 && threadIdx.x == 64) {
             stats[8] = (double)c.cyc_fwd; stats[9] = (double)c.cyc_l1; stats[10] = (double)c.cyc_wait1;
             stats[11] = (double)c.cyc_epi1; stats[12] = (double)c.cyc_waith; stats[13] = (double)c.cyc_epi2;
+            for (int i = 0; i < 5; ++i) stats[20 + i] = (double)c.cyc_x[i];
         }
     }
 };

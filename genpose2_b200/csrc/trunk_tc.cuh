@@ -73,6 +73,9 @@ struct Smem {
     double red[16];
     int obj[RT];
     unsigned long long full[NSTAGE], empty[NSTAGE], a_ready, dbar[5];
+    unsigned long long stage_ready;   // this CTA's combined partial sits in the staging area (4 warp arrivals)
+    unsigned long long xfull;         // the three peers' partials have landed in S.part (bulk-copy complete_tx)
+    unsigned long long xfree;         // the three peers have consumed what this CTA sent them (remote arrivals)
     uint32_t tmem_base;
 };
 
@@ -83,10 +86,12 @@ struct State {
     uint32_t a_phase = 0;    // MMA issuer: parity of the next a_ready completion
     uint32_t d_phase = 0;    // epilogue: parity of this evaluation's dbar completions
     uint32_t rank = 0;       // cluster rank = which 64 columns of every head
+    uint32_t evals = 0;      // evaluations done (parity of the exchange barriers)
     int tile_r0 = -1;        // tile whose obj / proj tables are loaded
     int slot_base = 0, nslots = 0;
     // cycle counters of one epilogue thread (phase breakdown of an evaluation, reported through `stats`)
     long long cyc_l1 = 0, cyc_wait1 = 0, cyc_epi1 = 0, cyc_waith = 0, cyc_epi2 = 0, cyc_fwd = 0;
+    long long cyc_x[5] = {0, 0, 0, 0, 0};  // tail: combine halves, barrier A, scatter, barrier B, final sum
 };
 
 // global head column (0..767) of this rank's local column i (0..191)
@@ -116,6 +121,9 @@ __device__ __forceinline__ void setup(Smem<NPASS> &S, State &st, const float *__
         for (int s = 0; s < NST; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
         mbar_init(&S.a_ready, 8);
         for (int i = 0; i < 5; ++i) mbar_init(&S.dbar[i], 1);
+        mbar_init(&S.stage_ready, 4);
+        mbar_init(&S.xfull, 1);
+        mbar_init(&S.xfree, CL - 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 256; i += NTHREADS) {
@@ -237,24 +245,34 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
     const uint32_t tmem = S.tmem_base;
     const uint32_t rank = st.rank;
     const long long t_begin = clock64();
+    long long tx = 0;
     float acc[9];   // epilogue threads: this row's partial output over the thread's columns
 
-    // cluster barrier A (arrive here, wait before the partial results are scattered): this CTA has consumed the
-    // previous evaluation's partials and is done using S.part as scratch
-    cluster_arrive();
+    const uint32_t xph = st.evals & 1;
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
         if (lane == 0) {
+            mbar_arrive_expect_tx(&S.xfull, (CL - 1) * 9 * RT * sizeof(float));  // this evaluation's incoming partials
             for (int i = 0; i < NCHUNK; ++i) {
                 const uint32_t L = st.loads;
                 mbar_wait(&S.empty[L % NST], ((L / NST) + 1) & 1);
                 issue_chunk<NPASS>(S, P, L, rank);
                 st.loads = L + 1;
             }
+            // exchange: once the combined partial of this CTA is staged and the peers have consumed the previous
+            // one, copy it into their S.part slot (async proxy, completes on their xfull: no thread fences)
+            mbar_wait(&S.stage_ready, xph);
+            if (st.evals > 0) mbar_wait(&S.xfree, xph ^ 1);
+            const float *stage = reinterpret_cast<const float *>(&S.abuf[0][0][0]);
+            for (uint32_t d = 0; d < (uint32_t)CL; ++d) {
+                if (d == rank) continue;
+                bulk_s2peer(mapa(smem_u32(&S.part[rank < d ? rank : rank - 1][0]), d), stage, 9 * RT * sizeof(float),
+                            mapa(smem_u32(&S.xfull), d));
+            }
+            bulk_wait_read();  // the staging area (A-operand buffer) is free again when forward() returns
         }
         __syncwarp();
-        cluster_wait();
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
@@ -319,7 +337,6 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
             }
         }
         __syncwarp();
-        cluster_wait();
     } else {
         // ---------------- epilogue warps ----------------
         const int e = warp - 2;
@@ -454,6 +471,7 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
             }
         }
         tc_fence_before();
+        tx = clock64();
         // the two column halves of a row meet through S.x (dead since the inputs were converted), then the row's
         // partial goes to the three peers
         if (half == 1) {
@@ -465,32 +483,41 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
 #pragma unroll
             for (int c = 0; c < 9; ++c) acc[c] += sxw[c * RT + row];
         }
-        cluster_wait();                                 // barrier A: every CTA has consumed the previous partials
+        { const long long t1 = clock64(); st.cyc_x[0] += t1 - tx; tx = t1; }
         if (half == 0) {
+            // stage the row's partial [c][row] in the (now idle) A-operand buffer for the producer thread's bulk copies
+            float *stage = reinterpret_cast<float *>(gp_dyn_smem + (smem_u32(&S.abuf[0][0][0]) - dyn0));
 #pragma unroll
-            for (uint32_t d = 0; d < (uint32_t)CL; ++d) {
-                if (d == rank) continue;
-                const uint32_t ra = mapa(smem_u32(&S.part[rank < d ? rank : rank - 1][row]), d);
+            for (int c = 0; c < 9; ++c) stage[c * RT + row] = acc[c];
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.stage_ready);
+            { const long long t1 = clock64(); st.cyc_x[2] += t1 - tx; tx = t1; }
+            // the peers' partials; every CTA adds the four in rank order: bit-identical f_theta in the whole cluster
+            mbar_wait(&S.xfull, xph);
+            // S.x turns from scratch into the output tile: every half-0 warp is past its scratch reads
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            { const long long t1 = clock64(); st.cyc_x[3] += t1 - tx; tx = t1; }
+            const float *spart = reinterpret_cast<const float *>(gp_dyn_smem + (smem_u32(&S.part[0][0]) - dyn0));
+            const float *sbo = reinterpret_cast<const float *>(gp_dyn_smem + (smem_u32(S.bo) - dyn0));
 #pragma unroll
-                for (int c = 0; c < 9; ++c) st_cluster_f32(ra + c * RT * 4, acc[c]);
+            for (int c = 0; c < 9; ++c) {
+                float p[CL];
+#pragma unroll
+                for (uint32_t s = 0; s < (uint32_t)CL; ++s)
+                    p[s] = s == rank ? acc[c] : spart[(s < rank ? s : s - 1) * 9 * RT + c * RT + row];
+                sxw[row * XS + c] = ((p[0] + p[1]) + (p[2] + p[3])) + sbo[c];
             }
         }
     }
-    // cluster barrier B: all partials of this evaluation have landed everywhere
-    cluster_arrive();
-    cluster_wait();
-    if (warp >= 2 && warp < 6) {
-        // every CTA adds the four partials in rank order: bit-identical f_theta in the whole cluster
-        const int row = 32 * (warp & 3) + lane;
-#pragma unroll
-        for (int c = 0; c < 9; ++c) {
-            float p[CL];
-#pragma unroll
-            for (uint32_t s = 0; s < (uint32_t)CL; ++s) p[s] = s == rank ? acc[c] : S.part[s < rank ? s : s - 1][c * RT + row];
-            S.x[row * XS + c] = ((p[0] + p[1]) + (p[2] + p[3])) + S.bo[c];
-        }
-    }
     __syncthreads();
+    // credit: this CTA has consumed the partials it received
+    if (tid == 32) {
+        for (uint32_t d = 0; d < (uint32_t)CL; ++d)
+            if (d != rank) mbar_arrive_peer_relaxed(mapa(smem_u32(&S.xfree), d));
+    }
+    st.evals += 1;
+    st.cyc_x[4] += clock64() - tx;
     st.cyc_fwd += clock64() - t_begin;
 }
 

@@ -19,4 +19,4 @@ for mode in ("bf16","fp32"):
     print(mode, "nfev", nf, "kernel cycles", st[14], "per eval", st[14]/nf)
     for n,v in zip(names, st[8:14]): print(f"   {n:12s} {v/nf:10.0f} cycles/eval")
     for n,v in zip(["stage_tq","stage_input","stage_K","err+gridsync"], st[16:20]): print(f"   {n:12s} {v/nf:10.0f} cycles/eval")
-    if st[23] > 0: print("   probe stage_input<6>: load", st[20]/st[23], "compute", st[21]/st[23], "sync", st[22]/st[23], "calls", st[23])
+    for n,v in zip(["x:combine","x:barrierA","x:scatter","x:barrierB","x:final"], st[20:25]): print(f"   {n:12s} {v/nf:10.0f} cycles/eval")
