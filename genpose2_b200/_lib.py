@@ -60,6 +60,9 @@ SIGNATURES = {
     "gp_gemm_gather_bias_relu": (c_int, [c_void_p, c_int, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_int,
                                          c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                          c_void_p, c_int, c_void_p]),
+    "gp_sa_mlp2_fused": (c_int, [c_void_p, c_int, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_int, c_int,
+                                 c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                 c_int, c_void_p]),
     "gp_trunk_packed_bytes": (c_size_t, []),
     "gp_trunk_pack": (c_int, [ctypes.POINTER(TrunkParams), c_void_p, c_void_p]),
     "gp_trunk_project": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

@@ -1,0 +1,365 @@
+// Layers 2 and 3 of a PointNet++ set-abstraction scale and its max-pool in ONE persistent tensor-core kernel
+// (P2/pointnet2_modules.py:45-66 on the rows produced by P2/pointnet2_utils.py:279-296):
+//
+//   A[r][k] = relu(P[batch(r) * n_src + gidx[r]][k] - Q[r / q_ns][k])          hoisted first layer, applied on the fly
+//   H       = relu(A . W1^T + b1)                                              [128 rows x c2], never leaves the SM
+//   out[g]  = max over the pool_ns rows of group g of relu(H . W2^T + b2)      [rows / pool_ns, c3]
+//
+// The (centre, sample) activation matrices of the reference -- c2 and c3 floats for each of B*npoint*nsample
+// rows -- never exist in HBM: a tile of 128 rows is gathered from the (L2 resident) per-point table P,
+// converted to bf16 (hi / lo) A-operand atoms in shared memory, multiplied on tcgen05 into TMEM, re-packed as
+// the next A operand by the epilogue warps, multiplied again and pooled straight out of TMEM.
+//
+// CTA = 10 warps, persistent over tiles: warp 0 streams the weight chunks (cp.async.bulk, [<=128 n][64 k]
+// images from the gp_gemm_pack layout) through a shared-memory ring and runs ahead across tiles; warp 1 issues
+// the MMAs (M128, N <= 128 per chunk, K16); warps 2..9 gather / convert / run both epilogues.
+// NPASS = 1: bf16 operands; NPASS = 3: split-bf16 (hi*hi + lo*hi + hi*lo), fp32-class.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace gp {
+namespace saf {
+
+using namespace gp::tc;
+
+constexpr int BM = 128;
+constexpr int NTHREADS = 320;
+constexpr int ATOM = 128 * 128;   // [128 rows][64 k] bf16
+constexpr int HALF = 128 * 128;   // weight chunk: up to [128 n][64 k] bf16
+
+struct Args {
+    const float *P;
+    int n_src, ldp;
+    const int *gidx;
+    long long R;
+    int rows_per_batch;
+    const float *Q;
+    int ldq, q_ns;
+    const uint8_t *W1p;
+    const float *b1;
+    int c1, c2;
+    const uint8_t *W2p;
+    const float *b2;
+    int c3;
+    int pool_ns;
+    float *pooled;
+    int ld_pooled;
+    int ntiles;
+};
+
+template <int NPASS>
+struct Cfg {
+    static constexpr int IMAGES = NPASS == 3 ? 2 : 1;
+    static constexpr int NST = NPASS == 3 ? 2 : 4;
+};
+
+__host__ __device__ inline int round16(int n) { return (n + 15) & ~15; }
+__host__ __device__ inline int atoms_of(int k) { return (k + 63) / 64; }
+
+// shared memory carve-up (bytes from a 1024-aligned base)
+template <int NPASS>
+struct Layout {
+    int natoms;
+    __host__ __device__ explicit Layout(int c1, int c2) : natoms(atoms_of(c1) > atoms_of(c2) ? atoms_of(c1) : atoms_of(c2)) {}
+    __host__ __device__ size_t ring() const { return 0; }
+    __host__ __device__ size_t abuf() const { return (size_t)Cfg<NPASS>::NST * Cfg<NPASS>::IMAGES * HALF; }
+    __host__ __device__ size_t bias() const { return abuf() + (size_t)Cfg<NPASS>::IMAGES * natoms * ATOM; }
+    __host__ __device__ size_t bars() const { return bias() + 512 * sizeof(float); }
+    __host__ __device__ size_t total() const { return bars() + 256 + 1024; }
+};
+
+// max over groups of GL consecutive rows (lanes) of 32 non-negative values per lane; lane (j % GL) of a group
+// keeps column j's result and stores it
+template <int GL>
+__device__ __forceinline__ void pool_store(const float (&v)[32], int lane, bool row_ok, long long grow, int ns, int nbase,
+                                           int N, float *pooled, int ld_pooled) {
+    constexpr int PER_LANE = 32 / GL;
+    const unsigned mask = GL == 32 ? 0xffffffffu : (((1u << GL) - 1u) << ((lane / GL) * GL));
+    float keep[PER_LANE];
+#pragma unroll
+    for (int q = 0; q < PER_LANE; ++q) keep[q] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const unsigned m = redux_max_u32(mask, __float_as_uint(v[j]));
+        if ((lane % GL) == (j % GL)) keep[j / GL] = __uint_as_float(m);
+    }
+    if (row_ok) {
+        const long long grp = grow / ns;
+#pragma unroll
+        for (int q = 0; q < PER_LANE; ++q) {
+            const int n = nbase + q * GL + (lane % GL);
+            if (n < N) pooled[grp * (long long)ld_pooled + n] = keep[q];
+        }
+    }
+}
+
+template <int NPASS>
+__global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
+    using C = Cfg<NPASS>;
+    constexpr int NST = C::NST, IM = C::IMAGES;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const Layout<NPASS> L(a.c1, a.c2);
+    uint8_t *ring = base + L.ring();
+    uint8_t *abuf = base + L.abuf();
+    float *sb1 = reinterpret_cast<float *>(base + L.bias());
+    float *sb2 = sb1 + 256;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(base + L.bars());
+    unsigned long long *full = bars, *empty = bars + NST, *a_ready = bars + 2 * NST, *dbar = bars + 2 * NST + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NST + 3);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k1 = atoms_of(a.c1), k2 = atoms_of(a.c2);
+    const int bn1 = round16(a.c2), bn2 = round16(a.c3);
+    const int nh1 = (bn1 + 127) / 128, nh2 = (bn2 + 127) / 128;
+    const int nper = k1 * nh1 + k2 * nh2;   // weight chunks per tile
+    const int my_tiles = a.ntiles > (int)blockIdx.x ? (a.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(a_ready, 8);
+        mbar_init(&dbar[0], 1);
+        mbar_init(&dbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 256; i += NTHREADS) {
+        sb1[i] = i < a.c2 ? __ldg(a.b1 + i) : 0.f;
+        sb2[i] = i < a.c3 ? __ldg(a.b2 + i) : 0.f;
+    }
+    __syncthreads();
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t abuf_a = smem_u32(abuf);
+
+    if (warp == 0) {
+        // ---------------- weight producer ----------------
+        if (lane == 0) {
+            const long long total = (long long)my_tiles * nper;
+            for (long long Lc = 0; Lc < total; ++Lc) {
+                const int s = (int)(Lc % NST);
+                if (Lc >= NST) mbar_wait(&empty[s], (uint32_t)((Lc / NST) + 1) & 1);
+                int i = (int)(Lc % nper);
+                const uint8_t *wp;
+                int bn, c, nh;
+                if (i < k1 * nh1) { wp = a.W1p; bn = bn1; c = i / nh1; nh = i % nh1; }
+                else { i -= k1 * nh1; wp = a.W2p; bn = bn2; c = i / nh2; nh = i % nh2; }
+                const uint32_t rows = (uint32_t)min(128, bn - 128 * nh);
+                const size_t img = (size_t)bn * 128;
+                mbar_arrive_expect_tx(&full[s], IM * rows * 128);
+                for (int w = 0; w < IM; ++w)
+                    bulk_g2s(ring + ((size_t)s * IM + w) * HALF, wp + ((size_t)c * IM + w) * img + (size_t)nh * HALF, rows * 128,
+                             &full[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            const uint32_t a_hi = abuf_a, a_lo = abuf_a + (NPASS == 3 ? L.natoms * ATOM : 0);
+            long long consumed = 0;
+            uint32_t a_phase = 0;
+            auto gemm = [&](int kat, int nh_cnt, int bn, uint32_t dcol) {
+                for (int c = 0; c < kat; ++c)
+                    for (int nh = 0; nh < nh_cnt; ++nh) {
+                        const int s = (int)(consumed % NST);
+                        mbar_wait(&full[s], (uint32_t)(consumed / NST) & 1);
+                        tc_fence_after();
+                        const uint32_t b_hi = smem_u32(ring + (size_t)s * IM * HALF);
+                        const uint32_t b_lo = b_hi + (NPASS == 3 ? HALF : 0);
+                        const uint32_t idesc = make_idesc_bf16(128, (uint32_t)min(128, bn - 128 * nh));
+                        const uint32_t d = tmem + dcol + nh * 128;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint32_t ao = c * ATOM + kk * 32, bo = kk * 32;
+                            umma_bf16(d, make_desc(a_hi + ao), make_desc(b_hi + bo), idesc, (c | kk) ? 1u : 0u);
+                            if (NPASS == 3) {
+                                umma_bf16(d, make_desc(a_lo + ao), make_desc(b_hi + bo), idesc, 1u);
+                                umma_bf16(d, make_desc(a_hi + ao), make_desc(b_lo + bo), idesc, 1u);
+                            }
+                        }
+                        umma_commit(&empty[s]);
+                        ++consumed;
+                    }
+            };
+            for (int t = 0; t < my_tiles; ++t) {
+                mbar_wait(a_ready, a_phase); a_phase ^= 1;   // gathered rows are in the A buffer
+                tc_fence_after();
+                gemm(k1, nh1, bn1, 0);
+                umma_commit(&dbar[0]);
+                mbar_wait(a_ready, a_phase); a_phase ^= 1;   // hidden activations are in the A buffer
+                tc_fence_after();
+                gemm(k2, nh2, bn2, 256);
+                umma_commit(&dbar[1]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------- gather / convert / epilogues ----------------
+        const int w = tid - 64;                    // 0..255
+        const int e = warp - 2;
+        const int quarter = warp & 3;              // TMEM lane quarter of this warp
+        const int half = e >> 2;                   // which 32-column groups (odd / even)
+        const int row = 32 * quarter + lane;       // epilogue row
+        const uint32_t lane_addr = tmem + ((uint32_t)(32 * quarter) << 16);
+        const uint32_t A_hi = abuf_a, A_lo = abuf_a + (NPASS == 3 ? L.natoms * ATOM : 0);
+        const int jv = w & 15;                     // float4 inside a 64-float chunk
+        const int rsub = w >> 4;                   // 0..15: row inside a pass
+        const int ns = a.pool_ns;
+        for (int t = 0; t < my_tiles; ++t) {
+            const long long row0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * BM;
+            const uint32_t dph = (uint32_t)t & 1;
+            // ---- gather: thread handles rows rsub + 16 p (p = 0..7), 16 bytes of every 64-float chunk ----
+            long long src[8];
+            int qoff[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const long long gr = row0 + rsub + 16 * p;
+                src[p] = -1;
+                qoff[p] = 0;
+                if (gr < a.R) {
+                    const int g32 = (int)gr;
+                    src[p] = ((long long)(g32 / a.rows_per_batch) * a.n_src + __ldg(a.gidx + gr)) * a.ldp;
+                    qoff[p] = (g32 / a.q_ns) * a.ldq;
+                }
+            }
+            for (int kc = 0; kc < k1; ++kc) {
+                const int k = kc * 64 + 4 * jv;
+                const bool k_ok = k < a.c1;
+                float4 pv[8], qv[8];
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    const bool ok = k_ok && src[p] >= 0;
+                    pv[p] = ok ? __ldg(reinterpret_cast<const float4 *>(a.P + src[p] + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    qv[p] = ok ? __ldg(reinterpret_cast<const float4 *>(a.Q + qoff[p] + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    const int rl = rsub + 16 * p;
+                    const uint32_t off = kc * ATOM + rl * 128 + (((jv >> 1) ^ (rl & 7)) << 4) + ((jv & 1) << 3);
+                    const float x0 = fmaxf(pv[p].x - qv[p].x, 0.f), x1 = fmaxf(pv[p].y - qv[p].y, 0.f);
+                    const float x2 = fmaxf(pv[p].z - qv[p].z, 0.f), x3 = fmaxf(pv[p].w - qv[p].w, 0.f);
+                    const __nv_bfloat162 h0 = __floats2bfloat162_rn(x0, x1), h1 = __floats2bfloat162_rn(x2, x3);
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(A_hi + off), "r"(*reinterpret_cast<const uint32_t *>(&h0)),
+                                 "r"(*reinterpret_cast<const uint32_t *>(&h1)));
+                    if (NPASS == 3) {
+                        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+                        const __nv_bfloat162 l0 = __floats2bfloat162_rn(x0 - f0.x, x1 - f0.y);
+                        const __nv_bfloat162 l1 = __floats2bfloat162_rn(x2 - f1.x, x3 - f1.y);
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(A_lo + off), "r"(*reinterpret_cast<const uint32_t *>(&l0)),
+                                     "r"(*reinterpret_cast<const uint32_t *>(&l1)));
+                    }
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
+
+            // ---- hidden layer: H = relu(D1 + b1) -> A buffer (zero beyond c2, up to whole k-atoms) ----
+            mbar_wait(&dbar[0], dph);
+            tc_fence_after();
+            for (int g = half; g < 2 * k2; g += 2) {
+                uint32_t r[32];
+                tmem_ld32(lane_addr + g * 32, r);
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    const int n0 = g * 32 + j8 * 8;
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = n0 + j < a.c2 ? fmaxf(__uint_as_float(r[j8 * 8 + j]) + sb1[n0 + j], 0.f) : 0.f;
+                    const __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+                    const __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+                    uint4 pk;
+                    pk.x = *reinterpret_cast<const uint32_t *>(&p0); pk.y = *reinterpret_cast<const uint32_t *>(&p1);
+                    pk.z = *reinterpret_cast<const uint32_t *>(&p2); pk.w = *reinterpret_cast<const uint32_t *>(&p3);
+                    const uint32_t off = (n0 >> 6) * ATOM + row * 128 + ((((n0 & 63) >> 3) ^ (row & 7)) << 4);
+                    sts_u4(A_hi + off, pk);
+                    if (NPASS == 3) {
+                        const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
+                        const float2 f2 = __bfloat1622float2(p2), f3 = __bfloat1622float2(p3);
+                        const __nv_bfloat162 l0 = __floats2bfloat162_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2bfloat162_rn(v[2] - f1.x, v[3] - f1.y);
+                        const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[4] - f2.x, v[5] - f2.y), l3 = __floats2bfloat162_rn(v[6] - f3.x, v[7] - f3.y);
+                        uint4 pl;
+                        pl.x = *reinterpret_cast<const uint32_t *>(&l0); pl.y = *reinterpret_cast<const uint32_t *>(&l1);
+                        pl.z = *reinterpret_cast<const uint32_t *>(&l2); pl.w = *reinterpret_cast<const uint32_t *>(&l3);
+                        sts_u4(A_lo + off, pl);
+                    }
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
+
+            // ---- output layer + max-pool over the pool_ns rows of each group ----
+            mbar_wait(&dbar[1], dph);
+            tc_fence_after();
+            const long long grow = row0 + row;
+            const bool row_ok = grow < a.R;
+            for (int g = half; g * 32 < a.c3; g += 2) {
+                uint32_t r[32];
+                tmem_ld32(lane_addr + 256 + g * 32, r);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = g * 32 + j;
+                    v[j] = (n < a.c3 && row_ok) ? fmaxf(__uint_as_float(r[j]) + sb2[n], 0.f) : 0.f;
+                }
+                if (ns == 32) pool_store<32>(v, lane, row_ok, grow, ns, g * 32, a.c3, a.pooled, a.ld_pooled);
+                else if (ns == 16) pool_store<16>(v, lane, row_ok, grow, ns, g * 32, a.c3, a.pooled, a.ld_pooled);
+                else pool_store<8>(v, lane, row_ok, grow, ns, g * 32, a.c3, a.pooled, a.ld_pooled);
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+template <int NPASS>
+static int launch(const Args &a, cudaStream_t st) {
+    const Layout<NPASS> L(a.c1, a.c2);
+    auto kern = sa_mlp2_kernel<NPASS>;
+    const size_t smem = L.total();
+    GP_REQUIRE(smem <= 227 * 1024, "gp_sa_mlp2_fused: layer widths need %zu bytes of shared memory", smem);
+    GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const int grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
+    kern<<<grid, NTHREADS, smem, st>>>(a);
+    GP_CHECK_LAUNCH("gp_sa_mlp2_fused");
+    return GP_OK;
+}
+
+}  // namespace saf
+}  // namespace gp
+
+using namespace gp;
+
+extern "C" int gp_sa_mlp2_fused(const float *P, int n_src, int ldp, const int32_t *gidx, long long R, int rows_per_batch,
+                                const float *Q, int ldq, int q_ns, const void *packed1, const float *bias1, int c1, int c2,
+                                const void *packed2, const float *bias2, int c3, int npass, int pool_ns, float *pooled,
+                                int ld_pooled, gp_stream_t s) {
+    GP_REQUIRE(R >= 0 && (npass == 1 || npass == 3), "gp_sa_mlp2_fused: bad arguments");
+    if (R == 0) return GP_OK;
+    GP_REQUIRE(P && gidx && Q && packed1 && bias1 && packed2 && bias2 && pooled, "gp_sa_mlp2_fused: null pointer");
+    GP_REQUIRE(c1 >= 4 && c1 <= 256 && (c1 & 3) == 0 && c2 >= 1 && c2 <= 256 && c3 >= 1 && c3 <= 256,
+               "gp_sa_mlp2_fused: widths must satisfy c1 %% 4 == 0 and c1, c2, c3 <= 256 (got %d, %d, %d)", c1, c2, c3);
+    GP_REQUIRE(ldp >= c1 && (ldp & 3) == 0 && ((uintptr_t)P & 15) == 0 && ldq >= c1 && (ldq & 3) == 0 && ((uintptr_t)Q & 15) == 0,
+               "gp_sa_mlp2_fused: P / Q rows must be 16-byte aligned and cover c1");
+    GP_REQUIRE(((uintptr_t)packed1 & 15) == 0 && ((uintptr_t)packed2 & 15) == 0, "gp_sa_mlp2_fused: packed weights must be 16-byte aligned");
+    GP_REQUIRE(rows_per_batch >= 1 && n_src >= 1 && q_ns >= 1, "gp_sa_mlp2_fused: bad gather geometry");
+    GP_REQUIRE((pool_ns == 8 || pool_ns == 16 || pool_ns == 32) && R % pool_ns == 0 && ld_pooled >= c3,
+               "gp_sa_mlp2_fused: pool_ns must be 8, 16 or 32 and divide R");
+    GP_REQUIRE(R < 2147483647LL && (R / q_ns + 1) * (long long)ldq < 2147483647LL, "gp_sa_mlp2_fused: too many rows");
+    saf::Args a;
+    a.P = P; a.n_src = n_src; a.ldp = ldp; a.gidx = gidx; a.R = R; a.rows_per_batch = rows_per_batch;
+    a.Q = Q; a.ldq = ldq; a.q_ns = q_ns;
+    a.W1p = (const uint8_t *)packed1; a.b1 = bias1; a.c1 = c1; a.c2 = c2;
+    a.W2p = (const uint8_t *)packed2; a.b2 = bias2; a.c3 = c3;
+    a.pool_ns = pool_ns; a.pooled = pooled; a.ld_pooled = ld_pooled;
+    a.ntiles = (int)((R + saf::BM - 1) / saf::BM);
+    return npass == 3 ? saf::launch<3>(a, as_stream(s)) : saf::launch<1>(a, as_stream(s));
+}

@@ -203,9 +203,14 @@ __device__ __forceinline__ void begin_tile(Smem<NPASS> &S, State &st, const floa
 // -> A operand buffers
 template <int NPASS>
 __device__ __forceinline__ void epi_hidden(uint32_t taddr, const float *sbias, int row, int c0, uint32_t A_hi, uint32_t A_lo) {
+    // two register buffers: the TMEM load of the next 32 columns is in flight while these are converted
+    // (tcgen05.ld is scoreboarded in hardware; the formal wait::ld before the first use compiles to nothing)
+    uint32_t r[2][32];
+    tmem_ld32_nowait(taddr + c0, r[0]);
+#pragma unroll
     for (int g = 0; g < 4; ++g) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c0 + g * 32, r);
+        if (g + 1 < 4) tmem_ld32_nowait(taddr + c0 + (g + 1) * 32, r[(g + 1) & 1]);
+        tmem_ld_wait();
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
             const int n0 = c0 + g * 32 + j8 * 8;
@@ -213,7 +218,7 @@ __device__ __forceinline__ void epi_hidden(uint32_t taddr, const float *sbias, i
             const float4 ba = *reinterpret_cast<const float4 *>(sbias + n0), bb = *reinterpret_cast<const float4 *>(sbias + n0 + 4);
             const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r[j8 * 8 + j]) + bv[j], 0.f);
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r[g & 1][j8 * 8 + j]) + bv[j], 0.f);
             const __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
             const __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
             uint4 pk;

@@ -219,6 +219,29 @@ def gemm_gather_bias_relu(P, n_src, gidx, rows_per_batch, Q, q_ns, packed, bias,
     return y
 
 
+def sa_mlp2_fused(P, n_src, gidx, rows_per_batch, Q, q_ns, packed1, bias1, c1, c2, packed2, bias2, c3, npass, pool_ns,
+                  pooled_out):
+    """pooled_out[g] = max_rows relu(relu(relu(P[gather] - Q) @ W1^T + b1) @ W2^T + b2)  (gp_sa_mlp2_fused):
+    the last two SharedMLP layers of a scale and its max-pool without materialising any (centre, sample) matrix."""
+    _lib.check_cuda(P, "P", torch.float32)
+    _lib.check_cuda(Q, "Q", torch.float32)
+    _lib.check_cuda(gidx, "gidx", torch.int32)
+    _lib.call("gp_sa_mlp2_fused", _lib.ptr(P), int(n_src), int(P.stride(0)), _lib.ptr(gidx), gidx.numel(),
+              int(rows_per_batch), _lib.ptr(Q), int(Q.stride(0)), int(q_ns), _lib.ptr(packed1), _lib.ptr(bias1), int(c1),
+              int(c2), _lib.ptr(packed2), _lib.ptr(bias2), int(c3), int(npass), int(pool_ns), _lib.ptr(pooled_out),
+              int(pooled_out.stride(-2)), device=P.device)
+    return pooled_out
+
+
+def sa_mlp2_fused_fits(c1, c2, c3, npass, pool_ns):
+    """Shape limits of gp_sa_mlp2_fused (widths and shared-memory budget)."""
+    if c1 % 4 or max(c1, c2, c3) > 256 or pool_ns not in (8, 16, 32):
+        return False
+    images, nst = (2, 2) if npass == 3 else (1, 4)
+    natoms = max((c1 + 63) // 64, (c2 + 63) // 64)
+    return nst * images * 16384 + images * natoms * 16384 + 2048 + 256 + 1024 <= 227 * 1024
+
+
 class QueryAndGroup(nn.Module):
     """pointnet2_utils.py:259-298."""
 

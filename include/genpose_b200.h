@@ -143,6 +143,18 @@ GP_API int gp_gemm_gather_bias_relu(const float *P, int n_src, int ldp, const in
                              const float *bias, int N, int K, int npass, float *Y, int ldy, int pool_ns,
                              float *pooled, int ld_pooled, gp_stream_t s);
 
+/* Layers 2 and 3 of a set-abstraction scale and its max-pool in one persistent kernel (P2/pointnet2_modules.py:
+ * 45-66): the gather of gp_gemm_gather_bias_relu, H = relu(A . W1^T + b1) kept on the SM (TMEM -> shared
+ * memory A operand), pooled[g] = max over the pool_ns rows of group g of relu(H . W2^T + b2).  The
+ * (centre, sample) activation matrices never exist in HBM.
+ *   packed1 = gp_gemm_pack(W1 [c2, c1]), packed2 = gp_gemm_pack(W2 [c3, c2]), same npass;
+ *   c1 %% 4 == 0, c1, c2, c3 <= 256 (and within the shared-memory budget: fails loudly otherwise);
+ *   pool_ns in {8, 16, 32}; pooled [R / pool_ns, ld_pooled], every element written once. */
+GP_API int gp_sa_mlp2_fused(const float *P, int n_src, int ldp, const int32_t *gidx, long long R, int rows_per_batch,
+                     const float *Q, int ldq, int q_ns, const void *packed1, const float *bias1, int c1, int c2,
+                     const void *packed2, const float *bias2, int c3, int npass, int pool_ns, float *pooled,
+                     int ld_pooled, gp_stream_t s);
+
 /* ---------------------------------------------------------------------------------------------
  * (2)(3) ScoreNet / EnergyNet trunk.  Raw parameters in the reference's state-dict layout
  * (SURVEY.md section 5): nn.Linear weights are [out,in] row-major.

@@ -55,26 +55,44 @@ def test_encoder_gemm_engines_vs_cpu_restatement(mode, tol):
 
 
 @pytest.mark.parametrize("npass,tol", [(3, 5e-5), (1, 3e-2)])
-def test_hoisted_scale_matches_direct_scale(npass, tol):
-    """the hoisted first layer + gather loader vs the direct (gather rows, 3 GEMMs) evaluation in float64"""
+@pytest.mark.parametrize("spec,ns,M", [((64, 96, 128), 16, 128),     # fused layers 2+3 (gp_sa_mlp2_fused), level-2 widths
+                                        ((128, 196, 256), 32, 100),   # fused, level-3 widths, partial last tile
+                                        ((64, 64, 128), 8, 128),      # fused, pool over 8
+                                        ((256, 384, 512), 16, 64)])   # too wide to fuse: gather GEMM + pooled GEMM
+def test_hoisted_scale_matches_direct_scale(npass, tol, spec, ns, M):
+    """the hoisted first layer + gather loader (+ fused layers 2, 3 and max-pool where the widths allow) vs the
+    direct (gather rows, 3 GEMMs, max) evaluation in float64"""
     from genpose2_b200 import pointnet2_utils as pu
     from genpose2_b200.pointnet2 import SharedMLP
-    B, N, M, ns, C = 3, 256, 128, 16, 96
+    B, N, C = 3, 256, 96
+    assert pu.sa_mlp2_fused_fits(*spec, npass, ns) == (max(spec) <= 256)
     g = torch.Generator().manual_seed(4)
     pts, _ = synthetic.make_point_clouds(B, N, seed=21)
     xyz = pts.cuda()
     idx, new_xyz = pu.furthest_point_sample_gather(xyz, M)
     bq = pu.ball_query(0.05, ns, xyz, new_xyz)
     feat_cl = torch.randn(B, N, C, generator=g).cuda()
-    mlp = SharedMLP([C + 3, 64, 96, 128]).cuda().eval()
-    sd = {k: v for k, v in synthetic.random_encoder_state_dict(3, prefix="").items() if k.startswith("SA_modules.1.mlps.1.")}
-    mlp.load_state_dict({k[len("SA_modules.1.mlps.1."):]: v for k, v in sd.items()})
+    mlp = SharedMLP([C + 3, *spec]).cuda().eval()
+    gw = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for name, prm in mlp.named_parameters():
+            if prm.dim() > 1:
+                prm.copy_(torch.randn(prm.shape, generator=gw) * (1.5 / prm.shape[1] ** 0.5))
+            elif name.endswith("weight"):
+                prm.copy_(torch.rand(prm.shape, generator=gw) + 0.5)
+            else:
+                prm.copy_(torch.randn(prm.shape, generator=gw) * 0.1)
+        for name, buf in mlp.named_buffers():
+            if name.endswith("running_var"):
+                buf.copy_(torch.rand(buf.shape, generator=gw) + 0.5)
+            elif name.endswith("running_mean"):
+                buf.copy_(torch.randn(buf.shape, generator=gw) * 0.1)
     rows = pu.group_rows(xyz, new_xyz, feat_cl, bq).double()
     h = rows
     for w, b in mlp._folded_layers():
         h = torch.relu(h @ w.double().t() + b.double())
     want = h.view(B * M, ns, -1).amax(1)
-    out = torch.empty(B * M, 128, device="cuda")
+    out = torch.full((B * M, spec[2]), -1.0, device="cuda")
     pts_rows = torch.cat([feat_cl, xyz, torch.zeros(B, N, 1, device="cuda")], -1).reshape(B * N, -1)
     mlp.forward_hoisted(pts_rows, N, new_xyz, bq, out, "bf16x3" if npass == 3 else "bf16")
     err = float((out.double() - want).abs().max() / want.abs().max())
