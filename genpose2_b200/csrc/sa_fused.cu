@@ -45,68 +45,87 @@ struct Args {
     float *pooled;
     int ld_pooled;
     int ntiles;
+    // launch configuration (host): ring stages, bytes per weight image slot, TMEM columns, TMEM column of D2
+    int nst, slot_bytes, tmem_cols, d2col;
+    int tile_in_batch;   // rows_per_batch % 128 == 0: all rows of a tile belong to one batch
+    int q_shift;         // log2(q_ns) if q_ns is a power of two, else -1
 };
 
 template <int NPASS>
 struct Cfg {
     static constexpr int IMAGES = NPASS == 3 ? 2 : 1;
-    static constexpr int NST = NPASS == 3 ? 2 : 4;
 };
+constexpr int MAX_NST = 4;
 
 __host__ __device__ inline int round16(int n) { return (n + 15) & ~15; }
 __host__ __device__ inline int atoms_of(int k) { return (k + 63) / 64; }
 
-// shared memory carve-up (bytes from a 1024-aligned base)
+// shared memory carve-up (bytes from a 1024-aligned base): weight ring | A buffer (= pool staging) | biases | barriers
 template <int NPASS>
 struct Layout {
-    int natoms;
-    __host__ __device__ explicit Layout(int c1, int c2) : natoms(atoms_of(c1) > atoms_of(c2) ? atoms_of(c1) : atoms_of(c2)) {}
+    int natoms, nst, slot;
+    __host__ __device__ Layout(int c1, int c2, int nst_, int slot_)
+        : natoms(atoms_of(c1) > atoms_of(c2) ? atoms_of(c1) : atoms_of(c2)), nst(nst_), slot(slot_) {}
     __host__ __device__ size_t ring() const { return 0; }
-    __host__ __device__ size_t abuf() const { return (size_t)Cfg<NPASS>::NST * Cfg<NPASS>::IMAGES * HALF; }
-    __host__ __device__ size_t bias() const { return abuf() + (size_t)Cfg<NPASS>::IMAGES * natoms * ATOM; }
+    __host__ __device__ size_t abuf() const { return (size_t)nst * Cfg<NPASS>::IMAGES * slot; }
+    // the A buffer doubles as the pooling stage (8 x [32][32] f32) once the second GEMM has read it
+    __host__ __device__ size_t abuf_bytes() const {
+        const size_t b = (size_t)Cfg<NPASS>::IMAGES * natoms * ATOM;
+        return b < 8 * 4096 ? 8 * 4096 : b;
+    }
+    __host__ __device__ size_t bias() const { return abuf() + abuf_bytes(); }
     __host__ __device__ size_t bars() const { return bias() + 512 * sizeof(float); }
     __host__ __device__ size_t total() const { return bars() + 256 + 1024; }
 };
 
-// max over groups of GL consecutive rows (lanes) of 32 non-negative values per lane; lane (j % GL) of a group
-// keeps column j's result and stores it
-template <int GL>
-__device__ __forceinline__ void pool_store(const float (&v)[32], int lane, bool row_ok, long long grow, int ns, int nbase,
-                                           int N, float *pooled, int ld_pooled) {
-    constexpr int PER_LANE = 32 / GL;
-    const unsigned mask = GL == 32 ? 0xffffffffu : (((1u << GL) - 1u) << ((lane / GL) * GL));
-    float keep[PER_LANE];
+// Max-pool of one warp's 32 rows x 32 columns block (v = this lane's row, values >= 0) over groups of `ns`
+// consecutive rows: transposed through a swizzled [32][32] shared-memory tile (bank = col ^ row on both sides),
+// then lane c reduces column c and stores it -- no cross-lane instructions, coalesced 128-byte stores.
+__device__ __forceinline__ void pool_block(const float (&v)[32], float *stg, int lane, long long grow0, long long R, int ns,
+                                           int nbase, int N, float *pooled, int ld_pooled) {
 #pragma unroll
-    for (int q = 0; q < PER_LANE; ++q) keep[q] = 0.f;
+    for (int j = 0; j < 32; ++j) stg[lane * 32 + (j ^ lane)] = v[j];
+    __syncwarp();
+    const int n = nbase + lane;
+    float m8[4];  // maxima of rows 0-7, 8-15, 16-23, 24-31 of column `lane` (all loads independent)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const unsigned m = redux_max_u32(mask, __float_as_uint(v[j]));
-        if ((lane % GL) == (j % GL)) keep[j / GL] = __uint_as_float(m);
+    for (int q = 0; q < 4; ++q) {
+        float t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = stg[(8 * q + i) * 32 + (lane ^ (8 * q + i))];
+        m8[q] = fmaxf(fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3])), fmaxf(fmaxf(t[4], t[5]), fmaxf(t[6], t[7])));
     }
-    if (row_ok) {
-        const long long grp = grow / ns;
+    if (n < N) {
+        if (ns == 32) {
+            if (grow0 < R) pooled[(grow0 / 32) * (long long)ld_pooled + n] = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+        } else if (ns == 16) {
+            if (grow0 < R) pooled[(grow0 / 16) * (long long)ld_pooled + n] = fmaxf(m8[0], m8[1]);
+            if (grow0 + 16 < R) pooled[(grow0 / 16 + 1) * (long long)ld_pooled + n] = fmaxf(m8[2], m8[3]);
+        } else {
 #pragma unroll
-        for (int q = 0; q < PER_LANE; ++q) {
-            const int n = nbase + q * GL + (lane % GL);
-            if (n < N) pooled[grp * (long long)ld_pooled + n] = keep[q];
+            for (int q = 0; q < 4; ++q)
+                if (grow0 + 8 * q < R) pooled[(grow0 / 8 + q) * (long long)ld_pooled + n] = m8[q];
         }
     }
+    __syncwarp();
 }
 
 template <int NPASS>
 __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
     using C = Cfg<NPASS>;
-    constexpr int NST = C::NST, IM = C::IMAGES;
+    constexpr int IM = C::IMAGES;
+    const int NST = a.nst;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const Layout<NPASS> L(a.c1, a.c2);
+    const Layout<NPASS> L(a.c1, a.c2, a.nst, a.slot_bytes);
     uint8_t *ring = base + L.ring();
     uint8_t *abuf = base + L.abuf();
+    float *stage_all = reinterpret_cast<float *>(abuf);
     float *sb1 = reinterpret_cast<float *>(base + L.bias());
     float *sb2 = sb1 + 256;
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(base + L.bars());
-    unsigned long long *full = bars, *empty = bars + NST, *a_ready = bars + 2 * NST, *dbar = bars + 2 * NST + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NST + 3);
+    unsigned long long *full = bars, *empty = bars + MAX_NST, *a_ready = bars + 2 * MAX_NST, *dbar = bars + 2 * MAX_NST + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_NST + 3);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int k1 = atoms_of(a.c1), k2 = atoms_of(a.c2);
@@ -127,7 +146,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
         sb2[i] = i < a.c3 ? __ldg(a.b2 + i) : 0.f;
     }
     __syncthreads();
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -150,8 +169,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
                 const size_t img = (size_t)bn * 128;
                 mbar_arrive_expect_tx(&full[s], IM * rows * 128);
                 for (int w = 0; w < IM; ++w)
-                    bulk_g2s(ring + ((size_t)s * IM + w) * HALF, wp + ((size_t)c * IM + w) * img + (size_t)nh * HALF, rows * 128,
-                             &full[s]);
+                    bulk_g2s(ring + ((size_t)s * IM + w) * a.slot_bytes, wp + ((size_t)c * IM + w) * img + (size_t)nh * HALF,
+                             rows * 128, &full[s]);
             }
         }
         __syncwarp();
@@ -167,8 +186,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
                         const int s = (int)(consumed % NST);
                         mbar_wait(&full[s], (uint32_t)(consumed / NST) & 1);
                         tc_fence_after();
-                        const uint32_t b_hi = smem_u32(ring + (size_t)s * IM * HALF);
-                        const uint32_t b_lo = b_hi + (NPASS == 3 ? HALF : 0);
+                        const uint32_t b_hi = smem_u32(ring + (size_t)s * IM * a.slot_bytes);
+                        const uint32_t b_lo = b_hi + (NPASS == 3 ? a.slot_bytes : 0);
                         const uint32_t idesc = make_idesc_bf16(128, (uint32_t)min(128, bn - 128 * nh));
                         const uint32_t d = tmem + dcol + nh * 128;
 #pragma unroll
@@ -191,7 +210,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
                 umma_commit(&dbar[0]);
                 mbar_wait(a_ready, a_phase); a_phase ^= 1;   // hidden activations are in the A buffer
                 tc_fence_after();
-                gemm(k2, nh2, bn2, 256);
+                gemm(k2, nh2, bn2, (uint32_t)a.d2col);
                 umma_commit(&dbar[1]);
             }
         }
@@ -208,22 +227,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
         const int jv = w & 15;                     // float4 inside a 64-float chunk
         const int rsub = w >> 4;                   // 0..15: row inside a pass
         const int ns = a.pool_ns;
+        // Rows rsub + 16 p (p = 0..7) of a tile belong to this thread's gather.  Their ball-query indices for tile
+        // t + 1 are requested while tile t is in its epilogues and only consumed at the next gather: the index load is
+        // the head of the gather's latency chain.
+        int gi[8];
+        auto request = [&](int t) {
+            const long long row0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * BM;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const long long gr = row0 + rsub + 16 * p;
+                gi[p] = -1;
+                if (t < my_tiles && gr < a.R) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(gi[p]) : "l"(a.gidx + gr));
+            }
+        };
+        request(0);
+        long long cy[6] = {0, 0, 0, 0, 0, 0};
+        long long tt = clock64();
+        auto lap = [&](int i) { const long long n = clock64(); cy[i] += n - tt; tt = n; };
         for (int t = 0; t < my_tiles; ++t) {
             const long long row0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * BM;
             const uint32_t dph = (uint32_t)t & 1;
             // ---- gather: thread handles rows rsub + 16 p (p = 0..7), 16 bytes of every 64-float chunk ----
             long long src[8];
             int qoff[8];
+            const int tile_batch = (int)(row0 / a.rows_per_batch);
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
-                const long long gr = row0 + rsub + 16 * p;
-                src[p] = -1;
-                qoff[p] = 0;
-                if (gr < a.R) {
-                    const int g32 = (int)gr;
-                    src[p] = ((long long)(g32 / a.rows_per_batch) * a.n_src + __ldg(a.gidx + gr)) * a.ldp;
-                    qoff[p] = (g32 / a.q_ns) * a.ldq;
-                }
+                const int g32 = (int)(row0 + rsub + 16 * p);
+                const int batch = a.tile_in_batch ? tile_batch : g32 / a.rows_per_batch;
+                const int qrow = a.q_shift >= 0 ? g32 >> a.q_shift : g32 / a.q_ns;
+                src[p] = gi[p] >= 0 ? ((long long)batch * a.n_src + gi[p]) * a.ldp : -1;
+                qoff[p] = gi[p] >= 0 ? qrow * a.ldq : 0;
             }
             for (int kc = 0; kc < k1; ++kc) {
                 const int k = kc * 64 + 4 * jv;
@@ -257,10 +291,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(a_ready);
+            lap(0);
+            request(t + 1);
+            lap(1);
 
             // ---- hidden layer: H = relu(D1 + b1) -> A buffer (zero beyond c2, up to whole k-atoms) ----
             mbar_wait(&dbar[0], dph);
             tc_fence_after();
+            lap(2);
             for (int g = half; g < 2 * k2; g += 2) {
                 uint32_t r[32];
                 tmem_ld32(lane_addr + g * 32, r);
@@ -295,37 +333,63 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
             if (lane == 0) mbar_arrive(a_ready);
 
             // ---- output layer + max-pool over the pool_ns rows of each group ----
+            lap(3);
             mbar_wait(&dbar[1], dph);
             tc_fence_after();
+            lap(4);
             const long long grow = row0 + row;
             const bool row_ok = grow < a.R;
             for (int g = half; g * 32 < a.c3; g += 2) {
                 uint32_t r[32];
-                tmem_ld32(lane_addr + 256 + g * 32, r);
+                tmem_ld32(lane_addr + a.d2col + g * 32, r);
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int n = g * 32 + j;
                     v[j] = (n < a.c3 && row_ok) ? fmaxf(__uint_as_float(r[j]) + sb2[n], 0.f) : 0.f;
                 }
-                if (ns == 32) pool_store<32>(v, lane, row_ok, grow, ns, g * 32, a.c3, a.pooled, a.ld_pooled);
-                else if (ns == 16) pool_store<16>(v, lane, row_ok, grow, ns, g * 32, a.c3, a.pooled, a.ld_pooled);
-                else pool_store<8>(v, lane, row_ok, grow, ns, g * 32, a.c3, a.pooled, a.ld_pooled);
+                pool_block(v, stage_all + e * 1024, lane, row0 + 32 * quarter, a.R, ns, g * 32, a.c3, a.pooled, a.ld_pooled);
             }
             tc_fence_before();
+            // the pooling stage lives in the A buffer: nobody gathers the next tile into it before all warps are done
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            lap(5);
         }
+#ifdef GP_SAF_PROBE
+        if (blockIdx.x == 0 && tid == 64)
+            printf("saf c=(%d,%d,%d) ns=%d tiles=%d per tile: gather %lld locate %lld wait_d0 %lld hidden %lld wait_d1 %lld pool %lld\n", a.c1, a.c2,
+                   a.c3, a.pool_ns, my_tiles, cy[0] / my_tiles, cy[1] / my_tiles, cy[2] / my_tiles, cy[3] / my_tiles, cy[4] / my_tiles, cy[5] / my_tiles);
+#endif
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 512);
+    if (warp == 1) tmem_dealloc(tmem, (uint32_t)a.tmem_cols);
 }
 
 template <int NPASS>
-static int launch(const Args &a, cudaStream_t st) {
-    const Layout<NPASS> L(a.c1, a.c2);
+static int launch(Args a, cudaStream_t st) {
+    constexpr int IM = Cfg<NPASS>::IMAGES;
+    const int bn1 = round16(a.c2), bn2 = round16(a.c3);
+    const int rows_max = (bn1 > bn2 ? bn1 : bn2) < 128 ? (bn1 > bn2 ? bn1 : bn2) : 128;
+    a.slot_bytes = rows_max * 128;
+    // D2 may reuse D1's TMEM columns (D1 is drained before the second GEMM starts): 256 columns per CTA
+    a.tmem_cols = 256;
+    a.d2col = 0;
+    a.tile_in_batch = a.rows_per_batch % BM == 0;
+    a.q_shift = -1;
+    for (int sh = 0; sh < 31; ++sh)
+        if ((1 << sh) == a.q_ns) a.q_shift = sh;
+    // one CTA per SM (its 10 warps are allocated as 12, two CTAs would leave 80 registers per thread); the weight
+    // ring is as deep as the shared memory allows
+    const size_t fixed = Layout<NPASS>(a.c1, a.c2, 0, a.slot_bytes).total();
+    const size_t stage = (size_t)IM * a.slot_bytes;
+    const size_t full_sm = 227 * 1024;
+    const int nst = fixed + stage <= full_sm ? (int)((full_sm - fixed) / stage) : 0;
+    GP_REQUIRE(nst >= 1, "gp_sa_mlp2_fused: layer widths need %zu bytes of shared memory", fixed + stage);
+    a.nst = nst > MAX_NST ? MAX_NST : nst;
+    const Layout<NPASS> L(a.c1, a.c2, a.nst, a.slot_bytes);
     auto kern = sa_mlp2_kernel<NPASS>;
     const size_t smem = L.total();
-    GP_REQUIRE(smem <= 227 * 1024, "gp_sa_mlp2_fused: layer widths need %zu bytes of shared memory", smem);
     GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const int grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
     kern<<<grid, NTHREADS, smem, st>>>(a);

@@ -1,14 +1,11 @@
 // ScoreNet / EnergyNet trunk kernels (FP32 path): weight packing, per-object head projection,
 // single evaluation, energy scoring, the device-resident Dormand-Prince (scipy-RK45-faithful)
 // integrator fused with the ScoreNet RHS, and the fixed-step predictor-corrector sampler.
-#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
-#include <type_traits>
+#include <cstdlib>
 
 #include "trunk_tc.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace gp {
 
@@ -345,8 +342,26 @@ struct OdeArgs {
     double *K[7];     // stage derivatives K[0..6]    [N][9]
     size_t replica;   // doubles between the private copies of y / K of the CTAs that share a tile (cluster evaluator)
     double *part;     // [2][3][ntiles] partial sums
+    unsigned int *gbar;  // grid barrier counter (zeroed before the launch)
     int ntiles;
 };
+
+// Grid-wide barrier of a launch whose CTAs are all resident (cooperative launch): one arrival per CTA on a
+// monotonically increasing counter (zeroed by the host before the launch), thread 0 spins on an acquire load.
+// `target` is this thread's running count of expected arrivals.
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int &target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();  // release: the CTA's global writes (made visible to thread 0 by the barrier above) first
+        atomicAdd(counter, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
 
 // sum part[0..ntiles) in a fixed order; identical in every CTA
 __device__ __forceinline__ double grid_total(const double *part, int ntiles, double *s_red) {
@@ -471,7 +486,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename EV::Smem &S = EV::smem(smem_raw);
     typename EV::Ctx ctx;
-    cg::grid_group grid = cg::this_grid();
+    unsigned int gbar_target = 0;
     const int tid = threadIdx.x;
     const float *P = a.P;
     const int N = a.N;
@@ -553,7 +568,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
         }
     }
     nfev += 1;
-    grid.sync();
+    grid_barrier(a.gbar, gbar_target);
     const double d0 = sqrt(grid_total(a.part + (pbuf * 3 + 0) * a.ntiles, a.ntiles, S.red) / n_total);
     const double d1 = sqrt(grid_total(a.part + (pbuf * 3 + 1) * a.ntiles, a.ntiles, S.red) / n_total);
     pbuf ^= 1;
@@ -595,7 +610,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
             if (tid == 0) a.part[(pbuf * 3 + 0) * a.ntiles + tile] = s2;
         }
         nfev += 1;
-        grid.sync();
+        grid_barrier(a.gbar, gbar_target);
     }
     const double d2 = sqrt(grid_total(a.part + (pbuf * 3 + 0) * a.ntiles, a.ntiles, S.red) / n_total) / h0;
     pbuf ^= 1;
@@ -676,7 +691,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
             }
             nfev += 6;
             const long long tg0 = clock64();
-            grid.sync();
+            grid_barrier(a.gbar, gbar_target);
             const double error_norm = sqrt(grid_total(a.part + (pbuf * 3 + 0) * a.ntiles, a.ntiles, S.red) / n_total);
             pbuf ^= 1;
             cyc_err += clock64() - tg0;
@@ -788,6 +803,7 @@ struct PcArgs {
     float *xs, *mean_x;
     float *x;      // [N][9] state
     double *part;  // [2][ntiles]
+    unsigned int *gbar;  // grid barrier counter (zeroed before the launch)
     int ntiles;
 };
 
@@ -797,7 +813,7 @@ __global__ void __launch_bounds__(EV::NT, 1) pc_kernel(PcArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename EV::Smem &S = EV::smem(smem_raw);
     typename EV::Ctx ctx;
-    cg::grid_group grid = cg::this_grid();
+    unsigned int gbar_target = 0;
     const int tid = threadIdx.x, N = a.N;
     const float *P = a.P;
     EV::setup(S, ctx, P);
@@ -844,7 +860,7 @@ __global__ void __launch_bounds__(EV::NT, 1) pc_kernel(PcArgs a) {
             if (tid == 0) a.part[pbuf * a.ntiles + tile] = sn;
             __syncthreads();
         }
-        grid.sync();
+        grid_barrier(a.gbar, gbar_target);
         const float grad_norm = (float)(grid_total(a.part + pbuf * a.ntiles, a.ntiles, S.red) / (double)N);
         pbuf ^= 1;
         // langevin_step_size = 2 * (snr * sqrt(9) / grad_norm) ** 2      (samplers.py:143-144).
@@ -921,7 +937,10 @@ static int launch_tiles(Kern kern, int tiles, bool cooperative, Args &args, cuda
         at[na].val.clusterDim.x = EV::CLUSTER; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
         ++na;
     }
-    if (cooperative) {
+    // GP_NONCOOPERATIVE_LAUNCH=1: same grid without the cooperative attribute, for profilers that cannot replay
+    // cooperative cluster launches (the grid is still clamped to what is co-resident on an otherwise idle GPU)
+    static const bool noncoop = getenv("GP_NONCOOPERATIVE_LAUNCH") && atoi(getenv("GP_NONCOOPERATIVE_LAUNCH")) != 0;
+    if (cooperative && !noncoop) {
         at[na].id = cudaLaunchAttributeCooperative;
         at[na].val.cooperative = 1;
         ++na;
@@ -1047,7 +1066,7 @@ extern "C" size_t gp_scorenet_ode_workspace_bytes(int N) {
     if (N < 0) return 0;
     const size_t state = ode_state_bytes(N);
     const size_t ntiles_max = (size_t)(N + 7) / 8 + 1;
-    return state * 9 * tc::CL + align256(2 * 3 * ntiles_max * sizeof(double)) + 256;
+    return state * 9 * tc::CL + align256(2 * 3 * ntiles_max * sizeof(double)) + 256 /*barrier*/ + 256;
 }
 
 extern "C" int gp_scorenet_ode(const void *packed, const float *proj, const double *x0, const float *pts_center,
@@ -1076,8 +1095,10 @@ extern "C" int gp_scorenet_ode(const void *packed, const float *proj, const doub
     for (int k = 0; k < 7; ++k) { a.K[k] = (double *)w; w += state; }
     a.replica = 9 * state / sizeof(double);
     w += (tc::CL - 1) * 9 * state;
-    a.part = (double *)w;
+    a.part = (double *)w; w += align256(2 * 3 * ((size_t)(N + 7) / 8 + 1) * sizeof(double));
+    a.gbar = (unsigned int *)w;
     cudaStream_t st = as_stream(s);
+    GP_CUDA(cudaMemsetAsync(a.gbar, 0, 256, st));
     const int sms = num_sms();
     if (mode == 1) return launch_ode<TcEval<1>>(a, st);
     if (mode == 2) return launch_ode<TcEval<3>>(a, st);
@@ -1101,7 +1122,7 @@ extern "C" int gp_traj_finalize(const double *traj, const float *pts_center, int
 
 extern "C" size_t gp_scorenet_pc_workspace_bytes(int N) {
     if (N < 0) return 0;
-    return align256((size_t)N * 9 * sizeof(float)) + align256(2 * ((size_t)(N + 7) / 8 + 1) * sizeof(double)) + 256;
+    return align256((size_t)N * 9 * sizeof(float)) + align256(2 * ((size_t)(N + 7) / 8 + 1) * sizeof(double)) + 256 /*barrier*/ + 256;
 }
 
 template <class EV>
@@ -1127,8 +1148,10 @@ extern "C" int gp_scorenet_pc(const void *packed, const float *proj, const float
     a.xs = xs; a.mean_x = mean_x;
     unsigned char *w = (unsigned char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     a.x = (float *)w; w += align256((size_t)N * 9 * sizeof(float));
-    a.part = (double *)w;
+    a.part = (double *)w; w += align256(2 * ((size_t)(N + 7) / 8 + 1) * sizeof(double));
+    a.gbar = (unsigned int *)w;
     cudaStream_t st = as_stream(s);
+    GP_CUDA(cudaMemsetAsync(a.gbar, 0, 256, st));
     const int sms = num_sms();
     if (mode == 1) return launch_pc<TcEval<1>>(a, st);
     if (mode == 2) return launch_pc<TcEval<3>>(a, st);

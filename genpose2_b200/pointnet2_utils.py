@@ -237,9 +237,10 @@ def sa_mlp2_fused_fits(c1, c2, c3, npass, pool_ns):
     """Shape limits of gp_sa_mlp2_fused (widths and shared-memory budget)."""
     if c1 % 4 or max(c1, c2, c3) > 256 or pool_ns not in (8, 16, 32):
         return False
-    images, nst = (2, 2) if npass == 3 else (1, 4)
+    images = 2 if npass == 3 else 1
     natoms = max((c1 + 63) // 64, (c2 + 63) // 64)
-    return nst * images * 16384 + images * natoms * 16384 + 2048 + 256 + 1024 <= 227 * 1024
+    slot = min(128, (max(c2, c3) + 15) // 16 * 16) * 128
+    return images * slot + max(images * natoms * 16384, 32768) + 2048 + 256 + 1024 <= 227 * 1024
 
 
 class QueryAndGroup(nn.Module):
