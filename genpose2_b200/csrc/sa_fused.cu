@@ -74,7 +74,7 @@ struct Layout {
         return b < 8 * 4096 ? 8 * 4096 : b;
     }
     __host__ __device__ size_t bias() const { return abuf() + abuf_bytes(); }
-    __host__ __device__ size_t bars() const { return bias() + 512 * sizeof(float); }
+    __host__ __device__ size_t bars() const { return bias() + 768 * sizeof(float); }
     __host__ __device__ size_t total() const { return bars() + 256 + 1024; }
 };
 
@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
         mbar_init(&dbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 256; i += NTHREADS) {
-        sb1[i] = i < a.c2 ? __ldg(a.b1 + i) : 0.f;
+    for (int i = tid; i < 512; i += NTHREADS) {
+        if (i < 256) sb1[i] = i < a.c2 ? __ldg(a.b1 + i) : 0.f;
         sb2[i] = i < a.c3 ? __ldg(a.b2 + i) : 0.f;
     }
     __syncthreads();
@@ -162,14 +162,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
                 if (Lc >= NST) mbar_wait(&empty[s], (uint32_t)((Lc / NST) + 1) & 1);
                 int i = (int)(Lc % nper);
                 const uint8_t *wp;
-                int bn, c, nh;
-                if (i < k1 * nh1) { wp = a.W1p; bn = bn1; c = i / nh1; nh = i % nh1; }
-                else { i -= k1 * nh1; wp = a.W2p; bn = bn2; c = i / nh2; nh = i % nh2; }
-                const uint32_t rows = (uint32_t)min(128, bn - 128 * nh);
-                const size_t img = (size_t)bn * 128;
+                int bn, c, nh, kat;
+                if (i < k1 * nh1) { wp = a.W1p; bn = bn1; kat = k1; c = i / nh1; nh = i % nh1; }
+                else { i -= k1 * nh1; wp = a.W2p; bn = bn2; kat = k2; c = i / nh2; nh = i % nh2; }
+                // gp_gemm_pack layout: n-tiles of 256 columns, per tile and k-chunk one image [bn_tile x 128 B] (hi, lo)
+                const int jt = nh >> 1, hh = nh & 1;
+                const int bnj = min(256, bn - 256 * jt);
+                const uint32_t rows = (uint32_t)min(128, bnj - 128 * hh);
+                const size_t img = (size_t)bnj * 128;
+                const uint8_t *tile = wp + (size_t)jt * kat * IM * (256 * 128);
                 mbar_arrive_expect_tx(&full[s], IM * rows * 128);
                 for (int w = 0; w < IM; ++w)
-                    bulk_g2s(ring + ((size_t)s * IM + w) * a.slot_bytes, wp + ((size_t)c * IM + w) * img + (size_t)nh * HALF,
+                    bulk_g2s(ring + ((size_t)s * IM + w) * a.slot_bytes, tile + ((size_t)c * IM + w) * img + (size_t)hh * HALF,
                              rows * 128, &full[s]);
             }
         }
@@ -372,8 +376,8 @@ static int launch(Args a, cudaStream_t st) {
     const int bn1 = round16(a.c2), bn2 = round16(a.c3);
     const int rows_max = (bn1 > bn2 ? bn1 : bn2) < 128 ? (bn1 > bn2 ? bn1 : bn2) : 128;
     a.slot_bytes = rows_max * 128;
-    // D2 may reuse D1's TMEM columns (D1 is drained before the second GEMM starts): 256 columns per CTA
-    a.tmem_cols = 256;
+    // D2 reuses D1's TMEM columns (D1 is drained before the second GEMM starts)
+    a.tmem_cols = (bn1 > 256 || bn2 > 256) ? 512 : 256;
     a.d2col = 0;
     a.tile_in_batch = a.rows_per_batch % BM == 0;
     a.q_shift = -1;
@@ -409,8 +413,8 @@ extern "C" int gp_sa_mlp2_fused(const float *P, int n_src, int ldp, const int32_
     GP_REQUIRE(R >= 0 && (npass == 1 || npass == 3), "gp_sa_mlp2_fused: bad arguments");
     if (R == 0) return GP_OK;
     GP_REQUIRE(P && gidx && Q && packed1 && bias1 && packed2 && bias2 && pooled, "gp_sa_mlp2_fused: null pointer");
-    GP_REQUIRE(c1 >= 4 && c1 <= 256 && (c1 & 3) == 0 && c2 >= 1 && c2 <= 256 && c3 >= 1 && c3 <= 256,
-               "gp_sa_mlp2_fused: widths must satisfy c1 %% 4 == 0 and c1, c2, c3 <= 256 (got %d, %d, %d)", c1, c2, c3);
+    GP_REQUIRE(c1 >= 4 && c1 <= 256 && (c1 & 3) == 0 && c2 >= 1 && c2 <= 256 && c3 >= 1 && c3 <= 512,
+               "gp_sa_mlp2_fused: widths must satisfy c1 %% 4 == 0, c1, c2 <= 256 and c3 <= 512 (got %d, %d, %d)", c1, c2, c3);
     GP_REQUIRE(ldp >= c1 && (ldp & 3) == 0 && ((uintptr_t)P & 15) == 0 && ldq >= c1 && (ldq & 3) == 0 && ((uintptr_t)Q & 15) == 0,
                "gp_sa_mlp2_fused: P / Q rows must be 16-byte aligned and cover c1");
     GP_REQUIRE(((uintptr_t)packed1 & 15) == 0 && ((uintptr_t)packed2 & 15) == 0, "gp_sa_mlp2_fused: packed weights must be 16-byte aligned");
