@@ -47,6 +47,8 @@ struct Args {
     int ntiles;
     // launch configuration (host): ring stages, bytes per weight image slot, TMEM columns, TMEM column of D2
     int nst, slot_bytes, tmem_cols, d2col;
+    int chunk_rows;      // output columns per weight chunk: 128, or 64 when shared memory is tight
+    int bias_smem;       // biases staged in shared memory (else read through L1)
     int tile_in_batch;   // rows_per_batch % 128 == 0: all rows of a tile belong to one batch
     int q_shift;         // log2(q_ns) if q_ns is a power of two, else -1
 };
@@ -63,9 +65,9 @@ __host__ __device__ inline int atoms_of(int k) { return (k + 63) / 64; }
 // shared memory carve-up (bytes from a 1024-aligned base): weight ring | A buffer (= pool staging) | biases | barriers
 template <int NPASS>
 struct Layout {
-    int natoms, nst, slot;
-    __host__ __device__ Layout(int c1, int c2, int nst_, int slot_)
-        : natoms(atoms_of(c1) > atoms_of(c2) ? atoms_of(c1) : atoms_of(c2)), nst(nst_), slot(slot_) {}
+    int natoms, nst, slot, bias_smem;
+    __host__ __device__ Layout(int c1, int c2, int nst_, int slot_, int bias_smem_)
+        : natoms(atoms_of(c1) > atoms_of(c2) ? atoms_of(c1) : atoms_of(c2)), nst(nst_), slot(slot_), bias_smem(bias_smem_) {}
     __host__ __device__ size_t ring() const { return 0; }
     __host__ __device__ size_t abuf() const { return (size_t)nst * Cfg<NPASS>::IMAGES * slot; }
     // the A buffer doubles as the pooling stage (8 x [32][32] f32) once the second GEMM has read it
@@ -74,7 +76,7 @@ struct Layout {
         return b < 8 * 4096 ? 8 * 4096 : b;
     }
     __host__ __device__ size_t bias() const { return abuf() + abuf_bytes(); }
-    __host__ __device__ size_t bars() const { return bias() + 768 * sizeof(float); }
+    __host__ __device__ size_t bars() const { return bias() + (bias_smem ? (384 + 512) * sizeof(float) : 0); }
     __host__ __device__ size_t total() const { return bars() + 256 + 1024; }
 };
 
@@ -117,12 +119,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
     const int NST = a.nst;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const Layout<NPASS> L(a.c1, a.c2, a.nst, a.slot_bytes);
+    const Layout<NPASS> L(a.c1, a.c2, a.nst, a.slot_bytes, a.bias_smem);
     uint8_t *ring = base + L.ring();
     uint8_t *abuf = base + L.abuf();
     float *stage_all = reinterpret_cast<float *>(abuf);
     float *sb1 = reinterpret_cast<float *>(base + L.bias());
-    float *sb2 = sb1 + 256;
+    float *sb2 = sb1 + 384;
+    const float *b1p = a.bias_smem ? sb1 : a.b1, *b2p = a.bias_smem ? sb2 : a.b2;   // valid for n < c2 / n < c3
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(base + L.bars());
     unsigned long long *full = bars, *empty = bars + MAX_NST, *a_ready = bars + 2 * MAX_NST, *dbar = bars + 2 * MAX_NST + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_NST + 3);
@@ -130,7 +133,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int k1 = atoms_of(a.c1), k2 = atoms_of(a.c2);
     const int bn1 = round16(a.c2), bn2 = round16(a.c3);
-    const int nh1 = (bn1 + 127) / 128, nh2 = (bn2 + 127) / 128;
+    const int CR = a.chunk_rows;
+    const int nh1 = (bn1 + CR - 1) / CR, nh2 = (bn2 + CR - 1) / CR;
     const int nper = k1 * nh1 + k2 * nh2;   // weight chunks per tile
     const int my_tiles = a.ntiles > (int)blockIdx.x ? (a.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
@@ -141,9 +145,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
         mbar_init(&dbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 512; i += NTHREADS) {
-        if (i < 256) sb1[i] = i < a.c2 ? __ldg(a.b1 + i) : 0.f;
-        sb2[i] = i < a.c3 ? __ldg(a.b2 + i) : 0.f;
+    if (a.bias_smem) {
+        for (int i = tid; i < 512; i += NTHREADS) {
+            if (i < 384) sb1[i] = i < a.c2 ? __ldg(a.b1 + i) : 0.f;
+            sb2[i] = i < a.c3 ? __ldg(a.b2 + i) : 0.f;
+        }
     }
     __syncthreads();
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
@@ -166,14 +172,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
                 if (i < k1 * nh1) { wp = a.W1p; bn = bn1; kat = k1; c = i / nh1; nh = i % nh1; }
                 else { i -= k1 * nh1; wp = a.W2p; bn = bn2; kat = k2; c = i / nh2; nh = i % nh2; }
                 // gp_gemm_pack layout: n-tiles of 256 columns, per tile and k-chunk one image [bn_tile x 128 B] (hi, lo)
-                const int jt = nh >> 1, hh = nh & 1;
+                const int ncol = nh * CR, jt = ncol >> 8, within = ncol & 255;
                 const int bnj = min(256, bn - 256 * jt);
-                const uint32_t rows = (uint32_t)min(128, bnj - 128 * hh);
+                const uint32_t rows = (uint32_t)min(CR, bnj - within);
                 const size_t img = (size_t)bnj * 128;
                 const uint8_t *tile = wp + (size_t)jt * kat * IM * (256 * 128);
                 mbar_arrive_expect_tx(&full[s], IM * rows * 128);
                 for (int w = 0; w < IM; ++w)
-                    bulk_g2s(ring + ((size_t)s * IM + w) * a.slot_bytes, tile + ((size_t)c * IM + w) * img + (size_t)hh * HALF,
+                    bulk_g2s(ring + ((size_t)s * IM + w) * a.slot_bytes, tile + ((size_t)c * IM + w) * img + (size_t)within * 128,
                              rows * 128, &full[s]);
             }
         }
@@ -192,8 +198,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
                         tc_fence_after();
                         const uint32_t b_hi = smem_u32(ring + (size_t)s * IM * a.slot_bytes);
                         const uint32_t b_lo = b_hi + (NPASS == 3 ? a.slot_bytes : 0);
-                        const uint32_t idesc = make_idesc_bf16(128, (uint32_t)min(128, bn - 128 * nh));
-                        const uint32_t d = tmem + dcol + nh * 128;
+                        const int ncol = nh * CR;
+                        const uint32_t idesc = make_idesc_bf16(128, (uint32_t)min(CR, min(256, bn - (ncol & ~255)) - (ncol & 255)));
+                        const uint32_t d = tmem + dcol + ncol;
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
                             const uint32_t ao = c * ATOM + kk * 32, bo = kk * 32;
@@ -311,7 +318,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
                     const int n0 = g * 32 + j8 * 8;
                     float v[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = n0 + j < a.c2 ? fmaxf(__uint_as_float(r[j8 * 8 + j]) + sb1[n0 + j], 0.f) : 0.f;
+                    for (int j = 0; j < 8; ++j) v[j] = n0 + j < a.c2 ? fmaxf(__uint_as_float(r[j8 * 8 + j]) + b1p[n0 + j], 0.f) : 0.f;
                     const __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
                     const __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
                     uint4 pk;
@@ -350,7 +357,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int n = g * 32 + j;
-                    v[j] = (n < a.c3 && row_ok) ? fmaxf(__uint_as_float(r[j]) + sb2[n], 0.f) : 0.f;
+                    v[j] = (n < a.c3 && row_ok) ? fmaxf(__uint_as_float(r[j]) + b2p[n], 0.f) : 0.f;
                 }
                 pool_block(v, stage_all + e * 1024, lane, row0 + 32 * quarter, a.R, ns, g * 32, a.c3, a.pooled, a.ld_pooled);
             }
@@ -374,8 +381,6 @@ template <int NPASS>
 static int launch(Args a, cudaStream_t st) {
     constexpr int IM = Cfg<NPASS>::IMAGES;
     const int bn1 = round16(a.c2), bn2 = round16(a.c3);
-    const int rows_max = (bn1 > bn2 ? bn1 : bn2) < 128 ? (bn1 > bn2 ? bn1 : bn2) : 128;
-    a.slot_bytes = rows_max * 128;
     // D2 reuses D1's TMEM columns (D1 is drained before the second GEMM starts)
     a.tmem_cols = (bn1 > 256 || bn2 > 256) ? 512 : 256;
     a.d2col = 0;
@@ -383,15 +388,26 @@ static int launch(Args a, cudaStream_t st) {
     a.q_shift = -1;
     for (int sh = 0; sh < 31; ++sh)
         if ((1 << sh) == a.q_ns) a.q_shift = sh;
-    // one CTA per SM (its 10 warps are allocated as 12, two CTAs would leave 80 registers per thread); the weight
-    // ring is as deep as the shared memory allows
-    const size_t fixed = Layout<NPASS>(a.c1, a.c2, 0, a.slot_bytes).total();
-    const size_t stage = (size_t)IM * a.slot_bytes;
+    // One CTA per SM (its 10 warps are allocated as 12, two CTAs would leave 80 registers per thread).  The weight
+    // ring wants >= 2 stages: 128-column chunks and biases in shared memory if that fits, else 64-column chunks,
+    // else biases through L1.
     const size_t full_sm = 227 * 1024;
-    const int nst = fixed + stage <= full_sm ? (int)((full_sm - fixed) / stage) : 0;
+    int nst = 0;
+    size_t fixed = 0, stage = 0;
+    const int tries[3][2] = {{128, 1}, {64, 1}, {64, 0}};
+    for (int t = 0; t < 3; ++t) {
+        const int widest = bn1 > bn2 ? bn1 : bn2;
+        a.chunk_rows = tries[t][0];
+        a.bias_smem = tries[t][1];
+        a.slot_bytes = (widest < a.chunk_rows ? widest : a.chunk_rows) * 128;
+        fixed = Layout<NPASS>(a.c1, a.c2, 0, a.slot_bytes, a.bias_smem).total();
+        stage = (size_t)IM * a.slot_bytes;
+        nst = fixed + stage <= full_sm ? (int)((full_sm - fixed) / stage) : 0;
+        if (nst >= 2) break;
+    }
     GP_REQUIRE(nst >= 1, "gp_sa_mlp2_fused: layer widths need %zu bytes of shared memory", fixed + stage);
     a.nst = nst > MAX_NST ? MAX_NST : nst;
-    const Layout<NPASS> L(a.c1, a.c2, a.nst, a.slot_bytes);
+    const Layout<NPASS> L(a.c1, a.c2, a.nst, a.slot_bytes, a.bias_smem);
     auto kern = sa_mlp2_kernel<NPASS>;
     const size_t smem = L.total();
     GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -413,8 +429,8 @@ extern "C" int gp_sa_mlp2_fused(const float *P, int n_src, int ldp, const int32_
     GP_REQUIRE(R >= 0 && (npass == 1 || npass == 3), "gp_sa_mlp2_fused: bad arguments");
     if (R == 0) return GP_OK;
     GP_REQUIRE(P && gidx && Q && packed1 && bias1 && packed2 && bias2 && pooled, "gp_sa_mlp2_fused: null pointer");
-    GP_REQUIRE(c1 >= 4 && c1 <= 256 && (c1 & 3) == 0 && c2 >= 1 && c2 <= 256 && c3 >= 1 && c3 <= 512,
-               "gp_sa_mlp2_fused: widths must satisfy c1 %% 4 == 0, c1, c2 <= 256 and c3 <= 512 (got %d, %d, %d)", c1, c2, c3);
+    GP_REQUIRE(c1 >= 4 && c1 <= 256 && (c1 & 3) == 0 && c2 >= 1 && c2 <= 384 && c3 >= 1 && c3 <= 512,
+               "gp_sa_mlp2_fused: widths must satisfy c1 %% 4 == 0, c1 <= 256, c2 <= 384 and c3 <= 512 (got %d, %d, %d)", c1, c2, c3);
     GP_REQUIRE(ldp >= c1 && (ldp & 3) == 0 && ((uintptr_t)P & 15) == 0 && ldq >= c1 && (ldq & 3) == 0 && ((uintptr_t)Q & 15) == 0,
                "gp_sa_mlp2_fused: P / Q rows must be 16-byte aligned and cover c1");
     GP_REQUIRE(((uintptr_t)packed1 & 15) == 0 && ((uintptr_t)packed2 & 15) == 0, "gp_sa_mlp2_fused: packed weights must be 16-byte aligned");

@@ -235,12 +235,12 @@ def sa_mlp2_fused(P, n_src, gidx, rows_per_batch, Q, q_ns, packed1, bias1, c1, c
 
 def sa_mlp2_fused_fits(c1, c2, c3, npass, pool_ns):
     """Shape limits of gp_sa_mlp2_fused (widths and shared-memory budget)."""
-    if c1 % 4 or max(c1, c2) > 256 or c3 > 512 or pool_ns not in (8, 16, 32):
+    if c1 % 4 or c1 > 256 or c2 > 384 or c3 > 512 or pool_ns not in (8, 16, 32):
         return False
     images = 2 if npass == 3 else 1
     natoms = max((c1 + 63) // 64, (c2 + 63) // 64)
-    slot = min(128, (max(c2, c3) + 15) // 16 * 16) * 128
-    return images * slot + max(images * natoms * 16384, 32768) + 3072 + 256 + 1024 <= 227 * 1024
+    slot = min(64, (max(c2, c3) + 15) // 16 * 16) * 128   # the smallest configuration the launcher falls back to
+    return images * slot + max(images * natoms * 16384, 32768) + 256 + 1024 <= 227 * 1024
 
 
 class QueryAndGroup(nn.Module):

@@ -148,7 +148,7 @@ GP_API int gp_gemm_gather_bias_relu(const float *P, int n_src, int ldp, const in
  * memory A operand), pooled[g] = max over the pool_ns rows of group g of relu(H . W2^T + b2).  The
  * (centre, sample) activation matrices never exist in HBM.
  *   packed1 = gp_gemm_pack(W1 [c2, c1]), packed2 = gp_gemm_pack(W2 [c3, c2]), same npass;
- *   c1 %% 4 == 0, c1, c2 <= 256, c3 <= 512 (and within the shared-memory budget: fails loudly otherwise);
+ *   c1 %% 4 == 0, c1 <= 256, c2 <= 384, c3 <= 512 (and within the shared-memory budget: fails loudly otherwise);
  *   pool_ns in {8, 16, 32}; pooled [R / pool_ns, ld_pooled], every element written once. */
 GP_API int gp_sa_mlp2_fused(const float *P, int n_src, int ldp, const int32_t *gidx, long long R, int rows_per_batch,
                      const float *Q, int ldq, int q_ns, const void *packed1, const float *bias1, int c1, int c2,
