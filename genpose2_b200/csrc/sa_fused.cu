@@ -80,15 +80,18 @@ struct Layout {
     __host__ __device__ size_t total() const { return bars() + 256 + 1024; }
 };
 
-// Max-pool of one warp's 32 rows x 32 columns block (v = this lane's row, values >= 0) over groups of `ns`
-// consecutive rows: transposed through a swizzled [32][32] shared-memory tile (bank = col ^ row on both sides),
-// then lane c reduces column c and stores it -- no cross-lane instructions, coalesced 128-byte stores.
+// Max-pool of one warp's 32 rows x 32 columns block of raw accumulators (v = this lane's row; -inf for rows that
+// do not exist) over groups of `ns` consecutive rows, then bias + ReLU once per pooled value: the bias is per
+// column and x -> relu(x + b) is monotone, so relu(max_r(x_r) + b) == max_r(relu(x_r + b)) bit for bit.
+// Transposed through a swizzled [32][32] shared-memory tile (bank = col ^ row on both sides); lane c reduces
+// column c and stores it -- no cross-lane instructions, coalesced 128-byte stores.
 __device__ __forceinline__ void pool_block(const float (&v)[32], float *stg, int lane, long long grow0, long long R, int ns,
-                                           int nbase, int N, float *pooled, int ld_pooled) {
+                                           int nbase, int N, const float *bias, float *pooled, int ld_pooled) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) stg[lane * 32 + (j ^ lane)] = v[j];
     __syncwarp();
     const int n = nbase + lane;
+    const float bn = n < N ? bias[n] : 0.f;
     float m8[4];  // maxima of rows 0-7, 8-15, 16-23, 24-31 of column `lane` (all loads independent)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -99,14 +102,14 @@ __device__ __forceinline__ void pool_block(const float (&v)[32], float *stg, int
     }
     if (n < N) {
         if (ns == 32) {
-            if (grow0 < R) pooled[(grow0 / 32) * (long long)ld_pooled + n] = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+            if (grow0 < R) pooled[(grow0 / 32) * (long long)ld_pooled + n] = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])) + bn, 0.f);
         } else if (ns == 16) {
-            if (grow0 < R) pooled[(grow0 / 16) * (long long)ld_pooled + n] = fmaxf(m8[0], m8[1]);
-            if (grow0 + 16 < R) pooled[(grow0 / 16 + 1) * (long long)ld_pooled + n] = fmaxf(m8[2], m8[3]);
+            if (grow0 < R) pooled[(grow0 / 16) * (long long)ld_pooled + n] = fmaxf(fmaxf(m8[0], m8[1]) + bn, 0.f);
+            if (grow0 + 16 < R) pooled[(grow0 / 16 + 1) * (long long)ld_pooled + n] = fmaxf(fmaxf(m8[2], m8[3]) + bn, 0.f);
         } else {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (grow0 + 8 * q < R) pooled[(grow0 / 8 + q) * (long long)ld_pooled + n] = m8[q];
+                if (grow0 + 8 * q < R) pooled[(grow0 / 8 + q) * (long long)ld_pooled + n] = fmaxf(m8[q] + bn, 0.f);
         }
     }
     __syncwarp();
@@ -355,11 +358,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
                 tmem_ld32(lane_addr + a.d2col + g * 32, r);
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = g * 32 + j;
-                    v[j] = (n < a.c3 && row_ok) ? fmaxf(__uint_as_float(r[j]) + b2p[n], 0.f) : 0.f;
-                }
-                pool_block(v, stage_all + e * 1024, lane, row0 + 32 * quarter, a.R, ns, g * 32, a.c3, a.pooled, a.ld_pooled);
+                for (int j = 0; j < 32; ++j) v[j] = row_ok ? __uint_as_float(r[j]) : -INFINITY;
+                pool_block(v, stage_all + e * 1024, lane, row0 + 32 * quarter, a.R, ns, g * 32, a.c3, b2p, a.pooled, a.ld_pooled);
             }
             tc_fence_before();
             // the pooling stage lives in the A buffer: nobody gathers the next tile into it before all warps are done
