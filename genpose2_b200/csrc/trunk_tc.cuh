@@ -452,16 +452,12 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
                 float ev[8];
                 const float4 ta = *reinterpret_cast<const float4 *>(stq + cb + j8 * 8);
                 const float4 tb = *reinterpret_cast<const float4 *>(stq + cb + j8 * 8 + 4);
-                if (use_pj) {
-                    const float4 ea = *reinterpret_cast<const float4 *>(pjrow + cb + j8 * 8);
-                    const float4 eb = *reinterpret_cast<const float4 *>(pjrow + cb + j8 * 8 + 4);
-                    ev[0] = ea.x + ta.x; ev[1] = ea.y + ta.y; ev[2] = ea.z + ta.z; ev[3] = ea.w + ta.w;
-                    ev[4] = eb.x + tb.x; ev[5] = eb.y + tb.y; ev[6] = eb.z + tb.z; ev[7] = eb.w + tb.w;
-                } else {
-                    const float tv[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) ev[j] = __ldg(prow + gcol + j8 * 8 + j) + tv[j];
-                }
+                // the object's proj columns: the shared-memory table, or (a tile spanning > MAX_SLOTS objects) global memory
+                const float *ebase = use_pj ? pjrow + cb : prow + gcol;
+                const float4 ea = *reinterpret_cast<const float4 *>(ebase + j8 * 8);
+                const float4 eb = *reinterpret_cast<const float4 *>(ebase + j8 * 8 + 4);
+                ev[0] = ea.x + ta.x; ev[1] = ea.y + ta.y; ev[2] = ea.z + ta.z; ev[3] = ea.w + ta.w;
+                ev[4] = eb.x + tb.x; ev[5] = eb.y + tb.y; ev[6] = eb.z + tb.z; ev[7] = eb.w + tb.w;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float z = fmaxf(__uint_as_float(r[j8 * 8 + j]) + ev[j], 0.f);
