@@ -186,7 +186,7 @@ GP_API int gp_trunk_project(const void *packed, const float *pts_feat, int B, fl
 /* One PoseScoreNet.forward (scorenet.py:215-275): x [N,9] f32, t [N] f32 (one value per row),
  * proj [B,768] with row i belonging to object i / rows_per_object -> score [N,9] f32
  * (= f_theta / (std + 1e-7)).  Used by GFObjectPose.forward(mode="score") (posenet.py:305-307).
- * mode: 0 = fp32 (FFMA) MLP, 1 = bf16 tensor-core MLP (tcgen05), as for gp_scorenet_ode. */
+ * mode: 0 = fp32 FFMA, 1 = bf16 tcgen05, 2 = split-bf16 x3 tcgen05 (fp32-class), as for gp_scorenet_ode. */
 GP_API int gp_scorenet_eval(const void *packed, const float *proj, const float *x, const float *t, int N,
                      int rows_per_object, float *score, int mode, gp_stream_t s);
 
@@ -199,6 +199,7 @@ enum gp_ode_stat {
     GP_STAT_T_FINAL = 4,
     GP_STAT_H_INITIAL = 5,
     GP_STAT_H_LAST = 6,
+    /* 8..24: cycle counters of the kernel's phases, CTA 0 (profiling aid, profiles/phase_breakdown.py) */
     GP_STAT_COUNT = 32
 };
 
@@ -217,7 +218,10 @@ GP_API size_t gp_scorenet_ode_workspace_bytes(int N);
  *   x_out       [N,9] f64   final pose (normalised rotation, centre added)
  *   traj        NULL, or [max_traj, N, 9] f64: raw state after every accepted step, slot 0 = x0
  *   stats       [GP_STAT_COUNT] f64 (device)
- *   mode        0 = fp32 (FFMA) MLP, 1 = bf16 tensor-core MLP (tcgen05)
+ *   mode        arithmetic of the MLP contractions: 0 = fp32 FFMA on CUDA cores; 1 = bf16 operands on tcgen05;
+ *               2 = tcgen05 with every operand split into two bf16 (hi*hi + lo*hi + hi*lo, fp32 accumulation in
+ *               TMEM: 16 mantissa bits per operand, indistinguishable from fp32 on the reference's fixtures).
+ *               Modes 1 and 2 run as 4-CTA clusters per 128-row tile (cooperative launch).
  */
 GP_API int gp_scorenet_ode(const void *packed, const float *proj, const double *x0,
                     const float *pts_center, int N, int rows_per_object, double T, double eps,
