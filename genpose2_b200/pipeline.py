@@ -62,6 +62,7 @@ class PosePipeline:
         self.energy_agent = PoseNet(c)
         c = copy.copy(cfg); c.agent_type = "scale"
         self.scale_agent = PoseNet(c)
+        self._side = None   # second stream: the energy encoder overlaps the sampler
 
     def load_state_dicts(self, score_sd, energy_sd, scale_sd):
         self.score_agent.net.load_state_dict(score_sd)
@@ -80,11 +81,24 @@ class PosePipeline:
         cfg = self.cfg
         R = cfg.eval_repeat_num if repeat_num is None else repeat_num
         T0 = cfg.T0 if T0 is None else T0
-        pred_pose, pred_q, geometry = self.score_agent.pred_func(
-            data=data, repeat_num=R, T0=T0, init_x=init_x, save_path=None, return_geometry=True)
-        score_feat = data["pts_feat"]
-        energy = self.energy_agent.get_energy(data=data, pose_samples=pred_pose, T=1e-5, mode="test",
-                                              extract_feature=True, geometry=geometry)
+        # The sampler is a cooperative launch of at most 33 four-CTA clusters (100 SMs at 64 x 50): the energy
+        # encoder, which only needs the cloud and the shared FPS / ball-query geometry, runs beside it on a second
+        # stream and fills the remaining SMs.  The sampler is enqueued first so that it gets its SMs first.
+        main = torch.cuda.current_stream()
+        score_feat, geometry = self.score_agent.net(data, mode="pts_feature", return_geometry=True)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        pred_pose, pred_q, _ = self.score_agent.pred_func(
+            data=data, repeat_num=R, T0=T0, init_x=init_x, save_path=None, return_geometry=True, geometry=geometry,
+            pts_feat=score_feat)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=score_feat.device)
+        self._side.wait_event(fork)
+        with torch.cuda.stream(self._side):
+            energy_feat = self.energy_agent.net(data, mode="pts_feature", geometry=geometry)
+        main.wait_stream(self._side)
+        energy = self.energy_agent.get_energy(data={"pts_feat": energy_feat, "pts_center": data["pts_center"]},
+                                              pose_samples=pred_pose, T=1e-5, mode="test", extract_feature=False)
         agg = aggregate_pose(pred_pose, energy, eval_repeat_num=R, retain_ratio=cfg.retain_ratio,
                              clustering=cfg.clustering, clustering_eps=cfg.clustering_eps,
                              clustering_minpts=cfg.clustering_minpts)

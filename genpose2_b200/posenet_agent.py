@@ -55,15 +55,18 @@ class PoseNet(nn.Module):
     # ------------------------------------------------------------------------------------------
     def pred_func(self, data, repeat_num, save_path="./visualization_results", return_average_res=False,
                   init_x: torch.Tensor = None, T0=None, return_process=False, geometry=None,
-                  return_geometry=False):
+                  return_geometry=False, pts_feat=None):
         self.is_testing = True
         self.net.eval()
         if getattr(self.cfg, "save_video", False):
             raise NotImplementedError("save_video (visualisation) is out of scope")
         with torch.no_grad():
-            feat = self.net(data, mode="pts_feature", geometry=geometry, return_geometry=return_geometry)
-            if return_geometry:
-                feat, geometry = feat
+            if pts_feat is not None:   # features already extracted by the caller (PosePipeline overlaps the encoders)
+                feat = pts_feat
+            else:
+                feat = self.net(data, mode="pts_feature", geometry=geometry, return_geometry=return_geometry)
+                if return_geometry:
+                    feat, geometry = feat
             data["pts_feat"] = feat
             data["rgb_feat"] = self.net(data, mode="rgb_feature")  # None
             bs = data["pts"].shape[0]
