@@ -96,6 +96,7 @@ class PosePipeline:
         self._side.wait_event(fork)
         with torch.cuda.stream(self._side):
             energy_feat = self.energy_agent.net(data, mode="pts_feature", geometry=geometry)
+            energy_feat.record_stream(main)
         main.wait_stream(self._side)
         energy = self.energy_agent.get_energy(data={"pts_feat": energy_feat, "pts_center": data["pts_center"]},
                                               pose_samples=pred_pose, T=1e-5, mode="test", extract_feature=False)
