@@ -60,6 +60,7 @@ SIGNATURES = {
     "gp_gemm_gather_bias_relu": (c_int, [c_void_p, c_int, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_int,
                                          c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                          c_void_p, c_int, c_void_p]),
+    "gp_centre_term": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "gp_sa_mlp2_fused": (c_int, [c_void_p, c_int, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_int, c_int,
                                  c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                  c_int, c_void_p]),

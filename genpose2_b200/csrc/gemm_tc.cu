@@ -415,6 +415,37 @@ extern "C" int gp_gemm_linear(const float *X, long long R, int ldx, const void *
     return npass == 3 ? gemm::launch<3>(a, as_stream(s)) : gemm::launch<1>(a, as_stream(s));
 }
 
+namespace gp {
+namespace gemm {
+// Q[r][k] = sum_j xyz[r][j] * Wt[j][k] - b[k] for k < c1, zero up to ldq: the per-centre term of a hoisted first layer
+__global__ void centre_term_kernel(const float *__restrict__ xyz, long long rows, const float *__restrict__ Wt,
+                                   const float *__restrict__ b, int c1, float *__restrict__ Q, int ldq) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * ldq) return;
+    const long long r = i / ldq;
+    const int k = (int)(i - r * ldq);
+    float v = 0.f;
+    if (k < c1) {
+        const float x = __ldg(xyz + r * 3), y = __ldg(xyz + r * 3 + 1), z = __ldg(xyz + r * 3 + 2);
+        // the order of torch.addmm's K = 3 dot product does not matter at this size; written as one chain
+        v = fmaf(z, __ldg(Wt + 2 * c1 + k), fmaf(y, __ldg(Wt + c1 + k), x * __ldg(Wt + k))) - __ldg(b + k);
+    }
+    Q[i] = v;
+}
+}  // namespace gemm
+}  // namespace gp
+
+extern "C" int gp_centre_term(const float *new_xyz, long long rows, const float *w0_xyz_t, const float *b0, int c1,
+                              float *Q, int ldq, gp_stream_t s) {
+    GP_REQUIRE(rows >= 0 && c1 >= 1 && ldq >= c1, "gp_centre_term: bad sizes");
+    if (rows == 0) return GP_OK;
+    GP_REQUIRE(new_xyz && w0_xyz_t && b0 && Q, "gp_centre_term: null pointer");
+    const long long total = rows * ldq;
+    gemm::centre_term_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(s)>>>(new_xyz, rows, w0_xyz_t, b0, c1, Q, ldq);
+    GP_CHECK_LAUNCH("gp_centre_term");
+    return GP_OK;
+}
+
 extern "C" int gp_gemm_gather_bias_relu(const float *P, int n_src, int ldp, const int32_t *gidx, long long R,
                                         int rows_per_batch, const float *Q, int ldq, int q_ns, const void *packed,
                                         const float *bias, int N, int K, int npass, float *Y, int ldy, int pool_ns,

@@ -128,8 +128,7 @@ class SharedMLP(nn.Module):
         t = self._tc_hoisted(npass)
         B, M, ns = bq_idx.shape
         P = pu.gemm_linear(pts_rows, t["p0"], t["c1"], t["k0"], npass)                 # [B*n_src, ldp]
-        Q = torch.zeros((B * M, P.shape[1]), dtype=torch.float32, device=P.device)
-        torch.addmm(-t["b0"], new_xyz.reshape(B * M, 3), t["w0_xyz_t"], out=Q[:, : t["c1"]])
+        Q = pu.centre_term(new_xyz.reshape(B * M, 3).contiguous(), t["w0_xyz_t"], t["b0"], P.shape[1])
         if pu.sa_mlp2_fused_fits(t["c1"], t["c2"], t["c3"], npass, ns):
             # layers 2, 3 and the max-pool in one kernel: no (centre, sample) matrix in HBM at all
             return pu.sa_mlp2_fused(P, n_src, bq_idx.reshape(-1), M * ns, Q, ns, t["p1"], t["b1"], t["c1"], t["c2"],

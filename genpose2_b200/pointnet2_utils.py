@@ -219,6 +219,16 @@ def gemm_gather_bias_relu(P, n_src, gidx, rows_per_batch, Q, q_ns, packed, bias,
     return y
 
 
+def centre_term(new_xyz_rows, w0_xyz_t, b0, ldq):
+    """Q [rows, ldq]: per-centre term  new_xyz @ W0_xyz^T - b0  of a hoisted first layer, zero-padded (gp_centre_term)."""
+    _lib.check_cuda(new_xyz_rows, "new_xyz", torch.float32)
+    rows, c1 = new_xyz_rows.shape[0], w0_xyz_t.shape[1]
+    Q = torch.empty((rows, ldq), dtype=torch.float32, device=new_xyz_rows.device)
+    _lib.call("gp_centre_term", _lib.ptr(new_xyz_rows), rows, _lib.ptr(w0_xyz_t), _lib.ptr(b0), int(c1), _lib.ptr(Q),
+              int(ldq), device=new_xyz_rows.device)
+    return Q
+
+
 def sa_mlp2_fused(P, n_src, gidx, rows_per_batch, Q, q_ns, packed1, bias1, c1, c2, packed2, bias2, c3, npass, pool_ns,
                   pooled_out):
     """pooled_out[g] = max_rows relu(relu(relu(P[gather] - Q) @ W1^T + b1) @ W2^T + b2)  (gp_sa_mlp2_fused):

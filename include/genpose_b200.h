@@ -133,6 +133,12 @@ GP_API int gp_gemm_bias_relu(const float *X, long long R, int ldx, const void *p
 GP_API int gp_gemm_linear(const float *X, long long R, int ldx, const void *packed, int N, int K, int npass,
                    float *Y, int ldy, gp_stream_t s);
 
+/* The per-centre term of a hoisted first layer:  Q[r][k] = sum_j new_xyz[r][j] * w0_xyz_t[j][k] - b0[k]  for k < c1,
+ * zero for c1 <= k < ldq.  new_xyz [rows,3], w0_xyz_t [3,c1] = the xyz columns of the folded first-layer weight,
+ * transposed. */
+GP_API int gp_centre_term(const float *new_xyz, long long rows, const float *w0_xyz_t, const float *b0, int c1,
+                   float *Q, int ldq, gp_stream_t s);
+
 /* Second SharedMLP layer with the hoisted first layer applied on the fly in the operand loader:
  *   A[r][k] = relu(P[(r / rows_per_batch) * n_src + gidx[r]][k] - Q[r / q_ns][k]),   Y = relu(A . W^T + bias)
  * P [batches * n_src, ldp] = per-point first-layer pre-activations (gp_gemm_linear), gidx [R] = ball-query
