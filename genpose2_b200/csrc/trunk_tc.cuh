@@ -315,14 +315,43 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
             // pose_encoder.2: D1 -> cols 256..511
             mbar_wait(&S.a_ready, st.a_phase); st.a_phase ^= 1;
             tc_fence_after();
-            for (int kc = 0; kc < 4; ++kc)
-                for (int nh = 0; nh < 2; ++nh) {
-                    next_chunk();
+            if (NST >= 4) {
+                // Consecutive MMAs into one accumulator form a dependent chain (~90-130 cycles each, an N128 MMA
+                // occupies the pipe for 64): with a deep ring the two column halves of a k-atom are multiplied
+                // interleaved, two independent accumulators in flight.
+                for (int kc = 0; kc < 4; ++kc) {
+                    const uint32_t g = st.consumed, s0 = g % NST, s1 = (g + 1) % NST;
+                    mbar_wait(&S.full[s0], (g / NST) & 1);
+                    mbar_wait(&S.full[s1], ((g + 1) / NST) & 1);
+                    tc_fence_after();
+                    const uint32_t b0 = smem_u32(&S.ring[s0][0][0]), b1 = smem_u32(&S.ring[s1][0][0]);
+                    const uint32_t bl0 = smem_u32(&S.ring[s0][NPASS == 3 ? 1 : 0][0]), bl1 = smem_u32(&S.ring[s1][NPASS == 3 ? 1 : 0][0]);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        mma(tmem + 256 + nh * 128, kc * ATOM_BYTES + kk * 32, kk * 32, kIdescN128, (kc | kk) ? 1u : 0u);
-                    chunk_done();
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t ao = kc * ATOM_BYTES + kk * 32, bo = kk * 32, acc = (kc | kk) ? 1u : 0u;
+                        umma_bf16(tmem + 256, make_desc(a_hi + ao), make_desc(b0 + bo), kIdescN128, acc);
+                        umma_bf16(tmem + 384, make_desc(a_hi + ao), make_desc(b1 + bo), kIdescN128, acc);
+                        if (NPASS == 3) {
+                            umma_bf16(tmem + 256, make_desc(a_lo + ao), make_desc(b0 + bo), kIdescN128, 1u);
+                            umma_bf16(tmem + 384, make_desc(a_lo + ao), make_desc(b1 + bo), kIdescN128, 1u);
+                            umma_bf16(tmem + 256, make_desc(a_hi + ao), make_desc(bl0 + bo), kIdescN128, 1u);
+                            umma_bf16(tmem + 384, make_desc(a_hi + ao), make_desc(bl1 + bo), kIdescN128, 1u);
+                        }
+                    }
+                    umma_commit(&S.empty[s0]);
+                    umma_commit(&S.empty[s1]);
+                    st.consumed = g + 2;
                 }
+            } else {
+                for (int kc = 0; kc < 4; ++kc)
+                    for (int nh = 0; nh < 2; ++nh) {
+                        next_chunk();
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            mma(tmem + 256 + nh * 128, kc * ATOM_BYTES + kk * 32, kk * 32, kIdescN128, (kc | kk) ? 1u : 0u);
+                        chunk_done();
+                    }
+            }
             umma_commit(&S.dbar[1]);
             // heads: this rank's 64 columns of each, D2_h -> cols 64h..64h+63 (D0 has been drained)
             mbar_wait(&S.a_ready, st.a_phase); st.a_phase ^= 1;
