@@ -38,7 +38,8 @@ T0 = 0.55
 NUM_POINTS = 1024
 L2_FLUSH_BYTES = 256 << 20
 
-NCU_DRAM_BYTES_PER_LAUNCH = {"fp32_ffma": 2270464 + 22784, "bf16": 1782784 + 12544, "fp32": None}  # profiles/README.md
+# dram__bytes_read.sum + dram__bytes_write.sum of the integrator kernel, `ncu --set full` captures in profiles/README.md
+NCU_DRAM_BYTES_PER_LAUNCH = {"fp32_ffma": 2270464 + 22784, "bf16": 1672448 + 12800, "fp32": 2240768 + 46848}
 
 # algorithmic work of the ScoreNet RHS after hoisting, in FLOP
 ROW_EVAL_FLOP = 2 * 266752
@@ -368,7 +369,8 @@ def run_b200(args):
                                    f"(encoder x2 + RK45 ScoreNet sampling + EnergyNet + aggregation + ScaleNet), "
                                    f"T0={T0}, rtol=atol=1e-5, {NUM_POINTS} pts/object, random-init weights",
                        "objects_per_gpu": B, "hypotheses": REPEAT, "T0": T0, "l2": "flushed between timed steps "
-                       f"({L2_FLUSH_BYTES >> 20} MiB memset)", "parallelism": f"object-sharded x{world}, no collective on the data path"},
+                       f"({L2_FLUSH_BYTES >> 20} MiB memset)", "parallelism": f"object-sharded x{world}, no collective on the data path",
+                       "streams": "the energy encoder runs on a second stream beside the cooperative sampler launch"},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                       "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
