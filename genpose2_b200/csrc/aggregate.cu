@@ -234,20 +234,35 @@ struct ScaleSmem {
     float h1[OB][256];
 };
 
-// out[o][n] = act(b[n] + sum_k W[n][k] in[o][k]); one warp per output n, lanes stride k.
+// out[o][n] = act(b[n] + sum_k W[n][k] in[o][k]); one warp per output n, every lane takes 4 consecutive k per step
+// (16-byte loads, up to 10 of them in flight: the weight row streams from L2 once per CTA).  K % 4 == 0.
 template <int OB, int K, int LD, bool RELU>
 __device__ __forceinline__ void dense_rows(const float *__restrict__ W, const float *__restrict__ bias, int NOUT,
                                            const float *in, float *out, int out_ld) {
+    static_assert(K % 4 == 0 && LD % 4 == 0, "16-byte rows");
+    constexpr int STEPS = (K / 4 + 31) / 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     for (int n = warp; n < NOUT; n += nw) {
+        const float4 *w = reinterpret_cast<const float4 *>(W + (size_t)n * K);
+        float4 wv[STEPS];
+#pragma unroll
+        for (int i = 0; i < STEPS; ++i) {
+            const int k4 = lane + 32 * i;
+            wv[i] = k4 < K / 4 ? __ldg(w + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float acc[OB];
 #pragma unroll
         for (int o = 0; o < OB; ++o) acc[o] = 0.f;
-        const float *w = W + (size_t)n * K;
-        for (int k = lane; k < K; k += 32) {
-            const float wv = __ldg(w + k);
 #pragma unroll
-            for (int o = 0; o < OB; ++o) acc[o] = fmaf(in[o * LD + k], wv, acc[o]);
+        for (int i = 0; i < STEPS; ++i) {
+            const int k4 = lane + 32 * i;
+            if (k4 < K / 4) {
+#pragma unroll
+                for (int o = 0; o < OB; ++o) {
+                    const float4 x = *reinterpret_cast<const float4 *>(in + o * LD + 4 * k4);
+                    acc[o] = fmaf(x.x, wv[i].x, fmaf(x.y, wv[i].y, fmaf(x.z, wv[i].z, fmaf(x.w, wv[i].w, acc[o]))));
+                }
+            }
         }
         const float bv = __ldg(bias + n);
 #pragma unroll
@@ -334,6 +349,7 @@ extern "C" int gp_scalenet(const gp_scalenet_params *p, const float *axes, int a
                "gp_scalenet: null parameter");
     GP_REQUIRE(B >= 0 && axes_batch_stride >= 9 && axes_row_stride >= 3, "gp_scalenet: bad sizes/strides");
     if (B == 0) return GP_OK;
+    if (B <= num_sms()) return launch_scalenet<1>(p, axes, axes_batch_stride, axes_row_stride, pts_feat, B, length, as_stream(s));
     if (B < 8 * num_sms()) return launch_scalenet<2>(p, axes, axes_batch_stride, axes_row_stride, pts_feat, B, length, as_stream(s));
     return launch_scalenet<8>(p, axes, axes_batch_stride, axes_row_stride, pts_feat, B, length, as_stream(s));
 }
