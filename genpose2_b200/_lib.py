@@ -72,6 +72,9 @@ SIGNATURES = {
     "gp_scorenet_ode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_double,
                                 c_double, c_double, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                 c_size_t, c_int, c_void_p]),
+    "gp_scorenet_ode_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_double,
+                                      c_double, c_double, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_size_t, c_int, c_void_p]),
     "gp_traj_finalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "gp_scorenet_pc_workspace_bytes": (c_size_t, [c_int]),
     "gp_scorenet_pc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,

@@ -13,7 +13,7 @@ constexpr int AG_MAXK = 32;     // retained hypotheses (DBSCAN neighbourhoods ar
 struct AggSmem {
     float e[AG_MAXR][2];
     int order[2][AG_MAXR];       // rank -> hypothesis, per energy channel
-    double q[AG_MAXK][4];        // retained quaternions (wxyz)
+    double q[AG_MAXR][4];        // retained quaternions (wxyz); more than AG_MAXK only without clustering
     double D[AG_MAXK][AG_MAXK];  // 1 - <qi,qj>^2
     unsigned nbr[AG_MAXK];
 };
@@ -97,10 +97,10 @@ __device__ void top_eigvec4(double A[4][4], double *out) {
 
 // A = sum over the members in `mask` of (oriented q)(oriented q)^T; scale is irrelevant to the
 // eigenvector, members are oriented to w > 0 exactly like ((Q[...,0:1] > 0) - 0.5) * 2 * Q.
-__device__ void average_quat(const double (*q)[4], unsigned mask, double *out) {
+__device__ void average_quat(const double (*q)[4], unsigned long long mask, double *out) {
     double A[4][4] = {};
-    for (int i = 0; i < AG_MAXK; ++i) {
-        if (!((mask >> i) & 1u)) continue;
+    for (int i = 0; i < AG_MAXR; ++i) {
+        if (!((mask >> i) & 1ull)) continue;
         const double sg = q[i][0] > 0 ? 1.0 : -1.0;
         double v[4] = {sg * q[i][0], sg * q[i][1], sg * q[i][2], sg * q[i][3]};
         for (int a = 0; a < 4; ++a)
@@ -148,8 +148,8 @@ aggregate_kernel(const double *__restrict__ poses, const float *__restrict__ ene
         rot6d_to_quat(d6, S.q[i]);
     }
     __syncwarp();
-    const unsigned all = retain >= 32 ? 0xffffffffu : ((1u << retain) - 1u);
-    unsigned member = all;
+    const unsigned long long all = retain >= 64 ? ~0ull : ((1ull << retain) - 1ull);
+    unsigned long long member = all;
     if (clustering) {
         for (int i = lane; i < retain * retain; i += 32) {
             const int r = i / retain, c = i - r * retain;
@@ -173,7 +173,7 @@ aggregate_kernel(const double *__restrict__ poses, const float *__restrict__ ene
         __syncwarp();
     }
     if (lane == 0) {
-        int labels[AG_MAXK];
+        int labels[AG_MAXR];
         for (int i = 0; i < retain; ++i) labels[i] = -1;
         if (clustering) {
             unsigned core = 0, labeled = 0;
@@ -323,7 +323,8 @@ extern "C" int gp_aggregate(const double *poses, const float *energy, int B, int
                             double *sorted_out, gp_stream_t s) {
     GP_REQUIRE(poses && energy && pose_out, "gp_aggregate: null pointer");
     GP_REQUIRE(B >= 0 && R >= 1 && R <= AG_MAXR, "gp_aggregate: R=%d must be in [1,%d]", R, AG_MAXR);
-    GP_REQUIRE(retain >= 1 && retain <= AG_MAXK && retain <= R, "gp_aggregate: retain=%d must be in [1,min(R,%d)]", retain, AG_MAXK);
+    GP_REQUIRE(retain >= 1 && retain <= (clustering ? AG_MAXK : AG_MAXR) && retain <= R,
+               "gp_aggregate: retain=%d must be in [1,min(R,%d)] (%d without clustering)", retain, AG_MAXK, AG_MAXR);
     if (B == 0) return GP_OK;
     aggregate_kernel<<<(B + AG_WARPS - 1) / AG_WARPS, AG_WARPS * 32, 0, as_stream(s)>>>(
         poses, energy, B, R, retain, clustering, clustering_eps, min_samples, pose_out, labels_out, sorted_out);

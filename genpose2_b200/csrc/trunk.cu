@@ -325,6 +325,16 @@ __constant__ double c_A[6][5] = {
 __constant__ double c_B[6] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
 __constant__ double c_E[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
 
+// dense-output coefficients (scipy rk.py RK45.P, [7 stages][4 powers])
+__constant__ double c_P[7][4] = {
+    {1.0, -8048581381.0 / 2820520608.0, 8663915743.0 / 2820520608.0, -12715105075.0 / 11282082432.0},
+    {0.0, 0.0, 0.0, 0.0},
+    {0.0, 131558114200.0 / 32700410799.0, -68118460800.0 / 10900136933.0, 87487479700.0 / 32700410799.0},
+    {0.0, -1754552775.0 / 470086768.0, 14199869525.0 / 1410260304.0, -10690763975.0 / 1880347072.0},
+    {0.0, 127303824393.0 / 49829197408.0, -318862633887.0 / 49829197408.0, 701980252875.0 / 199316789632.0},
+    {0.0, -282668133.0 / 205662961.0, 2019193451.0 / 616988883.0, -1453857185.0 / 822651844.0},
+    {0.0, 40617522.0 / 29380423.0, -110615467.0 / 29380423.0, 69997945.0 / 29380423.0}};
+
 struct OdeArgs {
     const float *P;
     const float *proj;
@@ -333,6 +343,10 @@ struct OdeArgs {
     int N, rpo;
     double T, eps, rtol, atol;
     int denoise;
+    double denoise_steps;   // the denoise step is (1 - eps) / denoise_steps (1000, or num_steps with dense output)
+    const double *t_eval;   // dense output: n_eval times in integration order (device), or nullptr
+    int n_eval;
+    double *dense;          // [n_eval][N][9] raw states at t_eval
     double *x_out;
     double *traj;
     int max_traj;
@@ -480,6 +494,35 @@ __device__ __noinline__ double ode_error_part(const double *y, const double *yne
     return se;
 }
 
+// Dense output of an accepted step (scipy rk.py:715-737, RkDenseOutput): y(te) = y_old + h * Q . [x, x^2, x^3, x^4],
+// Q = K^T . P, x = (te - t_old) / h, for the quads of one tile -> dst (rows of the whole batch).
+template <class EV>
+__device__ __noinline__ void ode_dense_point(const double *y, const double *k0, const double *k1, const double *k2,
+                                             const double *k3, const double *k4, const double *k5, const double *k6,
+                                             int tile, int N, double h, double x, double *dst) {
+    constexpr int RT = EV::RT;
+    const int q = threadIdx.x;
+    if (q >= RT * 9 / 4) return;
+    const size_t g = (size_t)tile * RT * 9 + 4 * q;
+    const int nvalid = min(RT, N - tile * RT) * 9;
+    const double *const ks[7] = {k0, k1, k2, k3, k4, k5, k6};
+    const double p1 = x, p2 = p1 * x, p3 = p2 * x, p4 = p3 * x;   // np.cumprod([x, x, x, x])
+    const D4 yv = ld_d4(y + g);
+    D4 kv[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) kv[j] = ld_d4(ks[j] + g);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        double qc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) qc[c] += kv[j].v[e] * c_P[j][c];
+        const double v = yv.v[e] + h * (((qc[0] * p1 + qc[1] * p2) + qc[2] * p3) + qc[3] * p4);
+        if (4 * q + e < nvalid) dst[g + e] = v;
+    }
+}
+
 template <class EV>
 __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
     constexpr int RT = EV::RT, NT = EV::NT, XS = EV::XS;
@@ -511,6 +554,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
     __shared__ float s_std[8];    // ... and sigma(t_s) as the network sees it
     long long cyc_tq = 0, cyc_x = 0, cyc_k = 0, cyc_err = 0;
     double nfev = 0, n_acc = 0, n_rej = 0;
+    int next_eval = 0;   // dense output: next requested time
     int status = 0;
     int pbuf = 0;
 
@@ -699,6 +743,23 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
                 double factor = (error_norm == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(error_norm, -0.2));
                 if (step_rejected) factor = fmin(1.0, factor);
                 h_abs *= factor;
+                if (a.t_eval != nullptr) {
+                    // t_eval handling of ivp.py: every requested time this step has reached or passed is interpolated
+                    // by it.  One CTA per tile writes the shared output; the last point (te == t_bound, x == 1) also
+                    // replaces y_new in every CTA's private state: the reference denoises res.y[:, -1].
+                    while (next_eval < a.n_eval && direction * (a.t_eval[next_eval] - t_new) <= 0.0) {
+                        const double xe = (a.t_eval[next_eval] - t) / h;
+                        for (int tile = tile0; tile < a.ntiles; tile += tile_step) {
+                            if (EV::writer(ctx))
+                                ode_dense_point<EV>(ycur, K0, K1, K2, K3, K4, K5, K6, tile, N, h, xe,
+                                                    a.dense + (size_t)next_eval * N * 9);
+                            if (next_eval == a.n_eval - 1 && t_new == t_bound)
+                                ode_dense_point<EV>(ycur, K0, K1, K2, K3, K4, K5, K6, tile, N, h, xe, ynew);
+                        }
+                        ++next_eval;
+                    }
+                    __syncthreads();
+                }
                 // accept: y <- y_new, f <- f_new (FSAL: K[6] becomes K[0]); pointer rotation only
                 double *ty = ycur; ycur = ynew; ynew = ty;
                 double *tk = K0; K0 = K6; K6 = tk;
@@ -745,7 +806,7 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
                 if (a.denoise) {
                     const float std = sigma_f32(eps_f);
                     const float dif = diffusion_f32(eps_f);
-                    const float step = (float)((1.0 - a.eps) / 1000.0);
+                    const float step = (float)((1.0 - a.eps) / a.denoise_steps);
 #pragma unroll
                     for (int c = 0; c < 9; ++c) {
                         const float grad = fo[r * XS + c] / (std + 1e-7f);
@@ -1069,15 +1130,17 @@ extern "C" size_t gp_scorenet_ode_workspace_bytes(int N) {
     return state * 9 * tc::CL + align256(2 * 3 * ntiles_max * sizeof(double)) + 256 /*barrier*/ + 256;
 }
 
-extern "C" int gp_scorenet_ode(const void *packed, const float *proj, const double *x0, const float *pts_center,
-                               int N, int rows_per_object, double T, double eps, double rtol, double atol,
-                               int denoise, double *x_out, double *traj, int max_traj, double *stats,
-                               void *workspace, size_t workspace_bytes, int mode, gp_stream_t s) {
+static int scorenet_ode_impl(const void *packed, const float *proj, const double *x0, const float *pts_center,
+                             int N, int rows_per_object, double T, double eps, double rtol, double atol,
+                             int denoise, double *x_out, double *traj, int max_traj, const double *t_eval, int n_eval,
+                             double *dense, double *stats, void *workspace, size_t workspace_bytes, int mode,
+                             gp_stream_t s) {
     GP_REQUIRE(packed && proj && x0 && pts_center && x_out && stats && workspace, "gp_scorenet_ode: null pointer");
     GP_REQUIRE(N >= 1 && rows_per_object >= 1, "gp_scorenet_ode: bad sizes N=%d rows_per_object=%d", N, rows_per_object);
     GP_REQUIRE(rtol > 0 && atol > 0, "gp_scorenet_ode: tolerances must be positive");
     GP_REQUIRE(traj == nullptr || max_traj >= 1, "gp_scorenet_ode: max_traj < 1");
     GP_REQUIRE(mode >= 0 && mode <= 2, "gp_scorenet_ode: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05)");
+    GP_REQUIRE((t_eval == nullptr) == (dense == nullptr) && (t_eval == nullptr || n_eval >= 1), "gp_scorenet_ode_dense: t_eval / dense / n_eval inconsistent");
     if (workspace_bytes < gp_scorenet_ode_workspace_bytes(N)) {
         set_error("gp_scorenet_ode: workspace too small (%zu < %zu)", workspace_bytes, gp_scorenet_ode_workspace_bytes(N));
         return GP_ERR_WORKSPACE;
@@ -1088,6 +1151,8 @@ extern "C" int gp_scorenet_ode(const void *packed, const float *proj, const doub
     a.P = (const float *)packed; a.proj = proj; a.x0 = x0; a.center = pts_center;
     a.N = N; a.rpo = rows_per_object; a.T = T; a.eps = eps; a.rtol = rtol; a.atol = atol;
     a.denoise = denoise; a.x_out = x_out; a.traj = traj; a.max_traj = max_traj; a.stats = stats;
+    a.t_eval = t_eval; a.n_eval = t_eval ? n_eval : 0; a.dense = dense;
+    a.denoise_steps = t_eval ? (double)n_eval : 1000.0;   // samplers.py:238-249
     unsigned char *w = (unsigned char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     const size_t state = ode_state_bytes(N);
     a.y[0] = (double *)w; w += state;
@@ -1108,6 +1173,23 @@ extern "C" int gp_scorenet_ode(const void *packed, const float *proj, const doub
         case 6: return launch_ode<SimtEval<6>>(a, st);
         default: return launch_ode<SimtEval<8>>(a, st);
     }
+}
+
+extern "C" int gp_scorenet_ode(const void *packed, const float *proj, const double *x0, const float *pts_center,
+                               int N, int rows_per_object, double T, double eps, double rtol, double atol,
+                               int denoise, double *x_out, double *traj, int max_traj, double *stats,
+                               void *workspace, size_t workspace_bytes, int mode, gp_stream_t s) {
+    return scorenet_ode_impl(packed, proj, x0, pts_center, N, rows_per_object, T, eps, rtol, atol, denoise, x_out, traj,
+                             max_traj, nullptr, 0, nullptr, stats, workspace, workspace_bytes, mode, s);
+}
+
+extern "C" int gp_scorenet_ode_dense(const void *packed, const float *proj, const double *x0, const float *pts_center,
+                                     int N, int rows_per_object, double T, double eps, double rtol, double atol,
+                                     int denoise, double *x_out, const double *t_eval, int n_eval, double *dense,
+                                     double *stats, void *workspace, size_t workspace_bytes, int mode, gp_stream_t s) {
+    GP_REQUIRE(t_eval && dense && n_eval >= 1, "gp_scorenet_ode_dense: t_eval / dense missing");
+    return scorenet_ode_impl(packed, proj, x0, pts_center, N, rows_per_object, T, eps, rtol, atol, denoise, x_out, nullptr,
+                             0, t_eval, n_eval, dense, stats, workspace, workspace_bytes, mode, s);
 }
 
 extern "C" int gp_traj_finalize(const double *traj, const float *pts_center, int S, int N, double *xs, gp_stream_t s) {

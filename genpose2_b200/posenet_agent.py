@@ -96,8 +96,8 @@ class PoseNet(nn.Module):
                 from .aggregation import _run
                 # average_quaternion_batch over all hypotheses + mean translation (posenet_agent.py:561-570)
                 ones = torch.zeros((bs, repeat_num, 2), dtype=torch.float32, device=res.device)
-                if repeat_num > 32:
-                    raise NotImplementedError("return_average_res with more than 32 hypotheses")
+                if repeat_num > 64:
+                    raise NotImplementedError("return_average_res with more than 64 hypotheses")
                 avg, _, _ = _run(pred_pose, ones, repeat_num, False, 0.0, 1)
                 avg_q = torch.zeros((bs, 7), device=res.device)
                 avg_q[:, :4] = matrix_to_quaternion(avg[:, :3, :3])

@@ -235,6 +235,19 @@ GP_API int gp_scorenet_ode(const void *packed, const float *proj, const double *
                     int max_traj, double *stats, void *workspace, size_t workspace_bytes, int mode,
                     gp_stream_t s);
 
+/* The same integration with scipy's dense output on a fixed grid (solve_ivp(..., t_eval=np.linspace(T, eps, num_steps)),
+ * samplers.py:222-235; RkDenseOutput, scipy rk.py:715-737): every requested time is interpolated by the accepted step
+ * that reaches it, y(te) = y_old + h * (K^T P) . [x, x^2, x^3, x^4], x = (te - t_old) / h.
+ *   t_eval  [n_eval] f64 (device), in integration order (t_eval[0] = T, t_eval[n_eval-1] = eps)
+ *   dense   [n_eval, N, 9] f64: raw states at t_eval (feed to gp_traj_finalize for the reference's `xs`)
+ * The final pose is taken from the last interpolated state and the denoise step is (1 - eps) / n_eval, as
+ * samplers.py:236-249 does when num_steps is given. */
+GP_API int gp_scorenet_ode_dense(const void *packed, const float *proj, const double *x0,
+                          const float *pts_center, int N, int rows_per_object, double T, double eps,
+                          double rtol, double atol, int denoise, double *x_out, const double *t_eval,
+                          int n_eval, double *dense, double *stats, void *workspace, size_t workspace_bytes,
+                          int mode, gp_stream_t s);
+
 /* Post-processing of a recorded trajectory into the reference's `xs` (samplers.py:251-255):
  * traj [S,N,9] f64 raw -> xs [N,S,9] f64 with Gram-Schmidt on the rotation part and the centre
  * added. */
@@ -272,7 +285,8 @@ GP_API int gp_energy(const void *packed, const float *proj, const double *poses,
  *   poses [B,R,9] f64, energy [B,R,2] f32 -> pose_out [B,4,4] f32;
  *   labels_out NULL or [B,retain] i32 (DBSCAN labels, for inspection);
  *   sorted_out NULL or [B,R,9] f64 (sort_poses_by_energy's first return value).
- * Requires R <= 64 and retain <= 32. */
+ * Requires R <= 64 and retain <= 32 (retain <= 64 when clustering == 0: plain quaternion average + mean
+ * translation over all hypotheses, posenet_agent.py:561-570 return_average_res). */
 GP_API int gp_aggregate(const double *poses, const float *energy, int B, int R, int retain,
                  int clustering, double clustering_eps, int min_samples, float *pose_out,
                  int32_t *labels_out, double *sorted_out, gp_stream_t s);

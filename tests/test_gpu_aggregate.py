@@ -86,3 +86,28 @@ def test_scalenet_matches_reference_golden():
     want = po.scalenet_forward(synthetic.random_scalenet_state_dict(int(g["scale_seed"])), axes, feat)
     got = net({"pts_feat": feat.cuda(), "axes": axes.cuda()}).cpu()
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=2e-5, atol=2e-6)
+
+
+def test_average_over_all_50_hypotheses_matches_oracle():
+    """return_average_res of pred_func (posenet_agent.py:561-570): average_quaternion_batch over all repeat_num = 50
+    hypotheses + mean translation, no energies, no clustering (retain > 32 is allowed without clustering)"""
+    from genpose2_b200.aggregation import _run
+    from oracle import pose_oracle as po
+    g = torch.Generator().manual_seed(5)
+    B, R = 7, 50
+    base = torch.randn(B, 1, 6, generator=g, dtype=torch.float64)
+    rot6 = base + 0.05 * torch.randn(B, R, 6, generator=g, dtype=torch.float64)
+    trans = torch.randn(B, R, 3, generator=g, dtype=torch.float64)
+    # normalise to valid (x-axis, y-axis) pairs like the sampler output
+    a1 = torch.nn.functional.normalize(rot6[..., :3], dim=-1)
+    a2 = rot6[..., 3:] - (a1 * rot6[..., 3:]).sum(-1, keepdim=True) * a1
+    a2 = torch.nn.functional.normalize(a2, dim=-1)
+    poses = torch.cat([a1, a2, trans], dim=-1)
+    out, _, _ = _run(poses.cuda(), torch.zeros(B, R, 2).cuda(), R, False, 0.0, 1)
+    quat = po.matrix_to_quaternion(po.get_rot_matrix(poses.reshape(B * R, 9)[:, :6])).reshape(B, R, 4)
+    want_q = po.average_quaternion_batch(quat)
+    want_R = po.quaternion_to_matrix(want_q)
+    from tests.util import geodesic_mats
+    rot_err = float(np.max(geodesic_mats(out[:, :3, :3].double().cpu().numpy(), want_R.numpy())))
+    t_err = float((out[:, :3, 3].double().cpu() - trans.mean(1)).abs().max())
+    assert rot_err < 1e-6 and t_err < 1e-6, (rot_err, t_err)

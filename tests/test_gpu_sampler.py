@@ -227,3 +227,34 @@ def test_bf16_ode_sampler_within_stated_bound(name):
     print(f"bf16 {name}: rot {rot:.3e} rad trans {trans:.3e}; nfev {st['nfev'] + 1} (reference {int(g['nfev'])})")
     assert st["status"] == 0
     assert rot <= BF16_ROT_TOL and trans <= BF16_TRANS_TOL, (rot, trans)
+
+
+@pytest.mark.parametrize("mlp_mode", ["fp32", "fp32_ffma"])
+def test_ode_sampler_dense_output_matches_reference_golden(mlp_mode):
+    """num_steps = 20: scipy's t_eval / RkDenseOutput path of cond_ode_sampler (samplers.py:222-249), scope row f2"""
+    from genpose2_b200 import samplers
+    g = load_golden("ode_b2_T055_steps20")
+    net = make_net(int(g["score_seed"]), mlp_mode=mlp_mode)
+    R, B, S = int(g["R"]), int(g["B"]), int(g["num_steps"])
+    feat, center = torch.from_numpy(g["feat"]).cuda(), torch.from_numpy(g["center"]).cuda()
+    noise = torch.from_numpy(g["noise"])
+    data = {"pts": torch.zeros(B * R, 1, 3), "pts_center": rep(center, R), "_gp_pts_feat_obj": feat,
+            "_gp_rows_per_object": R}
+    xs, x = samplers.cond_ode_sampler(net, data, lambda shape, T: noise.clone(), net.sde_fn, atol=1e-5, rtol=1e-5,
+                                      device="cuda", eps=1e-5, T=float(g["T0"]), num_steps=S, pose_mode="rot_matrix")
+    st = samplers.ode_stats()
+    assert st["status"] == 0 and st["nfev"] + 1 == int(g["nfev"])
+    assert xs.shape == (B * R, S, 9) and xs.dtype == torch.float64
+    for key, arr in (("x", x), ("xs_last", xs[:, -1]), ("xs_mid", xs[:, S // 2]), ("xs_first", xs[:, 0])):
+        rot, trans = pose_errors(arr.cpu().numpy(), g[key])
+        mag = max(1.0, float(np.abs(g[key][:, 6:]).max()))
+        print(f"dense {mlp_mode} {key}: rot {rot:.3e} trans {trans:.3e}")
+        assert rot <= ROT_TOL and trans <= TRANS_TOL * mag, (key, rot, trans)
+    # the interpolated grid against the oracle at every point
+    trunk = po.Trunk(synthetic.random_gfobjectpose_state_dict(int(g["score_seed"])))
+    xs_o, x_o, _ = po.cond_ode_sampler(trunk, rep(torch.from_numpy(g["feat"]), R), rep(torch.from_numpy(g["center"]), R), noise,
+                                       T=float(g["T0"]), num_steps=S)
+    for s_i in range(S):
+        rot, trans = pose_errors(xs[:, s_i].cpu().numpy(), xs_o[:, s_i].numpy())
+        mag = max(1.0, float(xs_o[:, s_i, 6:].abs().max()))
+        assert rot <= ROT_TOL and trans <= TRANS_TOL * mag, (s_i, rot, trans)
