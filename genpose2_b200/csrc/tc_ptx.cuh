@@ -67,7 +67,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
-constexpr uint32_t kIdesc = make_idesc_bf16(128, 256);
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -118,9 +117,6 @@ __device__ __forceinline__ uint32_t mapa(uint32_t cta_addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
-}
 // split cluster barrier: every thread of every CTA in the cluster arrives / waits (warp-convergent)
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 // bulk copy from this CTA's shared memory into a peer's (addresses from mapa), completing on the peer's mbarrier
@@ -137,18 +133,11 @@ __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void mbar_arrive_peer_relaxed(uint32_t bar_cluster_addr) {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
-// arrival without a memory fence: for threads that published nothing the peers will read
-__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 // explicit shared-state-space accesses (32-bit shared addresses): used where a structure is only reachable
 // through a generic pointer but the access is hot
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-// variants ordered against barriers (memory clobber): for data other threads wrote before a __syncthreads()
+// (memory clobber: ordered against barriers, for data other threads wrote before a __syncthreads())
 __device__ __forceinline__ float4 lds_f4_sync(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
@@ -159,21 +148,10 @@ __device__ __forceinline__ float2 lds_f2_sync(uint32_t addr) {
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
     return v;
 }
-__device__ __forceinline__ float lds_f(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ void sts_u4(uint32_t addr, const uint4 &v) {
     // volatile (ordered against the fences / mbarrier arrives, which are volatile too) but no "memory" clobber:
     // ordinary loads of the surrounding loop may be scheduled across the store
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
-}
-__device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
-    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v));
-}
-__device__ __forceinline__ void sts_f(uint32_t addr, float v) {
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
 }  // namespace tc

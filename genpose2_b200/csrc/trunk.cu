@@ -1,6 +1,7 @@
-// ScoreNet / EnergyNet trunk kernels (FP32 path): weight packing, per-object head projection,
-// single evaluation, energy scoring, the device-resident Dormand-Prince (scipy-RK45-faithful)
-// integrator fused with the ScoreNet RHS, and the fixed-step predictor-corrector sampler.
+// ScoreNet / EnergyNet trunk kernels: weight packing, per-object head projection, single evaluation, energy
+// scoring, the device-resident Dormand-Prince (scipy-RK45-faithful) integrator fused with the ScoreNet RHS (with
+// scipy's dense output), and the fixed-step predictor-corrector sampler.  The MLP evaluation itself is a policy:
+// SimtEval (FP32 FFMA, trunk.cuh) or TcEval (tcgen05, 4-CTA clusters, trunk_tc.cuh).
 #include <cuda_bf16.h>
 
 #include <cstdlib>
