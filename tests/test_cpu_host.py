@@ -193,3 +193,40 @@ def test_oracle_pointnet2_matches_bruteforce_numpy():
             assert set(got[:n]) <= set(np.nonzero(d2 < np.float32(0.9) ** 2 * 1.001)[0])
             assert (got[n:] == got[0]).all() or len(hits) >= 6
     assert pn.fps_block_size(1000) == 512 and pn.fps_block_size(1024) == 1024 and pn.fps_block_size(5000) == 1024
+
+
+def test_stage_files_are_plain_pickles_in_the_reference_layout(tmp_path):
+    """what evaluation_single.py:120,157,219,254 dump and :127,164-167,226-228 load"""
+    import pickle
+    from genpose2_b200 import stage_io
+    g = torch.Generator().manual_seed(0)
+    poses = [torch.randn(3, 50, 9, generator=g, dtype=torch.float64), torch.randn(2, 50, 9, generator=g, dtype=torch.float64)]
+    feats = [torch.randn(3, 1024, generator=g), torch.randn(2, 1024, generator=g)]
+    energy = [torch.randn(3, 50, 2, generator=g), torch.randn(2, 50, 2, generator=g)]
+    agg = [torch.eye(4).repeat(3, 1, 1), torch.eye(4).repeat(2, 1, 1)]
+    length = [torch.rand(3, 3, generator=g), torch.rand(2, 3, generator=g)]
+    p = stage_io.stage_paths(str(tmp_path / "run"), "score.pth", "energy.pth", "scale.pth")
+    p = {k: str(tmp_path / v) for k, v in p.items()}
+    stage_io.save_score_stage(p["score"], poses, feats)
+    stage_io.save_energy_stage(p["energy"], energy)
+    stage_io.save_aggregate_stage(p["aggregate"], agg)
+    stage_io.save_scale_stage(p["scale"], agg, length)
+    # read them back exactly as the reference does
+    all_pred_pose, all_score_feature = pickle.load(open(p["score"], "rb"))
+    assert len(all_pred_pose) == 2 and all_pred_pose[0].dtype == torch.float64 and tuple(all_pred_pose[1].shape) == (2, 50, 9)
+    assert set(all_score_feature[0]) == {"pts_feat", "rgb_feat"} and all_score_feature[0]["rgb_feat"] is None
+    assert torch.equal(all_score_feature[1]["pts_feat"], feats[1])
+    all_pred_energy = pickle.load(open(p["energy"], "rb"))
+    assert torch.equal(all_pred_energy[0], energy[0])
+    assert torch.equal(pickle.load(open(p["aggregate"], "rb"))[1], agg[1])
+    a2, l2 = pickle.load(open(p["scale"], "rb"))
+    assert torch.equal(a2[0], agg[0]) and torch.equal(l2[1], length[1])
+    # the runner's fallback box size (evaluation_single.py:232-250) against its own formulation
+    pcl = torch.randn(3, 64, 3, generator=g)
+    pose = torch.eye(4).repeat(3, 1, 1)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, 3, generator=g))
+    pose[:, :3, :3] = q
+    pose[:, :3, 3] = torch.randn(3, 3, generator=g)
+    rot_t = torch.repeat_interleave(pose[:, :3, :3].transpose(1, 2), 64, dim=0)
+    want = 2 * torch.bmm(rot_t, (pcl - pose[:, :3, 3].unsqueeze(1)).reshape(-1, 3, 1)).reshape(-1, 64, 3).abs().max(dim=1)[0]
+    assert torch.allclose(stage_io.bbox_length_from_points(pcl, pose), want, atol=1e-6)
