@@ -264,6 +264,21 @@ class Pointnet2ClsMSG(nn.Module):
         features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
         return xyz, features
 
+    def compute_geometry(self, pointcloud: torch.Tensor):
+        """FPS + both ball queries of every level (they depend on the coordinates only: level k samples the centres
+        of level k-1), as the list `forward(..., geometry=...)` takes.  Lets two encoders that see the same cloud
+        share one pass and start side by side."""
+        xyz = pointcloud[..., 0:3].contiguous()
+        geometry = []
+        for sa in self.SA_modules:
+            if sa.npoint is None:
+                geometry.append(None)
+                continue
+            idx, new_xyz = pu.furthest_point_sample_gather(xyz, sa.npoint)
+            geometry.append((idx, new_xyz, pu.ball_query2(sa.radii, sa.nsamples, xyz, new_xyz)))
+            xyz = new_xyz
+        return geometry
+
     def forward(self, pointcloud: torch.Tensor, geometry: Optional[list] = None, return_geometry=False):
         """pointcloud (B, N, 3 + C) -> (B, 1024).  `geometry`: per-level FPS / ball-query results of an
         earlier call on the same cloud (they depend on xyz only)."""

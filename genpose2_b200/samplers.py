@@ -33,6 +33,29 @@ def _mlp_mode(score_model):
     return MLP_MODES[_score_net(score_model).mlp_mode]
 
 
+_staging = {}
+
+
+def _to_device_async(t, device):
+    """Host tensor -> device without blocking the host: a pageable copy is synchronous AND ordered behind everything
+    already enqueued on the stream, so the prior draw (made on the CPU with the CPU generator, like the reference)
+    would stall the host until the encoder has finished.  Staged through a cached pinned buffer instead."""
+    if t.is_cuda:
+        return t.to(device)
+    key = (tuple(t.shape), t.dtype)
+    ent = _staging.get(key)
+    if ent is None:
+        ent = _staging[key] = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True), None]
+    buf, ev = ent
+    if ev is not None:
+        ev.synchronize()   # the previous copy out of this buffer (long finished in practice)
+    buf.copy_(t)
+    out = buf.to(device, non_blocking=True)
+    ent[1] = torch.cuda.Event()
+    ent[1].record(torch.cuda.current_stream(out.device))
+    return out
+
+
 def cond_ode_sampler(score_model, data, prior, sde_coeff, atol=1e-5, rtol=1e-5, device="cuda", eps=1e-5,
                      T=1.0, num_steps=None, pose_mode="quat_wxyz", denoise=True, init_x=None,
                      return_trajectory=True):
@@ -43,7 +66,7 @@ def cond_ode_sampler(score_model, data, prior, sde_coeff, atol=1e-5, rtol=1e-5, 
         raise NotImplementedError("accelerated sampler supports pose_mode='rot_matrix' only")
     net = _score_net(score_model)
     batch_size = data["pts"].shape[0]
-    noise = prior((batch_size, POSE_DIM), T=T).to(device)  # CPU generator, like samplers.py:197-201
+    noise = _to_device_async(prior((batch_size, POSE_DIM), T=T), device)  # CPU generator, like samplers.py:197-201
     x0 = noise if init_x is None else init_x + noise
     dev = x0.device
     x0 = x0.to(torch.float64).contiguous()  # scipy casts y0 to float64
@@ -118,7 +141,7 @@ def cond_pc_sampler(score_model, data, prior, sde_coeff, num_steps=500, snr=0.16
         raise NotImplementedError("accelerated sampler supports pose_mode='rot_matrix' only")
     net = _score_net(score_model)
     batch_size = data["pts"].shape[0]
-    x0 = prior((batch_size, POSE_DIM)).to(device) if init_x is None else init_x
+    x0 = _to_device_async(prior((batch_size, POSE_DIM)), device) if init_x is None else init_x
     dev = x0.device
     x0 = x0.to(torch.float32).contiguous()
     time_steps = torch.linspace(1.0, eps, num_steps, device=dev)
