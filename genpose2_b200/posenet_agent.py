@@ -57,7 +57,8 @@ class PoseNet(nn.Module):
                   init_x: torch.Tensor = None, T0=None, return_process=False, geometry=None,
                   return_geometry=False, pts_feat=None):
         self.is_testing = True
-        self.net.eval()
+        if self.net.training:   # eval() walks every sub-module: only when the flag actually has to change
+            self.net.eval()
         if getattr(self.cfg, "save_video", False):
             raise NotImplementedError("save_video (visualisation) is out of scope")
         with torch.no_grad():
@@ -112,7 +113,8 @@ class PoseNet(nn.Module):
     def pred_scale_func(self, data):
         """posenet_agent.py:586-606 -> (axes, length [bs,3])."""
         self.is_testing = True
-        self.net.eval()
+        if self.net.training:   # eval() walks every sub-module: only when the flag actually has to change
+            self.net.eval()
         with torch.no_grad():
             pred_len = self.net(data)
         return data["axes"], pred_len
@@ -122,7 +124,8 @@ class PoseNet(nn.Module):
         if mode != "test":
             raise NotImplementedError("get_energy(mode='train') is training-only")
         self.is_testing = True
-        self.net.eval()
+        if self.net.training:   # eval() walks every sub-module: only when the flag actually has to change
+            self.net.eval()
         bs, repeat_num = pose_samples.shape[0], pose_samples.shape[1]
         with torch.no_grad():
             pts_feat = data["pts_feat"] if not extract_feature else self.net(data, mode="pts_feature", geometry=geometry)
