@@ -400,10 +400,37 @@ __device__ __forceinline__ D4 ld_d4(const double *p) {
 // inputs of stage S (1..5: y + h * sum_j a_Sj K_j; 6: y_new, also stored) for one tile -> xin (float32).
 // Thread t owns elements 4t..4t+3 of the tile; its loads are unconditional (the buffers are padded to whole
 // tiles) and all issued before the first use: one memory round trip per stage.
+// this thread's quad of scipy's `fun` from the evaluator's output tile: K = 0 - coef * f_theta / (std + 1e-7)
+// (scorenet.py:262-264, samplers.py:219)
+template <class EV>
+__device__ __forceinline__ D4 rhs_quad(const float *fo, int q, float std, double coef) {
+    constexpr int XS = EV::XS;
+    float f[4];
+    if (XS == 9) {
+        const float4 v = *reinterpret_cast<const float4 *>(fo + 4 * q);
+        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) f[e] = fo[((4 * q + e) / 9) * XS + (4 * q + e) % 9];
+    }
+    D4 k;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) k.v[e] = 0.0 - coef * (double)(f[e] / (std + 1e-7f));
+    return k;
+}
+__device__ __forceinline__ void st_d4(double *p, const D4 &v) {
+    *reinterpret_cast<double2 *>(p) = make_double2(v.v[0], v.v[1]);
+    *reinterpret_cast<double2 *>(p + 2) = make_double2(v.v[2], v.v[3]);
+}
+
+// `k_store` (stages 2..6): the derivative of the previous stage has not been written yet -- it is formed here from the
+// evaluator's output tile `fo` (which the same thread then overwrites with the new inputs when the evaluator reuses
+// its input buffer), stored to k_store and used from registers: no separate pass over the tile, no extra barrier.
 template <class EV, int S>
 __device__ __noinline__ void ode_stage_input(const double *y, double *ynew, const double *k0, const double *k1,
                                              const double *k2, const double *k3, const double *k4, const double *k5,
-                                             float *xin, int tile, int N, double h) {
+                                             float *xin, int tile, int N, double h, const float *fo, double *k_store,
+                                             float std_prev, double coef_prev) {
     constexpr int RT = EV::RT, XS = EV::XS;
     constexpr int NK = S < 6 ? S : 6;
     static_assert(RT * 9 / 4 <= EV::NT && (RT * 9) % 4 == 0, "one quad per thread");
@@ -415,7 +442,12 @@ __device__ __noinline__ void ode_stage_input(const double *y, double *ynew, cons
         D4 kv[NK];
         const D4 yv = ld_d4(y + g);
 #pragma unroll
-        for (int j = 0; j < NK; ++j) kv[j] = ld_d4(ks[j] + g);
+        for (int j = 0; j < NK; ++j)
+            if (!(k_store != nullptr && j == S - 1)) kv[j] = ld_d4(ks[j] + g);
+        if (k_store != nullptr) {
+            kv[S - 1 < NK ? S - 1 : NK - 1] = rhs_quad<EV>(fo, q, std_prev, coef_prev);
+            st_d4(k_store + g, kv[S - 1 < NK ? S - 1 : NK - 1]);
+        }
         float v[4];
         D4 yn;
 #pragma unroll
@@ -466,19 +498,21 @@ __device__ __noinline__ void ode_store_k(const float *fo, double *Kd, int tile, 
 template <class EV>
 __device__ __noinline__ double ode_error_part(const double *y, const double *ynew, const double *k0, const double *k1,
                                               const double *k2, const double *k3, const double *k4, const double *k5,
-                                              const double *k6, int tile, int N, double h, double atol, double rtol,
-                                              double *traj_slot) {
+                                              double *k6, int tile, int N, double h, double atol, double rtol,
+                                              double *traj_slot, const float *fo, float std6, double coef6) {
     constexpr int RT = EV::RT;
     const int q = threadIdx.x;
     double se = 0.0;
     if (q < RT * 9 / 4) {
         const size_t g = (size_t)tile * RT * 9 + 4 * q;
         const int nvalid = min(RT, N - tile * RT) * 9;
-        const double *const ks[7] = {k0, k1, k2, k3, k4, k5, k6};
+        const double *const ks[6] = {k0, k1, k2, k3, k4, k5};
         D4 kv[7];
         const D4 y0 = ld_d4(y + g), y1 = ld_d4(ynew + g);
 #pragma unroll
-        for (int j = 0; j < 7; ++j) kv[j] = ld_d4(ks[j] + g);
+        for (int j = 0; j < 6; ++j) kv[j] = ld_d4(ks[j] + g);
+        kv[6] = rhs_quad<EV>(fo, q, std6, coef6);   // f(t + h, y_new): formed from the evaluator's output, kept for FSAL
+        st_d4(k6 + g, kv[6]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             double ev = 0.0;
@@ -701,35 +735,38 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
 
             for (int tile = tile0; tile < a.ntiles; tile += tile_step) {
                 set_obj(tile);
-                // rk_step (rk.py:14-78)
+                // rk_step (rk.py:14-78).  The derivative of stage s is written by the input pass of stage s + 1 (and the
+                // last one by the error pass), straight from the evaluator's output tile.
+                auto fwd = [&](int slot) { EV::forward(P, a.proj, S, ctx, tqtab + slot * EV::TQW); };
                 long long tx0 = clock64();
-                ode_stage_input<EV, 1>(ycur, ynew, K0, K1, K2, K3, K4, K5, xin, tile, N, h);
+                ode_stage_input<EV, 1>(ycur, ynew, K0, K1, K2, K3, K4, K5, xin, tile, N, h, fo, nullptr, 0.f, 0.0);
                 cyc_x += clock64() - tx0;
-                stage_eval_c(tile, 0, s_std[0], s_coef[0], K1);
+                fwd(0);
                 tx0 = clock64();
-                ode_stage_input<EV, 2>(ycur, ynew, K0, K1, K2, K3, K4, K5, xin, tile, N, h);
+                ode_stage_input<EV, 2>(ycur, ynew, K0, K1, K2, K3, K4, K5, xin, tile, N, h, fo, K1, s_std[0], s_coef[0]);
                 cyc_x += clock64() - tx0;
-                stage_eval_c(tile, 1, s_std[1], s_coef[1], K2);
+                fwd(1);
                 tx0 = clock64();
-                ode_stage_input<EV, 3>(ycur, ynew, K0, K1, K2, K3, K4, K5, xin, tile, N, h);
+                ode_stage_input<EV, 3>(ycur, ynew, K0, K1, K2, K3, K4, K5, xin, tile, N, h, fo, K2, s_std[1], s_coef[1]);
                 cyc_x += clock64() - tx0;
-                stage_eval_c(tile, 2, s_std[2], s_coef[2], K3);
+                fwd(2);
                 tx0 = clock64();
-                ode_stage_input<EV, 4>(ycur, ynew, K0, K1, K2, K3, K4, K5, xin, tile, N, h);
+                ode_stage_input<EV, 4>(ycur, ynew, K0, K1, K2, K3, K4, K5, xin, tile, N, h, fo, K3, s_std[2], s_coef[2]);
                 cyc_x += clock64() - tx0;
-                stage_eval_c(tile, 3, s_std[3], s_coef[3], K4);
+                fwd(3);
                 tx0 = clock64();
-                ode_stage_input<EV, 5>(ycur, ynew, K0, K1, K2, K3, K4, K5, xin, tile, N, h);
+                ode_stage_input<EV, 5>(ycur, ynew, K0, K1, K2, K3, K4, K5, xin, tile, N, h, fo, K4, s_std[3], s_coef[3]);
                 cyc_x += clock64() - tx0;
-                stage_eval_c(tile, 4, s_std[4], s_coef[4], K5);
+                fwd(4);
                 tx0 = clock64();
-                ode_stage_input<EV, 6>(ycur, ynew, K0, K1, K2, K3, K4, K5, xin, tile, N, h);
+                ode_stage_input<EV, 6>(ycur, ynew, K0, K1, K2, K3, K4, K5, xin, tile, N, h, fo, K5, s_std[4], s_coef[4]);
                 cyc_x += clock64() - tx0;
-                stage_eval_c(tile, 5, s_std[5], s_coef[5], K6);
+                fwd(5);
                 // error estimate (rk.py:139-147)
                 const long long te0 = clock64();
                 double *traj_slot = (a.traj && (int)n_acc + 1 < a.max_traj) ? a.traj + ((size_t)((int)n_acc + 1) * N) * 9 : nullptr;
-                double se = ode_error_part<EV>(ycur, ynew, K0, K1, K2, K3, K4, K5, K6, tile, N, h, a.atol, a.rtol, traj_slot);
+                double se = ode_error_part<EV>(ycur, ynew, K0, K1, K2, K3, K4, K5, K6, tile, N, h, a.atol, a.rtol, traj_slot,
+                                               fo, s_std[5], s_coef[5]);
                 se = block_sum(se, S.red);
                 if (tid == 0) a.part[(pbuf * 3 + 0) * a.ntiles + tile] = se;
                 cyc_err += clock64() - te0;
