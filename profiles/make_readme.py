@@ -142,13 +142,13 @@ def main():
                   f"{j['other_mode']['value']:.0f} {j['unit']} ({j['other_mode']['ms_per_step']:.2f} ms/step); CPU port: "
                   f"{j['cpu_baseline']['value']:.1f} {j['unit']} on {j['cpu_baseline']['cores']} cores; clocks {j['clocks']}.\n")
     md.append("## phase_breakdown.py — in-kernel cycle counters of the integrator\n")
-    md.append("`python profiles/phase_breakdown.py` reads `stats[8..24]` of `gp_scorenet_ode` (cycles per RHS evaluation, CTA 0).  Round-1 end:\n\n"
-              "| phase | bf16 | fp32 (x3) |\n|---|---|---|\n"
-              "| whole kernel / evaluation | 26.0k | 42.2k |\n| forward | 19.2k | 35.0k |\n"
-              "| - inputs + first layer + its epilogue | 3.1k | 4.9k |\n| - wait second layer MMAs | 3.6k | 8.4k |\n"
-              "| - second-layer epilogue | 1.9k | 3.3k |\n| - wait head MMAs | 2.9k | 8.7k |\n| - head epilogues | 3.9k | 4.0k |\n"
-              "| - combine + cluster exchange + final sum | 2.6k | 3.0k |\n| t-branch (6 stages, once per step) | 2.0k | 2.0k |\n"
-              "| stage inputs | 1.2k | 1.4k |\n| K store | 1.3k | 1.2k |\n| error norm + grid barrier | 1.6k | 1.8k |\n")
+    md.append("`python profiles/phase_breakdown.py` reads `stats[8..24]` of `gp_scorenet_ode` (cycles per RHS evaluation, CTA 0 of "
+              "cluster 0; forward = l1 + wait_d1 + epi1 + wait_heads + epi2 + the x:* exchange tail; the stage_* / err rows are the "
+              "integrator between evaluations).\n")
+    ph = os.path.join(GO, "phase.log")
+    if os.path.exists(ph):
+        shutil.copy(ph, os.path.join(PR, f"phase_breakdown_{ROUND}.txt"))
+        md.append("```\n" + open(ph).read().strip() + "\n```\n")
     open(os.path.join(PR, "README.md"), "w").write("\n".join(md))
     print("wrote profiles/README.md")
 
