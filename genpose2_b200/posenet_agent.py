@@ -55,7 +55,7 @@ class PoseNet(nn.Module):
     # ------------------------------------------------------------------------------------------
     def pred_func(self, data, repeat_num, save_path="./visualization_results", return_average_res=False,
                   init_x: torch.Tensor = None, T0=None, return_process=False, geometry=None,
-                  return_geometry=False, pts_feat=None):
+                  return_geometry=False, pts_feat=None, want_quat=True):
         self.is_testing = True
         if self.net.training:   # eval() walks every sub-module: only when the flag actually has to change
             self.net.eval()
@@ -89,9 +89,11 @@ class PoseNet(nn.Module):
             in_process_sample = in_process_sample.reshape(bs, repeat_num, in_process_sample.shape[1], -1)
             self.pts_feature = False
 
-            rot_matrix = get_rot_matrix(res[:, :-3], self.cfg.pose_mode)
-            quat_wxyz = matrix_to_quaternion(rot_matrix)
-            pred_pose_q_wxyz = torch.cat((quat_wxyz, res[:, -3:]), dim=-1).reshape(bs, repeat_num, -1)
+            pred_pose_q_wxyz = None
+            if want_quat or return_average_res:   # (the runners drop it: `pred_pose, _ = pred_results`)
+                rot_matrix = get_rot_matrix(res[:, :-3], self.cfg.pose_mode)
+                quat_wxyz = matrix_to_quaternion(rot_matrix)
+                pred_pose_q_wxyz = torch.cat((quat_wxyz, res[:, -3:]), dim=-1).reshape(bs, repeat_num, -1)
             extra = (geometry,) if return_geometry else ()
             if return_average_res:
                 from .aggregation import _run
