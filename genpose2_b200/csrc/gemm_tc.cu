@@ -126,17 +126,20 @@ __device__ __forceinline__ void pool_store(const float (&out)[32], int lane, boo
     }
 }
 
-template <int NPASS>
+// NS_ = shared-memory stages of the K loop.  Grids that cover the GPU at least twice run two CTAs per SM with few
+// stages each (the CTAs overlap each other's load / MMA / epilogue phases, which a single CTA executes serially);
+// small grids run one CTA per SM with a deeper pipeline.
+template <int NPASS, int NS_>
 struct Cfg {
     static constexpr int IMAGES = NPASS == 3 ? 2 : 1;
-    static constexpr int NS = NPASS == 3 ? 2 : 4;
+    static constexpr int NS = NS_;
     static constexpr int STAGE_BYTES = IMAGES * (A_TILE + B_TILE_MAX);
     static constexpr size_t SMEM = (size_t)NS * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int NPASS>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_bias_relu_kernel(Args a) {
-    using C = Cfg<NPASS>;
+template <int NPASS, int NS_>
+__global__ void __launch_bounds__(NTHREADS, 2) gemm_bias_relu_kernel(Args a) {
+    using C = Cfg<NPASS, NS_>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // pointer arithmetic on the __shared__ array keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t *base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -237,27 +240,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bias_relu_kernel(Args a) {
                 }
             }
         };
-        float4 va[16], vb[16];
-        load_chunk(0, va);
-        for (int c = 0; c < a.nchunks; c += 2) {
-            if (c + 1 < a.nchunks) load_chunk(c + 1, vb);
-            {
-                const int s = c % C::NS;
-                if (c >= C::NS) tc::mbar_wait(&empty[s], ((c / C::NS) + 1) & 1);
-                convert_store(s, c, va);
-                tc::fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&a_full[s]);
-            }
-            if (c + 1 < a.nchunks) {
-                if (c + 2 < a.nchunks) load_chunk(c + 2, va);
-                const int c1 = c + 1, s = c1 % C::NS;
-                if (c1 >= C::NS) tc::mbar_wait(&empty[s], ((c1 / C::NS) + 1) & 1);
-                convert_store(s, c1, vb);
-                tc::fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&a_full[s]);
-            }
+        float4 va[16];
+        for (int c = 0; c < a.nchunks; ++c) {
+            load_chunk(c, va);
+            const int s = c % C::NS;
+            if (c >= C::NS) tc::mbar_wait(&empty[s], ((c / C::NS) + 1) & 1);
+            convert_store(s, c, va);
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&a_full[s]);
         }
         // ------------------------- epilogue -------------------------
         tc::mbar_wait(d_full, 0);
@@ -343,14 +334,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bias_relu_kernel(Args a) {
     if (warp == 5) tc::tmem_dealloc(tmem, 256);
 }
 
-template <int NPASS>
-static int launch(const Args &a, cudaStream_t st) {
-    auto kern = gemm_bias_relu_kernel<NPASS>;
-    GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<NPASS>::SMEM));
+template <int NPASS, int NS_>
+static int launch_ns(const Args &a, cudaStream_t st) {
+    auto kern = gemm_bias_relu_kernel<NPASS, NS_>;
+    GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<NPASS, NS_>::SMEM));
     dim3 grid((unsigned)((a.R + BM - 1) / BM), (unsigned)((a.N + 255) / 256));
-    kern<<<grid, NTHREADS, Cfg<NPASS>::SMEM, st>>>(a);
+    kern<<<grid, NTHREADS, Cfg<NPASS, NS_>::SMEM, st>>>(a);
     GP_CHECK_LAUNCH("gp_gemm_bias_relu");
     return GP_OK;
+}
+
+template <int NPASS>
+static int launch(const Args &a, cudaStream_t st) {
+    const long long ctas = ((a.R + BM - 1) / BM) * ((a.N + 255) / 256);
+    const bool wide = ctas >= 2LL * num_sms();
+    // split-bf16: a stage is 96 KB (one per CTA when two CTAs share an SM, two otherwise); bf16: 48 KB (two / four)
+    if (NPASS == 3) return wide ? launch_ns<NPASS, 1>(a, st) : launch_ns<NPASS, 2>(a, st);
+    return wide ? launch_ns<NPASS, 2>(a, st) : launch_ns<NPASS, 4>(a, st);
 }
 
 }  // namespace gemm
