@@ -23,7 +23,6 @@ namespace saf {
 using namespace gp::tc;
 
 constexpr int BM = 128;
-constexpr int NTHREADS = 320;
 constexpr int ATOM = 128 * 128;   // [128 rows][64 k] bf16
 constexpr int HALF = 128 * 128;   // weight chunk: up to [128 n][64 k] bf16
 
@@ -115,10 +114,17 @@ __device__ __forceinline__ void pool_block(const float (&v)[32], float *stg, int
     __syncwarp();
 }
 
-template <int NPASS>
-__global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
+// NW worker warps (gather / convert / epilogues) + producer + MMA issuer.  NW = 8: one CTA per SM; NW = 4: 192-thread
+// CTAs, two per SM when a CTA needs at most half of the shared memory and 256 TMEM columns -- two tiles in flight per
+// SM, each CTA's serial gather -> MMA -> epilogue -> MMA -> pool chain overlapping the other's.
+template <int NPASS, int NW>
+__global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel(Args a) {
     using C = Cfg<NPASS>;
     constexpr int IM = C::IMAGES;
+    constexpr int NTHREADS = (NW + 2) * 32;
+    constexpr int HALVES = NW / 4;          // worker warps per TMEM lane quarter: they split the 32-column groups
+    constexpr int RSTEP = 2 * NW;           // rows covered by one gather pass (16 lanes per row)
+    constexpr int RP = 128 / RSTEP;         // rows of a tile per worker thread
     const int NST = a.nst;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(a_ready, 8);
+        mbar_init(a_ready, NW);
         mbar_init(&dbar[0], 1);
         mbar_init(&dbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -231,7 +237,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
         __syncwarp();
     } else {
         // ---------------- gather / convert / epilogues ----------------
-        const int w = tid - 64;                    // 0..255
+        const int w = tid - 64;                    // 0..32 NW - 1
         const int e = warp - 2;
         const int quarter = warp & 3;              // TMEM lane quarter of this warp
         const int half = e >> 2;                   // which 32-column groups (odd / even)
@@ -239,17 +245,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * quarter) << 16);
         const uint32_t A_hi = abuf_a, A_lo = abuf_a + (NPASS == 3 ? L.natoms * ATOM : 0);
         const int jv = w & 15;                     // float4 inside a 64-float chunk
-        const int rsub = w >> 4;                   // 0..15: row inside a pass
+        const int rsub = w >> 4;                   // row inside a pass
         const int ns = a.pool_ns;
-        // Rows rsub + 16 p (p = 0..7) of a tile belong to this thread's gather.  Their ball-query indices for tile
+        // Rows rsub + RSTEP p (p < RP) of a tile belong to this thread's gather.  Their ball-query indices for tile
         // t + 1 are requested while tile t is in its epilogues and only consumed at the next gather: the index load is
         // the head of the gather's latency chain.
-        int gi[8];
+        int gi[RP];
         auto request = [&](int t) {
             const long long row0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * BM;
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                const long long gr = row0 + rsub + 16 * p;
+            for (int p = 0; p < RP; ++p) {
+                const long long gr = row0 + rsub + RSTEP * p;
                 gi[p] = -1;
                 if (t < my_tiles && gr < a.R) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(gi[p]) : "l"(a.gidx + gr));
             }
@@ -261,43 +267,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
         for (int t = 0; t < my_tiles; ++t) {
             const long long row0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * BM;
             const uint32_t dph = (uint32_t)t & 1;
-            // ---- gather: thread handles rows rsub + 16 p (p = 0..7), 16 bytes of every 64-float chunk ----
-            long long src[8];
-            int qoff[8];
+            // ---- gather: thread handles rows rsub + RSTEP p (p < RP), 16 bytes of every 64-float chunk, 8 rows at a time ----
             const int tile_batch = (int)(row0 / a.rows_per_batch);
-#pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                const int g32 = (int)(row0 + rsub + 16 * p);
-                const int batch = a.tile_in_batch ? tile_batch : g32 / a.rows_per_batch;
-                const int qrow = a.q_shift >= 0 ? g32 >> a.q_shift : g32 / a.q_ns;
-                src[p] = gi[p] >= 0 ? ((long long)batch * a.n_src + gi[p]) * a.ldp : -1;
-                qoff[p] = gi[p] >= 0 ? qrow * a.ldq : 0;
-            }
-            for (int kc = 0; kc < k1; ++kc) {
-                const int k = kc * 64 + 4 * jv;
-                const bool k_ok = k < a.c1;
-                float4 pv[8], qv[8];
+#pragma unroll 1
+            for (int pb = 0; pb < RP; pb += 8) {
+                long long src[8];
+                int qoff[8];
 #pragma unroll
                 for (int p = 0; p < 8; ++p) {
-                    const bool ok = k_ok && src[p] >= 0;
-                    pv[p] = ok ? __ldg(reinterpret_cast<const float4 *>(a.P + src[p] + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    qv[p] = ok ? __ldg(reinterpret_cast<const float4 *>(a.Q + qoff[p] + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int g32 = (int)(row0 + rsub + RSTEP * (pb + p));
+                    const int batch = a.tile_in_batch ? tile_batch : g32 / a.rows_per_batch;
+                    const int qrow = a.q_shift >= 0 ? g32 >> a.q_shift : g32 / a.q_ns;
+                    const int gidx = gi[pb + p];
+                    src[p] = gidx >= 0 ? ((long long)batch * a.n_src + gidx) * a.ldp : -1;
+                    qoff[p] = gidx >= 0 ? qrow * a.ldq : 0;
                 }
+                for (int kc = 0; kc < k1; ++kc) {
+                    const int k = kc * 64 + 4 * jv;
+                    const bool k_ok = k < a.c1;
+                    float4 pv[8], qv[8];
 #pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    const int rl = rsub + 16 * p;
-                    const uint32_t off = kc * ATOM + rl * 128 + (((jv >> 1) ^ (rl & 7)) << 4) + ((jv & 1) << 3);
-                    const float x0 = fmaxf(pv[p].x - qv[p].x, 0.f), x1 = fmaxf(pv[p].y - qv[p].y, 0.f);
-                    const float x2 = fmaxf(pv[p].z - qv[p].z, 0.f), x3 = fmaxf(pv[p].w - qv[p].w, 0.f);
-                    const __nv_bfloat162 h0 = __floats2bfloat162_rn(x0, x1), h1 = __floats2bfloat162_rn(x2, x3);
-                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(A_hi + off), "r"(*reinterpret_cast<const uint32_t *>(&h0)),
-                                 "r"(*reinterpret_cast<const uint32_t *>(&h1)));
-                    if (NPASS == 3) {
-                        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-                        const __nv_bfloat162 l0 = __floats2bfloat162_rn(x0 - f0.x, x1 - f0.y);
-                        const __nv_bfloat162 l1 = __floats2bfloat162_rn(x2 - f1.x, x3 - f1.y);
-                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(A_lo + off), "r"(*reinterpret_cast<const uint32_t *>(&l0)),
-                                     "r"(*reinterpret_cast<const uint32_t *>(&l1)));
+                    for (int p = 0; p < 8; ++p) {
+                        const bool ok = k_ok && src[p] >= 0;
+                        pv[p] = ok ? __ldg(reinterpret_cast<const float4 *>(a.P + src[p] + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        qv[p] = ok ? __ldg(reinterpret_cast<const float4 *>(a.Q + qoff[p] + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) {
+                        const int rl = rsub + RSTEP * (pb + p);
+                        const uint32_t off = kc * ATOM + rl * 128 + (((jv >> 1) ^ (rl & 7)) << 4) + ((jv & 1) << 3);
+                        const float x0 = fmaxf(pv[p].x - qv[p].x, 0.f), x1 = fmaxf(pv[p].y - qv[p].y, 0.f);
+                        const float x2 = fmaxf(pv[p].z - qv[p].z, 0.f), x3 = fmaxf(pv[p].w - qv[p].w, 0.f);
+                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(x0, x1), h1 = __floats2bfloat162_rn(x2, x3);
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(A_hi + off), "r"(*reinterpret_cast<const uint32_t *>(&h0)),
+                                     "r"(*reinterpret_cast<const uint32_t *>(&h1)));
+                        if (NPASS == 3) {
+                            const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+                            const __nv_bfloat162 l0 = __floats2bfloat162_rn(x0 - f0.x, x1 - f0.y);
+                            const __nv_bfloat162 l1 = __floats2bfloat162_rn(x2 - f1.x, x3 - f1.y);
+                            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(A_lo + off), "r"(*reinterpret_cast<const uint32_t *>(&l0)),
+                                         "r"(*reinterpret_cast<const uint32_t *>(&l1)));
+                        }
                     }
                 }
             }
@@ -313,7 +323,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
             mbar_wait(&dbar[0], dph);
             tc_fence_after();
             lap(2);
-            for (int g = half; g < 2 * k2; g += 2) {
+            for (int g = half; g < 2 * k2; g += HALVES) {
                 uint32_t r[32];
                 tmem_ld32(lane_addr + g * 32, r);
 #pragma unroll
@@ -353,7 +363,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
             lap(4);
             const long long grow = row0 + row;
             const bool row_ok = grow < a.R;
-            for (int g = half; g * 32 < a.c3; g += 2) {
+            for (int g = half; g * 32 < a.c3; g += HALVES) {
                 uint32_t r[32];
                 tmem_ld32(lane_addr + a.d2col + g * 32, r);
                 float v[32];
@@ -363,7 +373,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_mlp2_kernel(Args a) {
             }
             tc_fence_before();
             // the pooling stage lives in the A buffer: nobody gathers the next tile into it before all warps are done
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
             lap(5);
         }
 #ifdef GP_SAF_PROBE
@@ -407,12 +417,27 @@ static int launch(Args a, cudaStream_t st) {
     }
     GP_REQUIRE(nst >= 1, "gp_sa_mlp2_fused: layer widths need %zu bytes of shared memory", fixed + stage);
     a.nst = nst > MAX_NST ? MAX_NST : nst;
+    // two 192-thread CTAs per SM when one of them (with at least one ring stage of 128-column chunks) fits in half
+    // of the shared memory and 256 TMEM columns
+    const size_t half_sm = 113 * 1024;
+    if (a.tmem_cols == 256 && a.chunk_rows == 128 && fixed + stage <= half_sm) {
+        const int nst2 = (int)((half_sm - fixed) / stage);
+        a.nst = nst2 > MAX_NST ? MAX_NST : nst2;
+        const Layout<NPASS> L2(a.c1, a.c2, a.nst, a.slot_bytes, a.bias_smem);
+        auto kern = sa_mlp2_kernel<NPASS, 4>;
+        GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        const int cap = 2 * num_sms();
+        kern<<<a.ntiles < cap ? a.ntiles : cap, 6 * 32, L2.total(), st>>>(a);
+        GP_CHECK_LAUNCH("gp_sa_mlp2_fused");
+        return GP_OK;
+    }
     const Layout<NPASS> L(a.c1, a.c2, a.nst, a.slot_bytes, a.bias_smem);
-    auto kern = sa_mlp2_kernel<NPASS>;
+    auto kern = sa_mlp2_kernel<NPASS, 8>;
     const size_t smem = L.total();
     GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const int grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
-    kern<<<grid, NTHREADS, smem, st>>>(a);
+    kern<<<grid, 10 * 32, smem, st>>>(a);
     GP_CHECK_LAUNCH("gp_sa_mlp2_fused");
     return GP_OK;
 }
