@@ -23,7 +23,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -70,81 +69,80 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
 
 
+_SAMPLER_CODE = r"""
+import sys, time
+idx = int(sys.argv[1])
+try:
+    import pynvml as n
+    n.nvmlInit()
+    h = n.nvmlDeviceGetHandleByIndex(idx)
+    get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+    mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+    print("ready nvml", flush=True)
+    while True:
+        print(time.time(), n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM), mx, int(get(h)), flush=True)
+        time.sleep(0.004)
+except Exception as e:
+    import subprocess
+    print("ready nvidia-smi", flush=True)
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    while True:
+        t = time.time()
+        out = subprocess.run(["nvidia-smi", "-i", str(idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"], capture_output=True, text=True).stdout
+        p = [x.strip() for x in out.strip().split(",")]
+        if len(p) >= 6:
+            bits = sum(b for b, v in zip((0x8, 0x40, 0x20, 0x4), p[2:6]) if v.lower().startswith("active"))
+            print(t, p[0], p[1], bits, flush=True)
+"""
+
+
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: NVML (every ~5 ms) when nvidia_ml_py can be
-    initialised, otherwise `nvidia-smi` (one call takes ~50-100 ms)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region by a helper process (NVML every ~4 ms, or
+    `nvidia-smi` when NVML cannot be initialised): a thread in this process would have to fight the step loop for
+    the GIL.  The helper is started at construction (before the warm-up); only its samples with a wall-clock stamp
+    inside [start(), stop()] are kept."""
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.index, self.rows, self.stop_flag, self.thread = index, [], False, None
-        self.nvml = None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            # torch's device index counts visible devices: map it through CUDA_VISIBLE_DEVICES when that is a list of indices
-            phys = index
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            if vis:
-                ids = [v.strip() for v in vis.split(",") if v.strip()]
-                if index < len(ids) and ids[index].isdigit():
-                    phys = int(ids[index])
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
-            self.nvml = pynvml
-        except Exception:
-            self.nvml = None
-
-    def _run_nvml(self):
-        n = self.nvml
-        bits = (("hw_slowdown", getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8)),
-                ("hw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
-                ("sw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
-                ("sw_power_cap", getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)))
-        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
-        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
-        while not self.stop_flag:
-            try:
-                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
-                r = int(get_reasons(self.handle))
-                self.rows.append([str(sm), str(mx)] + ["Active" if r & bit else "Not Active" for _, bit in bits])
-            except Exception:
-                pass
-            time.sleep(0.005)
-
-    def _run(self):
-        if self.nvml is not None:
-            return self._run_nvml()
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.rows.append(parts)
-            except Exception:
-                pass
-            time.sleep(0.1)
+        phys = index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:  # torch's index counts visible devices
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                phys = int(ids[index])
+        self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_CODE, str(phys)], stdout=subprocess.PIPE, text=True)
+        self.source = (self.proc.stdout.readline().split() + ["?", "?"])[1]
+        self.t0 = self.t1 = None
 
     def start(self):
-        self.thread = threading.Thread(target=self._run, daemon=True)
-        self.thread.start()
+        self.t0 = time.time()
 
     def stop(self):
-        self.stop_flag = True
-        if self.thread:
-            self.thread.join(timeout=6)
+        self.t1 = time.time()
+        time.sleep(0.02)
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            self.proc.kill()
+            out = ""
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        for line in out.splitlines():
+            p = line.split()
+            if len(p) != 4:
+                continue
             try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                t, clk, mxc, bits = float(p[0]), float(p[1]), float(p[2]), int(p[3])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+            if not (self.t0 <= t <= self.t1):
+                continue
+            sm.append(clk)
+            mx = max(mx, mxc)
+            reasons.update(name for name, b in self.BITS if bits & b)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
+                "samples": len(sm), "source": self.source}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -273,11 +271,12 @@ def run_b200(args):
             return pose, length
 
         torch.manual_seed(1234 + rank)
+        sampler = ClockSampler(local_rank) if with_clocks else None   # helper process: up and sampling before the timed region
         for _ in range(max(args.warmup, 3)):
             step_resident()
         torch.cuda.synchronize()
         _lib.reset_launch_count()
-        total_ms, clocks = timed(step_resident, args.steps, ClockSampler(local_rank) if with_clocks else None)
+        total_ms, clocks = timed(step_resident, args.steps, sampler)
         res = {"launches": _lib.launch_count(), "total_ms": total_ms, "clocks": clocks,
                "value": world * B * args.steps / (total_ms * 1e-3)}
         if with_e2e:
