@@ -216,105 +216,96 @@ extern "C" int gp_gather(const float *points, const int32_t *idx, int B, int C, 
 // ------------------------------------------------------------------------------------------
 namespace gp {
 
-constexpr int BQ_WARPS = 8;
-constexpr int BQ_CPW = 8;                       // centres per warp
-constexpr int BQ_CPB = BQ_WARPS * BQ_CPW;       // centres per block
-constexpr int BQ_CHUNK = 4096;                  // points staged per pass (48 KB, SoA)
+constexpr int BQ_THREADS = 128;                // one centre per thread
+constexpr int BQ_CHUNK = 3072;                  // points staged per pass (48 KB as float4)
 
+// One thread per centre, scanning the staged cloud in index order: every lane reads the same float4
+// (a shared-memory broadcast), so a point costs one LDS.128 + the reference's three-term distance +
+// one compare + one predicated OR per radius into a 32-point hit mask: the scan is branch-free and the
+// loads run ahead; the (rare, ~2 % of the pairs) hits are written from the masks once per 32 points.
+// The reference's thread-per-centre kernel has the same shape but reads the cloud from global memory and
+// branches per point; an earlier warp-per-centre version of this
+// kernel (ballot + popc compaction) was latency-bound on its ballot -> count -> branch chain
+// (116 us for level 1 at 64 objects, 1 % of HBM bandwidth, profiles/README.md).
 template <bool TWO>
-__global__ void __launch_bounds__(BQ_WARPS * 32)
+__global__ void __launch_bounds__(BQ_THREADS)
 ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz, int N, int M,
                   float r0sq, int ns0, int *__restrict__ idx0, float r1sq, int ns1,
                   int *__restrict__ idx1) {
-    extern __shared__ __align__(16) float s_pts[];  // sx[CH] sy[CH] sz[CH]
+    extern __shared__ __align__(16) float4 s_pts4[];  // [CH] (x, y, z, -)
     const int CH = min(N, BQ_CHUNK);
-    float *sx = s_pts, *sy = s_pts + CH, *sz = s_pts + 2 * CH;
     const int b = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const float *cloud = xyz + (size_t)b * N * 3;
-    const unsigned lt = (1u << lane) - 1u;
+    const int c = blockIdx.x * BQ_THREADS + tid;
+    const bool active = c < M;
 
-    const int c_first = blockIdx.x * BQ_CPB + warp * BQ_CPW;
-    float cx[BQ_CPW], cy[BQ_CPW], cz[BQ_CPW];
-    int cnt0[BQ_CPW], first0[BQ_CPW], cnt1[BQ_CPW], first1[BQ_CPW];
-#pragma unroll
-    for (int c = 0; c < BQ_CPW; ++c) {
-        const int i = min(c_first + c, M - 1);
-        const float *p = new_xyz + ((size_t)b * M + i) * 3;
-        cx[c] = __ldg(p + 0); cy[c] = __ldg(p + 1); cz[c] = __ldg(p + 2);
-        cnt0[c] = cnt1[c] = 0;
-        first0[c] = first1[c] = 0;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (active) {
+        const float *p = new_xyz + ((size_t)b * M + c) * 3;
+        cx = __ldg(p + 0); cy = __ldg(p + 1); cz = __ldg(p + 2);
     }
+    int *o0 = idx0 + ((size_t)b * M + (active ? c : 0)) * ns0;
+    int *o1 = TWO ? idx1 + ((size_t)b * M + (active ? c : 0)) * ns1 : nullptr;
+    int n0 = active ? 0 : ns0, n1 = (TWO && active) ? 0 : ns1;  // idle lanes count as full
+    int first0 = 0, first1 = 0;
 
     for (int base = 0; base < N; base += CH) {
         const int n_here = min(CH, N - base);
         if (base) __syncthreads();
-        // stage chunk: coalesced AoS read -> SoA shared
-        for (int i = tid; i < n_here * 3; i += BQ_WARPS * 32) {
+        // stage the chunk: coalesced AoS read -> one float4 per point
+        float *sp = reinterpret_cast<float *>(s_pts4);
+        for (int i = tid; i < n_here * 3; i += BQ_THREADS) {
             const float v = __ldg(cloud + (size_t)base * 3 + i);
             const int k = i / 3, a = i - 3 * k;
-            (a == 0 ? sx : (a == 1 ? sy : sz))[k] = v;
+            sp[4 * k + a] = v;
         }
+        for (int k = n_here + tid; k < ((n_here + 31) & ~31); k += BQ_THREADS)  // pad: never inside a ball
+            s_pts4[k] = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, 0.f);
         __syncthreads();
+        for (int k0 = 0; k0 < n_here; k0 += 32) {
+            if (__all_sync(0xffffffffu, n0 >= ns0 && (!TWO || n1 >= ns1))) break;  // warp-uniform
+            // 32 points, branch-free: one hit bit per point and radius
+            unsigned m0 = 0u, m1 = 0u;
 #pragma unroll
-        for (int c = 0; c < BQ_CPW; ++c) {
-            if (c_first + c >= M) break;
-            const bool need0 = cnt0[c] < ns0;
-            const bool need1 = TWO && cnt1[c] < ns1;
-            if (!need0 && !need1) continue;
-            int *o0 = idx0 + ((size_t)b * M + c_first + c) * ns0;
-            int *o1 = TWO ? idx1 + ((size_t)b * M + c_first + c) * ns1 : nullptr;
-            int n0 = cnt0[c], n1 = cnt1[c];
-            for (int k0 = 0; k0 < n_here; k0 += 32) {
-                const int k = k0 + lane;
-                const bool valid = k < n_here;
-                const int kk = valid ? k : 0;
+            for (int j = 0; j < 32; ++j) {
+                const float4 p = s_pts4[k0 + j];
                 // reference: (new_x - x)^2 + (new_y - y)^2 + (new_z - z)^2, fma pattern in sqdist_ref
-                const float d2 = sqdist_ref(cx[c] - sx[kk], cy[c] - sy[kk], cz[c] - sz[kk]);
-                const unsigned m0 = __ballot_sync(0xffffffffu, valid && d2 < r0sq);
-                if (n0 < ns0 && m0) {
-                    if (n0 == 0) first0[c] = base + k0 + __ffs(m0) - 1;
-                    const int pos = n0 + __popc(m0 & lt);
-                    if (((m0 >> lane) & 1u) && pos < ns0) o0[pos] = base + k;
-                    n0 += __popc(m0);
-                }
-                if (TWO) {
-                    const unsigned m1 = __ballot_sync(0xffffffffu, valid && d2 < r1sq);
-                    if (n1 < ns1 && m1) {
-                        if (n1 == 0) first1[c] = base + k0 + __ffs(m1) - 1;
-                        const int pos = n1 + __popc(m1 & lt);
-                        if (((m1 >> lane) & 1u) && pos < ns1) o1[pos] = base + k;
-                        n1 += __popc(m1);
-                    }
-                }
-                if (n0 >= ns0 && (!TWO || n1 >= ns1)) break;
+                const float d2 = sqdist_ref(cx - p.x, cy - p.y, cz - p.z);
+                m0 |= d2 < r0sq ? 1u << j : 0u;
+                if (TWO) m1 |= d2 < r1sq ? 1u << j : 0u;
             }
-            cnt0[c] = n0;
-            cnt1[c] = n1;
+            // the hits, in index order (about one per lane and group at the encoder's radii)
+            while (m0 && n0 < ns0) {
+                const int k = base + k0 + __ffs(m0) - 1;
+                m0 &= m0 - 1u;
+                if (n0 == 0) first0 = k;
+                o0[n0++] = k;
+            }
+            while (TWO && m1 && n1 < ns1) {
+                const int k = base + k0 + __ffs(m1) - 1;
+                m1 &= m1 - 1u;
+                if (n1 == 0) first1 = k;
+                o1[n1++] = k;
+            }
         }
     }
+    if (!active) return;
     // back-fill: first hit replicated into the unused slots; all zeros if the ball is empty
-#pragma unroll
-    for (int c = 0; c < BQ_CPW; ++c) {
-        if (c_first + c >= M) break;
-        int *o0 = idx0 + ((size_t)b * M + c_first + c) * ns0;
-        for (int sl = min(cnt0[c], ns0) + lane; sl < ns0; sl += 32) o0[sl] = cnt0[c] ? first0[c] : 0;
-        if (TWO) {
-            int *o1 = idx1 + ((size_t)b * M + c_first + c) * ns1;
-            for (int sl = min(cnt1[c], ns1) + lane; sl < ns1; sl += 32) o1[sl] = cnt1[c] ? first1[c] : 0;
-        }
-    }
+    for (int sl = n0; sl < ns0; ++sl) o0[sl] = first0;
+    if (TWO)
+        for (int sl = n1; sl < ns1; ++sl) o1[sl] = first1;
 }
 
 template <bool TWO>
 static int launch_bq(const float *new_xyz, const float *xyz, int B, int N, int M, float r0,
                      int ns0, int *idx0, float r1, int ns1, int *idx1, cudaStream_t st) {
     const int CH = N < BQ_CHUNK ? N : BQ_CHUNK;
-    size_t smem = (size_t)CH * 3 * sizeof(float);
-    dim3 grid((M + BQ_CPB - 1) / BQ_CPB, B);
+    size_t smem = (size_t)((CH + 31) & ~31) * sizeof(float4);
+    dim3 grid((M + BQ_THREADS - 1) / BQ_THREADS, B);
     // radius2 = radius * radius in float32 (ball_query_gpu.cu:23)
     const float r0sq = r0 * r0, r1sq = r1 * r1;
-    ball_query_kernel<TWO><<<grid, BQ_WARPS * 32, smem, st>>>(new_xyz, xyz, N, M, r0sq, ns0, idx0,
+    ball_query_kernel<TWO><<<grid, BQ_THREADS, smem, st>>>(new_xyz, xyz, N, M, r0sq, ns0, idx0,
                                                               r1sq, ns1, idx1);
     GP_CHECK_LAUNCH("gp_ball_query");
     return GP_OK;

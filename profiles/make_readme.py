@@ -127,6 +127,35 @@ def main():
         for i, d in enumerate(ms):
             md.append(f"| {i} | " + " | ".join(d.get(k, "") for k in keys) + " |")
         md.append(f"\n### top source lines — all six launches\n\n```\n{top_lines(sa)}\n```\n")
+    geo, geolog = os.path.join(GO, "geom.ncu-rep"), os.path.join(GO, "geom.log")
+    if os.path.exists(geo) and os.path.exists(geolog):
+        md.append("## geom — `ncu --set full` of FPS / ball query / grouping, the four encoder levels at 64 objects\n")
+        md.append("`ncu --profile-from-start off --set full --clock-control none -k regex:'fps_kernel|ball_query|group_kernel' "
+                  "python profiles/profile_geometry.py`.  `alg. bytes` are the algorithmic bytes of DESIGN.md 4.1-4.3 (cloud + centres "
+                  "read, indices / grouped tensor written); `GB/s` = alg. bytes / duration, against the measured copy bandwidth in "
+                  f"`MEASURED_PEAKS.json`; `dram` = dram__bytes_read + dram__bytes_write of the same launch (cold cache).\n")
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        ops = [json.loads(l) for l in open(geolog) if l.startswith("{")]
+        ms = raw_metrics(geo)
+        md.append("| op | level | kernel | grid | us | alg. bytes | GB/s | % of HBM peak | dram bytes | sm throughput % | warps active % |")
+        md.append("|---|---|---|---|---|---|---|---|---|---|---|")
+
+        def num(d, k):
+            v, u = (d.get(k, "0 ") + " ").split(" ")[:2]
+            v = float(v.replace(",", ""))
+            return v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}.get(u, 1.0)
+        for o, d in zip(ops, ms):
+            us = num(d, "gpu__time_duration.sum")
+            dram = num(d, "dram__bytes_read.sum") + num(d, "dram__bytes_write.sum")
+            gbs = o["algorithmic_bytes"] / us / 1e3
+            md.append(f"| {o['op']} | {o['level'] + 1} | `{re.sub(r'[(].*', '', d['name'])[:34]}` | {d.get('launch__grid_size', '').split(' ')[0]} | {us:.1f} | "
+                      f"{o['algorithmic_bytes']:,} | {gbs:.0f} | {100 * gbs / peak:.1f} | {dram:,.0f} | "
+                      f"{num(d, 'sm__throughput.avg.pct_of_peak_sustained_elapsed'):.0f} | "
+                      f"{num(d, 'sm__warps_active.avg.pct_of_peak_sustained_active'):.0f} |")
+        md.append("\nFPS is a chain of npoint - 1 dependent arg-max steps per object on 64 CTAs (one per object): it is bound by the "
+                  "latency of one step (distance update, two redux levels, one barrier), not by bytes -- 0.6 MB per launch. "
+                  "Ball query and grouping at these sizes are a few MB per launch and finish in 3-60 us, so they sit on the launch / "
+                  "ramp part of the bandwidth curve; the encoder's hot path no longer materialises the grouped tensor at all (DESIGN.md 4.4).\n")
     for name in ("bench_fp32.json", "bench_ffma.json"):
         src = os.path.join(GO, name)
         if os.path.exists(src):
