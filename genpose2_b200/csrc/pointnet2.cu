@@ -39,19 +39,39 @@ struct FpsOrder {
     }
 };
 
-template <int NWARPS, int PPT, bool COORDS_IN_REGS>
+// CHAIN (gp_fps_chain): the encoder samples level k+1 from the centres of level k, i.e. from a cloud that is
+// already in FPS order.  FPS of an FPS-ordered cloud is its own prefix 0, 1, ..., m-1 -- the point that maximised
+// the running distance over the superset also maximises it over the subset -- unless two candidates tied exactly
+// at some step (then the winner depends on the tie-break order, which differs between the levels).  So every run
+// records the first step at which the maximum was shared by two different locations (`tie_out`), and a run whose
+// input was tie-free for at least m steps (`tie_in[b] >= m`) writes the prefix and returns; anything else samples
+// for real.
+template <int NWARPS, int PPT, bool COORDS_IN_REGS, bool CHAIN>
 __global__ void __launch_bounds__(NWARPS * 32)
 fps_kernel(const float *__restrict__ xyz, int N, int m, FpsOrder order, int *__restrict__ idx,
-           float *__restrict__ new_xyz) {
+           float *__restrict__ new_xyz, const int *__restrict__ tie_in, int *__restrict__ tie_out) {
     constexpr int T = NWARPS * 32;
     extern __shared__ __align__(16) float s_raw[];  // [3*N] AoS copy of this object's cloud
     __shared__ uint2 s_part[2][32];
+    __shared__ int s_tie;
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const float *cloud = xyz + (size_t)b * N * 3;
     int *out = idx + (size_t)b * m;
     float *out_xyz = new_xyz ? new_xyz + (size_t)b * m * 3 : nullptr;
+
+    if (CHAIN) {
+        const int free_steps = tie_in ? __ldg(tie_in + b) : 0;
+        if (free_steps >= m && m <= N) {
+            for (int i = tid; i < m; i += T) out[i] = i;
+            if (out_xyz)
+                for (int i = tid; i < 3 * m; i += T) out_xyz[i] = __ldg(cloud + i);
+            if (tid == 0 && tie_out) tie_out[b] = free_steps;
+            return;
+        }
+        if (tid == 0) s_tie = m;
+    }
 
     // stage the cloud: 16-byte loads when the object's base is aligned (N % 4 == 0)
     const int nfl = N * 3;
@@ -81,6 +101,8 @@ fps_kernel(const float *__restrict__ xyz, int N, int m, FpsOrder order, int *__r
     }
 
     int old = 0;
+    unsigned prev_whi = 0u;
+    int first_bad = m;
     if (tid == 0) {
         out[0] = 0;
         if (out_xyz) {
@@ -92,6 +114,11 @@ fps_kernel(const float *__restrict__ xyz, int N, int m, FpsOrder order, int *__r
     const int lane = tid & 31, warp = tid >> 5;
     for (int j = 1; j < m; ++j) {
         const float x1 = s_raw[3 * old + 0], y1 = s_raw[3 * old + 1], z1 = s_raw[3 * old + 2];
+        // CHAIN: was the maximum of step j-1 (`dist` still holds that step's distances) held by one location only?
+        // Copies of the winner may share it: their distance drops to 0 now, so they are never sampled before the
+        // cloud is exhausted.  A holder that stays above 0, or an exhausted cloud (maximum 0), ends the tie-free
+        // prefix.
+        bool bad = false;
         unsigned best_hi = 0u, best_lo = 0u;
 #pragma unroll
         for (int i = 0; i < PPT; ++i) {
@@ -104,6 +131,7 @@ fps_kernel(const float *__restrict__ xyz, int N, int m, FpsOrder order, int *__r
             }
             const float d = sqdist_ref(x2 - x1, y2 - y1, z2 - z1);
             const float d2 = fminf(d, dist[i]);
+            if (CHAIN) bad |= __float_as_uint(dist[i]) == prev_whi && d2 != 0.f;
             dist[i] = d2;
             const unsigned hi = __float_as_uint(d2);
             const bool gt = (hi > best_hi) || (hi == best_hi && inv[i] > best_lo);
@@ -120,6 +148,10 @@ fps_kernel(const float *__restrict__ xyz, int N, int m, FpsOrder order, int *__r
             wlo = __reduce_max_sync(0xffffffffu, p.x == whi ? p.y : 0u);
         }
         old = order.index_of(wlo);
+        if (CHAIN) {  // no vote, no branch: every thread keeps the first bad step it saw
+            if (j > 1 && (bad || prev_whi == 0u)) first_bad = min(first_bad, j - 1);
+            prev_whi = whi;
+        }
         if (tid == 0) {
             out[j] = old;
             if (out_xyz) {
@@ -128,6 +160,12 @@ fps_kernel(const float *__restrict__ xyz, int N, int m, FpsOrder order, int *__r
                 out_xyz[3 * j + 2] = s_raw[3 * old + 2];
             }
         }
+    }
+    if (CHAIN && tie_out) {  // the last step is not checked: the prefix is vouched for up to m - 1 samples
+        first_bad = __reduce_min_sync(0xffffffffu, first_bad);
+        if (lane == 0) atomicMin(&s_tie, first_bad);
+        __syncthreads();
+        if (tid == 0) tie_out[b] = min(s_tie, m - 1);
     }
 }
 
@@ -140,12 +178,12 @@ static int ref_block_size(int n) {  // cuda_utils.h:10-14 opt_n_threads
 
 template <int NWARPS, int PPT, bool REGS>
 static int launch_fps(const float *xyz, int B, int N, int m, FpsOrder order, int *idx,
-                      float *new_xyz, cudaStream_t st) {
+                      float *new_xyz, bool chain, const int *tie_in, int *tie_out, cudaStream_t st) {
     size_t smem = (size_t)N * 3 * sizeof(float);
     smem = (smem + 15) & ~(size_t)15;
-    auto kern = fps_kernel<NWARPS, PPT, REGS>;
+    auto kern = chain ? fps_kernel<NWARPS, PPT, REGS, true> : fps_kernel<NWARPS, PPT, REGS, false>;
     if (smem > 40 * 1024) GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<B, NWARPS * 32, smem, st>>>(xyz, N, m, order, idx, new_xyz);
+    kern<<<B, NWARPS * 32, smem, st>>>(xyz, N, m, order, idx, new_xyz, tie_in, tie_out);
     GP_CHECK_LAUNCH("gp_fps");
     return GP_OK;
 }
@@ -154,13 +192,13 @@ static int launch_fps(const float *xyz, int B, int N, int m, FpsOrder order, int
 
 using namespace gp;
 
-extern "C" int gp_fps(const float *xyz, int B, int N, int m, int32_t *idx, float *new_xyz,
-                      gp_stream_t s) {
-    GP_REQUIRE(B >= 0 && N >= 1 && m >= 0, "gp_fps: bad sizes B=%d N=%d m=%d", B, N, m);
+static int fps_dispatch(const char *who, const float *xyz, int B, int N, int m, int32_t *idx, float *new_xyz,
+                        bool chain, const int *tie_in, int *tie_out, gp_stream_t s) {
+    GP_REQUIRE(B >= 0 && N >= 1 && m >= 0, "%s: bad sizes B=%d N=%d m=%d", who, B, N, m);
     if (B == 0 || m == 0) return GP_OK;
-    GP_REQUIRE(xyz && idx, "gp_fps: null pointer");
+    GP_REQUIRE(xyz && idx, "%s: null pointer", who);
     if (N > 16384) {
-        set_error("gp_fps: N=%d > 16384 is not supported (cloud must fit in shared memory)", N);
+        set_error("%s: N=%d > 16384 is not supported (cloud must fit in shared memory)", who, N);
         return GP_ERR_UNSUPPORTED;
     }
     const int BS = ref_block_size(N);
@@ -171,16 +209,29 @@ extern "C" int gp_fps(const float *xyz, int B, int N, int m, int32_t *idx, float
     order.SH = 0;
     while ((1 << order.SH) < J) ++order.SH;
     cudaStream_t st = as_stream(s);
-    if (N <= 32) return launch_fps<1, 1, true>(xyz, B, N, m, order, idx, new_xyz, st);
-    if (N <= 64) return launch_fps<1, 2, true>(xyz, B, N, m, order, idx, new_xyz, st);
-    if (N <= 128) return launch_fps<1, 4, true>(xyz, B, N, m, order, idx, new_xyz, st);
-    if (N <= 256) return launch_fps<2, 4, true>(xyz, B, N, m, order, idx, new_xyz, st);
-    if (N <= 512) return launch_fps<4, 4, true>(xyz, B, N, m, order, idx, new_xyz, st);
-    if (N <= 1024) return launch_fps<8, 4, true>(xyz, B, N, m, order, idx, new_xyz, st);
-    if (N <= 2048) return launch_fps<16, 4, true>(xyz, B, N, m, order, idx, new_xyz, st);
-    if (N <= 4096) return launch_fps<32, 4, true>(xyz, B, N, m, order, idx, new_xyz, st);
-    if (N <= 8192) return launch_fps<32, 8, false>(xyz, B, N, m, order, idx, new_xyz, st);
-    return launch_fps<32, 16, false>(xyz, B, N, m, order, idx, new_xyz, st);
+#define GP_FPS_CASE(W, P, R) return launch_fps<W, P, R>(xyz, B, N, m, order, idx, new_xyz, chain, tie_in, tie_out, st)
+    if (N <= 32) GP_FPS_CASE(1, 1, true);
+    if (N <= 64) GP_FPS_CASE(1, 2, true);
+    if (N <= 128) GP_FPS_CASE(1, 4, true);
+    if (N <= 256) GP_FPS_CASE(2, 4, true);
+    if (N <= 512) GP_FPS_CASE(4, 4, true);
+    if (N <= 1024) GP_FPS_CASE(8, 4, true);
+    if (N <= 2048) GP_FPS_CASE(16, 4, true);
+    if (N <= 4096) GP_FPS_CASE(32, 4, true);
+    if (N <= 8192) GP_FPS_CASE(32, 8, false);
+    GP_FPS_CASE(32, 16, false);
+#undef GP_FPS_CASE
+}
+
+extern "C" int gp_fps(const float *xyz, int B, int N, int m, int32_t *idx, float *new_xyz,
+                      gp_stream_t s) {
+    return fps_dispatch("gp_fps", xyz, B, N, m, idx, new_xyz, false, nullptr, nullptr, s);
+}
+
+extern "C" int gp_fps_chain(const float *xyz, int B, int N, int m, int32_t *idx, float *new_xyz,
+                            const int32_t *tie_free_in, int32_t *tie_free_out, gp_stream_t s) {
+    GP_REQUIRE(tie_free_out || B == 0 || m == 0, "gp_fps_chain: tie_free_out is null");
+    return fps_dispatch("gp_fps_chain", xyz, B, N, m, idx, new_xyz, true, tie_free_in, tie_free_out, s);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -269,12 +269,14 @@ class Pointnet2ClsMSG(nn.Module):
         of level k-1), as the list `forward(..., geometry=...)` takes.  Lets two encoders that see the same cloud
         share one pass and start side by side."""
         xyz = pointcloud[..., 0:3].contiguous()
-        geometry = []
+        geometry, tie_free = [], None
         for sa in self.SA_modules:
             if sa.npoint is None:
                 geometry.append(None)
                 continue
-            idx, new_xyz = pu.furthest_point_sample_gather(xyz, sa.npoint)
+            # each level samples the previous level's centres: an FPS-ordered cloud, whose FPS is its own prefix
+            # unless the earlier sampling hit an exact tie (pointnet2_utils.furthest_point_sample_chain)
+            idx, new_xyz, tie_free = pu.furthest_point_sample_chain(xyz, sa.npoint, tie_free)
             geometry.append((idx, new_xyz, pu.ball_query2(sa.radii, sa.nsamples, xyz, new_xyz)))
             xyz = new_xyz
         return geometry
@@ -285,8 +287,10 @@ class Pointnet2ClsMSG(nn.Module):
         xyz = pointcloud[..., 0:3].contiguous()
         feat_cl = pointcloud[..., 3:].contiguous() if pointcloud.size(-1) > 3 else None
         geo_out = []
+        if geometry is None:
+            geometry = self.compute_geometry(pointcloud)
         for k, sa in enumerate(self.SA_modules):
-            g = None if geometry is None else geometry[k]
+            g = geometry[k]
             xyz, feat_cl, g = sa.forward_cl(xyz, feat_cl, g)
             geo_out.append(g)
         out = feat_cl.squeeze(1)

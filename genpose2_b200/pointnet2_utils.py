@@ -34,6 +34,27 @@ def furthest_point_sample_gather(xyz: torch.Tensor, npoint: int) -> Tuple[torch.
     return idx, new_xyz
 
 
+def furthest_point_sample_chain(xyz: torch.Tensor, npoint: int, tie_free: torch.Tensor = None):
+    """FPS + gather for a cascade of levels (gp_fps_chain): returns (idx, new_xyz, tie_free_out).
+
+    `tie_free` must be the third result of the call that PRODUCED `xyz` (i.e. xyz is the previous level's new_xyz, in
+    FPS order); objects whose earlier sampling was tie-free for at least `npoint` steps get the prefix
+    0..npoint-1, which is what sampling them again would return -- bit-exact, tested against the reference ext.
+    Pass None for the first level."""
+    assert xyz.is_contiguous()
+    _lib.check_cuda(xyz, "xyz", torch.float32)
+    B, N, _ = xyz.size()
+    idx = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
+    new_xyz = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz.device)
+    out = torch.empty((B,), dtype=torch.int32, device=xyz.device)
+    if tie_free is not None:
+        _lib.check_cuda(tie_free, "tie_free", torch.int32)
+        assert tie_free.numel() == B
+    _lib.call("gp_fps_chain", _lib.ptr(xyz), B, N, int(npoint), _lib.ptr(idx), _lib.ptr(new_xyz),
+              _lib.ptr(tie_free), _lib.ptr(out), device=xyz.device)
+    return idx, new_xyz, out
+
+
 def gather_operation(features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     """pointnet2_utils.py:50-72.  features (B, C, N), idx (B, npoint) -> (B, C, npoint)."""
     assert features.is_contiguous()

@@ -58,6 +58,13 @@ GP_API void gp_launch_count_reset(void);
  * new_xyz (optional, may be NULL) [B,m,3] f32 receives xyz[b, idx[b,j], :] -- the fused
  * gather_operation of pointnet2_modules.py:43-47. */
 GP_API int gp_fps(const float *xyz, int B, int N, int m, int32_t *idx, float *new_xyz, gp_stream_t s);
+/* The same sampling for a cascade of levels (the encoder samples level k+1 from the centres of level k,
+ * pointnet2_modules.py:43-47 called from pointnet2.py:115-121).  tie_free_out[b] = T: the first T - 1 sampling
+ * steps of object b never had two different locations share the maximum distance.  tie_free_in (or NULL) must be
+ * the tie_free_out of the call that produced `xyz` as its new_xyz: objects with tie_free_in[b] >= m get
+ * idx = 0..m-1 (FPS of an FPS-ordered cloud is its own prefix when no step tied), the others are sampled. */
+GP_API int gp_fps_chain(const float *xyz, int B, int N, int m, int32_t *idx, float *new_xyz,
+                        const int32_t *tie_free_in, int32_t *tie_free_out, gp_stream_t s);
 
 /* Replaces pointnet2_cuda.gather_points_wrapper(b, c, n, npoints, points, idx, out)
  * (P2/src/sampling.cpp:13-25 -> sampling_gpu.cu:8-43).  points [B,C,N], idx [B,m] -> out [B,C,m]. */

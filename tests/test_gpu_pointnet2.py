@@ -74,6 +74,56 @@ def test_fps_encoder_levels_vs_reference_ext():
         xyz = new_xyz
 
 
+def _chain_case(kind, B, N):
+    if kind == "clouds":  # half the objects are tiled from 300..900 unique points (exact duplicates)
+        return clouds(B, N, seed=11)
+    if kind == "lattice":  # integer lattice: different locations tie exactly all the time
+        g = torch.stack(torch.meshgrid(*[torch.arange(16.0)] * 3, indexing="ij"), -1).reshape(-1, 3)
+        return torch.stack([g[torch.randperm(g.shape[0], generator=torch.Generator().manual_seed(b))[:N]] for b in range(B)]).cuda().contiguous()
+    if kind == "few":  # 40 distinct locations: the cloud is exhausted long before the first level ends
+        base = torch.randn(B, 40, 3)
+        return base[:, torch.arange(N) % 40].cuda().contiguous()
+    xyz = torch.randn(B, N, 3)
+    xyz[:] = xyz[:, :1]  # every point identical
+    return xyz.cuda().contiguous()
+
+
+@pytest.mark.parametrize("kind", ["clouds", "lattice", "few", "same"])
+@pytest.mark.parametrize("N", [1024, 1000, 300])
+def test_fps_chain_equals_level_by_level_sampling(kind, N):
+    """gp_fps_chain over the encoder's cascade (N -> N/2 -> N/4 -> ...): bit-exact with sampling every level (oracle),
+    whether or not the prefix shortcut applies."""
+    from genpose2_b200 import pointnet2_utils as pu
+    B = 16
+    xyz = _chain_case(kind, B, N)
+    tie, skipped = None, 0
+    for level, m in enumerate((N // 2, N // 4, N // 8, N // 16)):
+        idx, new_xyz, tie_next = pu.furthest_point_sample_chain(xyz, m, tie)
+        want = po.furthest_point_sample(xyz.cpu().numpy(), m)
+        np.testing.assert_array_equal(idx.cpu().numpy(), want, err_msg=f"{kind} level {level}")
+        np.testing.assert_array_equal(new_xyz.cpu().numpy(),
+                                      np.take_along_axis(xyz.cpu().numpy(), want[..., None].astype(np.int64), 1))
+        if tie is not None:
+            skipped += int((tie >= m).sum())
+        assert int(tie_next.max()) <= max(m - 1, int(tie.max()) if tie is not None else 0)
+        xyz, tie = new_xyz, tie_next
+    if kind == "clouds":  # the shortcut must actually be taken on ordinary clouds (tiled ones included)
+        assert skipped >= 3 * B * 3 // 4, skipped
+    if kind == "same":  # nothing to vouch for: every step ties
+        assert skipped == 0, skipped
+
+
+def test_fps_chain_without_history_is_plain_fps():
+    from genpose2_b200 import pointnet2_utils as pu
+    xyz = clouds(8, 512, seed=5)
+    idx, new_xyz, tie = pu.furthest_point_sample_chain(xyz, 128, None)
+    assert torch.equal(idx, pu.furthest_point_sample(xyz, 128))
+    # a history that does not vouch for enough steps is ignored
+    short = torch.full((8,), 100, dtype=torch.int32, device="cuda")
+    idx2, _, _ = pu.furthest_point_sample_chain(xyz, 128, short)
+    assert torch.equal(idx2, idx)
+
+
 @pytest.mark.parametrize("N,M,radius,ns", [(1024, 512, 0.01, 16), (1024, 512, 0.02, 32), (512, 256, 0.04, 32),
                                            (128, 64, 0.16, 32), (1000, 77, 0.03, 5), (5000, 300, 0.02, 16),
                                            (64, 64, 1e-6, 8)])
