@@ -102,6 +102,19 @@ class SharedMLP(nn.Module):
             self._tc_key = key
         return self._tc
 
+    def _tc_layers_featfirst(self, npass):
+        """_tc_layers with the first layer's columns permuted to the [feat | xyz] row layout of the encoder's
+        level buffers (the reference concatenates [xyz | feat], pointnet2_utils.py:321-326)."""
+        fold = self._folded_layers()
+        key = (self._fold_key, npass, "featfirst")
+        if getattr(self, "_tf_key", None) != key:
+            (w0, b0), rest = fold[0], fold[1:]
+            w0p = torch.cat([w0[:, 3:], w0[:, :3]], dim=1).contiguous()
+            self._tf = [(pu.gemm_pack(w0p, npass), b0, w0p.shape[0], w0p.shape[1])] + \
+                       [(pu.gemm_pack(w, npass), b, w.shape[0], w.shape[1]) for w, b in rest]
+            self._tf_key = key
+        return self._tf
+
     def _tc_hoisted(self, npass):
         """Operands for the hoisted form of a 3-layer scale (see forward_hoisted), cached."""
         fold = self._folded_layers()
@@ -139,14 +152,16 @@ class SharedMLP(nn.Module):
         pu.gemm_bias_relu(h2, t["p2"], t["b2"], t["c3"], t["c2"], npass, pool_ns=ns, pooled_out=out)
         return out
 
-    def forward_rows_pooled(self, rows, groups, nsample, out, gemm_mode):
+    def forward_rows_pooled(self, rows, groups, nsample, out, gemm_mode, feat_first=False):
         """rows (R, ld) -> SharedMLP -> max over `nsample` rows per group, written into `out` (groups, Cout).
-        gemm_mode: "cublas" (fp32 library GEMM), "bf16x3" (tcgen05, split-bf16, fp32-class) or "bf16" (tcgen05)."""
+        gemm_mode: "cublas" (fp32 library GEMM), "bf16x3" (tcgen05, split-bf16, fp32-class) or "bf16" (tcgen05).
+        feat_first: the rows are [feat | xyz | 0] (the encoder's level buffers) instead of [xyz | feat]."""
         if gemm_mode == "cublas":
+            assert not feat_first
             h = self.forward_rows(rows)
             return pu.maxpool_rows(h, groups, nsample, out=out)
         npass = {"bf16x3": 3, "bf16": 1}[gemm_mode]
-        layers = self._tc_layers(npass)
+        layers = self._tc_layers_featfirst(npass) if feat_first else self._tc_layers(npass)
         h = rows
         for i, (packed, b, N, K) in enumerate(layers):
             if i + 1 < len(layers):
@@ -183,58 +198,73 @@ class PointnetSAModuleMSG(nn.Module):
         new_xyz, out_cl, geometry = self.forward_cl(xyz, feat_cl, geometry)
         return new_xyz, out_cl.transpose(1, 2).contiguous(), geometry
 
-    def forward_cl(self, xyz, feat_cl=None, geometry=None):
+    def forward_cl(self, xyz, feat_cl=None, geometry=None, pts_rows=None, return_rows=False):
         """Channels-last fast path: feat_cl (B,N,C) -> new_xyz (B,npoint,3), out (B,npoint,sum Cout).
         FPS+gather, one two-radius ball query, then per scale: fused gather into GEMM rows, the SharedMLP
-        as a row-major GEMM chain, max-pool over the samples written straight into the concatenated output."""
+        as a row-major GEMM chain, max-pool over the samples written straight into the concatenated output.
+
+        Level buffers: the tensor-core scales read one row [feat | xyz | 0] per point.  With return_rows the output
+        is allocated four columns wider, the centres are copied into the tail, and the buffer comes back as a fourth
+        result to be handed to the next level as `pts_rows` -- no concatenation between levels."""
         B = xyz.shape[0]
         couts = [getattr(m, f"layer{m.n_layers - 1}").conv.out_channels for m in self.mlps]
+        C = sum(couts)
+        tc = self.gemm_mode != "cublas"
         if self.npoint is not None:
             if geometry is None:
                 idx, new_xyz = pu.furthest_point_sample_gather(xyz, self.npoint)
                 bq = pu.ball_query2(self.radii, self.nsamples, xyz, new_xyz)
                 geometry = (idx, new_xyz, bq)
-            idx, new_xyz, bq = geometry
+            idx, new_xyz, bq = geometry[:3]
             M = self.npoint
-            out = torch.empty((B, M, sum(couts)), dtype=torch.float32, device=xyz.device)
+            pad_rows = return_rows and tc and C % 4 == 0
+            out_full = torch.empty((B, M, C + 4 if pad_rows else C), dtype=torch.float32, device=xyz.device)
+            out, out2d = out_full[..., :C], out_full.view(B * M, -1)
             off = 0
-            pts_rows = None
             for i, mlp in enumerate(self.mlps):
-                if feat_cl is not None and self.gemm_mode != "cublas" and mlp.n_layers == 3 and feat_cl.shape[2] % 4 == 0:
+                if feat_cl is not None and tc and mlp.n_layers == 3 and feat_cl.shape[2] % 4 == 0:
                     if pts_rows is None:  # [feat | xyz | 0] per point, shared by both scales
                         N = xyz.shape[1]
                         pts_rows = torch.cat([feat_cl, xyz, torch.zeros((B, N, 1), dtype=torch.float32, device=xyz.device)],
                                              dim=-1).reshape(B * N, -1)
-                    mlp.forward_hoisted(pts_rows, xyz.shape[1], new_xyz, bq[i], out.view(B * M, -1)[:, off:off + couts[i]],
+                    mlp.forward_hoisted(pts_rows, xyz.shape[1], new_xyz, bq[i], out2d[:, off:off + couts[i]],
                                         self.gemm_mode)
                     off += couts[i]
                     continue
                 spec = tuple(getattr(mlp, f"layer{j}").conv.out_channels for j in range(mlp.n_layers))
-                if (feat_cl is None and self.gemm_mode != "cublas" and self.nsamples[i] in (16, 32)
+                if (feat_cl is None and tc and self.nsamples[i] in (16, 32)
                         and spec in ((16, 16, 32), (32, 32, 64))):
                     # first level: the whole scale in one FP32 kernel (channels too narrow for tensor cores)
-                    pu.sa_small_mlp(xyz, new_xyz, bq[i], mlp._folded_layers(), out.view(B * M, -1)[:, off:off + couts[i]])
+                    pu.sa_small_mlp(xyz, new_xyz, bq[i], mlp._folded_layers(), out2d[:, off:off + couts[i]])
                     off += couts[i]
                     continue
-                rows = pu.group_rows(xyz, new_xyz, feat_cl, bq[i], pad_to=1 if self.gemm_mode == "cublas" else 4)
-                mlp.forward_rows_pooled(rows, B * M, self.nsamples[i], out.view(B * M, -1)[:, off:off + couts[i]],
-                                        self.gemm_mode)
+                rows = pu.group_rows(xyz, new_xyz, feat_cl, bq[i], pad_to=4 if tc else 1)
+                mlp.forward_rows_pooled(rows, B * M, self.nsamples[i], out2d[:, off:off + couts[i]], self.gemm_mode)
                 off += couts[i]
-            return new_xyz, out, geometry
+            if pad_rows:
+                tail = geometry[3] if len(geometry) > 3 else torch.nn.functional.pad(new_xyz, (0, 1))
+                out_full[..., C:].copy_(tail)  # [x y z 0] of the centres
+            res = (new_xyz, out, geometry)
+            return res + (out2d if pad_rows else None,) if return_rows else res
         # GroupAll (pointnet2_utils.py:306-328): every point of the level is one sample of a single group
         N = xyz.shape[1]
-        parts = [xyz] if feat_cl is None else [xyz, feat_cl]
-        width = sum(p.shape[-1] for p in parts)
-        if self.gemm_mode != "cublas" and width % 4:
-            parts.append(torch.zeros((B, N, 4 - width % 4), dtype=torch.float32, device=xyz.device))
-        rows = torch.cat(parts, dim=-1).reshape(B * N, -1)
-        out = torch.empty((B, 1, sum(couts)), dtype=torch.float32, device=xyz.device)
+        out = torch.empty((B, 1, C), dtype=torch.float32, device=xyz.device)
+        feat_first = pts_rows is not None and tc and (N % 32 == 0 or 32 % N == 0)
+        if feat_first:
+            rows, gm = pts_rows, self.gemm_mode
+        else:
+            parts = [xyz] if feat_cl is None else [xyz, feat_cl]
+            width = sum(p.shape[-1] for p in parts)
+            if tc and width % 4:
+                parts.append(torch.zeros((B, N, 4 - width % 4), dtype=torch.float32, device=xyz.device))
+            rows = torch.cat(parts, dim=-1).reshape(B * N, -1)
+            gm = self.gemm_mode if (not tc or N % 32 == 0 or 32 % N == 0) else "cublas"
         off = 0
-        gm = self.gemm_mode if (self.gemm_mode == "cublas" or N % 32 == 0 or 32 % N == 0) else "cublas"
         for i, mlp in enumerate(self.mlps):
-            mlp.forward_rows_pooled(rows, B, N, out.view(B, -1)[:, off:off + couts[i]], gm)
+            mlp.forward_rows_pooled(rows, B, N, out.view(B, -1)[:, off:off + couts[i]], gm, feat_first=feat_first)
             off += couts[i]
-        return None, out, geometry
+        res = (None, out, geometry)
+        return res + (None,) if return_rows else res
 
 
 class Pointnet2ClsMSG(nn.Module):
@@ -277,7 +307,8 @@ class Pointnet2ClsMSG(nn.Module):
             # each level samples the previous level's centres: an FPS-ordered cloud, whose FPS is its own prefix
             # unless the earlier sampling hit an exact tie (pointnet2_utils.furthest_point_sample_chain)
             idx, new_xyz, tie_free = pu.furthest_point_sample_chain(xyz, sa.npoint, tie_free)
-            geometry.append((idx, new_xyz, pu.ball_query2(sa.radii, sa.nsamples, xyz, new_xyz)))
+            geometry.append((idx, new_xyz, pu.ball_query2(sa.radii, sa.nsamples, xyz, new_xyz),
+                             torch.nn.functional.pad(new_xyz, (0, 1))))  # [x y z 0]: the tail of the level buffers
             xyz = new_xyz
         return geometry
 
@@ -289,9 +320,10 @@ class Pointnet2ClsMSG(nn.Module):
         geo_out = []
         if geometry is None:
             geometry = self.compute_geometry(pointcloud)
+        rows = None
         for k, sa in enumerate(self.SA_modules):
             g = geometry[k]
-            xyz, feat_cl, g = sa.forward_cl(xyz, feat_cl, g)
+            xyz, feat_cl, g, rows = sa.forward_cl(xyz, feat_cl, g, pts_rows=rows, return_rows=True)
             geo_out.append(g)
         out = feat_cl.squeeze(1)
         return (out, geo_out) if return_geometry else out
