@@ -144,12 +144,16 @@ def call(name, *args, device=None):
         raise RuntimeError(f"{name} failed with status {rc}: {last_error()}")
 
 
-def check_cuda(t, name, dtype=None):
+def check_cuda(t, name, dtype=None, rows=False):
+    """rows=True: a 2-D row-major matrix that may be a column slice (unit column stride, any row stride)."""
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name} must be a torch.Tensor")
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor (genpose2_b200 has no CPU path)")
-    if not t.is_contiguous():
+    if rows:
+        if t.dim() != 2 or t.stride(1) != 1:
+            raise RuntimeError(f"{name} must be a row-major matrix (or a column slice of one)")
+    elif not t.is_contiguous():
         raise RuntimeError(f"{name} must be contiguous")
     if dtype is not None and t.dtype != dtype:
         raise TypeError(f"{name} must be {dtype}, got {t.dtype}")

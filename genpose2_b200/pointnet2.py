@@ -122,7 +122,7 @@ class SharedMLP(nn.Module):
         if getattr(self, "_th_key", None) != key:
             (w0, b0), (w1, b1), (w2, b2) = fold
             w0p = torch.cat([w0[:, 3:], w0[:, :3]], dim=1).contiguous()  # feature columns first, xyz last
-            self._th = dict(p0=pu.gemm_pack(w0p, npass), k0=w0p.shape[1], c1=w0.shape[0],
+            self._th = dict(p0=pu.gemm_pack(w0p, npass), k0=w0p.shape[1], c1=w0.shape[0], w0p=w0p,
                             w0_xyz_t=w0[:, :3].t().contiguous(), b0=b0,
                             p1=pu.gemm_pack(w1, npass), b1=b1, c2=w1.shape[0],
                             p2=pu.gemm_pack(w2, npass), b2=b2, c3=w2.shape[0])
@@ -142,6 +142,14 @@ class SharedMLP(nn.Module):
         B, M, ns = bq_idx.shape
         P = pu.gemm_linear(pts_rows, t["p0"], t["c1"], t["k0"], npass)                 # [B*n_src, ldp]
         Q = pu.centre_term(new_xyz.reshape(B * M, 3).contiguous(), t["w0_xyz_t"], t["b0"], P.shape[1])
+        return self.hoisted_tail(P, Q, n_src, bq_idx, out, gemm_mode)
+
+    def hoisted_tail(self, P, Q, n_src, bq_idx, out, gemm_mode):
+        """Layers 2, 3 and the max-pool of forward_hoisted, given the per-point table P and the per-centre term Q
+        (both may be column slices of tables shared by the scales of a level)."""
+        npass = {"bf16x3": 3, "bf16": 1}[gemm_mode]
+        t = self._tc_hoisted(npass)
+        B, M, ns = bq_idx.shape
         if pu.sa_mlp2_fused_fits(t["c1"], t["c2"], t["c3"], npass, ns):
             # layers 2, 3 and the max-pool in one kernel: no (centre, sample) matrix in HBM at all
             return pu.sa_mlp2_fused(P, n_src, bq_idx.reshape(-1), M * ns, Q, ns, t["p1"], t["b1"], t["c1"], t["c2"],
@@ -198,6 +206,22 @@ class PointnetSAModuleMSG(nn.Module):
         new_xyz, out_cl, geometry = self.forward_cl(xyz, feat_cl, geometry)
         return new_xyz, out_cl.transpose(1, 2).contiguous(), geometry
 
+    def _merged_first_layer(self, npass):
+        """The hoisted first layers of all scales of this level as ONE per-point GEMM and ONE per-centre term: the
+        scales read the same rows, so their weights are stacked along the output channels and each scale takes its
+        column slice of P / Q.  None when a slice would not start on a 64-column (one operand atom) boundary."""
+        ths = [m._tc_hoisted(npass) for m in self.mlps]
+        if len(ths) < 2 or any(t["c1"] % 64 for t in ths) or len({t["k0"] for t in ths}) != 1:
+            return None
+        key = tuple(m._th_key for m in self.mlps)
+        if getattr(self, "_mf_key", None) != key:
+            self._mf = dict(p0=pu.gemm_pack(torch.cat([t["w0p"] for t in ths], dim=0).contiguous(), npass),
+                            k0=ths[0]["k0"], n=sum(t["c1"] for t in ths),
+                            w0_xyz_t=torch.cat([t["w0_xyz_t"] for t in ths], dim=1).contiguous(),
+                            b0=torch.cat([t["b0"] for t in ths]).contiguous())
+            self._mf_key = key
+        return self._mf
+
     def forward_cl(self, xyz, feat_cl=None, geometry=None, pts_rows=None, return_rows=False):
         """Channels-last fast path: feat_cl (B,N,C) -> new_xyz (B,npoint,3), out (B,npoint,sum Cout).
         FPS+gather, one two-radius ball query, then per scale: fused gather into GEMM rows, the SharedMLP
@@ -221,14 +245,30 @@ class PointnetSAModuleMSG(nn.Module):
             out_full = torch.empty((B, M, C + 4 if pad_rows else C), dtype=torch.float32, device=xyz.device)
             out, out2d = out_full[..., :C], out_full.view(B * M, -1)
             off = 0
+            hoist = feat_cl is not None and tc and feat_cl.shape[2] % 4 == 0
+            P_all = Q_all = None
+            if hoist:
+                if pts_rows is None:  # [feat | xyz | 0] per point, shared by both scales
+                    N = xyz.shape[1]
+                    pts_rows = torch.cat([feat_cl, xyz, torch.zeros((B, N, 1), dtype=torch.float32, device=xyz.device)],
+                                         dim=-1).reshape(B * N, -1)
+                if all(m.n_layers == 3 for m in self.mlps):
+                    npass = {"bf16x3": 3, "bf16": 1}[self.gemm_mode]
+                    mf = self._merged_first_layer(npass)
+                    if mf is not None:
+                        P_all = pu.gemm_linear(pts_rows, mf["p0"], mf["n"], mf["k0"], npass)
+                        Q_all = pu.centre_term(new_xyz.reshape(B * M, 3), mf["w0_xyz_t"], mf["b0"], P_all.shape[1])
+            col = 0
             for i, mlp in enumerate(self.mlps):
-                if feat_cl is not None and tc and mlp.n_layers == 3 and feat_cl.shape[2] % 4 == 0:
-                    if pts_rows is None:  # [feat | xyz | 0] per point, shared by both scales
-                        N = xyz.shape[1]
-                        pts_rows = torch.cat([feat_cl, xyz, torch.zeros((B, N, 1), dtype=torch.float32, device=xyz.device)],
-                                             dim=-1).reshape(B * N, -1)
-                    mlp.forward_hoisted(pts_rows, xyz.shape[1], new_xyz, bq[i], out2d[:, off:off + couts[i]],
-                                        self.gemm_mode)
+                if hoist and mlp.n_layers == 3:
+                    dst = out2d[:, off:off + couts[i]]
+                    if P_all is not None:
+                        c1 = mlp.layer0.conv.out_channels
+                        mlp.hoisted_tail(P_all[:, col:col + c1], Q_all[:, col:col + c1], xyz.shape[1], bq[i], dst,
+                                         self.gemm_mode)
+                        col += c1
+                    else:
+                        mlp.forward_hoisted(pts_rows, xyz.shape[1], new_xyz, bq[i], dst, self.gemm_mode)
                     off += couts[i]
                     continue
                 spec = tuple(getattr(mlp, f"layer{j}").conv.out_channels for j in range(mlp.n_layers))

@@ -223,8 +223,8 @@ def gemm_linear(x, packed, N, K, npass):
 def gemm_gather_bias_relu(P, n_src, gidx, rows_per_batch, Q, q_ns, packed, bias, N, K, npass, pool_ns=0,
                           pooled_out=None):
     """relu(relu(P[batch * n_src + gidx] - Q[row // q_ns]) @ W^T + bias)  (gp_gemm_gather_bias_relu)."""
-    _lib.check_cuda(P, "P", torch.float32)
-    _lib.check_cuda(Q, "Q", torch.float32)
+    _lib.check_cuda(P, "P", torch.float32, rows=True)
+    _lib.check_cuda(Q, "Q", torch.float32, rows=True)
     _lib.check_cuda(gidx, "gidx", torch.int32)
     R = gidx.numel()
     if pool_ns:
@@ -254,8 +254,8 @@ def sa_mlp2_fused(P, n_src, gidx, rows_per_batch, Q, q_ns, packed1, bias1, c1, c
                   pooled_out):
     """pooled_out[g] = max_rows relu(relu(relu(P[gather] - Q) @ W1^T + b1) @ W2^T + b2)  (gp_sa_mlp2_fused):
     the last two SharedMLP layers of a scale and its max-pool without materialising any (centre, sample) matrix."""
-    _lib.check_cuda(P, "P", torch.float32)
-    _lib.check_cuda(Q, "Q", torch.float32)
+    _lib.check_cuda(P, "P", torch.float32, rows=True)
+    _lib.check_cuda(Q, "Q", torch.float32, rows=True)
     _lib.check_cuda(gidx, "gidx", torch.int32)
     _lib.call("gp_sa_mlp2_fused", _lib.ptr(P), int(n_src), int(P.stride(0)), _lib.ptr(gidx), gidx.numel(),
               int(rows_per_batch), _lib.ptr(Q), int(Q.stride(0)), int(q_ns), _lib.ptr(packed1), _lib.ptr(bias1), int(c1),
