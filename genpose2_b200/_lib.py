@@ -127,19 +127,26 @@ def ptr(t):
     return None if t is None else c_void_p(t.data_ptr())
 
 
-def stream_ptr():
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)  # ~50x cheaper than current_stream()
+
+
+def stream_ptr(index=None):
+    """cudaStream_t of torch's current stream on the current (or the given) device."""
+    if _raw_stream is not None:
+        return c_void_p(_raw_stream(torch.cuda.current_device() if index is None else index))
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def call(name, *args, device=None):
-    """Invoke `name`, raising RuntimeError (with gp_last_error) on a non-zero status."""
-    lib = load()
+    """Invoke `name` on torch's current stream, raising RuntimeError (with gp_last_error) on a non-zero status."""
+    lib = _lib if _lib is not None else load()
     fn = getattr(lib, name)
-    if device is not None and device.index is not None and device.index != torch.cuda.current_device():
+    cur = torch.cuda.current_device()
+    if device is not None and device.index is not None and device.index != cur:
         with torch.cuda.device(device):
-            rc = fn(*args, stream_ptr())
+            rc = fn(*args, stream_ptr(device.index))
     else:
-        rc = fn(*args, stream_ptr())
+        rc = fn(*args, stream_ptr(cur))
     if rc != 0:
         raise RuntimeError(f"{name} failed with status {rc}: {last_error()}")
 

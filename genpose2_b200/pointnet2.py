@@ -79,8 +79,12 @@ class SharedMLP(nn.Module):
         h = self.forward_rows(rows)
         return pu.maxpool_rows(h, B * M, ns).view(B, M, -1).permute(0, 2, 1).contiguous()
 
+    _trusted = False  # set by Pointnet2ClsMSG.forward for the duration of one pass, after it has checked the cache
+
     def _folded_layers(self):
         """BatchNorm(eval) folded into the 1x1 convs, cached until a parameter / buffer changes."""
+        if self._trusted:
+            return self._fold
         ts = []
         for i in range(self.n_layers):
             l = getattr(self, f"layer{i}")
@@ -360,10 +364,20 @@ class Pointnet2ClsMSG(nn.Module):
         geo_out = []
         if geometry is None:
             geometry = self.compute_geometry(pointcloud)
-        rows = None
-        for k, sa in enumerate(self.SA_modules):
-            g = geometry[k]
-            xyz, feat_cl, g, rows = sa.forward_cl(xyz, feat_cl, g, pts_rows=rows, return_rows=True)
-            geo_out.append(g)
+        # the folded / packed weight caches are validated once per pass (parameter versions), not once per use
+        mlps = [m for sa in self.SA_modules for m in sa.mlps]
+        for m in mlps:
+            m._trusted = False
+            m._folded_layers()
+            m._trusted = True
+        try:
+            rows = None
+            for k, sa in enumerate(self.SA_modules):
+                g = geometry[k]
+                xyz, feat_cl, g, rows = sa.forward_cl(xyz, feat_cl, g, pts_rows=rows, return_rows=True)
+                geo_out.append(g)
+        finally:
+            for m in mlps:
+                m._trusted = False
         out = feat_cl.squeeze(1)
         return (out, geo_out) if return_geometry else out

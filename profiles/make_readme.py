@@ -153,10 +153,12 @@ def main():
                       f"{num(d, 'sm__throughput.avg.pct_of_peak_sustained_elapsed'):.0f} | "
                       f"{num(d, 'sm__warps_active.avg.pct_of_peak_sustained_active'):.0f} |")
         md.append("\nFPS is a chain of npoint - 1 dependent arg-max steps per object on 64 CTAs (one per object): it is bound by the "
-                  "latency of one step (distance update, two redux levels, one barrier), not by bytes -- 0.6 MB per launch. "
-                  "Ball query and grouping at these sizes are a few MB per launch and finish in 3-60 us, so they sit on the launch / "
-                  "ramp part of the bandwidth curve; the encoder's hot path no longer materialises the grouped tensor at all (DESIGN.md 4.4).\n")
-    for name in ("bench_fp32.json", "bench_ffma.json"):
+                  "latency of one step (distance update, two redux levels, one barrier), not by bytes -- 0.6 MB per launch; "
+                  "`fps_chain` is what the encoder calls (levels 2-4 take the FPS-order prefix, DESIGN.md 4.1). "
+                  "Ball query is issue-bound (one thread per centre, 11.7 instructions per centre-point pair); grouping at these "
+                  "sizes reaches 53-63 % of the copy bandwidth, and the encoder's hot path no longer materialises the grouped "
+                  "tensor at all (DESIGN.md 4.4).\n")
+    for name in ("bench_fp32.json", "bench_ffma.json", "bench_4gpu.json", "bench_8gpu.json"):
         src = os.path.join(GO, name)
         if os.path.exists(src):
             dst = os.path.join(PR, f"bench_{ROUND}_{name[6:]}")
@@ -170,6 +172,13 @@ def main():
                   f"({100 * j['roofline']['frac']:.1f} % of the sustained bf16 tensor peak, x3 issued); bf16 mode: "
                   f"{j['other_mode']['value']:.0f} {j['unit']} ({j['other_mode']['ms_per_step']:.2f} ms/step); CPU port: "
                   f"{j['cpu_baseline']['value']:.1f} {j['unit']} on {j['cpu_baseline']['cores']} cores; clocks {j['clocks']}.\n")
+        for n in (4, 8):
+            bn = os.path.join(GO, f"bench_{n}gpu.json")
+            if os.path.exists(bn):
+                jn = json.loads(open(bn).read().strip().splitlines()[-1])
+                md.append(f"bench_{ROUND}_{n}gpu.json (`torchrun --nproc-per-node {n} bench.py --gpus {n} --steps 20 --warmup 3`): "
+                          f"{jn['value']:.0f} {jn['unit']} = {jn['value'] / j['value']:.2f} x the one-GPU line above "
+                          f"({jn['ms_per_step']:.2f} ms/step, max over ranks).\n")
     md.append("## phase_breakdown.py — in-kernel cycle counters of the integrator\n")
     md.append("`python profiles/phase_breakdown.py` reads `stats[8..24]` of `gp_scorenet_ode` (cycles per RHS evaluation, CTA 0 of "
               "cluster 0; forward = l1 + wait_d1 + epi1 + wait_heads + epi2 + the x:* exchange tail; the stage_* / err rows are the "

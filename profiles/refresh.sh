@@ -1,0 +1,32 @@
+#!/bin/bash
+# Everything profiles/README.md is built from, on one B200 (run through gpurun; then `python profiles/make_readme.py` here).
+# Each ncu pass runs only after the same command has exited 0 without ncu.
+# Two parts because one gpurun call brings back at most 64 MiB:  refresh.sh core | refresh.sh extra
+set -u
+O=gpurun_out
+mkdir -p $O
+if [ "${1:-core}" = "extra" ]; then
+export GP_NONCOOPERATIVE_LAUNCH=1
+ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:sa_mlp2 -c 6 \
+    -o $O/sa_mlp2 -f python profiles/profile_step.py > $O/ncu_sa.log 2>&1
+python profiles/profile_geometry.py > /dev/null 2>&1 && \
+ncu --profile-from-start off --set full --clock-control none -k regex:"fps_kernel|ball_query|group_kernel" \
+    -o $O/geom -f python profiles/profile_geometry.py > $O/geom.log 2>&1
+echo refresh extra done
+exit 0
+fi
+python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; tail -2 $O/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -1 $O/smoke.log
+python bench.py --steps 20 --warmup 3 > $O/bench_fp32.json 2> $O/bench.err
+python bench.py --steps 20 --warmup 3 --mlp_mode fp32_ffma --single_mode > $O/bench_ffma.json 2>> $O/bench.err
+python profiles/phase_breakdown.py > $O/phase.log 2>&1
+export GP_NONCOOPERATIVE_LAUNCH=1
+for m in fp32 bf16; do
+  python profiles/profile_step.py --mlp_mode $m > /dev/null 2>&1 && \
+  ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+      --log-file $O/launches_r01_${m}_step.csv python profiles/profile_step.py --mlp_mode $m > /dev/null 2>&1
+  python profiles/profile_step.py --what sampler --mlp_mode $m > /dev/null 2>&1 && \
+  ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:ode_rk45 -c 1 \
+      -o $O/ode_$m -f python profiles/profile_step.py --what sampler --mlp_mode $m > $O/ncu_ode_$m.log 2>&1
+done
+echo refresh done
