@@ -38,7 +38,7 @@ NUM_POINTS = 1024
 L2_FLUSH_BYTES = 256 << 20
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the integrator kernel, `ncu --set full` captures in profiles/README.md
-NCU_DRAM_BYTES_PER_LAUNCH = {"fp32_ffma": 2270464 + 22784, "bf16": 1686528 + 35584, "fp32": 2249472 + 77824}
+NCU_DRAM_BYTES_PER_LAUNCH = {"fp32_ffma": 2270464 + 22784, "bf16": 1686784 + 58368, "fp32": 2249472 + 72960}
 
 # algorithmic work of the ScoreNet RHS after hoisting, in FLOP
 ROW_EVAL_FLOP = 2 * 266752
