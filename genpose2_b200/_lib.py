@@ -52,6 +52,8 @@ SIGNATURES = {
     "gp_maxpool_rows": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gp_sa_small_mlp": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p),
                                 ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "gp_sa_small_mlp_hostw": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p),
+                                ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "gp_gemm_packed_bytes": (c_size_t, [c_int, c_int, c_int]),
     "gp_gemm_pack": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gp_gemm_bias_relu": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -658,6 +658,81 @@ sa_small_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz
     }
 }
 
+// The same scale with the weights in the kernel's parameter space (constant bank): every weight is the same for
+// all lanes, so FFMA takes it as a constant operand and the LDS.128 per four FFMAs disappears.  The host passes
+// HOST copies of the folded weights (they are copied into the launch, private to it -- no staging kernel, no race
+// between the two encoders' launches).
+template <int C1, int C2, int C3>
+struct SaSmallConst {
+    float w0[3 * C1], b0[C1];      // [k][n]
+    float w1[C1 * C2], b1[C2];
+    float w2[C2 * C3], b2[C3];
+};
+
+template <int CIN, int COUT>
+__device__ __forceinline__ void dense_relu_c(const float (&in)[CIN], const float *w /*[CIN][COUT], constant*/,
+                                             const float *b, float (&out)[COUT]) {
+#pragma unroll
+    for (int n = 0; n < COUT; ++n) out[n] = b[n];
+#pragma unroll
+    for (int k = 0; k < CIN; ++k)
+#pragma unroll
+        for (int n = 0; n < COUT; ++n) out[n] = fmaf(in[k], w[k * COUT + n], out[n]);
+#pragma unroll
+    for (int n = 0; n < COUT; ++n) out[n] = fmaxf(out[n], 0.f);
+}
+
+template <int C1, int C2, int C3, int NS>
+__global__ void __launch_bounds__(256)
+sa_small_const_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz, const int *__restrict__ idx,
+                      int N, int M, long long rows_total, const __grid_constant__ SaSmallConst<C1, C2, C3> W,
+                      float *__restrict__ out, int ld_out) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long row = (long long)blockIdx.x * 256 + tid;
+    const bool ok = row < rows_total;
+    const long long rr = ok ? row : rows_total - 1;
+    const long long bp = rr / NS;           // b*M + p
+    const int b = (int)(bp / M);
+    const int id = __ldg(idx + rr);
+    float a0[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) a0[c] = __ldg(xyz + ((size_t)b * N + id) * 3 + c) - __ldg(new_xyz + bp * 3 + c);
+    float h1[C1], h2[C2], h3[C3];
+    dense_relu_c<3, C1>(a0, W.w0, W.b0, h1);
+    dense_relu_c<C1, C2>(h1, W.w1, W.b1, h2);
+    dense_relu_c<C2, C3>(h2, W.w2, W.b2, h3);
+    constexpr int GL = NS < 32 ? NS : 32;
+    const unsigned mask = GL == 32 ? 0xffffffffu : (((1u << GL) - 1u) << ((lane / GL) * GL));
+    float keep[C3 / GL > 0 ? C3 / GL : 1];
+#pragma unroll
+    for (int n = 0; n < C3; ++n) {
+        const unsigned m = redux_max_u32(mask, ok ? __float_as_uint(h3[n]) : 0u);
+        if ((lane % GL) == (n % GL)) keep[n / GL] = __uint_as_float(m);
+    }
+    if (ok) {
+        float *dst = out + bp * (long long)ld_out;
+#pragma unroll
+        for (int q = 0; q < C3 / GL; ++q) dst[q * GL + (lane % GL)] = keep[q];
+    }
+}
+
+template <int C1, int C2, int C3>
+static int launch_sa_small_const(const float *xyz, const float *new_xyz, const int *idx, int B, int N, int M, int ns,
+                                 const float *const *w, const float *const *b, float *out, int ld_out, cudaStream_t st) {
+    SaSmallConst<C1, C2, C3> W;   // host weights [Cout][Cin] -> [k][n]
+    for (int n = 0; n < C1; ++n) { for (int k = 0; k < 3; ++k) W.w0[k * C1 + n] = w[0][n * 3 + k]; W.b0[n] = b[0][n]; }
+    for (int n = 0; n < C2; ++n) { for (int k = 0; k < C1; ++k) W.w1[k * C2 + n] = w[1][n * C1 + k]; W.b1[n] = b[1][n]; }
+    for (int n = 0; n < C3; ++n) { for (int k = 0; k < C2; ++k) W.w2[k * C3 + n] = w[2][n * C2 + k]; W.b2[n] = b[2][n]; }
+    const long long rows = (long long)B * M * ns;
+    const unsigned grid = (unsigned)((rows + 255) / 256);
+    if (ns == 16)
+        sa_small_const_kernel<C1, C2, C3, 16><<<grid, 256, 0, st>>>(xyz, new_xyz, idx, N, M, rows, W, out, ld_out);
+    else
+        sa_small_const_kernel<C1, C2, C3, 32><<<grid, 256, 0, st>>>(xyz, new_xyz, idx, N, M, rows, W, out, ld_out);
+    GP_CHECK_LAUNCH("gp_sa_small_mlp_hostw");
+    return GP_OK;
+}
+
 template <int C1, int C2, int C3>
 static int launch_sa_small(const float *xyz, const float *new_xyz, const int *idx, int B, int N, int M, int ns,
                            const float *const *w, const float *const *b, float *out, int ld_out, cudaStream_t st) {
@@ -684,5 +759,21 @@ extern "C" int gp_sa_small_mlp(const float *xyz, const float *new_xyz, const int
     if (C1 == 32 && C2 == 32 && C3 == 64)
         return launch_sa_small<32, 32, 64>(xyz, new_xyz, idx, B, N, M, nsample, weights, biases, out, ld_out, as_stream(s));
     set_error("gp_sa_small_mlp: channel spec %d-%d-%d is not instantiated (16-16-32, 32-32-64)", C1, C2, C3);
+    return GP_ERR_UNSUPPORTED;
+}
+
+extern "C" int gp_sa_small_mlp_hostw(const float *xyz, const float *new_xyz, const int32_t *idx, int B, int N, int M,
+                                     int nsample, const float *const *host_weights, const float *const *host_biases,
+                                     int C1, int C2, int C3, float *out, int ld_out, gp_stream_t s) {
+    GP_REQUIRE(B >= 0 && N >= 1 && M >= 0 && (nsample == 16 || nsample == 32), "gp_sa_small_mlp_hostw: nsample must be 16 or 32");
+    if ((long long)B * M == 0) return GP_OK;
+    GP_REQUIRE(xyz && new_xyz && idx && host_weights && host_biases && out && ld_out >= C3,
+               "gp_sa_small_mlp_hostw: null pointer / bad ld_out");
+    for (int i = 0; i < 3; ++i) GP_REQUIRE(host_weights[i] && host_biases[i], "gp_sa_small_mlp_hostw: null layer %d", i);
+    if (C1 == 16 && C2 == 16 && C3 == 32)
+        return gp::launch_sa_small_const<16, 16, 32>(xyz, new_xyz, idx, B, N, M, nsample, host_weights, host_biases, out, ld_out, gp::as_stream(s));
+    if (C1 == 32 && C2 == 32 && C3 == 64)
+        return gp::launch_sa_small_const<32, 32, 64>(xyz, new_xyz, idx, B, N, M, nsample, host_weights, host_biases, out, ld_out, gp::as_stream(s));
+    gp::set_error("gp_sa_small_mlp_hostw: channel spec %d-%d-%d is not instantiated (16-16-32, 32-32-64)", C1, C2, C3);
     return GP_ERR_UNSUPPORTED;
 }

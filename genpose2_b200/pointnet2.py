@@ -97,6 +97,15 @@ class SharedMLP(nn.Module):
             self._fold_key = key
         return self._fold
 
+    def _folded_layers_host(self):
+        """CPU copies of the folded layers (one device-to-host copy per checkpoint), for kernels that take their
+        weights through the launch's parameter space."""
+        fold = self._folded_layers()
+        if getattr(self, "_fh_key", None) != self._fold_key:
+            self._fh = [(w.detach().float().cpu().contiguous(), b.detach().float().cpu().contiguous()) for w, b in fold]
+            self._fh_key = self._fold_key
+        return self._fh
+
     def _tc_layers(self, npass):
         """(packed weights, bias, N, K) per layer for the tcgen05 GEMM, cached like the folded weights."""
         fold = self._folded_layers()
@@ -279,7 +288,7 @@ class PointnetSAModuleMSG(nn.Module):
                 if (feat_cl is None and tc and self.nsamples[i] in (16, 32)
                         and spec in ((16, 16, 32), (32, 32, 64))):
                     # first level: the whole scale in one FP32 kernel (channels too narrow for tensor cores)
-                    pu.sa_small_mlp(xyz, new_xyz, bq[i], mlp._folded_layers(), out2d[:, off:off + couts[i]])
+                    pu.sa_small_mlp_hostw(xyz, new_xyz, bq[i], mlp._folded_layers_host(), out2d[:, off:off + couts[i]])
                     off += couts[i]
                     continue
                 rows = pu.group_rows(xyz, new_xyz, feat_cl, bq[i], pad_to=4 if tc else 1)

@@ -179,6 +179,26 @@ def sa_small_mlp(xyz, new_xyz, idx, layers, out):
     return out
 
 
+def sa_small_mlp_hostw(xyz, new_xyz, idx, host_layers, out):
+    """sa_small_mlp with HOST copies of the folded weights (gp_sa_small_mlp_hostw): they travel in the launch's
+    parameter space and the kernel reads them as constant operands.  `host_layers` = [(W, b)] x 3, CPU fp32."""
+    import ctypes
+    _lib.check_cuda(xyz, "xyz", torch.float32)
+    _lib.check_cuda(new_xyz, "new_xyz", torch.float32)
+    _lib.check_cuda(idx, "idx", torch.int32)
+    for w, b in host_layers:
+        if w.is_cuda or b.is_cuda or w.dtype != torch.float32 or not w.is_contiguous() or not b.is_contiguous():
+            raise TypeError("host_layers must be contiguous fp32 CPU tensors")
+    B, N, _ = xyz.size()
+    _, M, ns = idx.size()
+    ws = (ctypes.c_void_p * 3)(*[w.data_ptr() for w, _ in host_layers])
+    bs = (ctypes.c_void_p * 3)(*[b.data_ptr() for _, b in host_layers])
+    C1, C2, C3 = (w.shape[0] for w, _ in host_layers)
+    _lib.call("gp_sa_small_mlp_hostw", _lib.ptr(xyz), _lib.ptr(new_xyz), _lib.ptr(idx), B, N, M, ns, ws, bs, C1, C2, C3,
+              _lib.ptr(out), int(out.stride(-2)), device=xyz.device)
+    return out
+
+
 def gemm_pack(weight: torch.Tensor, npass: int) -> torch.Tensor:
     """Pack W [N, K] fp32 into the pre-swizzled bf16 (npass=1) / bf16 hi+lo (npass=3) chunk images the
     tcgen05 GEMM streams with TMA (gp_gemm_pack).  Do once per checkpoint."""

@@ -117,6 +117,11 @@ GP_API int gp_maxpool_rows(const float *h, long long G, int nsample, int C, int 
 GP_API int gp_sa_small_mlp(const float *xyz, const float *new_xyz, const int32_t *idx, int B, int N, int M,
                     int nsample, const float *const *weights, const float *const *biases, int C1, int C2, int C3,
                     float *out, int ld_out, gp_stream_t s);
+/* The same scale with HOST copies of the folded weights: they travel in the launch's parameter space (constant
+ * bank), so the kernel's FFMAs take them as constant operands instead of loading them from shared memory. */
+GP_API int gp_sa_small_mlp_hostw(const float *xyz, const float *new_xyz, const int32_t *idx, int B, int N, int M,
+                    int nsample, const float *const *host_weights, const float *const *host_biases, int C1, int C2,
+                    int C3, float *out, int ld_out, gp_stream_t s);
 
 /* One SharedMLP layer (P2/pytorch_utils.py:5-33: conv1x1 + BatchNorm(eval) folded + ReLU) on channels-last
  * rows, on the tcgen05 tensor cores: Y = relu(X . W^T + bias), optionally fused with the max-pool over

@@ -100,3 +100,36 @@ def test_hoisted_scale_matches_direct_scale(npass, tol, spec, ns, M):
     err = float((out.double() - want).abs().max() / want.abs().max())
     print("hoisted scale rel err", npass, err)
     assert err < tol, err
+
+
+@pytest.mark.parametrize("spec,ns", [((16, 16, 32), 16), ((32, 32, 64), 32), ((32, 32, 64), 16)])
+def test_first_level_scale_kernels_match_float64_and_each_other(spec, ns):
+    """gp_sa_small_mlp (weights staged in shared memory) and gp_sa_small_mlp_hostw (weights as constant operands
+    through the launch's parameter space): same operation order, so bit-identical; both against float64."""
+    from genpose2_b200 import pointnet2_utils as pu
+    from genpose2_b200.pointnet2 import SharedMLP
+    B, N, M = 5, 1024, 512
+    pts, _ = synthetic.make_point_clouds(B, N, seed=33)
+    xyz = pts.cuda()
+    idx, new_xyz = pu.furthest_point_sample_gather(xyz, M)
+    bq = pu.ball_query(0.02, ns, xyz, new_xyz)
+    mlp = SharedMLP([3, *spec]).cuda().eval()
+    gw = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for name, prm in mlp.named_parameters():
+            prm.copy_(torch.randn(prm.shape, generator=gw) * (1.5 / prm.shape[1] ** 0.5) if prm.dim() > 1
+                      else torch.rand(prm.shape, generator=gw) + 0.5 if name.endswith("weight")
+                      else torch.randn(prm.shape, generator=gw) * 0.1)
+    rows = pu.group_rows(xyz, new_xyz, None, bq).double()[:, :3]
+    h = rows
+    for w, b in mlp._folded_layers():
+        h = torch.relu(h @ w.double().t() + b.double())
+    want = h.view(B * M, ns, -1).amax(1)
+    a = torch.full((B * M, spec[2] + 4), -1.0, device="cuda")
+    b_ = torch.full((B * M, spec[2] + 4), -1.0, device="cuda")
+    pu.sa_small_mlp(xyz, new_xyz, bq, mlp._folded_layers(), a[:, : spec[2]])
+    pu.sa_small_mlp_hostw(xyz, new_xyz, bq, mlp._folded_layers_host(), b_[:, : spec[2]])
+    assert torch.equal(a, b_)
+    assert (a[:, spec[2]:] == -1).all()  # the column slice only
+    err = float((a[:, : spec[2]].double() - want).abs().max() / want.abs().max())
+    assert err < 1e-5, err
