@@ -157,3 +157,23 @@ def test_dbscan_restated_matches_sklearn_random():
         a = DBSCAN(eps=eps, min_samples=3).fit(D).labels_
         b = po.dbscan_restated(D, eps, 3)
         np.testing.assert_array_equal(a, b)
+
+
+def test_fps_of_an_fps_ordered_cloud_is_its_prefix():
+    """The identity gp_fps_chain relies on, on the reference restatement alone: sampling the
+    centres of the previous level again returns 0, 1, ..., m-1 as long as no step tied; with exact ties between
+    different locations (a lattice) it does not have to, which is why the kernel keeps the tie bookkeeping."""
+    from oracle import pointnet2_oracle as p2
+    pts, _ = synthetic.make_point_clouds(6, 1024, seed=3, dup_fraction=0.0)
+    xyz = pts.numpy()
+    idx = p2.furthest_point_sample(xyz, 512)
+    level1 = np.take_along_axis(xyz, idx[..., None].astype(np.int64), 1)
+    for m in (256, 128, 64):
+        again = p2.furthest_point_sample(level1, m)
+        np.testing.assert_array_equal(again, np.broadcast_to(np.arange(m, dtype=again.dtype), again.shape))
+        level1 = level1[:, :m]
+    g = np.stack(np.meshgrid(*[np.arange(8.0)] * 3, indexing="ij"), -1).reshape(1, -1, 3).astype(np.float32)
+    lat = g[:, np.random.default_rng(0).permutation(g.shape[1])]
+    i1 = p2.furthest_point_sample(lat, 256)
+    l1 = np.take_along_axis(lat, i1[..., None].astype(np.int64), 1)
+    assert not np.array_equal(p2.furthest_point_sample(l1, 128)[0], np.arange(128))
