@@ -29,6 +29,18 @@ def test_library_exports_every_declared_symbol():
     assert lib2.gp_scorenet_ode_workspace_bytes(3200) >= 9 * 3200 * 9 * 8
 
 
+def test_ctypes_signatures_have_the_declared_arity():
+    """ABI drift guard: every prototype in the header has as many parameters as its ctypes signature."""
+    from genpose2_b200 import _lib
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "genpose_b200.h")).read(), flags=re.S)
+    protos = re.findall(r"GP_API [^;(]*?\b(gp_[a-z0-9_]+)\(([^;]*?)\);", header, flags=re.S)
+    assert len(protos) == len(_lib.SIGNATURES)
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))
+
+
 def test_bad_arguments_return_status_not_exit():
     from genpose2_b200 import _lib
     lib = _lib.load()
