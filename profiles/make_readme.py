@@ -63,14 +63,14 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__cluster_size", "
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max"]
 
 
-def raw_metrics(rep):
+def raw_metrics(rep, want=None):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     H, U = rows[0], rows[1]
     res = []
     for r in rows[2:]:
         d = {"name": r[H.index("Kernel Name")]}
-        for w in WANT:
+        for w in (want or WANT):
             if w in H:
                 d[w] = f"{r[H.index(w)]} {U[H.index(w)]}".strip()
         res.append(d)
@@ -127,6 +127,21 @@ def main():
         for i, d in enumerate(ms):
             md.append(f"| {i} | " + " | ".join(d.get(k, "") for k in keys) + " |")
         md.append(f"\n### top source lines — all six launches\n\n```\n{top_lines(sa)}\n```\n")
+    sas = os.path.join(GO, "sa_small.ncu-rep")
+    if os.path.exists(sas):
+        md.append("## sa_small — `ncu --set full` of the level-1 kernel (weights as uniform operands from the launch's parameter space)\n")
+        md.append("`ncu --set full -k regex:sa_small -c 2 python profiles/profile_step.py` (the two scales of one encoder)\n")
+        keys = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size",
+                "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                "sm__warps_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum"]
+        ms = raw_metrics(sas, keys)
+        md.append("| kernel | " + " | ".join(k.split(".")[0] for k in keys) + " |")
+        md.append("|---|" + "---|" * len(keys))
+        for d in ms:
+            md.append(f"| `{re.sub(r'[(].*', '', d['name'])[5:]}` | " + " | ".join(d.get(k, "") for k in keys) + " |")
+        md.append("\nThe wide scale issues on 83 % of the cycles and the FMA pipe is busy 59 % of them: it is issue-bound, the "
+                  "rest of the slots are the `LDCU.128` that feed the uniform registers (one per four FFMAs), the pooling `REDUX` "
+                  "and the gather.  With the weights staged in shared memory (`gp_sa_small_mlp`) the same launch took 267 us.\n")
     geo, geolog = os.path.join(GO, "geom.ncu-rep"), os.path.join(GO, "geom.log")
     if os.path.exists(geo) and os.path.exists(geolog):
         md.append("## geom — `ncu --set full` of FPS / ball query / grouping, the four encoder levels at 64 objects\n")
