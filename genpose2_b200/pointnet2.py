@@ -365,9 +365,11 @@ class Pointnet2ClsMSG(nn.Module):
             xyz = new_xyz
         return geometry
 
-    def forward(self, pointcloud: torch.Tensor, geometry: Optional[list] = None, return_geometry=False):
+    def forward(self, pointcloud: torch.Tensor, geometry: Optional[list] = None, return_geometry=False,
+                levels: Optional[list] = None):
         """pointcloud (B, N, 3 + C) -> (B, 1024).  `geometry`: per-level FPS / ball-query results of an
-        earlier call on the same cloud (they depend on xyz only)."""
+        earlier call on the same cloud (they depend on xyz only).  `levels`: a list that receives every level's
+        (new_xyz, pooled features channels-last) -- the reference's l_xyz / l_features (pointnet2.py:247-251)."""
         xyz = pointcloud[..., 0:3].contiguous()
         feat_cl = pointcloud[..., 3:].contiguous() if pointcloud.size(-1) > 3 else None
         geo_out = []
@@ -385,6 +387,8 @@ class Pointnet2ClsMSG(nn.Module):
                 g = geometry[k]
                 xyz, feat_cl, g, rows = sa.forward_cl(xyz, feat_cl, g, pts_rows=rows, return_rows=True)
                 geo_out.append(g)
+                if levels is not None:
+                    levels.append((xyz, feat_cl))
         finally:
             for m in mlps:
                 m._trusted = False

@@ -2,8 +2,10 @@
 /root/reference inside THIS container so that golden vectors can be generated and
 the oracle restatements can be pinned against it.
 
-Nothing in the product path (genpose2_b200/), bench.py's GPU arm or the -m gpu tests
-may import this module: /root/reference does not exist on the GPU box.
+Nothing in the product path (genpose2_b200/) may import this module.  /root/reference does not
+exist on the GPU box; there the -m gpu parity tests and bench.py's reference legs import the
+byte-for-byte copy of the same modules that oracle/vendor_ref.py put into oracle/_ref/refpkg
+(next to the reference's CUDA extension built by oracle/build_ref_ext.py).
 
 The reference parses argv at import time (configs/config.py, executed from
 networks/pts_encoder/pointnet2.py:28) and imports a handful of packages that are not
@@ -15,8 +17,22 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("GENPOSE2_REFERENCE_ROOT", "/root/reference")
 _REF_EXT_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+# The build container has the reference tree; the GPU box only has the byte-for-byte copy of the hot-path
+# modules that oracle/vendor_ref.py placed in oracle/_ref/refpkg (git-ignored, travels with the snapshot).
+VENDORED_ROOT = os.path.join(_REF_EXT_DIR, "refpkg")
+
+
+def _default_root():
+    env = os.environ.get("GENPOSE2_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/networks"):
+        return "/root/reference"
+    return VENDORED_ROOT
+
+
+REFERENCE_ROOT = _default_root()
 
 
 class _Anything(types.ModuleType):
@@ -76,6 +92,13 @@ def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "networks"))
 
 
+def has_cuda_ext():
+    """True when the reference's own CUDA extension (oracle/_ref/pointnet2_cuda.so) is importable: the reference
+    encoder can then run for real (GPU box)."""
+    install_stubs()
+    return not isinstance(sys.modules.get("pointnet2_cuda"), _Anything)
+
+
 def load(argv=("x", "--dino", "none", "--sampler_mode", "ode")):
     """Return a namespace with the reference modules on the hot path."""
     if not available():
@@ -101,6 +124,9 @@ def load(argv=("x", "--dino", "none", "--sampler_mode", "ode")):
         ns.rotconv = importlib.import_module("utils.transforms.rotation_conversions")
         ns.posenet = importlib.import_module("networks.posenet")
         ns.posenet_agent = importlib.import_module("networks.posenet_agent")
+        ns.pointnet2 = importlib.import_module("networks.pts_encoder.pointnet2")
+        ns.pointnet2_utils = importlib.import_module(
+            "networks.pts_encoder.pointnet2_utils.pointnet2.pointnet2_utils")
         ns.cfg = ns.config.get_config()
     finally:
         sys.argv = old_argv

@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 
 from genpose2_b200 import synthetic  # noqa: E402
 from oracle import ref_shim  # noqa: E402
+from oracle.ref_runner import reference_aggregate  # noqa: E402
 
 
 def to_np(d):
@@ -223,35 +224,6 @@ def main():
     np.savez_compressed(os.path.join(HERE, "energy_b3.npz"), **to_np(dict(
         feat=efeat, center=center, poses=poses, energy=energy)), **meta)
     print("energy", energy.shape)
-
-
-def reference_aggregate(ns, pred_pose, pred_energy, repeat_num, retain_ratio=0.4, eps=0.05,
-                        minpts=0.1667):
-    """evaluation_single.py:179-215, called function by function (see module docstring)."""
-    from sklearn.cluster import DBSCAN
-
-    sorted_pose, _ = ns.reward.sort_poses_by_energy(pred_pose, pred_energy)
-    bs = pred_pose.shape[0]
-    retain_num = int(repeat_num * retain_ratio)
-    good_pose = sorted_pose[:, :retain_num, :]
-    rot_matrix = ns.misc.get_rot_matrix(good_pose[:, :, :-3].reshape(bs * retain_num, -1), "rot_matrix")
-    quat_wxyz = ns.rotconv.matrix_to_quaternion(rot_matrix).reshape(bs, retain_num, -1)
-    agg_q = ns.misc.average_quaternion_batch(quat_wxyz)
-    all_labels = []
-    for j in range(bs):
-        pd = 1 - torch.sum(quat_wxyz[j].unsqueeze(0) * quat_wxyz[j].unsqueeze(1), dim=2) ** 2
-        labels = DBSCAN(eps=eps, min_samples=int(minpts * retain_num)).fit(pd.cpu().cpu().numpy()).labels_
-        all_labels.append(labels)
-        if np.any(labels >= 0):
-            bins = np.bincount(labels[labels >= 0])
-            best = np.argmax(bins)
-            agg_q[j] = ns.misc.average_quaternion_batch(quat_wxyz[j, labels == best].unsqueeze(0))[0]
-    agg_t = torch.mean(good_pose[:, :, -3:], dim=1)
-    out = torch.zeros(bs, 4, 4)
-    out[:, 3, 3] = 1
-    out[:, :3, :3] = ns.rotconv.quaternion_to_matrix(agg_q)
-    out[:, :3, 3] = agg_t
-    return out, np.stack(all_labels)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,145 @@
+"""GPU: the CUDA path against THE REFERENCE ITSELF run on the same box -- the reference's own Python modules
+(byte-for-byte copy in oracle/_ref/refpkg, see oracle/vendor_ref.py) with the reference's own CUDA extension
+(oracle/_ref/pointnet2_cuda.so, see oracle/build_ref_ext.py), cuDNN/cuBLAS TF32 disabled (SURVEY.md 8(c) trap 6).
+
+  * every set-abstraction level's pooled features and the final [B,1024] of Pointnet2ClsMSG
+    (pointnet2.py:244-252, pointnet2_modules.py:19-74, pytorch_utils.py:5-33) -- rows a3 / a8 / f1;
+  * the CPU restatement oracle/pose_oracle.py:pointnet2_encoder against the same tensors (pins the oracle);
+  * the whole path with the REAL encoder on both sides: reference agents (pred_func -> get_energy ->
+    aggregation block -> pred_scale_func) vs PosePipeline, north-star gate 1e-3 rad / 1e-4.
+"""
+import numpy as np
+import pytest
+import torch
+
+from genpose2_b200 import synthetic
+from tests.util import geodesic_mats, pose_errors
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ref_ns():
+    from oracle import ref_shim
+    assert ref_shim.available(), (
+        "oracle/_ref/refpkg is missing: run `python oracle/vendor_ref.py` in the build container "
+        "(it travels to the GPU box with the snapshot)")
+    assert ref_shim.has_cuda_ext(), "oracle/_ref/pointnet2_cuda.so is missing: run `python oracle/build_ref_ext.py`"
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return ref_shim.load()
+
+
+def reference_levels(ns, sd, pts):
+    """Pointnet2ClsMSG.forward (pointnet2.py:244-252) level by level, with the FPS indices."""
+    ref = ns.pointnet2.Pointnet2ClsMSG(0).cuda().eval()
+    ref.load_state_dict(sd)
+    with torch.no_grad():
+        xyz, features = ref._break_up_pc(pts)
+        l_xyz, l_feat, l_idx = [xyz], [features], []
+        for m in ref.SA_modules:
+            nx, nf, idx = m(l_xyz[-1], l_feat[-1], return_idx=True)
+            l_xyz.append(nx)
+            l_feat.append(nf)
+            l_idx.append(idx)
+        final = ref(pts)
+    assert torch.equal(final, l_feat[-1].squeeze(-1))
+    return l_xyz, l_feat, l_idx, final
+
+
+# fp32 mode is held to 1e-4 of each level's feature scale (observed ~1e-5: split-bf16 x3 keeps 16 mantissa bits
+# per operand); bf16 mode rounds every GEMM operand to 8 bits: stated bound 3e-2 of the feature scale.
+@pytest.mark.parametrize("gemm_mode,tol", [("bf16x3", 1e-4), ("bf16", 3e-2)])
+def test_encoder_levels_match_reference(ref_ns, gemm_mode, tol):
+    from genpose2_b200.pointnet2 import Pointnet2ClsMSG
+    sd = synthetic.random_encoder_state_dict(7, prefix="")
+    B = 64
+    pts, _ = synthetic.make_point_clouds(B, 1024, seed=9, dup_fraction=0.25)   # camera frame, 16 tiled clouds
+    pts = pts.cuda()
+    l_xyz, l_feat, l_idx, final = reference_levels(ref_ns, sd, pts)
+
+    enc = Pointnet2ClsMSG(0).cuda().eval()
+    enc.load_state_dict(sd)
+    enc.set_gemm_mode(gemm_mode)
+    levels = []
+    with torch.no_grad():
+        got, geo = enc(pts, return_geometry=True, levels=levels)
+    errs = []
+    for k in range(5):
+        want = l_feat[k + 1]                       # (B, C, npoint)
+        ours = levels[k][1].transpose(1, 2)        # channels-last -> (B, C, npoint)
+        assert ours.shape == want.shape, (k, ours.shape, want.shape)
+        if k < 4:
+            assert torch.equal(geo[k][0], l_idx[k]), f"level {k}: FPS indices differ from the reference ext"
+            assert torch.equal(levels[k][0], l_xyz[k + 1]), f"level {k}: centres differ"
+        rel = float((ours - want).abs().max() / want.abs().max())
+        errs.append(rel)
+    final_rel = float((got - final).abs().max() / final.abs().max())
+    print(f"encoder vs reference [{gemm_mode}]: per-level rel err {['%.2e' % e for e in errs]} final {final_rel:.2e}")
+    assert max(errs) <= tol and final_rel <= tol, (errs, final_rel)
+    assert got.shape == (B, 1024)
+
+
+def test_oracle_encoder_restatement_matches_reference(ref_ns):
+    """Pins oracle/pose_oracle.py:pointnet2_encoder (+ _shared_mlp: BN folding, layout, pooling) to the reference."""
+    from oracle import pose_oracle as po
+    sd = synthetic.random_encoder_state_dict(7, prefix="")
+    pts, _ = synthetic.make_point_clouds(4, 1024, seed=9, dup_fraction=0.5)
+    l_xyz, l_feat, l_idx, final = reference_levels(ref_ns, sd, pts.cuda())
+    want, trace = po.pointnet2_encoder({"pts_encoder." + k: v for k, v in sd.items()}, pts, return_indices=True)
+    fps = [t for t in trace if t[0] == "fps"]
+    feats = [t for t in trace if t[0] == "feat"]
+    for k in range(4):
+        assert torch.equal(fps[k][2].to(torch.int32), l_idx[k].cpu()), k
+    for k in range(5):
+        w = l_feat[k + 1].cpu()
+        rel = float((feats[k][2] - w).abs().max() / w.abs().max())
+        assert rel <= 2e-5, (k, rel)
+    rel = float((want - final.cpu()).abs().max() / final.abs().max())
+    assert rel <= 2e-5, rel
+
+
+def _agents(device):
+    from oracle.ref_runner import ReferenceAgents
+    return ReferenceAgents(synthetic.random_gfobjectpose_state_dict(100), synthetic.random_gfobjectpose_state_dict(200),
+                           synthetic.random_scalenet_state_dict(300), device=device)
+
+
+@pytest.mark.parametrize("B,T0,tracking", [(8, 0.55, False), (4, 0.25, True)])
+def test_full_path_real_encoder_vs_reference(ref_ns, B, T0, tracking):
+    """Reference agents on the GPU (real encoder through the reference ext, torch fp32 nets, scipy RK45 on the host,
+    sklearn DBSCAN) vs PosePipeline on the same clouds, weights and injected prior noise."""
+    from genpose2_b200.pipeline import PosePipeline
+    R = 50
+    pts, center = synthetic.make_point_clouds(B, 1024, seed=71, dup_fraction=0.25)
+    init = None
+    if tracking:
+        R0 = synthetic._random_rotations(np.random.default_rng(72), B)
+        init = torch.zeros(B, 9)
+        init[:, :3] = torch.from_numpy(R0[:, :, 0]).float()
+        init[:, 3:6] = torch.from_numpy(R0[:, :, 1]).float()
+        init[:, 6:] = torch.randn(B, 3, generator=torch.Generator().manual_seed(73)) * 0.02
+    ref = _agents("cuda")
+    want = ref.full(pts, center, R, T0, init_x=init, noise_seed=5)
+
+    pipe = PosePipeline(device="cuda").load_synthetic_weights((100, 200, 300))
+    torch.manual_seed(5)   # the prior draws from the global CPU generator on both sides (sde.py:34)
+    out = pipe({"pts": pts.cuda(), "pts_center": center.cuda()}, repeat_num=R, T0=T0,
+               init_x=None if init is None else init.cuda(), return_all=True)
+    feat_rel = float((out["pts_feat"] - want["score_feat"]).abs().max() / want["score_feat"].abs().max())
+    rot, trans = pose_errors(out["pred_pose"].cpu().numpy(), want["pred_pose"].cpu().numpy())
+    print(f"full path vs reference (real encoder) B={B} T0={T0}: feat {feat_rel:.2e} pose {rot:.2e} rad {trans:.2e}")
+    assert feat_rel <= 1e-4
+    assert rot <= 1e-3 and trans <= 1e-4, (rot, trans)
+    assert out["pred_pose"].dtype == want["pred_pose"].dtype == torch.float64
+    from genpose2_b200 import samplers
+    assert samplers.ode_stats()["nfev"] + 1 == want["nfev"], (samplers.ode_stats(), want["nfev"])  # + the denoise eval
+    q_err = np.abs(np.abs(out["pred_pose_q_wxyz"].cpu().numpy()) - np.abs(want["pred_q"].cpu().numpy())).max()
+    assert q_err <= 1e-3
+    e, we = out["energy"].cpu().numpy(), want["energy"].cpu().numpy()
+    assert np.abs(e - we).max() <= 2e-3 * np.abs(we).max()
+    agg = out["aggregated_pose"].cpu().numpy().astype(np.float64)
+    wagg = want["aggregated_pose"].cpu().numpy().astype(np.float64)
+    assert geodesic_mats(agg[:, :3, :3], wagg[:, :3, :3]).max() <= 1e-3
+    assert np.abs(agg[:, :3, 3] - wagg[:, :3, 3]).max() <= 1e-4
+    np.testing.assert_allclose(out["length"].cpu().numpy(), want["length"].cpu().numpy(), rtol=0, atol=1e-4)
