@@ -85,6 +85,7 @@ SIGNATURES = {
     "gp_energy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "gp_aggregate": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_int, c_void_p,
                              c_void_p, c_void_p, c_void_p]),
+    "gp_pose_to_quat": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "gp_scalenet": (c_int, [ctypes.POINTER(ScaleNetParams), c_void_p, c_int, c_int, c_void_p, c_int,
                             c_void_p, c_void_p]),
 }

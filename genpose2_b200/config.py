@@ -42,8 +42,6 @@ def build_parser():
     p.add_argument("--retain_ratio", type=float, default=0.4)
     # not in the reference: numerical mode of the fused MLP kernels (fp32 | fp32_ffma | bf16), see scorenet.MLP_MODES
     p.add_argument("--mlp_mode", type=str, default="fp32")
-    # not in the reference: SharedMLP GEMM engine (default: bf16x3 in fp32 mode, bf16 in bf16 mode; "cublas" = fp32 library)
-    p.add_argument("--encoder_gemm", type=str, default=None)
     return p
 
 

@@ -314,9 +314,31 @@ scalenet_kernel(gp_scalenet_params p, const float *__restrict__ axes, int bstrid
     }
 }
 
+// pred_pose_q_wxyz of PoseNet.pred_func (posenet_agent.py:547-559): [x-axis(3) y-axis(3) t(3)] f64 -> [q_wxyz(4) t(3)]
+__global__ void pose_to_quat_kernel(const double *__restrict__ poses, int N, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double v[9], q[4];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) v[c] = poses[(size_t)i * 9 + c];
+    rot6d_to_quat(v, q);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[(size_t)i * 7 + c] = q[c];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[(size_t)i * 7 + 4 + c] = v[6 + c];
+}
+
 }  // namespace gp
 
 using namespace gp;
+
+extern "C" int gp_pose_to_quat(const double *poses, int N, double *out, gp_stream_t s) {
+    GP_REQUIRE(poses && out && N >= 0, "gp_pose_to_quat: bad arguments");
+    if (N == 0) return GP_OK;
+    pose_to_quat_kernel<<<(N + 127) / 128, 128, 0, as_stream(s)>>>(poses, N, out);
+    GP_CHECK_LAUNCH("gp_pose_to_quat");
+    return GP_OK;
+}
 
 extern "C" int gp_aggregate(const double *poses, const float *energy, int B, int R, int retain, int clustering,
                             double clustering_eps, int min_samples, float *pose_out, int32_t *labels_out,

@@ -90,7 +90,7 @@ class PosePipeline:
         fork.record(main)
         pred_pose, pred_q, _ = self.score_agent.pred_func(
             data=data, repeat_num=R, T0=T0, init_x=init_x, save_path=None, return_geometry=True, geometry=geometry,
-            pts_feat=score_feat, want_quat=return_all)
+            pts_feat=score_feat)
         if self._side is None:
             self._side = torch.cuda.Stream(device=score_feat.device)
         self._side.wait_event(fork)

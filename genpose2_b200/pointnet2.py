@@ -12,10 +12,11 @@ level, instead of the reference's FPS, 3 gathers / transposes, 2 ball queries an
 The geometry (FPS / ball-query indices) depends on xyz only, so `forward` can return it and accept
 it back: the score and the energy encoder see the same cloud and share one geometry pass.
 
-The per-scale SharedMLP (conv1x1 + BatchNorm(eval) + ReLU, pytorch_utils.py:5-33) is "next" row f1 of
-SURVEY.md section 8: activations are kept channels-last (one GEMM row per sample), each layer is one
-library GEMM with bias + ReLU in its epilogue (cuBLASLt, fp32, BatchNorm folded into the weights), and
-the gather into rows and the max-pool over the samples are kernels of libgenpose_b200.so.
+The per-scale SharedMLP (conv1x1 + BatchNorm(eval) + ReLU, pytorch_utils.py:5-33) is row f1 of SURVEY.md
+section 8: BatchNorm is folded into the weights once per checkpoint, activations are channels-last (one GEMM
+row per sample) and every layer runs on the tcgen05 kernels of libgenpose_b200.so (csrc/gemm_tc.cu,
+csrc/sa_fused.cu; level 1 on the FP32 kernel of csrc/pointnet2.cu).  There is no library-GEMM backend:
+`gemm_mode` only selects the operand precision ("bf16x3" = split-bf16 x3, fp32-class; "bf16").
 """
 from typing import List, Optional
 
@@ -76,8 +77,14 @@ class SharedMLP(nn.Module):
         """Reference layout: x (B, C, M, ns) -> (B, Cout, M): conv+BN+ReLU stack then max over ns."""
         B, C, M, ns = x.shape
         rows = x.permute(0, 2, 3, 1).reshape(B * M * ns, C)
-        h = self.forward_rows(rows)
-        return pu.maxpool_rows(h, B * M, ns).view(B, M, -1).permute(0, 2, 1).contiguous()
+        if C % 4:   # the GEMM loader reads 16-byte groups; padding columns meet zero weights
+            rows = torch.nn.functional.pad(rows, (0, 4 - C % 4))
+        cout = getattr(self, f"layer{self.n_layers - 1}").conv.out_channels
+        out = torch.empty((B * M, cout), dtype=torch.float32, device=x.device)
+        self.forward_rows_pooled(rows.contiguous(), B * M, ns, out, self.gemm_mode)
+        return out.view(B, M, -1).permute(0, 2, 1).contiguous()
+
+    gemm_mode = "bf16x3"   # operand precision of the tensor-core GEMMs: "bf16x3" (fp32-class) | "bf16"
 
     _trusted = False  # set by Pointnet2ClsMSG.forward for the duration of one pass, after it has checked the cache
 
@@ -175,12 +182,8 @@ class SharedMLP(nn.Module):
 
     def forward_rows_pooled(self, rows, groups, nsample, out, gemm_mode, feat_first=False):
         """rows (R, ld) -> SharedMLP -> max over `nsample` rows per group, written into `out` (groups, Cout).
-        gemm_mode: "cublas" (fp32 library GEMM), "bf16x3" (tcgen05, split-bf16, fp32-class) or "bf16" (tcgen05).
+        gemm_mode: "bf16x3" (tcgen05, split-bf16, fp32-class) or "bf16" (tcgen05).
         feat_first: the rows are [feat | xyz | 0] (the encoder's level buffers) instead of [xyz | feat]."""
-        if gemm_mode == "cublas":
-            assert not feat_first
-            h = self.forward_rows(rows)
-            return pu.maxpool_rows(h, groups, nsample, out=out)
         npass = {"bf16x3": 3, "bf16": 1}[gemm_mode]
         layers = self._tc_layers_featfirst(npass) if feat_first else self._tc_layers(npass)
         h = rows
@@ -192,14 +195,6 @@ class SharedMLP(nn.Module):
                 pu.gemm_bias_relu(h, packed, b, N, K, npass, pool_ns=nsample, pooled_out=out)
         return out
 
-    def forward_rows(self, rows: torch.Tensor) -> torch.Tensor:
-        """Channels-last: rows (R, Cin) -> (R, Cout); each layer is relu(rows @ W^T + b) with the bias and
-        the ReLU in the GEMM epilogue (cuBLASLt through torch._addmm_activation) -- SURVEY section 8 row f1."""
-        h = rows
-        for w, b in self._folded_layers():
-            h = torch._addmm_activation(b, h[:, : w.shape[1]] if h.shape[1] != w.shape[1] else h, w.t())
-        return h
-
 
 class PointnetSAModuleMSG(nn.Module):
     """pointnet2_modules.py:77-121 + forward :19-74 (max_pool, use_xyz=True, bn=True)."""
@@ -207,7 +202,7 @@ class PointnetSAModuleMSG(nn.Module):
     def __init__(self, *, npoint, radii, nsamples, mlps):
         super().__init__()
         self.npoint, self.radii, self.nsamples = npoint, radii, nsamples
-        self.gemm_mode = "cublas"  # "cublas" | "bf16x3" | "bf16" (see SharedMLP.forward_rows_pooled)
+        self.gemm_mode = "bf16x3"  # "bf16x3" | "bf16" (see SharedMLP.forward_rows_pooled)
         self.groupers = nn.ModuleList(
             [pu.QueryAndGroup(r, n) if npoint is not None else pu.GroupAll() for r, n in zip(radii, nsamples)])
         self.mlps = nn.ModuleList([SharedMLP([spec[0] + 3] + spec[1:]) for spec in mlps])
@@ -246,7 +241,7 @@ class PointnetSAModuleMSG(nn.Module):
         B = xyz.shape[0]
         couts = [getattr(m, f"layer{m.n_layers - 1}").conv.out_channels for m in self.mlps]
         C = sum(couts)
-        tc = self.gemm_mode != "cublas"
+        tc = True   # every SharedMLP layer runs on the library's own kernels
         if self.npoint is not None:
             if geometry is None:
                 idx, new_xyz = pu.furthest_point_sample_gather(xyz, self.npoint)
@@ -302,7 +297,11 @@ class PointnetSAModuleMSG(nn.Module):
         # GroupAll (pointnet2_utils.py:306-328): every point of the level is one sample of a single group
         N = xyz.shape[1]
         out = torch.empty((B, 1, C), dtype=torch.float32, device=xyz.device)
-        feat_first = pts_rows is not None and tc and (N % 32 == 0 or 32 % N == 0)
+        if not (N % 32 == 0 or 32 % N == 0):
+            raise NotImplementedError(
+                f"GroupAll over {N} points: the pooled tensor-core GEMM needs N to divide or be a multiple of 32 "
+                "(GP_ERR_UNSUPPORTED; there is no library fallback)")
+        feat_first = pts_rows is not None
         if feat_first:
             rows, gm = pts_rows, self.gemm_mode
         else:
@@ -311,7 +310,7 @@ class PointnetSAModuleMSG(nn.Module):
             if tc and width % 4:
                 parts.append(torch.zeros((B, N, 4 - width % 4), dtype=torch.float32, device=xyz.device))
             rows = torch.cat(parts, dim=-1).reshape(B * N, -1)
-            gm = self.gemm_mode if (not tc or N % 32 == 0 or 32 % N == 0) else "cublas"
+            gm = self.gemm_mode
         off = 0
         for i, mlp in enumerate(self.mlps):
             mlp.forward_rows_pooled(rows, B, N, out.view(B, -1)[:, off:off + couts[i]], gm, feat_first=feat_first)
@@ -333,12 +332,14 @@ class Pointnet2ClsMSG(nn.Module):
             channel_in = sum(m[-1] for m in mlps)
 
     def set_gemm_mode(self, mode):
-        """SharedMLP GEMM engine for every level: "cublas" (fp32 library GEMM), "bf16x3" (tcgen05 split-bf16,
-        fp32-class accuracy) or "bf16" (tcgen05 bf16)."""
-        if mode not in ("cublas", "bf16x3", "bf16"):
+        """Operand precision of the tensor-core SharedMLP GEMMs for every level: "bf16x3" (split-bf16 x3,
+        fp32-class accuracy) or "bf16"."""
+        if mode not in ("bf16x3", "bf16"):
             raise ValueError(mode)
         for sa in self.SA_modules:
             sa.gemm_mode = mode
+            for m in sa.mlps:
+                m.gemm_mode = mode
         return self
 
     @staticmethod

@@ -91,9 +91,10 @@ class PoseNet(nn.Module):
 
             pred_pose_q_wxyz = None
             if want_quat or return_average_res:   # (the runners drop it: `pred_pose, _ = pred_results`)
-                rot_matrix = get_rot_matrix(res[:, :-3], self.cfg.pose_mode)
-                quat_wxyz = matrix_to_quaternion(rot_matrix)
-                pred_pose_q_wxyz = torch.cat((quat_wxyz, res[:, -3:]), dim=-1).reshape(bs, repeat_num, -1)
+                resc = _lib.check_cuda(res.contiguous(), "res", torch.float64)
+                qt = torch.empty((N, 7), dtype=torch.float64, device=res.device)
+                _lib.call("gp_pose_to_quat", _lib.ptr(resc), N, _lib.ptr(qt), device=res.device)
+                pred_pose_q_wxyz = qt.reshape(bs, repeat_num, -1)
             extra = (geometry,) if return_geometry else ()
             if return_average_res:
                 from .aggregation import _run

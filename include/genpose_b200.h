@@ -303,6 +303,11 @@ GP_API int gp_aggregate(const double *poses, const float *energy, int B, int R, 
                  int clustering, double clustering_eps, int min_samples, float *pose_out,
                  int32_t *labels_out, double *sorted_out, gp_stream_t s);
 
+/* Replaces the tail of PoseNet.pred_func (networks/posenet_agent.py:547-559): get_rot_matrix (utils/misc.py:121-160:
+ * rotation_6d_to_matrix(.).permute(0,2,1)) + matrix_to_quaternion (utils/transforms/rotation_conversions.py:102-161)
+ * + cat with the translation.  poses [N,9] f64 -> out [N,7] f64 = [q_wxyz | t]. */
+GP_API int gp_pose_to_quat(const double *poses, int N, double *out, gp_stream_t s);
+
 typedef struct gp_scalenet_params {
     const float *axes_w0; /* axes_encoder.0.weight [256,180] (networks/scalenet.py:20-25) */
     const float *axes_b0;

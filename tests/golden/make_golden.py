@@ -150,6 +150,26 @@ def main():
         steps=steps)), **meta)
     print("pc", xs.shape)
 
+    # ---- PC sampler at the reference's default length (samplers.py:118: num_steps=500) -------------------
+    # The 2 x 500 noise tensors are not stored: the test regenerates them from the same seed in the same call
+    # order (torch's CPU generator is reproducible across machines for a given torch version).
+    steps = 500
+    torch.manual_seed(6)
+    xs, mean_x = ns.samplers.cond_pc_sampler(
+        score_model=net, data=data, prior=net.prior_fn, sde_coeff=net.sde_fn, num_steps=steps,
+        snr=0.16, device="cpu", eps=net.sampling_eps, pose_mode="rot_matrix", init_x=None)
+    torch.set_num_threads(1)   # the reference against itself with another sgemm summation order
+    torch.manual_seed(6)
+    _, mean_x_1t = ns.samplers.cond_pc_sampler(
+        score_model=net, data=dict(data), prior=net.prior_fn, sde_coeff=net.sde_fn, num_steps=steps,
+        snr=0.16, device="cpu", eps=net.sampling_eps, pose_mode="rot_matrix", init_x=None)
+    torch.set_num_threads(8)
+    keep = [0, 1, 10, 100, 250, 400, 499]
+    np.savez_compressed(os.path.join(HERE, "pc_b2_500.npz"), **to_np(dict(
+        feat=feat, center=center, noise_seed=6, xs_keep=xs[:, keep], keep=np.array(keep), mean_x=mean_x,
+        mean_x_1thread=mean_x_1t, B=B, R=R, steps=steps)), **meta)
+    print("pc500", xs.shape)
+
     # ---- full path through the agents: pred_func -> get_energy -> aggregate -> scale ----------
     def run_full(name, B, R, T0, seed, tracking=False):
         g = torch.Generator().manual_seed(seed)

@@ -1,15 +1,19 @@
-"""How well is the T0 = 1.0 fixture (ode_c1_T1) determined at all?
+"""How well do float32 arithmetic and the problem itself determine the two "long" fixtures?
 
-    python tests/golden/make_sensitivity.py        # writes tests/golden/ode_c1_T1_sens.npz
+    python tests/golden/make_sensitivity.py     # writes tests/golden/ode_c1_T1_sens.npz, pc_b2_500_sens.npz
 
-At T0 = 1.0 (sigma_max = 50, random weights) the probability-flow ODE amplifies float32-rounding-sized
-changes of the score by three to four orders of magnitude: the reference's own result moves by 4e-4 rad /
-6.5e-4 between 1 and 8 CPU threads (fixture field x_1thread).  One such pair is a single draw from a
-heavy-tailed distribution, so this script draws more: it runs the CPU oracle (pinned to the reference by
-tests/test_oracle_golden.py) on the fixture's inputs with every score evaluation multiplied by
-1 + 1e-6 * N(0, 1) -- the size of a changed sgemm summation order -- and records the deviation of the final
-poses from the fixture for each trial.  The GPU parity test bounds its own deviation at T0 = 1.0 by the
-envelope of these draws; at the evaluation settings (T0 = 0.55 / 0.25) the plain north-star tolerance applies.
+ * ode_c1_T1 (T0 = 1.0: sigma_max = 50, random weights): the probability-flow ODE amplifies float32-rounding-sized
+   changes of the score by three to four orders of magnitude; the reference's own result moves by 4e-4 rad / 6.5e-4
+   between 1 and 8 CPU threads (fixture field x_1thread).
+ * pc_b2_500 (cond_pc_sampler at its default 500 steps, float32 state): 500 Langevin + Euler-Maruyama steps with a
+   batch-wide step size.
+
+One 1-vs-8-thread pair is a single draw from a heavy-tailed distribution, so this script draws more, FROM THE REFERENCE
+ITSELF (imported through oracle/ref_shim.py): it re-runs the reference's own cond_ode_sampler / cond_pc_sampler on the
+fixture's inputs with every output of PoseScoreNet.forward multiplied by 1 + 1e-6 * N(0, 1) -- the size of a changed
+sgemm summation order -- and records the deviation of the final poses from the fixture for each trial.  The GPU
+parity tests bound their own deviation on these two fixtures by the envelope of these draws (and assert the observed
+value); at the evaluation settings (T0 = 0.55 / 0.25) the plain north-star tolerance applies.
 """
 import os
 import sys
@@ -22,36 +26,68 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 from genpose2_b200 import synthetic  # noqa: E402
-from oracle import pose_oracle as po  # noqa: E402
+from oracle import ref_shim  # noqa: E402
 from tests.util import load_golden, pose_errors, rep  # noqa: E402
 
-TRIALS = 32
 REL = 1e-6
 
 
+@torch.no_grad()
 def main():
     torch.set_num_threads(8)
+    ns = ref_shim.load()
+    cfg = ns.cfg
+    cfg.device = "cpu"
+    cfg.sampler_mode = ["ode"]
+    cfg.agent_type = "score"
+    agent = ns.posenet_agent.PoseNet(cfg)
+    net = agent.net
+    base_forward = net.pose_score_net.forward
+
+    def perturbed(gen):
+        def fwd(d):
+            s = base_forward(d)
+            return s * (1 + REL * torch.randn(s.shape, generator=gen))
+        return fwd
+
+    # ---- ODE sampler at T0 = 1.0 ----
     g = load_golden("ode_c1_T1")
-    trunk = po.Trunk(synthetic.random_gfobjectpose_state_dict(int(g["score_seed"])))
-    R = int(g["R"])
+    net.load_state_dict(synthetic.random_gfobjectpose_state_dict(int(g["score_seed"])))
+    R, B = int(g["R"]), int(g["B"])
     feat, center, noise = torch.from_numpy(g["feat"]), torch.from_numpy(g["center"]), torch.from_numpy(g["noise"])
-    base_score = trunk.score
-    rot, trans, nfev = [], [], []
-    for trial in range(TRIALS):
-        gen = torch.Generator().manual_seed(1000 + trial)
-
-        def score(pf, x, t, _g=gen):
-            s = base_score(pf, x, t)
-            return s * (1 + REL * torch.randn(s.shape, generator=_g))
-
-        trunk.score = score
-        _, x, st = po.cond_ode_sampler(trunk, rep(feat, R), rep(center, R), noise, T=float(g["T0"]))
+    data = {"pts": torch.zeros(B * R, 4, 3), "pts_feat": rep(feat, R), "pts_center": rep(center, R)}
+    rot, trans = [], []
+    for trial in range(32):
+        net.pose_score_net.forward = perturbed(torch.Generator().manual_seed(1000 + trial))
+        _, x = ns.samplers.cond_ode_sampler(
+            score_model=net, data=dict(data), prior=lambda shape, T=1.0: noise.clone(), sde_coeff=net.sde_fn,
+            atol=1e-5, rtol=1e-5, device="cpu", eps=net.sampling_eps, T=float(g["T0"]), num_steps=None,
+            pose_mode="rot_matrix", denoise=True, init_x=None)
         r, t = pose_errors(x.numpy(), g["x"])
-        print(f"trial {trial}: nfev {st['nfev']} rot {r:.3e} trans {t:.3e}", flush=True)
-        rot.append(r), trans.append(t), nfev.append(st["nfev"])
-    np.savez(os.path.join(HERE, "ode_c1_T1_sens.npz"), rot=np.array(rot), trans=np.array(trans),
-             nfev=np.array(nfev), rel=np.array(REL), trials=np.array(TRIALS))
-    print("median", np.median(rot), np.median(trans), "max", np.max(rot), np.max(trans))
+        print(f"ode trial {trial}: rot {r:.3e} trans {t:.3e}", flush=True)
+        rot.append(r), trans.append(t)
+    np.savez(os.path.join(HERE, "ode_c1_T1_sens.npz"), rot=np.array(rot), trans=np.array(trans), rel=np.array(REL),
+             trials=np.array(32), source=np.array("reference cond_ode_sampler, score x (1 + 1e-6 N(0,1))"))
+    print("ode median", np.median(rot), np.median(trans), "max", np.max(rot), np.max(trans))
+
+    # ---- PC sampler, 500 steps ----
+    g = load_golden("pc_b2_500")
+    R, B, steps = int(g["R"]), int(g["B"]), int(g["steps"])
+    feat, center = torch.from_numpy(g["feat"]), torch.from_numpy(g["center"])
+    data = {"pts": torch.zeros(B * R, 4, 3), "pts_feat": rep(feat, R), "pts_center": rep(center, R)}
+    rot, trans = [], []
+    for trial in range(16):
+        net.pose_score_net.forward = perturbed(torch.Generator().manual_seed(2000 + trial))
+        torch.manual_seed(int(g["noise_seed"]))
+        _, mean_x = ns.samplers.cond_pc_sampler(
+            score_model=net, data=dict(data), prior=net.prior_fn, sde_coeff=net.sde_fn, num_steps=steps, snr=0.16,
+            device="cpu", eps=net.sampling_eps, pose_mode="rot_matrix", init_x=None)
+        r, t = pose_errors(mean_x.numpy(), g["mean_x"])
+        print(f"pc trial {trial}: rot {r:.3e} trans {t:.3e}", flush=True)
+        rot.append(r), trans.append(t)
+    np.savez(os.path.join(HERE, "pc_b2_500_sens.npz"), rot=np.array(rot), trans=np.array(trans), rel=np.array(REL),
+             trials=np.array(16), source=np.array("reference cond_pc_sampler, score x (1 + 1e-6 N(0,1))"))
+    print("pc median", np.median(rot), np.median(trans), "max", np.max(rot), np.max(trans))
 
 
 if __name__ == "__main__":

@@ -1,5 +1,5 @@
 """GPU: the tcgen05 SharedMLP-layer GEMM (gp_gemm_bias_relu) vs a float64 torch reference, and the
-encoder with its three GEMM engines vs the CPU restatement."""
+encoder in both operand precisions vs the CPU restatement."""
 import numpy as np
 import pytest
 import torch
@@ -39,7 +39,7 @@ def test_gemm_bias_relu_matches_float64(R, K, N, ldx, npass):
         assert (out[:, :4] == 0).all() and (out[:, 4 + N:] == 0).all()
 
 
-@pytest.mark.parametrize("mode,tol", [("cublas", 1e-4), ("bf16x3", 2e-4), ("bf16", 5e-2)])
+@pytest.mark.parametrize("mode,tol", [("bf16x3", 1e-4), ("bf16", 3e-2)])
 def test_encoder_gemm_engines_vs_cpu_restatement(mode, tol):
     from genpose2_b200.pointnet2 import Pointnet2ClsMSG
     sd = synthetic.random_encoder_state_dict(7, prefix="")

@@ -143,3 +143,34 @@ def test_full_path_real_encoder_vs_reference(ref_ns, B, T0, tracking):
     assert geodesic_mats(agg[:, :3, :3], wagg[:, :3, :3]).max() <= 1e-3
     assert np.abs(agg[:, :3, 3] - wagg[:, :3, 3]).max() <= 1e-4
     np.testing.assert_allclose(out["length"].cpu().numpy(), want["length"].cpu().numpy(), rtol=0, atol=1e-4)
+
+
+def test_get_energy_random_T_branch_vs_reference(ref_ns):
+    """PoseNet.get_energy(T=None) (posenet_agent.py:677-687, used by runners/infer.py:136): one random T in
+    [1e-5, 1e-4) per object drawn from the global CPU generator -- same seed, same draw on both sides."""
+    from genpose2_b200.config import get_config
+    from genpose2_b200.posenet_agent import PoseNet
+    B, R = 5, 50
+    ref = _agents("cuda")
+    pts, center = synthetic.make_point_clouds(B, 1024, seed=81)
+    poses = synthetic.make_cluster_quaternion_poses(B, R, seed=82)
+    poses[:, :, 6:] += center.unsqueeze(1).double()
+    data = {"pts": pts.cuda(), "pts_center": center.cuda()}
+    torch.manual_seed(17)
+    with torch.no_grad():
+        want = ref.energy_agent.get_energy(data=dict(data), pose_samples=poses.cuda(), T=None, mode="test",
+                                           extract_feature=True)
+    cfg = get_config()
+    cfg.agent_type = "energy"
+    agent = PoseNet(cfg)
+    agent.net.load_state_dict(synthetic.random_gfobjectpose_state_dict(200))
+    torch.manual_seed(17)
+    got = agent.get_energy(dict(data), poses.cuda(), T=None, mode="test", extract_feature=True)
+    assert got.shape == want.shape == (B, R, 2) and got.dtype == torch.float32
+    rel = float((got - want).abs().max() / want.abs().max())
+    print(f"get_energy(T=None) vs reference: rel err {rel:.2e}")
+    assert rel <= 1e-3, rel
+    # the draw is consumed from the generator: another seed gives other T values, hence other energies
+    torch.manual_seed(18)
+    other = agent.get_energy(dict(data), poses.cuda(), T=None, mode="test", extract_feature=True)
+    assert not torch.equal(other, got)

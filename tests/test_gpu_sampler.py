@@ -89,8 +89,8 @@ def test_ode_sampler_matches_reference_golden(name, mlp_mode):
     # evaluation settings T0 = 0.55 / 0.25 the reference's own 1-thread and 8-thread CPU results (x_1thread vs x)
     # agree to < 1e-5.  At T0 = 1.0 (sigma_max = 50, random weights) they do not: the ODE amplifies
     # float32-rounding-sized changes of the score by 1e3..1e4, heavy-tailed (a hypothesis now and then lands in
-    # another basin).  tests/golden/make_sensitivity.py measures that envelope -- 32 runs of the pinned oracle
-    # with the score perturbed by 1e-6 relative, the size of a changed sgemm summation order: median
+    # another basin).  tests/golden/make_sensitivity.py measures that envelope -- 32 runs of THE REFERENCE's own
+    # cond_ode_sampler with the score perturbed by 1e-6 relative, the size of a changed sgemm summation order: median
     # 8e-4 rad / 9e-4, max 7.8e-3 rad / 1.7e-2 -- and the T0 = 1.0 case is bounded by its maximum.  T0 = 1.0 is
     # not an evaluation setting; step counts must still match the reference exactly (asserted above).
     self_rot, self_trans = pose_errors(g["x_1thread"], g["x"])
@@ -159,7 +159,44 @@ def test_pc_sampler_matches_reference_golden(mlp_mode):
     mag = np.abs(ref_xs).max(axis=(0, 2))
     assert (err <= 2e-3 * np.maximum(mag, 1.0)).all(), err / np.maximum(mag, 1.0)
     rot, trans = pose_errors(mean_x.cpu().numpy(), g["mean_x"])
-    assert rot <= 5e-3 and trans <= 5e-3, (rot, trans)
+    print(f"pc 25 steps [{mlp_mode}]: rot {rot:.3e} trans {trans:.3e}; xs rel err max {float((err / np.maximum(mag, 1.0)).max()):.3e}")
+    assert rot <= ROT_TOL and trans <= TRANS_TOL, (rot, trans)
+
+
+@pytest.mark.parametrize("mlp_mode", ["fp32", "fp32_ffma"])
+def test_pc_sampler_500_steps_matches_reference_golden(mlp_mode):
+    """cond_pc_sampler at the reference's default num_steps = 500 (samplers.py:118), float32 state like the reference.
+    The prior and the 2 x 500 noise tensors are redrawn from the fixture's seed in the reference's call order.
+    Rotation is held to the north-star 1e-3 rad.  Translation: the reference does not reproduce ITSELF to 1e-4 over 500
+    float32 steps (1 vs 8 CPU threads: 1.1e-4, fixture field mean_x_1thread); tests/golden/make_sensitivity.py
+    measures the envelope on the reference's own sampler (16 runs, score perturbed by 1e-6 relative: median 1.9e-4,
+    max 2.5e-4) and the bound is twice the largest draw; the observed value is printed and asserted."""
+    from genpose2_b200 import samplers
+    g = load_golden("pc_b2_500")
+    sens = load_golden("pc_b2_500_sens")
+    net = make_net(int(g["score_seed"]), mlp_mode=mlp_mode)
+    R, B, steps = int(g["R"]), int(g["B"]), int(g["steps"])
+    feat, center = torch.from_numpy(g["feat"]).cuda(), torch.from_numpy(g["center"]).cuda()
+    torch.manual_seed(int(g["noise_seed"]))
+    init = net.prior_fn((B * R, 9))
+    noises = torch.stack([torch.stack([torch.randn(B * R, 9), torch.randn(B * R, 9)]) for _ in range(steps)])
+    data = {"pts": torch.zeros(B * R, 1, 3), "pts_center": rep(center, R), "_gp_pts_feat_obj": feat,
+            "_gp_rows_per_object": R}
+    xs, mean_x = samplers.cond_pc_sampler(net, data, None, net.sde_fn, num_steps=steps, snr=0.16, device="cuda",
+                                          eps=1e-5, pose_mode="rot_matrix", init_x=init.cuda(), noise=noises.cuda())
+    assert xs.shape == (B * R, steps, 9) and xs.dtype == torch.float32
+    keep = [int(k) for k in g["keep"]]
+    got = xs[:, keep].cpu().numpy()
+    err = np.abs(got - g["xs_keep"]).max(axis=(0, 2))
+    mag = np.maximum(np.abs(g["xs_keep"]).max(axis=(0, 2)), 1.0)
+    rot, trans = pose_errors(mean_x.cpu().numpy(), g["mean_x"])
+    self_rot, self_trans = pose_errors(g["mean_x_1thread"], g["mean_x"])
+    print(f"pc 500 steps [{mlp_mode}]: rot {rot:.3e} trans {trans:.3e} (reference self-distance {self_rot:.3e} / "
+          f"{self_trans:.3e}, envelope max {float(sens['rot'].max()):.3e} / {float(sens['trans'].max()):.3e}); "
+          f"xs rel err at steps {keep}: {np.round(err / mag, 6).tolist()}")
+    assert self_trans <= 2 * float(sens["trans"].max())   # the reference's own draw fits its envelope
+    assert rot <= ROT_TOL and trans <= 2 * float(sens["trans"].max()), (rot, trans)
+    assert (err <= 2e-3 * mag).all(), (err / mag)
 
 
 def test_energy_matches_reference_golden():
