@@ -6,7 +6,7 @@
 
 #include <cstdlib>
 
-#include "trunk_tc.cuh"
+#include "trunk_solo.cuh"
 
 namespace gp {
 
@@ -63,6 +63,7 @@ __global__ void pack_trunk_kernel(RawTrunk raw, float *__restrict__ P) {
             // destination float slot -> (chunk q, image hi/lo, row n, 16-byte unit, element pair)
             const size_t f = i - TrunkLayout::W_TC;
             const size_t per_img = 128 * 64 / 2;
+            // chunks 34..57 are the whole-head chunks of the one-CTA-per-tile evaluator (W_SOLO follows W_TC directly)
             const size_t q = f / (2 * per_img), which = (f / per_img) % 2, o = (f % per_img) * 4;
             const size_t nl = o / 128, wb = o % 128;
             const size_t logical16 = (wb / 16) ^ (nl & 7);      // undo the SWIZZLE_128B XOR
@@ -75,9 +76,13 @@ __global__ void pack_trunk_kernel(RawTrunk raw, float *__restrict__ P) {
             } else if (q < 10) {         // pose_encoder.2
                 const size_t kc = (q - 2) / 2, nh = (q - 2) % 2, n = nh * 128 + nl, k = kc * 64 + kl;
                 for (int t = 0; t < 2; ++t) src[t] = p.pose_w1[n * 256 + k + t];
-            } else {                     // head columns of one cluster rank, two k-atoms per image
+            } else if (q < TrunkLayout::TC_CHUNKS) {   // head columns of one cluster rank, two k-atoms per image
                 const size_t r = (q - 10) / 6, hh = ((q - 10) % 6) / 2, j = (q - 10) % 2;
                 const size_t kc = 2 * j + nl / 64, n = 64 * r + nl % 64, k = kc * 64 + kl;
+                for (int t = 0; t < 2; ++t) src[t] = p.head_w0[hh][n * 1408 + 1152 + k + t];
+            } else {                     // whole heads: [h][kc][nh] images of [128 n][64 k]
+                const size_t qs = q - TrunkLayout::TC_CHUNKS;
+                const size_t hh = qs / 8, kc = (qs % 8) / 2, nh = qs % 2, n = nh * 128 + nl, k = kc * 64 + kl;
                 for (int t = 0; t < 2; ++t) src[t] = p.head_w0[hh][n * 1408 + 1152 + k + t];
             }
             float e[2];
@@ -220,6 +225,49 @@ struct TcEval {
         }
     }
 };
+// One CTA per 128-row tile, no cluster: the throughput shape for batches of more tiles than the GPU has clusters
+// (trunk_solo.cuh).  Same interface; one copy of the integrator state.
+template <int NPASS>
+struct TcSolo {
+    static constexpr int RT = tc::RT;
+    static constexpr int NT = tc::NTHREADS;
+    static constexpr int XS = tc::XS;
+    static constexpr int TQW = 768;
+    static constexpr int CLUSTER = 1;
+    using Smem = solo::Smem<NPASS>;
+    using Ctx = solo::State;
+    static constexpr size_t smem_bytes() { return sizeof(Smem) + 1024; }
+    static __device__ __forceinline__ Smem &smem(unsigned char *raw) {
+        return *reinterpret_cast<Smem *>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    }
+    static __device__ __forceinline__ int tile_first() { return blockIdx.x; }
+    static __device__ __forceinline__ int tile_step() { return gridDim.x; }
+    static __device__ __forceinline__ bool writer(const Ctx &) { return true; }
+    static __device__ __forceinline__ size_t replica_index(const Ctx &) { return 0; }
+    static __device__ __forceinline__ void tile_sync() {}
+    static __device__ __forceinline__ float *xin(Smem &S) { return S.x; }
+    static __device__ __forceinline__ float *outp(Smem &S) { return S.x; }   // forward() overwrites its inputs
+    static __device__ __forceinline__ float *tq(Smem &S) { return S.tq; }
+    static __device__ __forceinline__ void setup(Smem &S, Ctx &c, const float *P) { solo::setup<NPASS>(S, c, P); }
+    static __device__ __forceinline__ void teardown(Smem &S, Ctx &c) { solo::teardown<NPASS>(S, c); }
+    static __device__ __forceinline__ void stage_tq(const float *P, Smem &S, Ctx &, int ns) { solo::compute_tq_all<NPASS>(P, S, ns); }
+    static __device__ __forceinline__ void begin_tile(Smem &S, Ctx &c, const float *proj, int r0, int N, int rpo) {
+        solo::begin_tile<NPASS>(S, c, proj, r0, N, rpo);
+    }
+    static __device__ __forceinline__ void forward(const float *P, const float *proj, Smem &S, Ctx &c, const float *tq) {
+        solo::forward<NPASS>(P, proj, S, c, tq);
+    }
+    static __device__ __forceinline__ void report(Ctx &c, double *stats) {
+        if (blockIdx.x == 0 && threadIdx.x == 64) {
+            stats[8] = (double)c.cyc_fwd; stats[9] = (double)c.cyc_l1; stats[10] = (double)c.cyc_wait1;
+            stats[11] = (double)c.cyc_epi1; stats[12] = (double)c.cyc_waith; stats[13] = (double)c.cyc_epi2;
+            stats[20] = (double)c.cyc_tail;
+        }
+    }
+};
+// static shared memory of the kernels built on the evaluators (stage constants, per-row t) must fit beside it
+static_assert(sizeof(solo::Smem<3>) + 1024 + 768 <= 227 * 1024, "solo evaluator shared memory exceeds 227 KB");
+static_assert(sizeof(solo::Smem<1>) + 1024 + 768 <= 227 * 1024, "solo evaluator shared memory exceeds 227 KB");
 static_assert(sizeof(tc::Smem<3>) + 1024 <= 227 * 1024, "TC evaluator shared memory exceeds 227 KB");
 static_assert(sizeof(tc::Smem<1>) + 1024 <= 227 * 1024, "TC evaluator shared memory exceeds 227 KB");
 
@@ -1073,6 +1121,19 @@ static int launch_ode(OdeArgs &a, cudaStream_t st) {
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// `mode` of the public entries: bits 0..1 = arithmetic (0 FFMA, 1 bf16, 2 split-bf16), GP_MODE_SOLO / GP_MODE_CLUSTER
+// force the shape of the tensor-core evaluator; by default a batch of more 128-row tiles than the GPU holds 4-CTA
+// clusters at once (33 on a B200) runs one CTA per tile.
+static bool use_solo(int mode, int N) {
+    if (mode & GP_MODE_SOLO) return true;
+    if (mode & GP_MODE_CLUSTER) return false;
+    return (N + tc::RT - 1) / tc::RT > 32;
+}
+static bool mode_ok(int mode) {
+    const int a = mode & 3;
+    return a <= 2 && (mode & ~(3 | GP_MODE_SOLO | GP_MODE_CLUSTER)) == 0 && (mode & (GP_MODE_SOLO | GP_MODE_CLUSTER)) != (GP_MODE_SOLO | GP_MODE_CLUSTER);
+}
+
 // Rows per compute thread of the FFMA evaluator (tile = 4x that many rows): the choice that minimises the
 // per-CTA critical path  waves(tiles / SMs) x rows-per-tile; ties go to the larger tile (fewer weight streams).
 static int simt_rows_per_thread(int N, int sms) {
@@ -1132,7 +1193,11 @@ static int launch_eval(const void *packed, const float *proj, const float *x, co
                        cudaStream_t st, const char *name) {
     if (N == 0) return GP_OK;
     int rc;
-    if (mode == 1) rc = launch_eval_ev<TcEval<1>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
+    const bool solo_shape = use_solo(mode, N);
+    mode &= 3;
+    if (mode == 1 && solo_shape) rc = launch_eval_ev<TcSolo<1>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
+    else if (mode == 2 && solo_shape) rc = launch_eval_ev<TcSolo<3>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
+    else if (mode == 1) rc = launch_eval_ev<TcEval<1>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
     else if (mode == 2) rc = launch_eval_ev<TcEval<3>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
     else if (N <= 16 * num_sms()) rc = launch_eval_ev<SimtEval<4>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
     else rc = launch_eval_ev<SimtEval<8>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
@@ -1145,7 +1210,7 @@ extern "C" int gp_scorenet_eval(const void *packed, const float *proj, const flo
     GP_REQUIRE(N >= 0 && rows_per_object >= 1, "gp_scorenet_eval: bad sizes");
     if (N == 0) return GP_OK;
     GP_REQUIRE(packed && proj && x && t && score, "gp_scorenet_eval: null pointer");
-    GP_REQUIRE(mode >= 0 && mode <= 2, "gp_scorenet_eval: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05)");
+    GP_REQUIRE(mode_ok(mode), "gp_scorenet_eval: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05) [| GP_MODE_SOLO / GP_MODE_CLUSTER]");
     return launch_eval<0>(packed, proj, x, nullptr, nullptr, t, N, rows_per_object, score, mode, as_stream(s), "gp_scorenet_eval");
 }
 
@@ -1154,7 +1219,7 @@ extern "C" int gp_energy(const void *packed, const float *proj, const double *po
     GP_REQUIRE(N >= 0 && rows_per_object >= 1, "gp_energy: bad sizes");
     if (N == 0) return GP_OK;
     GP_REQUIRE(packed && proj && poses && pts_center && t_rows && energy, "gp_energy: null pointer");
-    GP_REQUIRE(mode >= 0 && mode <= 2, "gp_energy: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05)");
+    GP_REQUIRE(mode_ok(mode), "gp_energy: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05) [| GP_MODE_SOLO / GP_MODE_CLUSTER]");
     return launch_eval<1>(packed, proj, nullptr, poses, pts_center, t_rows, N, rows_per_object, energy, mode, as_stream(s), "gp_energy");
 }
 
@@ -1177,7 +1242,7 @@ static int scorenet_ode_impl(const void *packed, const float *proj, const double
     GP_REQUIRE(N >= 1 && rows_per_object >= 1, "gp_scorenet_ode: bad sizes N=%d rows_per_object=%d", N, rows_per_object);
     GP_REQUIRE(rtol > 0 && atol > 0, "gp_scorenet_ode: tolerances must be positive");
     GP_REQUIRE(traj == nullptr || max_traj >= 1, "gp_scorenet_ode: max_traj < 1");
-    GP_REQUIRE(mode >= 0 && mode <= 2, "gp_scorenet_ode: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05)");
+    GP_REQUIRE(mode_ok(mode), "gp_scorenet_ode: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05) [| GP_MODE_SOLO / GP_MODE_CLUSTER]");
     GP_REQUIRE((t_eval == nullptr) == (dense == nullptr) && (t_eval == nullptr || n_eval >= 1), "gp_scorenet_ode_dense: t_eval / dense / n_eval inconsistent");
     if (workspace_bytes < gp_scorenet_ode_workspace_bytes(N)) {
         set_error("gp_scorenet_ode: workspace too small (%zu < %zu)", workspace_bytes, gp_scorenet_ode_workspace_bytes(N));
@@ -1203,8 +1268,10 @@ static int scorenet_ode_impl(const void *packed, const float *proj, const double
     cudaStream_t st = as_stream(s);
     GP_CUDA(cudaMemsetAsync(a.gbar, 0, 256, st));
     const int sms = num_sms();
-    if (mode == 1) return launch_ode<TcEval<1>>(a, st);
-    if (mode == 2) return launch_ode<TcEval<3>>(a, st);
+    const bool solo_shape = use_solo(mode, N);
+    mode &= 3;
+    if (mode == 1) return solo_shape ? launch_ode<TcSolo<1>>(a, st) : launch_ode<TcEval<1>>(a, st);
+    if (mode == 2) return solo_shape ? launch_ode<TcSolo<3>>(a, st) : launch_ode<TcEval<3>>(a, st);
     switch (simt_rows_per_thread(N, sms)) {
         case 2: return launch_ode<SimtEval<2>>(a, st);
         case 4: return launch_ode<SimtEval<4>>(a, st);
@@ -1257,7 +1324,7 @@ extern "C" int gp_scorenet_pc(const void *packed, const float *proj, const float
                               size_t workspace_bytes, int mode, gp_stream_t s) {
     GP_REQUIRE(packed && proj && x0 && noise && pts_center && time_steps && mean_x && workspace, "gp_scorenet_pc: null pointer");
     GP_REQUIRE(N >= 1 && rows_per_object >= 1 && num_steps >= 2, "gp_scorenet_pc: bad sizes");
-    GP_REQUIRE(mode >= 0 && mode <= 2, "gp_scorenet_pc: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05)");
+    GP_REQUIRE(mode_ok(mode), "gp_scorenet_pc: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05) [| GP_MODE_SOLO / GP_MODE_CLUSTER]");
     if (workspace_bytes < gp_scorenet_pc_workspace_bytes(N)) {
         set_error("gp_scorenet_pc: workspace too small");
         return GP_ERR_WORKSPACE;
@@ -1273,8 +1340,10 @@ extern "C" int gp_scorenet_pc(const void *packed, const float *proj, const float
     cudaStream_t st = as_stream(s);
     GP_CUDA(cudaMemsetAsync(a.gbar, 0, 256, st));
     const int sms = num_sms();
-    if (mode == 1) return launch_pc<TcEval<1>>(a, st);
-    if (mode == 2) return launch_pc<TcEval<3>>(a, st);
+    const bool solo_shape = use_solo(mode, N);
+    mode &= 3;
+    if (mode == 1) return solo_shape ? launch_pc<TcSolo<1>>(a, st) : launch_pc<TcEval<1>>(a, st);
+    if (mode == 2) return solo_shape ? launch_pc<TcSolo<3>>(a, st) : launch_pc<TcEval<3>>(a, st);
     switch (simt_rows_per_thread(N, sms)) {
         case 2: return launch_pc<SimtEval<2>>(a, st);
         case 4: return launch_pc<SimtEval<4>>(a, st);

@@ -38,7 +38,11 @@ struct TrunkLayout {
     // lo = bf16(w - hi) for the split-bf16 (fp32-class) mode.  Offsets counted in floats; 1024-byte aligned.
     static constexpr size_t TC_CHUNKS = 34;
     static constexpr size_t W_TC = (F32_END + 255) / 256 * 256;
-    static constexpr size_t END = W_TC + TC_CHUNKS * 2 * (128 * 64 / 2);
+    // the one-CTA-per-tile evaluator (trunk_solo.cuh) multiplies whole heads: 24 more chunks x {hi, lo},
+    //   q' = 8*h + 2*kc + nh   head h, k-atom kc, output columns 128*nh .. 128*nh + 127 (pose_feat columns)
+    static constexpr size_t SOLO_CHUNKS = 24;
+    static constexpr size_t W_SOLO = W_TC + TC_CHUNKS * 2 * (128 * 64 / 2);
+    static constexpr size_t END = W_SOLO + SOLO_CHUNKS * 2 * (128 * 64 / 2);
 };
 
 constexpr float kFloatPi = 3.14159265358979323846f;  // np.pi cast to float32 by torch

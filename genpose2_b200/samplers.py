@@ -29,8 +29,7 @@ def _score_net(score_model):
 
 
 def _mlp_mode(score_model):
-    from .scorenet import MLP_MODES
-    return MLP_MODES[_score_net(score_model).mlp_mode]
+    return _score_net(score_model).mode_arg()
 
 
 _staging = {}

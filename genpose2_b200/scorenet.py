@@ -22,6 +22,9 @@ from . import _lib
 #   "fp32_ffma" plain FP32 FFMA on the CUDA cores
 #   "bf16"      bf16 operands on the tensor cores, fp32 accumulation (stated looser bound)
 MLP_MODES = {"fp32_ffma": 0, "bf16": 1, "fp32": 2}
+# shape of the tensor-core evaluator (include/genpose_b200.h, gp_mode_flag): "auto" = one CTA per 128-row tile for
+# batches of more than 32 tiles, a 4-CTA cluster per tile below; "solo" / "cluster" force one
+EVAL_SHAPES = {"auto": 0, "solo": 16, "cluster": 32}
 
 
 def zero_module(module):
@@ -61,6 +64,7 @@ class _Trunk(nn.Module):
                     nn.Sequential(nn.Linear(128 + 256 + 1024, 256), self.act, zero_module(nn.Linear(256, 3))))
         self.marginal_prob_func = marginal_prob_func
         self.mlp_mode = "fp32"  # see MLP_MODES (set by GFObjectPose from cfg.mlp_mode)
+        self.eval_shape = "auto"  # see EVAL_SHAPES
         self._packed = None
         self._packed_key = None
 
@@ -92,6 +96,11 @@ class _Trunk(nn.Module):
             _lib.call("gp_trunk_pack", ctypes.byref(p), _lib.ptr(blob), device=dev)
             self._packed, self._packed_key = blob, key
         return self._packed
+
+    def mode_arg(self):
+        """the `mode` argument of the C entries: arithmetic | evaluator-shape flag"""
+        m = MLP_MODES[self.mlp_mode]
+        return m | (EVAL_SHAPES[self.eval_shape] if m else 0)
 
     def project(self, pts_feat):
         """Per-object hoisted head projection [B,768] (gp_trunk_project)."""
@@ -135,7 +144,7 @@ class PoseScoreNet(_Trunk):
         t = data["t"].reshape(-1).to(torch.float32).contiguous()
         out = torch.empty((N, 9), dtype=torch.float32, device=x.device)
         _lib.call("gp_scorenet_eval", _lib.ptr(self.packed()), _lib.ptr(proj), _lib.ptr(x), _lib.ptr(t), N, rpo,
-                  _lib.ptr(out), MLP_MODES[self.mlp_mode], device=x.device)
+                  _lib.ptr(out), self.mode_arg(), device=x.device)
         return out
 
 
@@ -153,7 +162,7 @@ class PoseEnergyNet(_Trunk):
         N = poses_f64.shape[0]
         out = torch.empty((N, 2), dtype=torch.float32, device=poses_f64.device)
         _lib.call("gp_energy", _lib.ptr(self.packed()), _lib.ptr(proj), _lib.ptr(poses_f64), _lib.ptr(pts_center),
-                  _lib.ptr(t_rows), N, int(rows_per_object), _lib.ptr(out), MLP_MODES[self.mlp_mode],
+                  _lib.ptr(t_rows), N, int(rows_per_object), _lib.ptr(out), self.mode_arg(),
                   device=poses_f64.device)
         return out
 

@@ -208,6 +208,16 @@ GP_API int gp_trunk_project(const void *packed, const float *pts_feat, int B, fl
 GP_API int gp_scorenet_eval(const void *packed, const float *proj, const float *x, const float *t, int N,
                      int rows_per_object, float *score, int mode, gp_stream_t s);
 
+/* Flags that may be OR-ed into the `mode` argument of gp_scorenet_eval / _ode / _ode_dense / _pc / gp_energy when it
+ * selects a tensor-core arithmetic (1 or 2).  The tensor-core evaluator has two shapes: a 4-CTA cluster per 128-row
+ * tile (shortest critical path; every CTA re-evaluates the pose encoder and integrates a private copy of the state)
+ * and one CTA per tile (no redundant work, one state copy: the throughput shape).  Default: one CTA per tile when the
+ * batch has more than 32 tiles (more than the GPU holds clusters at once), clusters otherwise. */
+enum gp_mode_flag {
+    GP_MODE_SOLO = 16,    /* force one CTA per tile */
+    GP_MODE_CLUSTER = 32  /* force a 4-CTA cluster per tile */
+};
+
 /* Integrator statistics written by gp_scorenet_ode (device, 16 doubles). */
 enum gp_ode_stat {
     GP_STAT_NFEV = 0,      /* RHS evaluations inside the solver (scipy res.nfev) */
