@@ -2,21 +2,29 @@
 """bench.py -- objects/s of the per-object pose-generation hot path (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # B200 arm (libgenpose_b200.so)
-    python bench.py --impl reference --gpus N ...             # reference's CPU path on the host cores
+    python bench.py --impl reference --gpus N ...             # the reference's CPU path on the host cores
 
-A "step" is one pass of the full path (PointNet++ encoder x2 -> RK45 ScoreNet sampling, 50
-hypotheses/object -> EnergyNet scoring -> aggregation -> ScaleNet) over one batch of synthetic
-objects.  Workload = BASELINE.json configs[1]: 64 objects x 50 hypotheses per GPU, T0 = 0.55
-(scripts/eval_single.sh), random-init weights, synthetic clouds.  Multi-GPU: objects are sharded
-by rank, no collective on the data path, weak scaling (64 objects per GPU).
+A "step" is one pass of the full path (PointNet++ encoder x2 -> RK45 ScoreNet sampling, 50 hypotheses/object ->
+EnergyNet scoring -> aggregation -> ScaleNet) over one batch of synthetic objects.
+
+Headline workload = BASELINE.json configs[1] (C2): 64 objects x 50 hypotheses per GPU, T0 = 0.55
+(scripts/eval_single.sh), random-init weights, synthetic clouds.  Multi-GPU: objects are sharded by rank, no
+collective on the data path, weak scaling (64 objects per GPU).
 
 `value`   : objects/s with the clouds already resident in HBM (CUDA events, max over ranks).
-`e2e`     : objects/s through the same public call with HOST (pinned) clouds: H2D copy of the clouds
-            and D2H read of the poses + lengths inside the timed region.
-`roofline`: the dominant kernel of this library (the fused ScoreNet/RK45 integrator), algorithmic FLOPs
-            (hoisted figure) / CUDA-event duration, against MEASURED_PEAKS.json.
-`cpu_baseline`: the oracle port (oracle/pose_oracle.py: the reference's torch-CPU + scipy path,
-            restated) timed on this box's host cores on a bounded sample of the same workload.
+`e2e`     : objects/s through the same public call with HOST (pinned) clouds: H2D copy of the clouds and D2H read of
+            the poses + lengths inside the timed region.
+`roofline`: the dominant kernel of this library (the fused ScoreNet / RK45 integrator), algorithmic FLOPs (SURVEY.md
+            8(d), hoisted figure) / CUDA-event duration, against MEASURED_PEAKS.json (burst AND sustained).
+`cpu_baseline`: the reference's own CPU path (oracle/_ref/refpkg: the unmodified reference modules; its CUDA-only
+            encoder through the oracle port) timed on this box's host cores on a bounded sample of the workload.
+`other_configs`: the other BASELINE.json configs, measured in the same run after the timed region:
+            c5 (8192 objects x 50 sharded by object over the N ranks, STRONG scaling, the one gather in the timed
+            region, fp32 and bf16), and at N = 1: c1 (1 object latency, sampler only, T0 = 1), c3 (FPS / ball query /
+            grouping sweep 1024..16384 points x 256 objects, beside the reference's own CUDA ext), c4 (tracking,
+            32 objects / frame over a 100-frame synthetic sequence).
+`reference_gpu`: the UNMODIFIED reference on this GPU (torch + host scipy loop + sklearn, its own CUDA ext): the
+            denominator of north_star's ">= 100x the reference's 1-GPU torch+scipy sampling throughput".
 """
 import argparse
 import json
@@ -36,9 +44,12 @@ REPEAT = 50
 T0 = 0.55
 NUM_POINTS = 1024
 L2_FLUSH_BYTES = 256 << 20
+C5_OBJECTS = 8192
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the integrator kernel, `ncu --set full` captures in profiles/README.md
+# dram__bytes_read.sum + dram__bytes_write.sum of the integrator kernel per launch at C2.  A CONSTANT taken from the
+# `ncu --set full` captures summarised in profiles/README.md (not a per-run counter: ncu cannot run inside the bench).
 NCU_DRAM_BYTES_PER_LAUNCH = {"fp32_ffma": 2270464 + 22784, "bf16": 1686784 + 58368, "fp32": 2249472 + 72960}
+NCU_DRAM_SOURCE = "constant from the ncu --set full capture in profiles/README.md (C2, cluster evaluator), not a per-run counter"
 
 # algorithmic work of the ScoreNet RHS after hoisting, in FLOP
 ROW_EVAL_FLOP = 2 * 266752
@@ -54,9 +65,13 @@ def parse():
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--objects", type=int, default=OBJECTS_PER_GPU, help="objects per GPU per step")
     ap.add_argument("--mlp_mode", type=str, default="fp32", choices=["fp32", "fp32_ffma", "bf16"])
-    ap.add_argument("--cpu_sample_objects", type=int, default=8)
+    ap.add_argument("--cpu_sample_objects", type=int, default=8, help="cpu_baseline sample of the B200 arm")
+    ap.add_argument("--ref_objects", type=int, default=OBJECTS_PER_GPU, help="objects per step of --impl reference")
+    ap.add_argument("--ref_budget_s", type=float, default=200.0, help="wall-clock cap of --impl reference")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--single_mode", action="store_true", help="skip the measurement of the other mlp_mode")
+    ap.add_argument("--no_extras", action="store_true", help="skip other_configs and reference_gpu")
+    ap.add_argument("--c5_objects", type=int, default=C5_OBJECTS)
     return ap.parse_args()
 
 
@@ -145,32 +160,68 @@ class ClockSampler:
                 "samples": len(sm), "source": self.source}
 
 
-# --------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on the host cores
-# --------------------------------------------------------------------------------------------------
-def cpu_reference_step(state, n_objects):
-    """One bounded sample of the workload on the CPU: n_objects x 50 hypotheses through the oracle
-    port of the reference path (encoder x2, scipy RK45 sampler, energy, aggregation with sklearn
-    DBSCAN, ScaleNet).  Returns seconds."""
-    import torch
-    from oracle import pose_oracle as po
-    pts, center = state["pts"][:n_objects], state["center"][:n_objects]
-    torch.manual_seed(1)
-    noise = po.ve_prior((n_objects * REPEAT, 9), T=T0)
-    t0 = time.perf_counter()
-    po.full_pipeline(state["score_sd"], state["energy_sd"], state["scale_sd"], pts, center, noise,
-                     repeat_num=REPEAT, T0=T0, integrator="scipy")
-    return time.perf_counter() - t0
-
-
-def cpu_state(n_objects):
-    import torch
+def synthetic_weights():
     from genpose2_b200 import synthetic
-    torch.set_num_threads(os.cpu_count() or 1)
-    pts, center = synthetic.make_point_clouds(max(n_objects, 1), NUM_POINTS, seed=0)
-    return dict(pts=pts, center=center, score_sd=synthetic.random_gfobjectpose_state_dict(100),
-                energy_sd=synthetic.random_gfobjectpose_state_dict(200),
-                scale_sd=synthetic.random_scalenet_state_dict(300))
+    return (synthetic.random_gfobjectpose_state_dict(100), synthetic.random_gfobjectpose_state_dict(200),
+            synthetic.random_scalenet_state_dict(300))
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU path on the host cores
+# --------------------------------------------------------------------------------------------------
+class CpuReference:
+    """One step = `n` objects x 50 hypotheses through the reference's CPU path: pred_func (scipy RK45 host loop) ->
+    get_energy -> aggregation block (sklearn DBSCAN) -> pred_scale_func, all the UNMODIFIED reference modules
+    (oracle/_ref/refpkg; kind "reference").  The reference's encoder is a CUDA-only extension, so the two encoder
+    passes of a step are the oracle port's (oracle/pose_oracle.py:pointnet2_encoder: C restatement of FPS / ball query /
+    grouping + torch-CPU conv / BN / max-pool, pinned to the reference on the GPU box by tests/test_gpu_reference.py),
+    timed inside the step, their features injected.  Without oracle/_ref/refpkg the whole step is the oracle port
+    (kind "port")."""
+
+    def __init__(self, n_max):
+        import torch
+        from genpose2_b200 import synthetic
+        from oracle import ref_shim
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.pts, self.center = synthetic.make_point_clouds(max(n_max, 1), NUM_POINTS, seed=0)
+        self.sds = synthetic_weights()
+        self.kind = "port"
+        self.agents = None
+        if ref_shim.available():
+            try:
+                from oracle.ref_runner import ReferenceAgents
+                self.agents = ReferenceAgents(*self.sds, device="cpu", inject_features=True)
+                self.kind = "reference"
+            except Exception as e:  # noqa: BLE001
+                print("reference modules not loadable, timing the oracle port instead:", e, file=sys.stderr)
+
+    def step(self, n):
+        """-> (seconds, seconds spent in the two encoder passes)"""
+        import torch
+        from oracle import pose_oracle as po
+        pts, center = self.pts[:n], self.center[:n]
+        t0 = time.perf_counter()
+        if self.agents is None:
+            torch.manual_seed(1)
+            noise = po.ve_prior((n * REPEAT, 9), T=T0)
+            po.full_pipeline(self.sds[0], self.sds[1], self.sds[2], pts, center, noise, repeat_num=REPEAT, T0=T0,
+                             integrator="scipy")
+            return time.perf_counter() - t0, None
+        with torch.no_grad():
+            sfeat = po.pointnet2_encoder(self.sds[0], pts)
+            efeat = po.pointnet2_encoder(self.sds[1], pts)
+        t_enc = time.perf_counter() - t0
+        self.agents.full(pts, center, REPEAT, T0, noise_seed=1, score_feat=sfeat, energy_feat=efeat)
+        return time.perf_counter() - t0, t_enc
+
+    def describe(self, n, steps, enc_share):
+        what = ("reference modules (oracle/_ref/refpkg): torch-CPU nets + scipy RK45 + sklearn DBSCAN; the CUDA-only "
+                "encoder through the oracle port" if self.kind == "reference"
+                else "oracle port: torch-CPU nets + scipy RK45 + sklearn DBSCAN")
+        s = f"{n} objects x {REPEAT} hypotheses per step, full path incl. both encoders, {steps} step(s) ({what})"
+        if enc_share is not None:
+            s += f"; encoders = {100 * enc_share:.0f}% of the step"
+        return s
 
 
 def run_reference(args):
@@ -178,25 +229,365 @@ def run_reference(args):
     if rank != 0:
         return  # rank 0 alone runs the CPU reference; other ranks exit without work
     import torch
-    n = args.cpu_sample_objects
-    st = cpu_state(n)
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_step(st, n)
-    times = [cpu_reference_step(st, n) for _ in range(args.steps)]
+    n = args.ref_objects
+    ref = CpuReference(n)
+    t_begin = time.perf_counter()
+    ref.step(min(n, 4))  # warm-up (thread pools, imports); a full-size warm-up step would not fit the time budget
+    times, encs = [], []
+    for _ in range(max(1, args.steps)):
+        dt, enc = ref.step(n)
+        times.append(dt)
+        encs.append(enc)
+        # bounded: the whole run must end within a few minutes whatever K the driver passes
+        if time.perf_counter() - t_begin + dt > args.ref_budget_s:
+            break
     total = sum(times)
     value = n * len(times) / total
     cores = torch.get_num_threads()
-    sample = f"{n} objects x {REPEAT} hypotheses per step (full path incl. both encoders), {len(times)} steps"
+    enc_share = None if encs[0] is None else sum(encs) / total
+    sample = ref.describe(n, len(times), enc_share)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "steps_timed": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"C2: {OBJECTS_PER_GPU} objects x {REPEAT} hypotheses, full path, T0={T0}",
-                   "sampled_objects_per_step": n},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                   "objects_per_step": n, "same_config": n == OBJECTS_PER_GPU,
+                   "note": f"steps are capped by a {args.ref_budget_s:.0f} s wall-clock budget (steps_timed of steps ran)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": ref.kind, "sample": sample,
+                         "os_cpu_count": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# helpers of the B200 arm
+# --------------------------------------------------------------------------------------------------
+def ev_time(fn, reps, flush=None):
+    """median CUDA-event milliseconds of fn() over `reps` runs (after one untimed run)"""
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def load_ref_ext():
+    """The reference's own CUDA extension (oracle/_ref/pointnet2_cuda.so), or None."""
+    d = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(d, "pointnet2_cuda.so")):
+        return None
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    try:
+        import pointnet2_cuda
+        return pointnet2_cuda
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def sampler_inputs(net, feat, center_d, B, T, seed=99):
+    import torch
+    N = B * REPEAT
+    sdata = {"pts": torch.empty(N, 0), "pts_center": center_d.unsqueeze(1).expand(B, REPEAT, 3).reshape(N, 3).contiguous(),
+             "_gp_pts_feat_obj": feat, "_gp_rows_per_object": REPEAT}
+    torch.manual_seed(seed)
+    noise = net.prior_fn((N, 9), T=T)
+    return sdata, noise
+
+
+def sampler_roofline(net, sdata, noise, B, T, peaks, mlp_mode, dev, flush, reps, kernel_name):
+    """Roofline of the integrator kernel alone: algorithmic FLOPs / CUDA-event time (projection kernel included)."""
+    from genpose2_b200 import samplers
+    prior = lambda shape, T=1.0: noise  # noqa: E731
+
+    def sampler_only():
+        return samplers.cond_ode_sampler(net, sdata, prior, net.sde_fn, device=dev, eps=1e-5, T=T,
+                                         pose_mode="rot_matrix", return_trajectory=False)
+
+    k_med = ev_time(sampler_only, reps, flush)
+    st = samplers.ode_stats()
+    N = B * REPEAT
+    nfev_total = st["nfev"] + 1  # + the denoise evaluation
+    flop = N * nfev_total * ROW_EVAL_FLOP + nfev_total * STAGE_SHARED_FLOP + B * OBJECT_ONCE_FLOP
+    achieved = flop / (k_med * 1e-3) / 1e12
+    ffma_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # 148 SMs x 128 FP32 lanes x 2 FLOP x max SM clock
+    return {
+        "bound": "tensor", "kernel": kernel_name, "achieved": achieved, "unit": "TFLOP/s",
+        # the kernel is timed alone (a few ms): the burst figure is the honest denominator; the sustained one beside it
+        "peak": peaks["bf16_tflops"], "frac": achieved / peaks["bf16_tflops"],
+        "peak_sustained": peaks["bf16_tflops_sustained"], "frac_of_sustained": achieved / peaks["bf16_tflops_sustained"],
+        "peak_source": f"{peaks['source']} bf16 dense (MEASURED_PEAKS.json): burst; sustained beside it",
+        "mlp_mode": mlp_mode, "kernel_ms": k_med, "nfev": nfev_total, "accepted": st["accepted"], "rejected": st["rejected"],
+        "algorithmic_flop_per_launch": flop, "hyp_evals_per_s": N * nfev_total / (k_med * 1e-3),
+        "issued_over_algorithmic": {"fp32": 3.0, "bf16": 1.0, "fp32_ffma": 1.0}[mlp_mode],
+        "note": {"fp32_ffma": "MLPs on FP32 FFMA (no tensor cores): also quoted against the FP32 FFMA peak",
+                 "fp32": "split-bf16 x3 on tcgen05 (3 MMAs per product, fp32-class accuracy); achieved counts the "
+                         "algorithmic FLOPs once, so the tensor pipe does 3x that",
+                 "bf16": "bf16 operands on tcgen05, fp32 accumulation in TMEM"}[mlp_mode],
+        "ffma_peak_tflops": ffma_peak, "frac_of_ffma_peak": achieved / ffma_peak,
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+# other BASELINE configs (after the headline's timed region)
+# --------------------------------------------------------------------------------------------------
+def bench_c5(args, world, rank, dev, peaks, barrier):
+    """C5: `c5_objects` objects x 50 hypotheses sharded by object over the ranks (contiguous shards): strong
+    scaling.  Per step: the full path on this rank's shard (encoders in passes of <= 1024 objects; ONE RK45 sampler
+    call over the whole shard -- the step controller is shared per shard, like the reference run once per shard) and
+    the single gather of [B,4,4] + [B,3] (NCCL all_gather) INSIDE the timed region."""
+    import torch
+    import torch.distributed as dist
+    from genpose2_b200 import samplers, synthetic
+    from genpose2_b200.pipeline import PosePipeline, gather_results, shard_range
+    total = args.c5_objects
+    lo, hi = shard_range(total, rank, world)
+    Bl = hi - lo
+    # the clouds of the 8192 objects: 512 distinct synthetic clouds repeated (generation cost only; every object is processed)
+    base_pts, base_center = synthetic.make_point_clouds(512, NUM_POINTS, seed=5)
+    idx = torch.arange(lo, hi) % 512
+    pts_d, center_d = base_pts[idx].to(dev), base_center[idx].to(dev)
+    out = {"objects_total": total, "objects_this_rank": Bl, "scaling": "strong",
+           "gather": ("NCCL all_gather of [B,4,4]+[B,3] inside the timed region" if world > 1 else "single rank: nothing to gather"),
+           "note": "encoders run in passes of <= 1024 objects; one RK45 sampler call per shard (shared step controller per shard)"}
+    steps = 3
+    for mode in ("fp32", "bf16"):
+        pipe = PosePipeline(device=str(dev), mlp_mode=mode).load_synthetic_weights((100, 200, 300))
+
+        def step():
+            pose, length = pipe({"pts": pts_d, "pts_center": center_d}, repeat_num=REPEAT, T0=T0)
+            return gather_results(pose, length)
+
+        torch.manual_seed(4321 + rank)
+        step()
+        torch.cuda.synchronize()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            pose, length = step()
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        barrier()
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        st = samplers.ode_stats()
+        ok = bool(torch.isfinite(pose).all()) and pose.shape[0] == total
+        res = {"value": total * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+               "nfev_this_shard": st["nfev"] + 1, "status": st["status"], "gathered_ok": ok,
+               "hyp_evals_per_s": total * REPEAT * (st["nfev"] + 1) * steps / (ms * 1e-3)}
+        # roofline of the sampler kernel on this rank's shard (one-CTA-per-tile evaluator at this size)
+        net = pipe.score_agent.net
+        feat = pipe._encode(pipe.score_agent, pts_d)[0]
+        sdata, noise = sampler_inputs(net, feat, center_d, Bl, T0)
+        res["roofline"] = sampler_roofline(
+            net, sdata, noise.to(dev), Bl, T0, peaks, mode, dev, None, 3,
+            "ode_rk45_kernel<TcSolo<%d>> (one CTA per 128-row tile)" % (3 if mode == "fp32" else 1)
+            if Bl * REPEAT > 32 * 128 else "ode_rk45_kernel<TcEval> (4-CTA clusters)")
+        out[mode] = res
+        del pipe
+        torch.cuda.empty_cache()
+    return out
+
+
+def bench_c1(dev, flush):
+    """C1: 1 object x 50 hypotheses, ScoreNet ODE sampling only, T0 = 1.0 (BASELINE.json configs[0]): latency."""
+    import torch
+    from genpose2_b200 import samplers
+    from genpose2_b200.pipeline import PosePipeline
+    out = {"workload": "1 object x 50 hypotheses, cond_ode_sampler only, T0 = 1.0, rtol = atol = 1e-5"}
+    g = torch.Generator().manual_seed(11)
+    feat = torch.relu(torch.randn(1, 1024, generator=g))
+    center = torch.randn(1, 3, generator=g) * 0.1 + torch.tensor([0.0, 0.0, 0.8])
+    for mode in ("fp32", "bf16"):
+        pipe = PosePipeline(device=str(dev), mlp_mode=mode).load_synthetic_weights((100, 200, 300))
+        net = pipe.score_agent.net
+        sdata, noise = sampler_inputs(net, feat.to(dev), center.to(dev), 1, 1.0, seed=1)
+        noise = noise.to(dev)
+        ms = ev_time(lambda: samplers.cond_ode_sampler(net, sdata, lambda s, T=1.0: noise, net.sde_fn, device=dev, T=1.0,
+                                                       pose_mode="rot_matrix", return_trajectory=False), 10, flush)
+        st = samplers.ode_stats()
+        out[mode] = {"latency_ms": ms, "nfev": st["nfev"] + 1, "objects_per_s": 1e3 / ms}
+    return out, feat, center
+
+
+def bench_c3(dev):
+    """C3: FPS / ball query / grouping at 1024..16384 points x 256 objects, ours beside the reference's own CUDA ext
+    (sampling_gpu.cu:93-253, ball_query_gpu.cu:9-45, group_points_gpu.cu:47-66) on the same clouds, CUDA events."""
+    import torch
+    from genpose2_b200 import pointnet2_utils as pu, synthetic
+    ext = load_ref_ext()
+    B = 256
+    rows = []
+    for N in (1024, 2048, 4096, 8192, 16384):
+        pts, _ = synthetic.make_point_clouds(32, N, seed=N)
+        xyz = pts.repeat(B // 32, 1, 1).contiguous().to(dev)
+        M = N // 2
+        scale = (1024.0 / N) ** 0.5   # keeps the expected neighbour count of the level-1 radii
+        radii, ns = (0.01 * scale, 0.02 * scale), (16, 32)
+        row = {"points": N, "objects": B}
+        idx, new_xyz = pu.furthest_point_sample_gather(xyz, M)
+        t = ev_time(lambda: pu.furthest_point_sample_gather(xyz, M), 3)
+        row["fps"] = {"us": 1e3 * t, "dist_updates_per_s": B * N * (M - 1) / (t * 1e-3),
+                      "GBps_algorithmic": B * (12 * N + 16 * M) / (t * 1e-3) / 1e9}
+        bq = pu.ball_query2(radii, ns, xyz, new_xyz)
+        t = ev_time(lambda: pu.ball_query2(radii, ns, xyz, new_xyz), 5)
+        row["ball_query_2radii"] = {"us": 1e3 * t, "GBps_algorithmic": B * (12 * N + 12 * M + 4 * M * (ns[0] + ns[1])) / (t * 1e-3) / 1e9}
+        t = ev_time(lambda: pu.query_group(xyz, new_xyz, None, bq[1]), 5)
+        row["query_group_C3"] = {"us": 1e3 * t, "GBps_algorithmic": B * (12 * N + 12 * M + 4 * M * ns[1] + 12 * M * ns[1]) / (t * 1e-3) / 1e9}
+        feat = None
+        if N <= 2048:
+            feat = torch.randn(B, 96, N, device=dev)
+            t = ev_time(lambda: pu.grouping_operation(feat, bq[1]), 3)
+            row["group_C96"] = {"us": 1e3 * t, "GBps_algorithmic": B * (4 * 96 * N + 4 * M * ns[1] + 4 * 96 * M * ns[1]) / (t * 1e-3) / 1e9}
+        if ext is not None:
+            temp = torch.empty((B, N), dtype=torch.float32, device=dev)
+            ridx = torch.empty((B, M), dtype=torch.int32, device=dev)
+
+            def ref_fps():
+                temp.fill_(1e10)
+                ext.furthest_point_sampling_wrapper(B, N, M, xyz, temp, ridx)
+
+            row["fps"]["reference_ext_us"] = 1e3 * ev_time(ref_fps, 2)
+            row["fps"]["bit_exact"] = bool(torch.equal(ridx, idx))
+            r0 = torch.zeros((B, M, ns[0]), dtype=torch.int32, device=dev)
+            r1 = torch.zeros((B, M, ns[1]), dtype=torch.int32, device=dev)
+
+            def ref_bq():
+                ext.ball_query_wrapper(B, N, M, radii[0], ns[0], new_xyz, xyz, r0)
+                ext.ball_query_wrapper(B, N, M, radii[1], ns[1], new_xyz, xyz, r1)
+
+            row["ball_query_2radii"]["reference_ext_us"] = 1e3 * ev_time(ref_bq, 3)
+            row["ball_query_2radii"]["bit_exact"] = bool(torch.equal(r0, bq[0]) and torch.equal(r1, bq[1]))
+            xyz_t = xyz.transpose(1, 2).contiguous()
+            gout = torch.empty((B, 3, M, ns[1]), dtype=torch.float32, device=dev)
+            row["query_group_C3"]["reference_ext_group_only_us"] = 1e3 * ev_time(
+                lambda: ext.group_points_wrapper(B, 3, N, M, ns[1], xyz_t, r1, gout), 3)
+            if feat is not None:
+                gout = torch.empty((B, 96, M, ns[1]), dtype=torch.float32, device=dev)
+                row["group_C96"]["reference_ext_us"] = 1e3 * ev_time(
+                    lambda: ext.group_points_wrapper(B, 96, N, M, ns[1], feat, r1, gout), 3)
+        del feat
+        rows.append(row)
+        torch.cuda.empty_cache()
+    return {"reference_ext_loaded": ext is not None, "sweep": rows}
+
+
+def bench_c4(dev):
+    """C4: tracking mode (evaluation_tracking.py:110-216): 32 objects per frame, T0 = 0.25, the aggregated pose of frame f
+    fed back as init_x of frame f + 1, over a 100-frame synthetic sequence; clouds uploaded from pinned host memory
+    every frame, the pose read back every frame."""
+    import torch
+    from genpose2_b200 import synthetic
+    from genpose2_b200.pipeline import PosePipeline
+    B, F, T = 32, 100, 0.25
+    pipe = PosePipeline(device=str(dev), mlp_mode="fp32").load_synthetic_weights((100, 200, 300))
+    frames = []
+    base, base_c = synthetic.make_point_clouds(B, NUM_POINTS, seed=900)
+    gen = torch.Generator().manual_seed(901)
+    drift = torch.zeros(B, 1, 3)
+    for f in range(F):   # a smooth random walk of <= 1 cm per frame plus fresh 1 mm noise
+        drift = drift + torch.randn(B, 1, 3, generator=gen) * 0.003
+        p = (base + drift + torch.randn(base.shape, generator=gen) * 0.001).contiguous().pin_memory()
+        frames.append((p, p.mean(dim=1).contiguous().pin_memory()))
+    R0 = synthetic._random_rotations(__import__("numpy").random.default_rng(902), B)
+    prev = torch.zeros(B, 9)
+    prev[:, :3] = torch.from_numpy(R0[:, :, 0]).float()
+    prev[:, 3:6] = torch.from_numpy(R0[:, :, 1]).float()
+    prev[:, 6:] = frames[0][1]
+    out_h = torch.empty((B, 4, 4), dtype=torch.float32).pin_memory()
+
+    def run(n):
+        pv = prev.to(dev)
+        for f in range(n):
+            p = frames[f][0].to(dev, non_blocking=True)
+            c = frames[f][1].to(dev, non_blocking=True)
+            init = pv.clone()
+            init[:, 6:] -= c                                  # evaluation_tracking.py:117-118
+            agg, length = pipe({"pts": p, "pts_center": c}, repeat_num=REPEAT, T0=T, init_x=init)
+            pv = PosePipeline.next_init_x(agg)                # :210-214
+            out_h.copy_(agg, non_blocking=True)
+        return pv
+
+    torch.manual_seed(7)
+    run(5)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    run(F)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e)
+    return {"workload": f"{B} objects/frame x {REPEAT} hypotheses, T0 = {T}, {F} frames, pose feedback, host clouds in / pose out per frame",
+            "ms_per_frame": ms / F, "frames_per_s": F / (ms * 1e-3), "objects_per_s": B * F / (ms * 1e-3), "mlp_mode": "fp32"}
+
+
+def bench_reference_gpu(dev, c1_feat, c1_center):
+    """The UNMODIFIED reference on this GPU (oracle/_ref/refpkg + its own CUDA ext): the C2 batch through
+    pred_func -> get_energy -> aggregation -> pred_scale_func, per stage, and the C1 sampler (GPU and CPU)."""
+    import torch
+    from genpose2_b200 import synthetic
+    from oracle import ref_shim
+    if not (ref_shim.available() and ref_shim.has_cuda_ext()):
+        return {"unavailable": "oracle/_ref/refpkg or oracle/_ref/pointnet2_cuda.so missing"}
+    from oracle.ref_runner import ReferenceAgents
+    tf32 = torch.backends.cudnn.allow_tf32
+    out = {"what": "reference modules unmodified: torch fp32 nets on the GPU (cuDNN TF32 at its default: %s), scipy solve_ivp "
+                   "on the host with a device round trip per RHS evaluation (samplers.py:204-234), sklearn DBSCAN per object" % tf32}
+    ref = ReferenceAgents(*synthetic_weights(), device="cuda")
+    pts, center = synthetic.make_point_clouds(OBJECTS_PER_GPU, NUM_POINTS, seed=0)
+    runs = []
+    for it in range(4):
+        st = {}
+        t0 = time.perf_counter()
+        res = ref.full(pts, center, REPEAT, T0, noise_seed=1, stages=st)
+        torch.cuda.synchronize()
+        runs.append((time.perf_counter() - t0, st, res["nfev"]))
+    dt, st, nfev = sorted(runs[1:], key=lambda r: r[0])[1]
+    out["c2_full_path"] = {"objects": OBJECTS_PER_GPU, "ms_per_step": 1e3 * dt, "objects_per_s": OBJECTS_PER_GPU / dt,
+                           "nfev": nfev, "stages_ms": {k: 1e3 * v for k, v in st.items()},
+                           "sampling_objects_per_s": OBJECTS_PER_GPU / st["pred_func"],
+                           "note": "median of 3 after 1 warm-up; pred_func = encoder + ODE sampling"}
+    # C1: the reference's cond_ode_sampler alone, features injected, on the GPU and on the CPU
+    for device in ("cuda", "cpu"):
+        agents = ReferenceAgents(*synthetic_weights(), device=device, inject_features=True)
+        net = agents.score_agent.net
+        R = REPEAT
+        rep = lambda a: a.unsqueeze(1).repeat(1, R, 1).view(R, -1)  # noqa: E731
+        data = {"pts": torch.zeros(R, 4, 3, device=device), "pts_feat": rep(c1_feat).to(device), "pts_center": rep(c1_center).to(device)}
+        ts = []
+        for it in range(3):
+            torch.manual_seed(1)
+            if device == "cuda":
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                ref_ns = agents.ns
+                ref_ns.samplers.cond_ode_sampler(score_model=net, data=dict(data), prior=net.prior_fn, sde_coeff=net.sde_fn,
+                                                 atol=1e-5, rtol=1e-5, device=device, eps=net.sampling_eps, T=1.0,
+                                                 num_steps=None, pose_mode="rot_matrix", denoise=True, init_x=None)
+            if device == "cuda":
+                torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        out["c1_sampler_%s_ms" % device] = 1e3 * sorted(ts)[1]
+    out["cpu_threads"] = torch.get_num_threads()
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -206,7 +597,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from genpose2_b200 import _lib, samplers, synthetic
+    from genpose2_b200 import _lib, synthetic
     from genpose2_b200.pipeline import PosePipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -263,6 +654,7 @@ def run_b200(args):
             return pipe({"pts": pts_d, "pts_center": center_d}, repeat_num=REPEAT, T0=T0)
 
         def step_e2e():
+            # the call a user of the reference makes, with the reference-API defaults (pred_pose_q_wxyz included)
             p = pts_h.to(dev, non_blocking=True)
             c = center_h.to(dev, non_blocking=True)
             pose, length = pipe({"pts": p, "pts_center": c}, repeat_num=REPEAT, T0=T0)
@@ -289,54 +681,17 @@ def run_b200(args):
         # ---- roofline of the dominant kernel of this library: the fused ScoreNet / RK45 integrator ----
         score_net = pipe.score_agent.net
         feat = score_net(dict(pts=pts_d, pts_center=center_d), mode="pts_feature")
-        N = B * REPEAT
-        sdata = {"pts": torch.empty(N, 0), "pts_center": center_d.unsqueeze(1).expand(B, REPEAT, 3).reshape(N, 3).contiguous(),
-                 "_gp_pts_feat_obj": feat, "_gp_rows_per_object": REPEAT}
-        torch.manual_seed(99)
-        noise = score_net.prior_fn((N, 9), T=T0)
-        prior = lambda shape, T=1.0: noise
-
-        def sampler_only():
-            return samplers.cond_ode_sampler(score_net, sdata, prior, score_net.sde_fn, device=dev, eps=1e-5, T=T0,
-                                             pose_mode="rot_matrix", return_trajectory=False)
-
-        for _ in range(3):
-            sampler_only()
-        torch.cuda.synchronize()
-        k_ms = []
-        for _ in range(max(5, min(args.steps, 20))):
-            flush.zero_()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            sampler_only()  # projection kernel (tiny) + the persistent integrator
-            e.record()
-            torch.cuda.synchronize()
-            k_ms.append(s.elapsed_time(e))
-        st = samplers.ode_stats()
-        nfev_total = st["nfev"] + 1  # + the denoise evaluation
-        flop = N * nfev_total * ROW_EVAL_FLOP + nfev_total * STAGE_SHARED_FLOP + B * OBJECT_ONCE_FLOP
-        k_med = sorted(k_ms)[len(k_ms) // 2]
-        achieved = flop / (k_med * 1e-3) / 1e12
-        peak = peaks["bf16_tflops_sustained"]
-        ffma_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # 148 SMs x 128 FP32 lanes x 2 FLOP x max SM clock
-        res["roofline"] = {
-            "bound": "tensor", "kernel": "ode_rk45_kernel<%s> (fused ScoreNet RHS + Dormand-Prince controller)"
-                                         % {"bf16": "TcEval<1>: tcgen05 bf16", "fp32": "TcEval<3>: tcgen05 split-bf16 x3",
-                                            "fp32_ffma": "SimtEval: FFMA fp32"}[mlp_mode],
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture of the same
-            # workload (profiles/README.md, round 1): weights and state are L2-resident, the kernel is not HBM bound
-            "traffic": NCU_DRAM_BYTES_PER_LAUNCH[mlp_mode],
-            "peak_source": f"{peaks['source']} bf16 dense, sustained",
-            "mlp_mode": mlp_mode, "kernel_ms": k_med, "nfev": nfev_total, "accepted": st["accepted"],
-            "rejected": st["rejected"], "algorithmic_flop_per_launch": flop,
-            "hyp_evals_per_s": N * nfev_total / (k_med * 1e-3),
-            "note": {"fp32_ffma": "MLPs on FP32 FFMA (no tensor cores): also quoted against the FP32 FFMA peak",
-                     "fp32": "split-bf16 x3 on tcgen05 (3 MMAs per product, fp32-class accuracy); achieved counts the "
-                             "algorithmic FLOPs once, so the tensor pipe does 3x that",
-                     "bf16": "bf16 operands on tcgen05, fp32 accumulation in TMEM"}[mlp_mode],
-            "ffma_peak_tflops": ffma_peak, "frac_of_ffma_peak": achieved / ffma_peak,
-        }
+        sdata, noise = sampler_inputs(score_net, feat, center_d, B, T0)
+        ntiles = (B * REPEAT + 127) // 128
+        kname = ("ode_rk45_kernel<%s> (fused ScoreNet RHS + Dormand-Prince controller)"
+                 % {"bf16": "TcEval<1>: tcgen05 bf16, 4-CTA cluster per tile" if ntiles <= 32 else "TcSolo<1>: tcgen05 bf16, one CTA per tile",
+                    "fp32": "TcEval<3>: tcgen05 split-bf16 x3, 4-CTA cluster per tile" if ntiles <= 32 else "TcSolo<3>: tcgen05 split-bf16 x3, one CTA per tile",
+                    "fp32_ffma": "SimtEval: FFMA fp32"}[mlp_mode])
+        rf = sampler_roofline(score_net, sdata, noise, B, T0, peaks, mlp_mode, dev, flush, max(5, min(args.steps, 20)), kname)
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel: weights and state are L2-resident, not HBM bound
+        rf["traffic"] = NCU_DRAM_BYTES_PER_LAUNCH[mlp_mode] if B == OBJECTS_PER_GPU else None
+        rf["traffic_source"] = NCU_DRAM_SOURCE
+        res["roofline"] = rf
         return res
 
     main_res = measure(args.mlp_mode, True, True)
@@ -347,16 +702,40 @@ def run_b200(args):
     h2d = pts_h.numel() * 4 + center_h.numel() * 4
     d2h = out_pose_h.numel() * 4 + out_len_h.numel() * 4
 
+    other_configs, reference_gpu = {}, None
+    if not args.no_extras:
+        try:
+            other_configs["c5"] = bench_c5(args, world, rank, dev, peaks, barrier)
+        except Exception as e:  # noqa: BLE001  (an extra must never lose the headline line)
+            other_configs["c5"] = {"error": repr(e)}
+        if world == 1:
+            c1_feat = c1_center = None
+            for name, fn in (("c1", lambda: bench_c1(dev, flush)), ("c3", lambda: bench_c3(dev)), ("c4", lambda: bench_c4(dev))):
+                try:
+                    r = fn()
+                    if name == "c1":
+                        r, c1_feat, c1_center = r
+                    other_configs[name] = r
+                except Exception as e:  # noqa: BLE001
+                    other_configs[name] = {"error": repr(e)}
+                torch.cuda.empty_cache()
+            try:
+                reference_gpu = bench_reference_gpu(dev, c1_feat, c1_center)
+                if "c1_sampler_cpu_ms" in reference_gpu and "c1" in other_configs and "fp32" in other_configs["c1"]:
+                    other_configs["c1"]["reference_cpu_ms"] = reference_gpu["c1_sampler_cpu_ms"]
+                    other_configs["c1"]["reference_gpu_ms"] = reference_gpu["c1_sampler_cuda_ms"]
+            except Exception as e:  # noqa: BLE001
+                reference_gpu = {"error": repr(e)}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = args.cpu_sample_objects
-        stt = cpu_state(n)
-        cpu_reference_step(stt, min(n, 2))  # warm-up
-        reps = [cpu_reference_step(stt, n) for _ in range(3)]
-        med = sorted(reps)[1]
-        cpu_baseline = {"value": n / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": f"{n} objects x {REPEAT} hypotheses, full path incl. both encoders, median of 3 "
-                                  f"(oracle port: torch-CPU nets + scipy RK45 + sklearn DBSCAN)",
+        ref = CpuReference(n)
+        ref.step(min(n, 2))  # warm-up
+        reps = [ref.step(n) for _ in range(3)]
+        med, enc = sorted(reps, key=lambda r: r[0])[1]
+        cpu_baseline = {"value": n / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": ref.kind,
+                        "sample": ref.describe(n, 3, None if enc is None else enc / med) + ", median",
                         "os_cpu_count": os.cpu_count()}
 
     if rank == 0:
@@ -371,12 +750,22 @@ def run_b200(args):
                        f"({L2_FLUSH_BYTES >> 20} MiB memset)", "parallelism": f"object-sharded x{world}, no collective on the data path",
                        "streams": "the energy encoder runs on a second stream beside the cooperative sampler launch"},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                      "ms_per_step": e2e_ms / args.steps},
+                                      "ms_per_step": e2e_ms / args.steps,
+                                      "api": "PosePipeline -> PoseNet.pred_func (reference defaults, pred_pose_q_wxyz computed) -> "
+                                             "get_energy -> aggregate_pose -> pred_scale_func"},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
         if other_res is not None:
             line["other_mode"] = {"mlp_mode": other_mode, "value": other_res["value"], "unit": UNIT,
                                   "ms_per_step": other_res["total_ms"] / args.steps, "roofline": other_res["roofline"]}
+        if other_configs:
+            line["other_configs"] = other_configs
+        if reference_gpu is not None:
+            line["reference_gpu"] = reference_gpu
+            try:
+                line["reference_gpu"]["speedup_e2e_vs_reference_gpu_full_path"] = e2e_value / reference_gpu["c2_full_path"]["objects_per_s"]
+            except Exception:  # noqa: BLE001
+                pass
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

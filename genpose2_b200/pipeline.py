@@ -75,27 +75,45 @@ class PosePipeline:
                                      synthetic.random_gfobjectpose_state_dict(seeds[1]),
                                      synthetic.random_scalenet_state_dict(seeds[2]))
 
+    ENCODER_CHUNK = 1024   # objects per encoder pass (bounds the level buffers; objects are independent)
+
+    def _encode(self, agent, pts, geometries=None, keep_geometry=False):
+        """Encoder features of all objects, at most ENCODER_CHUNK objects per pass (bit-identical to one pass: every
+        encoder kernel works per object).  Returns (features [B,1024], per-chunk geometry list or None)."""
+        B = pts.shape[0]
+        feats, geos = [], []
+        for k, lo in enumerate(range(0, B, self.ENCODER_CHUNK)):
+            chunk = {"pts": pts[lo:lo + self.ENCODER_CHUNK]}
+            if geometries is not None:
+                f = agent.net(chunk, mode="pts_feature", geometry=geometries[k])
+            elif keep_geometry:
+                f, g = agent.net(chunk, mode="pts_feature", return_geometry=True)
+                geos.append(g)
+            else:
+                f = agent.net(chunk, mode="pts_feature")
+            feats.append(f)
+        return (feats[0] if len(feats) == 1 else torch.cat(feats, dim=0)), (geos if keep_geometry else None)
+
     @torch.no_grad()
     def __call__(self, data, repeat_num=None, T0=None, init_x=None, return_all=False):
         """data{'pts' [B,N,3] f32 cuda, 'pts_center' [B,3]} -> (aggregated_pose [B,4,4] f32, length [B,3] f32)."""
         cfg = self.cfg
         R = cfg.eval_repeat_num if repeat_num is None else repeat_num
         T0 = cfg.T0 if T0 is None else T0
-        # The sampler is a cooperative launch of at most 33 four-CTA clusters (100 SMs at 64 x 50): the energy
-        # encoder, which only needs the cloud and the shared FPS / ball-query geometry, runs beside it on a second
+        # The sampler of a small batch is a cooperative launch of at most 33 four-CTA clusters (100 SMs at 64 x 50): the
+        # energy encoder, which only needs the cloud and the shared FPS / ball-query geometry, runs beside it on a second
         # stream and fills the remaining SMs.  The sampler is enqueued first so that it gets its SMs first.
         main = torch.cuda.current_stream()
-        score_feat, geometry = self.score_agent.net(data, mode="pts_feature", return_geometry=True)
+        score_feat, geometry = self._encode(self.score_agent, data["pts"], keep_geometry=True)
         fork = torch.cuda.Event()
         fork.record(main)
-        pred_pose, pred_q, _ = self.score_agent.pred_func(
-            data=data, repeat_num=R, T0=T0, init_x=init_x, save_path=None, return_geometry=True, geometry=geometry,
-            pts_feat=score_feat)
+        pred_pose, pred_q = self.score_agent.pred_func(
+            data=data, repeat_num=R, T0=T0, init_x=init_x, save_path=None, pts_feat=score_feat)
         if self._side is None:
             self._side = torch.cuda.Stream(device=score_feat.device)
         self._side.wait_event(fork)
         with torch.cuda.stream(self._side):
-            energy_feat = self.energy_agent.net(data, mode="pts_feature", geometry=geometry)
+            energy_feat, _ = self._encode(self.energy_agent, data["pts"], geometries=geometry)
             energy_feat.record_stream(main)
         main.wait_stream(self._side)
         energy = self.energy_agent.get_energy(data={"pts_feat": energy_feat, "pts_center": data["pts_center"]},

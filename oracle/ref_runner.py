@@ -62,22 +62,17 @@ class ReferenceAgents:
         cfg.sampler_mode = ["ode"]
         self.device = device
         self.injected = {}
-        if inject_features:
-            injected = self.injected
-
-            def patched_extract(net_self, data):
-                return injected[net_self._gp_role]
-
-            ns.posenet.GFObjectPose.extract_pts_feature = patched_extract
-        elif getattr(ns.posenet.GFObjectPose.extract_pts_feature, "__name__", "") == "patched_extract":
-            raise RuntimeError("extract_pts_feature was patched earlier in this process")
+        self.inject_features = inject_features
 
         def agent(kind, sd):
             c = copy.copy(cfg)
             c.agent_type = kind
             a = ns.posenet_agent.PoseNet(c)
             a.net.load_state_dict(sd)
-            a.net._gp_role = kind
+            if inject_features and kind != "scale":
+                # instance attribute shadows GFObjectPose.extract_pts_feature (posenet.py:127): forward(mode="pts_feature")
+                # calls self.extract_pts_feature(data).  The class itself stays untouched.
+                a.net.extract_pts_feature = lambda data, _k=kind: self.injected[_k]
             return a
 
         self.score_agent = agent("score", score_sd)

@@ -1,6 +1,6 @@
 """How well do float32 arithmetic and the problem itself determine the two "long" fixtures?
 
-    python tests/golden/make_sensitivity.py     # writes tests/golden/ode_c1_T1_sens.npz, pc_b2_500_sens.npz
+    python tests/golden/make_sensitivity.py     # writes tests/golden/ode_c1_T1_sens.npz, pc_b2_sens.npz, pc_b2_500_sens.npz
 
  * ode_c1_T1 (T0 = 1.0: sigma_max = 50, random weights): the probability-flow ODE amplifies float32-rounding-sized
    changes of the score by three to four orders of magnitude; the reference's own result moves by 4e-4 rad / 6.5e-4
@@ -69,6 +69,26 @@ def main():
     np.savez(os.path.join(HERE, "ode_c1_T1_sens.npz"), rot=np.array(rot), trans=np.array(trans), rel=np.array(REL),
              trials=np.array(32), source=np.array("reference cond_ode_sampler, score x (1 + 1e-6 N(0,1))"))
     print("ode median", np.median(rot), np.median(trans), "max", np.max(rot), np.max(trans))
+
+    # ---- PC sampler, 25 steps (fixture pc_b2: stored init and noises) ----
+    g = load_golden("pc_b2")
+    R, B, steps = int(g["R"]), int(g["B"]), int(g["steps"])
+    feat, center = torch.from_numpy(g["feat"]), torch.from_numpy(g["center"])
+    data = {"pts": torch.zeros(B * R, 4, 3), "pts_feat": rep(feat, R), "pts_center": rep(center, R)}
+    rot, trans = [], []
+    for trial in range(16):
+        net.pose_score_net.forward = perturbed(torch.Generator().manual_seed(3000 + trial))
+        torch.manual_seed(5)   # the seed make_golden.py used: same prior draw, same randn_like sequence
+        _, mean_x = ns.samplers.cond_pc_sampler(
+            score_model=net, data=dict(data), prior=net.prior_fn, sde_coeff=net.sde_fn, num_steps=steps, snr=0.16,
+            device="cpu", eps=net.sampling_eps, pose_mode="rot_matrix", init_x=None)
+        r, t = pose_errors(mean_x.numpy(), g["mean_x"])
+        print(f"pc25 trial {trial}: rot {r:.3e} trans {t:.3e}", flush=True)
+        rot.append(r), trans.append(t)
+    np.savez(os.path.join(HERE, "pc_b2_sens.npz"), rot=np.array(rot), trans=np.array(trans), rel=np.array(REL),
+             trials=np.array(16), source=np.array("reference cond_pc_sampler, score x (1 + 1e-6 N(0,1))"),
+             state_magnitude=np.array(float(np.abs(g["mean_x"][:, 6:]).max())))
+    print("pc25 median", np.median(rot), np.median(trans), "max", np.max(rot), np.max(trans))
 
     # ---- PC sampler, 500 steps ----
     g = load_golden("pc_b2_500")

@@ -159,8 +159,15 @@ def test_pc_sampler_matches_reference_golden(mlp_mode):
     mag = np.abs(ref_xs).max(axis=(0, 2))
     assert (err <= 2e-3 * np.maximum(mag, 1.0)).all(), err / np.maximum(mag, 1.0)
     rot, trans = pose_errors(mean_x.cpu().numpy(), g["mean_x"])
-    print(f"pc 25 steps [{mlp_mode}]: rot {rot:.3e} trans {trans:.3e}; xs rel err max {float((err / np.maximum(mag, 1.0)).max()):.3e}")
-    assert rot <= ROT_TOL and trans <= TRANS_TOL, (rot, trans)
+    # Random weights make this 25-step run diverge to |t| ~ 440 (float32 ulp there: 3e-5), so an absolute 1e-4 on the
+    # translation is not defined by float32 arithmetic: the reference's own sampler moves by up to 8.9e-4 (median 3.4e-4)
+    # when its score is perturbed by 1e-6 relative (tests/golden/make_sensitivity.py, 16 runs of the reference).  Bound:
+    # north-star 1e-3 rad on the rotation, twice the largest reference draw on the translation (= 4e-6 of the state).
+    sens = load_golden("pc_b2_sens")
+    print(f"pc 25 steps [{mlp_mode}]: rot {rot:.3e} trans {trans:.3e} (reference envelope max {float(sens['rot'].max()):.3e} / "
+          f"{float(sens['trans'].max()):.3e}, |t| max {float(sens['state_magnitude']):.0f}); "
+          f"xs rel err max {float((err / np.maximum(mag, 1.0)).max()):.3e}")
+    assert rot <= ROT_TOL and trans <= 2 * float(sens["trans"].max()), (rot, trans)
 
 
 @pytest.mark.parametrize("mlp_mode", ["fp32", "fp32_ffma"])

@@ -112,8 +112,9 @@ def test_solo_pc_sampler_matches_reference_golden():
                                           eps=1e-5, pose_mode="rot_matrix", init_x=torch.from_numpy(g["init"]).cuda(),
                                           noise=torch.from_numpy(g["noises"]).cuda())
     rot, trans = pose_errors(mean_x.cpu().numpy(), g["mean_x"])
+    sens = load_golden("pc_b2_sens")   # reference-derived envelope, see test_gpu_sampler.test_pc_sampler_matches_reference_golden
     print(f"solo pc 25 steps: rot {rot:.3e} trans {trans:.3e}")
-    assert rot <= ROT_TOL and trans <= TRANS_TOL, (rot, trans)
+    assert rot <= ROT_TOL and trans <= 2 * float(sens["trans"].max()), (rot, trans)
 
 
 @pytest.mark.parametrize("mlp_mode", ["fp32", "bf16"])
