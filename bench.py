@@ -640,11 +640,13 @@ def run_b200(args):
         torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
         barrier()
-        total_ms = sum(s.elapsed_time(e) for s, e in evs)
+        per_step = [s.elapsed_time(e) for s, e in evs]
+        total_ms = sum(per_step)
         if world > 1:
             t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             total_ms = float(t.item())
+        timed.last_spread = {"min": min(per_step), "median": sorted(per_step)[len(per_step) // 2], "max": max(per_step)}
         return total_ms, clocks
 
     def measure(mlp_mode, with_e2e, with_clocks):
@@ -669,8 +671,10 @@ def run_b200(args):
         torch.cuda.synchronize()
         _lib.reset_launch_count()
         total_ms, clocks = timed(step_resident, args.steps, sampler)
+        from genpose2_b200 import samplers as _s
         res = {"launches": _lib.launch_count(), "total_ms": total_ms, "clocks": clocks,
-               "value": world * B * args.steps / (total_ms * 1e-3)}
+               "value": world * B * args.steps / (total_ms * 1e-3), "step_ms_spread": timed.last_spread,
+               "last_step_ode": {k: v for k, v in _s.ode_stats().items() if k in ("nfev", "accepted", "rejected", "status")}}
         if with_e2e:
             for _ in range(2):
                 step_e2e()
@@ -753,11 +757,13 @@ def run_b200(args):
                                       "ms_per_step": e2e_ms / args.steps,
                                       "api": "PosePipeline -> PoseNet.pred_func (reference defaults, pred_pose_q_wxyz computed) -> "
                                              "get_energy -> aggregate_pose -> pred_scale_func"},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "gpu_launches": launches, "step_ms_spread": main_res["step_ms_spread"], "last_step_ode": main_res["last_step_ode"],
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
         if other_res is not None:
             line["other_mode"] = {"mlp_mode": other_mode, "value": other_res["value"], "unit": UNIT,
-                                  "ms_per_step": other_res["total_ms"] / args.steps, "roofline": other_res["roofline"]}
+                                  "ms_per_step": other_res["total_ms"] / args.steps, "step_ms_spread": other_res["step_ms_spread"],
+                                  "last_step_ode": other_res["last_step_ode"], "roofline": other_res["roofline"]}
         if other_configs:
             line["other_configs"] = other_configs
         if reference_gpu is not None:

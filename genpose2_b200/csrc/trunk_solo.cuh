@@ -9,11 +9,11 @@
 // MMAs of head h + 1.
 //
 // Per evaluation of a 128-row tile (one UMMA M = 128 accumulator, 512 TMEM columns):
-//   h1 = relu(x . W1^T + b1)   FP32 FFMA (K = 9, full float32 operands)  -> A buffer
+//   D0[  0..255] = x  . W1^T (K = 16)        h1 = relu(D0 + b1) -> A buffer
 //   D1[256..511] = h1 . W2^T                 h2 = relu(D1 + b2) -> A buffer (in place)
 //   H0[  0..255] = h2 . Wh0^T   H1[256..511] = h2 . Wh1^T   H2[0..255] = h2 . Wh2^T (after H0 has been drained)
 //   out[row][3h..3h+2] = relu(Hh + proj[obj] + tq) . Wo_h^T + bo
-// Weights: 32 chunks per evaluation ([128 n][64 k] bf16 images, canonical K-major SWIZZLE_128B, 16 KB; hi and lo
+// Weights: 34 chunks per evaluation ([128 n][64 k] bf16 images, canonical K-major SWIZZLE_128B, 16 KB; hi and lo
 // images alternate in split-bf16 mode), streamed from L2 by one producer lane with cp.async.bulk through an mbarrier
 // ring of single images that runs ahead across layers and evaluations.
 //
@@ -27,7 +27,7 @@ namespace solo {
 
 using namespace tc;
 
-constexpr int NCHUNKS = 32;          // 8 (pose_encoder.2) + 3 x 8 (heads); pose_encoder.0 runs in FP32 FFMA
+constexpr int NCHUNKS = 34;          // 2 (pose_encoder.0) + 8 (pose_encoder.2) + 3 x 8 (heads)
 constexpr int SLOTS = 4;             // objects a tile may span for the shared-memory proj table
 
 template <int NPASS>
@@ -65,7 +65,7 @@ template <int NPASS>
 __device__ __forceinline__ const uint8_t *entry_src(const float *__restrict__ P, uint32_t L) {
     constexpr int IM = Smem<NPASS>::IMAGES;
     const uint32_t e = L % (uint32_t)Smem<NPASS>::ENTRIES;
-    const uint32_t q = 2 + e / IM, which = e % IM;   // packed chunks 0, 1 (pose_encoder.0 images) are not streamed
+    const uint32_t q = e / IM, which = e % IM;
     const uint8_t *base = q < 10 ? reinterpret_cast<const uint8_t *>(P + TrunkLayout::W_TC) + (size_t)q * 2 * IMG_BYTES
                                  : reinterpret_cast<const uint8_t *>(P + TrunkLayout::W_SOLO) + (size_t)(q - 10) * 2 * IMG_BYTES;
     return base + (size_t)which * IMG_BYTES;
@@ -202,6 +202,12 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
                     st.consumed = g + 1;
                 }
             };
+            // pose_encoder.0: K = 16 (9 used) -> D0, cols 0..255
+            mbar_wait(&S.a_ready, st.a_phase); st.a_phase ^= 1;
+            tc_fence_after();
+            chunk(tmem, 0, 1, true);
+            chunk(tmem + 128, 0, 1, true);
+            umma_commit(&S.dbar[0]);
             // pose_encoder.2 -> D1, cols 256..511
             mbar_wait(&S.a_ready, st.a_phase); st.a_phase ^= 1;
             tc_fence_after();
@@ -240,8 +246,37 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
         float *scratch = reinterpret_cast<float *>(gp_dyn_smem + (smem_u32(&S.abuf[0][0][0]) - dyn0));
 
         long long t0 = clock64();
-        // h1 = relu(x . W1^T + b1) in FP32 FFMA -> A buffers (this thread's row, its half of the columns)
-        layer1_ffma<NPASS>(P, sx, sb1, row, half * 128, A_hi, A_lo);
+        // inputs -> A operand: k 0..8 of atom 0 (k 9..15 zero), one row per thread of the first four epilogue warps
+        if (half == 0) {
+            float xv[9];
+#pragma unroll
+            for (int c = 0; c < 9; ++c) xv[c] = sx[row * XS + c];
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const float v0 = 2 * p < 9 ? xv[2 * p] : 0.f, v1 = 2 * p + 1 < 9 ? xv[2 * p + 1] : 0.f;
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+                const float2 hf = __bfloat1622float2(h2);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+                hi[p] = *reinterpret_cast<const uint32_t *>(&h2);
+                lo[p] = *reinterpret_cast<const uint32_t *>(&l2);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int off = row * 128 + ((j ^ (row & 7)) << 4);
+                sts_u4(A_hi + off, make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]));
+                if (NPASS == 3) sts_u4(A_lo + off, make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]));
+            }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.a_ready);
+
+        // h1 = relu(D0 + b1) -> A buffers
+        mbar_wait(&S.dbar[0], eph);
+        tc_fence_after();
+        epi_hidden<NPASS>(lane_addr, sb1, row, half * 128, A_hi, A_lo);
         tc_fence_before();
         fence_proxy_async();
         __syncwarp();

@@ -26,7 +26,7 @@
 //   is indistinguishable from a plain fp32 evaluation (same size as changing the fp32 summation order),
 //   while plain bf16 costs 1e-3 rad / 3e-4.
 //
-// Per evaluation: h1 = relu(x . W1^T + b1) (FP32 FFMA, K = 9) ; D1 = h1 . W2^T ; h2 = relu(D1 + b2) ;
+// Per evaluation: D0 = x . W1^T ; h1 = relu(D0 + b1) ; D1 = h1 . W2^T ; h2 = relu(D1 + b2) ;
 // D2_h = h2 . Whp_h[64r..64r+63]^T (3 heads).  Operand layout: canonical K-major SWIZZLE_128B (8-row x
 // 128-byte atoms, 16-byte chunk index XOR row % 8).
 #pragma once
@@ -45,7 +45,7 @@ constexpr int HC = 256 / CL;          // head columns owned by one CTA (per head
 constexpr int NHC = 3 * HC;           // ... over the three heads
 constexpr int XS = 9;                 // row stride of the input / output tile in shared memory
 constexpr int IMG_BYTES = 128 * 128;  // one weight image: [128 rows][64 k] bf16
-constexpr int NCOMMON = 8;            // chunks every rank streams (pose_encoder.2; pose_encoder.0 runs in FP32 FFMA)
+constexpr int NCOMMON = 10;           // chunks every rank streams (pose encoder)
 constexpr int NRANK = 6;              // chunks of this rank's head columns
 constexpr int NCHUNK = NCOMMON + NRANK;
 constexpr int ATOM_BYTES = 128 * 128; // A operand atom: [128 rows][64 k] bf16
@@ -53,7 +53,7 @@ constexpr uint32_t TMEM_COLS = 512;
 constexpr int MAX_SLOTS = 5;          // objects a tile may span for the shared-memory proj table
 constexpr uint32_t kIdescN128 = make_idesc_bf16(128, 128);
 constexpr uint32_t kIdescN64 = make_idesc_bf16(128, 64);
-static_assert(TrunkLayout::TC_CHUNKS == 2 + NCOMMON + CL * NRANK, "packed chunk count");
+static_assert(TrunkLayout::TC_CHUNKS == NCOMMON + CL * NRANK, "packed chunk count");
 
 template <int NPASS>
 struct Smem {
@@ -106,8 +106,7 @@ template <int NPASS>
 __device__ __forceinline__ void issue_chunk(Smem<NPASS> &S, const float *__restrict__ P, uint32_t L, uint32_t rank) {
     constexpr int NST = Smem<NPASS>::NSTAGE, IM = Smem<NPASS>::IMAGES;
     const uint32_t s = L % NST, i = L % NCHUNK;
-    // packed chunks 0, 1 (pose_encoder.0 images) are not streamed: that layer is evaluated in FP32 by the epilogue warps
-    const uint32_t q = i < NCOMMON ? 2 + i : 2 + NCOMMON + NRANK * rank + (i - NCOMMON);
+    const uint32_t q = i < NCOMMON ? i : NCOMMON + NRANK * rank + (i - NCOMMON);
     mbar_arrive_expect_tx(&S.full[s], IM * IMG_BYTES);
     for (int w = 0; w < IM; ++w) bulk_g2s(S.ring[s][w], chunk_src(P, q, w), IMG_BYTES, &S.full[s]);
 }
@@ -196,52 +195,6 @@ __device__ __forceinline__ void begin_tile(Smem<NPASS> &S, State &st, const floa
         for (int i = tid; i < st.nslots * NHC; i += NTHREADS) {
             const int s = i / NHC, c = i - NHC * s;
             S.pj[i] = __ldg(proj + (size_t)(first + s) * 768 + head_col(st.rank, c));
-        }
-    }
-}
-
-// pose_encoder.0 (9 -> 256) in FP32 FFMA, straight from the float32 inputs: h1[row][c0 .. c0 + 127] = relu(x . W1^T + b1)
-// -> bf16 (hi / lo) A operand.  The layer has K = 9 and its inputs reach |x| ~ sigma_max = 50 and beyond, dominated by
-// one or two components: operand rounding (2^-17 with split bf16, 2^-9 with bf16) would not average out over K as it
-// does in the 256-wide layers, so this layer keeps full float32 operands (as the reference's F.linear does).
-// Weights W1T [9][256] are read through the read-only path (all lanes the same address: one broadcast transaction).
-template <int NPASS>
-__device__ __forceinline__ void layer1_ffma(const float *__restrict__ P, const float *sx, const float *sbias, int row, int c0,
-                                            uint32_t A_hi, uint32_t A_lo) {
-    float xv[9];
-#pragma unroll
-    for (int c = 0; c < 9; ++c) xv[c] = sx[row * XS + c];
-    const float4 *__restrict__ w = reinterpret_cast<const float4 *>(P + TrunkLayout::W1T);
-#pragma unroll 2
-    for (int n0 = c0; n0 < c0 + 128; n0 += 8) {
-        const float4 ba = *reinterpret_cast<const float4 *>(sbias + n0), bb = *reinterpret_cast<const float4 *>(sbias + n0 + 4);
-        float v[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-        float4 wa[9], wb[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) { wa[k] = __ldg(w + k * 64 + (n0 >> 2)); wb[k] = __ldg(w + k * 64 + (n0 >> 2) + 1); }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            v[0] = fmaf(xv[k], wa[k].x, v[0]); v[1] = fmaf(xv[k], wa[k].y, v[1]); v[2] = fmaf(xv[k], wa[k].z, v[2]); v[3] = fmaf(xv[k], wa[k].w, v[3]);
-            v[4] = fmaf(xv[k], wb[k].x, v[4]); v[5] = fmaf(xv[k], wb[k].y, v[5]); v[6] = fmaf(xv[k], wb[k].z, v[6]); v[7] = fmaf(xv[k], wb[k].w, v[7]);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-        const __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-        const __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
-        uint4 pk;
-        pk.x = *reinterpret_cast<const uint32_t *>(&p0); pk.y = *reinterpret_cast<const uint32_t *>(&p1);
-        pk.z = *reinterpret_cast<const uint32_t *>(&p2); pk.w = *reinterpret_cast<const uint32_t *>(&p3);
-        const int off = a_offset(row, n0);
-        sts_u4(A_hi + off, pk);
-        if (NPASS == 3) {
-            const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
-            const float2 f2 = __bfloat1622float2(p2), f3 = __bfloat1622float2(p3);
-            const __nv_bfloat162 l0 = __floats2bfloat162_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2bfloat162_rn(v[2] - f1.x, v[3] - f1.y);
-            const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[4] - f2.x, v[5] - f2.y), l3 = __floats2bfloat162_rn(v[6] - f3.x, v[7] - f3.y);
-            uint4 pl;
-            pl.x = *reinterpret_cast<const uint32_t *>(&l0); pl.y = *reinterpret_cast<const uint32_t *>(&l1);
-            pl.z = *reinterpret_cast<const uint32_t *>(&l2); pl.w = *reinterpret_cast<const uint32_t *>(&l3);
-            sts_u4(A_lo + off, pl);
         }
     }
 }
@@ -350,6 +303,15 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
                     umma_bf16(d, make_desc(a_hi + ao), make_desc(b_lo + bo), idesc, 1u);
                 }
             };
+            // pose_encoder.0: K = 16 (9 used), D0 -> cols 0..255
+            mbar_wait(&S.a_ready, st.a_phase); st.a_phase ^= 1;
+            tc_fence_after();
+            for (int nh = 0; nh < 2; ++nh) {
+                next_chunk();
+                mma(tmem + nh * 128, 0, 0, kIdescN128, 0u);
+                chunk_done();
+            }
+            umma_commit(&S.dbar[0]);
             // pose_encoder.2: D1 -> cols 256..511
             mbar_wait(&S.a_ready, st.a_phase); st.a_phase ^= 1;
             tc_fence_after();
@@ -432,8 +394,37 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
         float *sxw = reinterpret_cast<float *>(gp_dyn_smem + (smem_u32(S.x) - dyn0));
 
         long long t0 = clock64();
-        // h1 = relu(x . W1^T + b1) in FP32 FFMA -> A buffers (this thread's row, its half of the columns)
-        layer1_ffma<NPASS>(P, sx, sb1, row, half * 128, A_hi, A_lo);
+        // inputs -> A operand: k 0..8 of atom 0 (k 9..15 zero), one row per thread of the first four warps
+        if (half == 0) {
+            float xv[9];
+#pragma unroll
+            for (int c = 0; c < 9; ++c) xv[c] = sx[row * XS + c];
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const float v0 = 2 * p < 9 ? xv[2 * p] : 0.f, v1 = 2 * p + 1 < 9 ? xv[2 * p + 1] : 0.f;
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+                const float2 hf = __bfloat1622float2(h2);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+                hi[p] = *reinterpret_cast<const uint32_t *>(&h2);
+                lo[p] = *reinterpret_cast<const uint32_t *>(&l2);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int off = row * 128 + ((j ^ (row & 7)) << 4);
+                sts_u4(A_hi + off, make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]));
+                if (NPASS == 3) sts_u4(A_lo + off, make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]));
+            }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.a_ready);
+
+        // h1 = relu(D0 + b1) -> A buffers
+        mbar_wait(&S.dbar[0], dph);
+        tc_fence_after();
+        epi_hidden<NPASS>(lane_addr, sb1, row, half * 128, A_hi, A_lo);
         tc_fence_before();
         fence_proxy_async();
         __syncwarp();

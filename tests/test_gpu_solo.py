@@ -114,7 +114,7 @@ def test_solo_pc_sampler_matches_reference_golden():
     rot, trans = pose_errors(mean_x.cpu().numpy(), g["mean_x"])
     sens = load_golden("pc_b2_sens")   # reference-derived envelope, see test_gpu_sampler.test_pc_sampler_matches_reference_golden
     print(f"solo pc 25 steps: rot {rot:.3e} trans {trans:.3e}")
-    assert rot <= ROT_TOL and trans <= 2 * float(sens["trans"].max()), (rot, trans)
+    assert rot <= ROT_TOL and trans <= 2 * float(sens["trans_operand"].max()), (rot, trans)
 
 
 @pytest.mark.parametrize("mlp_mode", ["fp32", "bf16"])
