@@ -903,6 +903,10 @@ __global__ void __launch_bounds__(EV::NT, 1) ode_rk45_kernel(OdeArgs a) {
                 gram_schmidt6<double>(v);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) v[6 + c] += (double)a.center[(size_t)(r0 + r) * 3 + c];
+                if (status != 0) {   // step-size underflow / attempt cap: the state is not a solution -- poison it in band
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) v[c] = __longlong_as_double(0x7ff8000000000000LL);
+                }
 #pragma unroll
                 for (int c = 0; c < 9; ++c) a.x_out[(size_t)(r0 + r) * 9 + c] = v[c];
             }

@@ -256,16 +256,19 @@ class PointnetSAModuleMSG(nn.Module):
             hoist = feat_cl is not None and tc and feat_cl.shape[2] % 4 == 0
             P_all = Q_all = None
             if hoist:
+                shifted = len(geometry) > 5      # compute_geometry's per-object shift (see there)
+                q_xyz = geometry[4] if shifted else new_xyz
                 if pts_rows is None:  # [feat | xyz | 0] per point, shared by both scales
                     N = xyz.shape[1]
-                    pts_rows = torch.cat([feat_cl, xyz, torch.zeros((B, N, 1), dtype=torch.float32, device=xyz.device)],
+                    pts_rows = torch.cat([feat_cl, xyz - geometry[5] if shifted else xyz,
+                                          torch.zeros((B, N, 1), dtype=torch.float32, device=xyz.device)],
                                          dim=-1).reshape(B * N, -1)
                 if all(m.n_layers == 3 for m in self.mlps):
                     npass = {"bf16x3": 3, "bf16": 1}[self.gemm_mode]
                     mf = self._merged_first_layer(npass)
                     if mf is not None:
                         P_all = pu.gemm_linear(pts_rows, mf["p0"], mf["n"], mf["k0"], npass)
-                        Q_all = pu.centre_term(new_xyz.reshape(B * M, 3), mf["w0_xyz_t"], mf["b0"], P_all.shape[1])
+                        Q_all = pu.centre_term(q_xyz.reshape(B * M, 3), mf["w0_xyz_t"], mf["b0"], P_all.shape[1])
             col = 0
             for i, mlp in enumerate(self.mlps):
                 if hoist and mlp.n_layers == 3:
@@ -276,7 +279,7 @@ class PointnetSAModuleMSG(nn.Module):
                                          self.gemm_mode)
                         col += c1
                     else:
-                        mlp.forward_hoisted(pts_rows, xyz.shape[1], new_xyz, bq[i], dst, self.gemm_mode)
+                        mlp.forward_hoisted(pts_rows, xyz.shape[1], q_xyz, bq[i], dst, self.gemm_mode)
                     off += couts[i]
                     continue
                 spec = tuple(getattr(mlp, f"layer{j}").conv.out_channels for j in range(mlp.n_layers))
@@ -353,16 +356,27 @@ class Pointnet2ClsMSG(nn.Module):
         of level k-1), as the list `forward(..., geometry=...)` takes.  Lets two encoders that see the same cloud
         share one pass and start side by side."""
         xyz = pointcloud[..., 0:3].contiguous()
+        # Per-object shift for the hoisted first layers.  W0 . [xyz[idx] - new_xyz ; feat[idx]] only sees coordinate
+        # DIFFERENCES, so the per-point table P = W0_xyz . (xyz - c) and the per-centre term Q = W0_xyz . (new_xyz - c) - b0
+        # give the same result for any c.  The clouds are in the camera frame (|xyz| ~ 1 m, posenet.py:135) while the
+        # differences are <= the ball radius (0.02 .. 0.16 m): with c = the object's first point (FPS starts there, so it
+        # is also every level's first centre) the GEMM operands are object-sized and their bf16 / split-bf16 rounding
+        # scales with the object, not with its distance from the camera.
+        shift = xyz[:, 0:1, :].contiguous()
+        n_levels = sum(1 for sa in self.SA_modules if sa.npoint is not None)
         geometry, tie_free = [], None
-        for sa in self.SA_modules:
+        for k, sa in enumerate(self.SA_modules):
             if sa.npoint is None:
                 geometry.append(None)
                 continue
             # each level samples the previous level's centres: an FPS-ordered cloud, whose FPS is its own prefix
             # unless the earlier sampling hit an exact tie (pointnet2_utils.furthest_point_sample_chain)
             idx, new_xyz, tie_free = pu.furthest_point_sample_chain(xyz, sa.npoint, tie_free)
-            geometry.append((idx, new_xyz, pu.ball_query2(sa.radii, sa.nsamples, xyz, new_xyz),
-                             torch.nn.functional.pad(new_xyz, (0, 1))))  # [x y z 0]: the tail of the level buffers
+            rel = new_xyz - shift
+            # tail of this level's buffer = the xyz columns the NEXT level reads: shifted for a hoisted level, absolute
+            # for the GroupAll level (its SharedMLP sees the coordinates themselves, pointnet2_utils.py:321-326)
+            tail = torch.nn.functional.pad(rel if k + 1 < n_levels else new_xyz, (0, 1))   # [x y z 0]
+            geometry.append((idx, new_xyz, pu.ball_query2(sa.radii, sa.nsamples, xyz, new_xyz), tail, rel, shift))
             xyz = new_xyz
         return geometry
 

@@ -7,7 +7,7 @@ What changes: the scipy `solve_ivp` host loop with a host<->device round trip pe
 (samplers.py:204-234) is one persistent device kernel (gp_scorenet_ode); the 500-step PC loop is
 one persistent kernel (gp_scorenet_pc).
 """
-import warnings
+import threading
 
 import numpy as np
 import torch
@@ -19,6 +19,34 @@ POSE_DIM = 9  # get_pose_dim("rot_matrix"), utils/genpose_utils.py:34-35
 MAX_TRAJ = 512  # accepted-step slots recorded when the trajectory is requested
 
 last_ode_stats = {}  # statistics of the most recent cond_ode_sampler call (nfev, accepted, ...)
+
+# Failure of the device integrator (status -1: step size underflow, -2: attempt cap) must not pass silently, and
+# checking it must not stall the stream: every call copies its statistics to pinned host memory asynchronously; the
+# copies that have landed are inspected at the next sampler call / ode_stats() and a failed integration raises there.
+# (In band, the kernel also turns x_out of a failed integration into NaN.)
+_pending_stats = []
+
+
+def _watch(stats):
+    host = torch.empty(stats.shape, dtype=stats.dtype, pin_memory=True)
+    host.copy_(stats, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(stats.device))
+    _pending_stats.append((ev, host))
+    if len(_pending_stats) > 64:
+        _pending_stats.pop(0)[0].synchronize()
+
+
+def check_pending(wait=False):
+    """Raise if an earlier device integration failed (only looks at statistics that have already reached the host
+    unless wait=True)."""
+    while _pending_stats and (wait or _pending_stats[0][0].query()):
+        ev, host = _pending_stats.pop(0)
+        ev.synchronize()
+        status = int(host[_lib.STAT_STATUS])
+        if status != 0:
+            raise RuntimeError(f"device RK45 integration failed with status {status} "
+                               "(-1: step size underflow, -2: attempt cap); its poses are NaN")
 
 
 def _score_net(score_model):
@@ -33,6 +61,7 @@ def _mlp_mode(score_model):
 
 
 _staging = {}
+_staging_lock = threading.Lock()
 
 
 def _to_device_async(t, device):
@@ -41,17 +70,23 @@ def _to_device_async(t, device):
     would stall the host until the encoder has finished.  Staged through a cached pinned buffer instead."""
     if t.is_cuda:
         return t.to(device)
-    key = (tuple(t.shape), t.dtype)
-    ent = _staging.get(key)
-    if ent is None:
-        ent = _staging[key] = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True), None]
+    # one staging buffer per (device, host thread, shape, dtype): two threads / devices never share one, so a buffer
+    # is only reused after the event of ITS previous copy; the cache is bounded (least recently created entry goes)
+    key = (str(device), threading.get_ident(), tuple(t.shape), t.dtype)
+    with _staging_lock:
+        ent = _staging.get(key)
+        if ent is None:
+            if len(_staging) >= 16:
+                _staging.pop(next(iter(_staging)))
+            ent = _staging[key] = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True), None]
     buf, ev = ent
     if ev is not None:
         ev.synchronize()   # the previous copy out of this buffer (long finished in practice)
     buf.copy_(t)
     out = buf.to(device, non_blocking=True)
-    ent[1] = torch.cuda.Event()
-    ent[1].record(torch.cuda.current_stream(out.device))
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(out.device))
+    ent[1] = ev
     return out
 
 
@@ -64,6 +99,7 @@ def cond_ode_sampler(score_model, data, prior, sde_coeff, atol=1e-5, rtol=1e-5, 
     if pose_mode != "rot_matrix":
         raise NotImplementedError("accelerated sampler supports pose_mode='rot_matrix' only")
     net = _score_net(score_model)
+    check_pending()
     batch_size = data["pts"].shape[0]
     noise = _to_device_async(prior((batch_size, POSE_DIM), T=T), device)  # CPU generator, like samplers.py:197-201
     x0 = noise if init_x is None else init_x + noise
@@ -89,6 +125,7 @@ def cond_ode_sampler(score_model, data, prior, sde_coeff, atol=1e-5, rtol=1e-5, 
         _lib.call("gp_traj_finalize", _lib.ptr(dense), _lib.ptr(center), int(num_steps), batch_size, _lib.ptr(xs), device=dev)
         last_ode_stats.clear()
         last_ode_stats["device_stats"] = stats
+        _watch(stats)
         return xs, x_out
     traj = None
     if return_trajectory:
@@ -109,6 +146,7 @@ def cond_ode_sampler(score_model, data, prior, sde_coeff, atol=1e-5, rtol=1e-5, 
         xs = x_out.unsqueeze(1)
         last_ode_stats.clear()
         last_ode_stats["device_stats"] = stats
+        _watch(stats)
     return xs, x_out
 
 
@@ -119,15 +157,17 @@ def _record_stats(st):
         status=int(st[_lib.STAT_STATUS]), t_final=float(st[_lib.STAT_T_FINAL]),
         h_initial=float(st[_lib.STAT_H_INITIAL]), h_last=float(st[_lib.STAT_H_LAST]))
     if last_ode_stats["status"] != 0:
-        # the reference ignores solve_ivp's status as well (samplers.py:226-236); say so loudly
-        warnings.warn(f"device RK45 ended with status {last_ode_stats['status']} "
-                      "(-1: step size underflow, -2: attempt cap)")
+        # the reference ignores solve_ivp's status (samplers.py:226-236); here a failed integration is an error
+        raise RuntimeError(f"device RK45 integration failed with status {last_ode_stats['status']} "
+                           "(-1: step size underflow, -2: attempt cap); its poses are NaN")
 
 
 def ode_stats():
     """Statistics of the last cond_ode_sampler call as a dict (synchronises if still on device)."""
     if "device_stats" in last_ode_stats:
-        _record_stats(last_ode_stats["device_stats"].cpu())
+        st = last_ode_stats["device_stats"].cpu()
+        _pending_stats.clear()   # the call being read is the newest one; older ones were checked when it was issued
+        _record_stats(st)
     return dict(last_ode_stats)
 
 

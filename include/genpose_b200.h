@@ -243,7 +243,9 @@ GP_API size_t gp_scorenet_ode_workspace_bytes(int N);
  *   pts_center  [N,3] f32
  *   T, eps, rtol, atol      as in the reference call (posenet.py:253-266)
  *   denoise     0/1
- *   x_out       [N,9] f64   final pose (normalised rotation, centre added)
+ *   x_out       [N,9] f64   final pose (normalised rotation, centre added); all NaN when the integration failed
+ *                           (stats[GP_STAT_STATUS] != 0: step size underflow or attempt cap) -- the reference ignores
+ *                           solve_ivp's status (samplers.py:226-236), this library poisons the result in band
  *   traj        NULL, or [max_traj, N, 9] f64: raw state after every accepted step, slot 0 = x0
  *   stats       [GP_STAT_COUNT] f64 (device)
  *   mode        arithmetic of the MLP contractions: 0 = fp32 FFMA on CUDA cores; 1 = bf16 operands on tcgen05;

@@ -242,3 +242,42 @@ def test_stage_files_are_plain_pickles_in_the_reference_layout(tmp_path):
     rot_t = torch.repeat_interleave(pose[:, :3, :3].transpose(1, 2), 64, dim=0)
     want = 2 * torch.bmm(rot_t, (pcl - pose[:, :3, 3].unsqueeze(1)).reshape(-1, 3, 1)).reshape(-1, 64, 3).abs().max(dim=1)[0]
     assert torch.allclose(stage_io.bbox_length_from_points(pcl, pose), want, atol=1e-6)
+
+
+def test_load_ckpt_reads_a_checkpoint_written_by_the_reference(tmp_path):
+    """PoseNet.load_ckpt (posenet_agent.py:171-203) on a file produced by the REFERENCE's own
+    PoseNet.save_ckpt (posenet_agent.py:141-169: torch.save of {clock, model_state_dict, optimizer_state_dict,
+    scheduler_state_dict} after the EMA copy) -- for the score, energy and scale agents."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference modules not available (neither /root/reference nor oracle/_ref/refpkg)")
+    import copy
+    from genpose2_b200 import synthetic
+    from genpose2_b200.config import get_config
+    from genpose2_b200.posenet_agent import PoseNet
+    ns = ref_shim.load()
+    for kind, sd in (("score", synthetic.random_gfobjectpose_state_dict(100)),
+                     ("energy", synthetic.random_gfobjectpose_state_dict(200)),
+                     ("scale", synthetic.random_scalenet_state_dict(300))):
+        rcfg = copy.copy(ns.cfg)
+        rcfg.device, rcfg.agent_type = "cpu", kind
+        ref_agent = ns.posenet_agent.PoseNet(rcfg)
+        ref_agent.net.load_state_dict(sd)
+        # save_ckpt stores the EMA shadow (initialised from the construction-time weights): refresh it like a
+        # training step would have, so that the file holds the weights loaded above
+        ref_agent.ema = type(ref_agent.ema)(ref_agent.net.parameters(), decay=rcfg.ema_rate)
+        ref_agent.model_dir = str(tmp_path)
+        ref_agent.save_ckpt(name=f"ckpt_{kind}")
+        path = tmp_path / f"ckpt_{kind}.pth"
+        assert path.exists()
+        cfg = get_config()
+        cfg.device, cfg.agent_type = "cpu", kind
+        agent = PoseNet(cfg)
+        agent.load_ckpt(model_dir=str(path), model_path=True, load_model_only=True)
+        got = agent.net.state_dict()
+        want = ref_agent.net.state_dict()
+        assert set(got.keys()) == set(want.keys())
+        for k in want:
+            assert torch.equal(got[k].cpu(), want[k].cpu()), k
+            if k in sd:
+                assert torch.equal(got[k].cpu(), sd[k]), k

@@ -307,3 +307,34 @@ def test_ode_sampler_dense_output_matches_reference_golden(mlp_mode):
         rot, trans = pose_errors(xs[:, s_i].cpu().numpy(), xs_o[:, s_i].numpy())
         mag = max(1.0, float(xs_o[:, s_i, 6:].abs().max()))
         assert rot <= ROT_TOL and trans <= TRANS_TOL * mag, (s_i, rot, trans)
+
+
+def test_failed_integration_is_loud():
+    """An integration the controller cannot finish (tolerances far below float32 RHS noise -> step size underflow,
+    scipy status -1) poisons its poses with NaN in band and raises at the next look at the statistics: the reference
+    ignores solve_ivp's status (samplers.py:226-236), the accelerated path does not pass a failure silently."""
+    from genpose2_b200 import samplers
+    net = make_net(100)
+    g = torch.Generator().manual_seed(9)
+    B, R = 2, 8
+    feat = torch.relu(torch.randn(B, 1024, generator=g)).cuda()
+    center = torch.zeros(B, 3).cuda()
+    noise = torch.randn(B * R, 9, generator=g) * po.ve_marginal_std(1.0)
+    data = {"pts": torch.zeros(B * R, 1, 3), "pts_center": rep(center, R), "_gp_pts_feat_obj": feat,
+            "_gp_rows_per_object": R}
+    _, x = samplers.cond_ode_sampler(net, data, lambda shape, T: noise.clone(), net.sde_fn, atol=1e-30, rtol=1e-15,
+                                     device="cuda", T=1.0, pose_mode="rot_matrix", return_trajectory=False)
+    assert torch.isnan(x).all()
+    with pytest.raises(RuntimeError, match="status -1"):
+        samplers.ode_stats()
+    # the asynchronous watch raises at the next sampler call once the statistics have reached the host
+    _, x = samplers.cond_ode_sampler(net, data, lambda shape, T: noise.clone(), net.sde_fn, atol=1e-30, rtol=1e-15,
+                                     device="cuda", T=1.0, pose_mode="rot_matrix", return_trajectory=False)
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="status -1"):
+        samplers.check_pending()
+    samplers._pending_stats.clear()
+    # and a healthy call afterwards is unaffected
+    _, x = samplers.cond_ode_sampler(net, data, lambda shape, T: noise.clone(), net.sde_fn, device="cuda", T=0.3,
+                                     pose_mode="rot_matrix", return_trajectory=False)
+    assert torch.isfinite(x).all() and samplers.ode_stats()["status"] == 0
