@@ -72,6 +72,8 @@ def parse():
     ap.add_argument("--single_mode", action="store_true", help="skip the measurement of the other mlp_mode")
     ap.add_argument("--no_extras", action="store_true", help="skip other_configs and reference_gpu")
     ap.add_argument("--c5_objects", type=int, default=C5_OBJECTS)
+    ap.add_argument("--graph", type=str, default="on", choices=["on", "off"],
+                    help="replay the step as one CUDA graph (PosePipeline(use_graph=True)); falls back to eager launches if the capture fails")
     return ap.parse_args()
 
 
@@ -650,7 +652,18 @@ def run_b200(args):
         return total_ms, clocks
 
     def measure(mlp_mode, with_e2e, with_clocks):
-        pipe = PosePipeline(device=f"cuda:{local_rank}", mlp_mode=mlp_mode).load_synthetic_weights((100, 200, 300))
+        pipe = PosePipeline(device=f"cuda:{local_rank}", mlp_mode=mlp_mode, use_graph=args.graph == "on").load_synthetic_weights((100, 200, 300))
+        graph_note = "off"
+        if pipe.use_graph:
+            try:
+                torch.manual_seed(1)
+                pipe({"pts": pts_d, "pts_center": center_d}, repeat_num=REPEAT, T0=T0)
+                torch.cuda.synchronize()
+                graph_note = "one CUDA graph per step (%d kernels of this library per replay)" % pipe.graph_launches
+            except Exception as e:  # noqa: BLE001  (bench-level fallback: eager launches of the same kernels)
+                print("CUDA graph capture failed, measuring eager launches:", repr(e)[:300], file=sys.stderr)
+                pipe = PosePipeline(device=f"cuda:{local_rank}", mlp_mode=mlp_mode).load_synthetic_weights((100, 200, 300))
+                graph_note = "capture failed: eager launches"
 
         def step_resident():
             return pipe({"pts": pts_d, "pts_center": center_d}, repeat_num=REPEAT, T0=T0)
@@ -672,7 +685,8 @@ def run_b200(args):
         _lib.reset_launch_count()
         total_ms, clocks = timed(step_resident, args.steps, sampler)
         from genpose2_b200 import samplers as _s
-        res = {"launches": _lib.launch_count(), "total_ms": total_ms, "clocks": clocks,
+        launches = pipe.graph_launches * args.steps if pipe.use_graph else _lib.launch_count()
+        res = {"launches": launches, "graph": graph_note, "total_ms": total_ms, "clocks": clocks,
                "value": world * B * args.steps / (total_ms * 1e-3), "step_ms_spread": timed.last_spread,
                "last_step_ode": {k: v for k, v in _s.ode_stats().items() if k in ("nfev", "accepted", "rejected", "status")}}
         if with_e2e:
@@ -752,7 +766,8 @@ def run_b200(args):
                                    f"T0={T0}, rtol=atol=1e-5, {NUM_POINTS} pts/object, random-init weights",
                        "objects_per_gpu": B, "hypotheses": REPEAT, "T0": T0, "l2": "flushed between timed steps "
                        f"({L2_FLUSH_BYTES >> 20} MiB memset)", "parallelism": f"object-sharded x{world}, no collective on the data path",
-                       "streams": "the energy encoder runs on a second stream beside the cooperative sampler launch"},
+                       "streams": "the energy encoder runs on a second stream beside the cooperative sampler launch",
+                       "cuda_graph": main_res["graph"]},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                       "ms_per_step": e2e_ms / args.steps,
                                       "api": "PosePipeline -> PoseNet.pred_func (reference defaults, pred_pose_q_wxyz computed) -> "

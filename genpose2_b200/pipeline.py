@@ -12,7 +12,7 @@ import copy
 import torch
 import torch.distributed as dist
 
-from . import synthetic
+from . import _lib, synthetic
 from .aggregation import aggregate_pose
 from .config import get_config
 from .posenet_agent import PoseNet
@@ -49,7 +49,11 @@ def gather_results(pose, length, group=None):
 class PosePipeline:
     """score + energy + scale agents wired together; every stage runs on libgenpose_b200.so."""
 
-    def __init__(self, cfg=None, device="cuda", mlp_mode="fp32"):
+    def __init__(self, cfg=None, device="cuda", mlp_mode="fp32", use_graph=False):
+        """use_graph: replay the whole step as ONE CUDA graph per input signature (batch size, points, hypotheses, T0):
+        ~80 kernel launches, the two-stream fork / join and the cooperative sampler launch become one graph launch; the
+        only host work left per step is drawing the prior noise with the CPU generator (exactly like the reference,
+        sde.py:34) and one pinned upload.  The captured graph bakes in the packed weights: load_state_dicts() drops it."""
         cfg = copy.copy(cfg) if cfg is not None else get_config()
         cfg.device = device
         cfg.mlp_mode = mlp_mode
@@ -63,11 +67,15 @@ class PosePipeline:
         c = copy.copy(cfg); c.agent_type = "scale"
         self.scale_agent = PoseNet(c)
         self._side = None   # second stream: the energy encoder overlaps the sampler
+        self.use_graph = bool(use_graph)
+        self._graphs = {}
+        self.graph_launches = 0
 
     def load_state_dicts(self, score_sd, energy_sd, scale_sd):
         self.score_agent.net.load_state_dict(score_sd)
         self.energy_agent.net.load_state_dict(energy_sd)
         self.scale_agent.net.load_state_dict(scale_sd)
+        self._graphs.clear()
         return self
 
     def load_synthetic_weights(self, seeds=(100, 200, 300)):
@@ -100,6 +108,72 @@ class PosePipeline:
         cfg = self.cfg
         R = cfg.eval_repeat_num if repeat_num is None else repeat_num
         T0 = cfg.T0 if T0 is None else T0
+        if self.use_graph and not return_all:
+            return self._graph_step(data, R, float(T0), init_x)
+        return self._step(data, R, T0, init_x, return_all)
+
+    def _graph_step(self, data, R, T0, init_x):
+        """The step as a CUDA graph: copy the inputs into the graph's static buffers, draw + upload the prior noise,
+        replay.  Returns clones of the two small results (the static ones are overwritten by the next replay)."""
+        from . import samplers
+        pts, center = data["pts"], data["pts_center"]
+        B, N = pts.shape[0], pts.shape[1]
+        key = (B, N, R, T0, init_x is not None, pts.device.index)
+        ent = self._graphs.get(key)
+        net = self.score_agent.net
+        real_prior = net.prior_fn
+        if ent is None:
+            dev = pts.device
+            st = dict(pts=torch.empty_like(pts), center=torch.empty_like(center, dtype=torch.float32),
+                      init=None if init_x is None else torch.empty_like(init_x),
+                      noise=torch.empty((B * R, 9), dtype=torch.float32, device=dev),
+                      noise_host=torch.empty((B * R, 9), dtype=torch.float32, pin_memory=True))
+            st["pts"].copy_(pts); st["center"].copy_(center)
+            if init_x is not None:
+                st["init"].copy_(init_x)
+            st["noise"].copy_(real_prior((B * R, 9), T=T0))
+            sdata = {"pts": st["pts"], "pts_center": st["center"]}
+            net.prior_fn = lambda shape, T=1.0: st["noise"]    # device tensor: no host work inside the capture
+            try:
+                warm = torch.cuda.Stream(device=dev)
+                warm.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(warm):
+                    for _ in range(2):   # packs weights, sets kernel attributes, sizes the allocator pools
+                        self._step(sdata, R, T0, st["init"], False)
+                torch.cuda.current_stream(dev).wait_stream(warm)
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                n0 = _lib.launch_count()
+                with torch.cuda.graph(graph):
+                    out = self._step(sdata, R, T0, st["init"], False)
+                self.graph_launches = _lib.launch_count() - n0   # kernels of this library inside one replay
+                stats = samplers.last_ode_stats.get("device_stats")
+            finally:
+                net.prior_fn = real_prior
+            ent = self._graphs[key] = (graph, st, out, stats)
+        graph, st, out, stats = ent
+        if pts.data_ptr() != st["pts"].data_ptr():
+            st["pts"].copy_(pts, non_blocking=True)
+        st["center"].copy_(center, non_blocking=True)
+        if init_x is not None:
+            st["init"].copy_(init_x, non_blocking=True)
+        # prior noise: drawn on the CPU from the global generator in the reference's call order (samplers.py:197-201)
+        ev = st.get("noise_event")
+        if ev is not None:
+            ev.synchronize()     # the previous upload out of the pinned buffer (long finished in practice)
+        st["noise_host"].copy_(real_prior((B * R, 9), T=T0))
+        st["noise"].copy_(st["noise_host"], non_blocking=True)
+        st["noise_event"] = torch.cuda.Event()
+        st["noise_event"].record()
+        graph.replay()
+        if stats is not None:
+            samplers.last_ode_stats.clear()
+            samplers.last_ode_stats["device_stats"] = stats
+        return out[0].clone(), out[1].clone()
+
+    def _step(self, data, R, T0, init_x, return_all):
+        cfg = self.cfg
+        capturing = torch.cuda.is_current_stream_capturing()
         # The sampler of a small batch is a cooperative launch of at most 33 four-CTA clusters (100 SMs at 64 x 50): the
         # energy encoder, which only needs the cloud and the shared FPS / ball-query geometry, runs beside it on a second
         # stream and fills the remaining SMs.  The sampler is enqueued first so that it gets its SMs first.
@@ -114,7 +188,8 @@ class PosePipeline:
         self._side.wait_event(fork)
         with torch.cuda.stream(self._side):
             energy_feat, _ = self._encode(self.energy_agent, data["pts"], geometries=geometry)
-            energy_feat.record_stream(main)
+            if not capturing:
+                energy_feat.record_stream(main)
         main.wait_stream(self._side)
         energy = self.energy_agent.get_energy(data={"pts_feat": energy_feat, "pts_center": data["pts_center"]},
                                               pose_samples=pred_pose, T=1e-5, mode="test", extract_feature=False)

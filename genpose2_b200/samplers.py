@@ -28,6 +28,8 @@ _pending_stats = []
 
 
 def _watch(stats):
+    if torch.cuda.is_current_stream_capturing():
+        return   # no host allocations / events inside a graph capture; the graph's owner watches the static stats
     host = torch.empty(stats.shape, dtype=stats.dtype, pin_memory=True)
     host.copy_(stats, non_blocking=True)
     ev = torch.cuda.Event()
@@ -40,6 +42,8 @@ def _watch(stats):
 def check_pending(wait=False):
     """Raise if an earlier device integration failed (only looks at statistics that have already reached the host
     unless wait=True)."""
+    if torch.cuda.is_current_stream_capturing():
+        return
     while _pending_stats and (wait or _pending_stats[0][0].query()):
         ev, host = _pending_stats.pop(0)
         ev.synchronize()
