@@ -59,6 +59,23 @@ __global__ void pack_trunk_kernel(RawTrunk raw, float *__restrict__ P) {
             v = c < 9 ? p.head_b1[c / 3][c % 3] : 0.f;
         } else if (i < TrunkLayout::W_TC) {
             v = 0.f;  // alignment padding
+        } else if (i >= TrunkLayout::W_WIDE) {
+            // wide head images of the cluster evaluator: [rank][kc][hi/lo] x [192 n][64 k]
+            const size_t f = i - TrunkLayout::W_WIDE;
+            const size_t per_img = TrunkLayout::WIDE_IMG_FLOATS;
+            const size_t im = f / per_img, which = im % 2, kc = (im / 2) % 4, r = im / 8, o = (f % per_img) * 4;
+            const size_t nl = o / 128, wb = o % 128;
+            const size_t logical16 = (wb / 16) ^ (nl & 7);
+            const size_t kl = logical16 * 8 + (wb % 16) / 2;
+            const size_t hh = nl / 64, n = 64 * r + nl % 64, k = kc * 64 + kl;
+            float e[2];
+            for (int t = 0; t < 2; ++t) {
+                const float src = p.head_w0[hh][n * 1408 + 1152 + k + t];
+                const float hi = __bfloat162float(__float2bfloat16_rn(src));
+                e[t] = which == 0 ? hi : src - hi;
+            }
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(e[0], e[1]);
+            v = *reinterpret_cast<float *>(&h2);
         } else {
             // destination float slot -> (chunk q, image hi/lo, row n, 16-byte unit, element pair)
             const size_t f = i - TrunkLayout::W_TC;

@@ -42,7 +42,11 @@ struct TrunkLayout {
     //   q' = 8*h + 2*kc + nh   head h, k-atom kc, output columns 128*nh .. 128*nh + 127 (pose_feat columns)
     static constexpr size_t SOLO_CHUNKS = 24;
     static constexpr size_t W_SOLO = W_TC + TC_CHUNKS * 2 * (128 * 64 / 2);
-    static constexpr size_t END = W_SOLO + SOLO_CHUNKS * 2 * (128 * 64 / 2);
+    // the cluster evaluator multiplies a rank's three 64-column head slices as one N = 192 MMA: per (rank r, k-atom kc)
+    // one image [192 n][64 k] x {hi, lo} (24 KB each), row 64*h + c = head h, output column 64*r + c
+    static constexpr size_t WIDE_IMG_FLOATS = 192 * 64 / 2;
+    static constexpr size_t W_WIDE = W_SOLO + SOLO_CHUNKS * 2 * (128 * 64 / 2);
+    static constexpr size_t END = W_WIDE + 4 * 4 * 2 * WIDE_IMG_FLOATS;
 };
 
 constexpr float kFloatPi = 3.14159265358979323846f;  // np.pi cast to float32 by torch

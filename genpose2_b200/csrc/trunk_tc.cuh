@@ -46,20 +46,26 @@ constexpr int NHC = 3 * HC;           // ... over the three heads
 constexpr int XS = 9;                 // row stride of the input / output tile in shared memory
 constexpr int IMG_BYTES = 128 * 128;  // one weight image: [128 rows][64 k] bf16
 constexpr int NCOMMON = 10;           // chunks every rank streams (pose encoder)
-constexpr int NRANK = 6;              // chunks of this rank's head columns
-constexpr int NCHUNK = NCOMMON + NRANK;
+constexpr int NRANK = 6;              // packed [128][64] chunks per rank of the narrow head layout (kept in the blob)
+constexpr int WIDE_BYTES = NHC * 128; // one wide head image: [192 n = this rank's 3 x 64 head columns][64 k] bf16, 24 KB
 constexpr int ATOM_BYTES = 128 * 128; // A operand atom: [128 rows][64 k] bf16
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int MAX_SLOTS = 5;          // objects a tile may span for the shared-memory proj table
 constexpr uint32_t kIdescN128 = make_idesc_bf16(128, 128);
 constexpr uint32_t kIdescN64 = make_idesc_bf16(128, 64);
+constexpr uint32_t kIdescN192 = make_idesc_bf16(128, NHC);
 static_assert(TrunkLayout::TC_CHUNKS == NCOMMON + CL * NRANK, "packed chunk count");
+static_assert(TrunkLayout::WIDE_IMG_FLOATS * 4 == WIDE_BYTES, "wide head image size");
 
 template <int NPASS>
 struct Smem {
     static constexpr int IMAGES = NPASS == 3 ? 2 : 1;
     static constexpr int NSTAGE = NPASS == 3 ? 2 : 4;
-    uint8_t ring[NSTAGE][IMAGES][IMG_BYTES];  // 64 KB; the struct sits on a 1024-byte boundary
+    // one ring slot holds a pose-encoder chunk ([128][64] image; hi + lo in split mode) or ONE wide head image (24 KB)
+    static constexpr int SLOT = NPASS == 3 ? 2 * IMG_BYTES : WIDE_BYTES;
+    // ring entries per evaluation: 10 pose-encoder chunks + 4 k-atoms of the wide head image (hi, lo separately)
+    static constexpr int ENTRIES = NCOMMON + 4 * IMAGES;
+    uint8_t ring[NSTAGE][SLOT];               // 64 / 96 KB; the struct sits on a 1024-byte boundary
     uint8_t abuf[IMAGES][4][ATOM_BYTES];      // x / h1 / h2 as A operand (hi, lo), 4 k-atoms each
     float part[CL - 1][9 * RT];               // [peer][c][row] partial outputs, written by the other CTAs of the cluster;
                                               // compute_tq scratch between evaluations
@@ -101,14 +107,22 @@ __device__ __forceinline__ const uint8_t *chunk_src(const float *__restrict__ P,
     return reinterpret_cast<const uint8_t *>(P + TrunkLayout::W_TC) + ((size_t)q * 2 + which) * IMG_BYTES;
 }
 
-// chunk L of the endless per-CTA stream: position i = L % 16 inside an evaluation
+// entry L of the endless per-CTA stream: position i = L % ENTRIES inside an evaluation
 template <int NPASS>
 __device__ __forceinline__ void issue_chunk(Smem<NPASS> &S, const float *__restrict__ P, uint32_t L, uint32_t rank) {
-    constexpr int NST = Smem<NPASS>::NSTAGE, IM = Smem<NPASS>::IMAGES;
-    const uint32_t s = L % NST, i = L % NCHUNK;
-    const uint32_t q = i < NCOMMON ? i : NCOMMON + NRANK * rank + (i - NCOMMON);
-    mbar_arrive_expect_tx(&S.full[s], IM * IMG_BYTES);
-    for (int w = 0; w < IM; ++w) bulk_g2s(S.ring[s][w], chunk_src(P, q, w), IMG_BYTES, &S.full[s]);
+    constexpr int NST = Smem<NPASS>::NSTAGE, IM = Smem<NPASS>::IMAGES, E = Smem<NPASS>::ENTRIES;
+    const uint32_t s = L % NST, i = L % E;
+    if (i < NCOMMON) {
+        mbar_arrive_expect_tx(&S.full[s], IM * IMG_BYTES);
+        for (int w = 0; w < IM; ++w) bulk_g2s(S.ring[s] + w * IMG_BYTES, chunk_src(P, i, w), IMG_BYTES, &S.full[s]);
+    } else {
+        // wide head image of this rank: k-atom kc, hi or lo ([192 n][64 k], TrunkLayout::W_WIDE)
+        const uint32_t j = i - NCOMMON, kc = j / IM, which = j % IM;
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(P + TrunkLayout::W_WIDE) +
+                             ((size_t)((rank * 4 + kc) * 2 + which)) * WIDE_BYTES;
+        mbar_arrive_expect_tx(&S.full[s], WIDE_BYTES);
+        bulk_g2s(S.ring[s], src, WIDE_BYTES, &S.full[s]);
+    }
 }
 
 // one-time setup / teardown (all threads call)
@@ -259,7 +273,7 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
         // ---------------- TMA producer ----------------
         if (lane == 0) {
             mbar_arrive_expect_tx(&S.xfull, (CL - 1) * 9 * RT * sizeof(float));  // this evaluation's incoming partials
-            for (int i = 0; i < NCHUNK; ++i) {
+            for (int i = 0; i < Smem<NPASS>::ENTRIES; ++i) {
                 const uint32_t L = st.loads;
                 mbar_wait(&S.empty[L % NST], ((L / NST) + 1) & 1);
                 issue_chunk<NPASS>(S, P, L, rank);
@@ -289,8 +303,8 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
                 stage = g % NST;
                 mbar_wait(&S.full[stage], (g / NST) & 1);
                 tc_fence_after();
-                b_hi = smem_u32(&S.ring[stage][0][0]);
-                b_lo = smem_u32(&S.ring[stage][NPASS == 3 ? 1 : 0][0]);
+                b_hi = smem_u32(&S.ring[stage][0]);
+                b_lo = b_hi + (NPASS == 3 ? IMG_BYTES : 0);
             };
             auto chunk_done = [&]() {
                 umma_commit(&S.empty[stage]);
@@ -324,8 +338,8 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
                     mbar_wait(&S.full[s0], (g / NST) & 1);
                     mbar_wait(&S.full[s1], ((g + 1) / NST) & 1);
                     tc_fence_after();
-                    const uint32_t b0 = smem_u32(&S.ring[s0][0][0]), b1 = smem_u32(&S.ring[s1][0][0]);
-                    const uint32_t bl0 = smem_u32(&S.ring[s0][NPASS == 3 ? 1 : 0][0]), bl1 = smem_u32(&S.ring[s1][NPASS == 3 ? 1 : 0][0]);
+                    const uint32_t b0 = smem_u32(&S.ring[s0][0]), b1 = smem_u32(&S.ring[s1][0]);
+                    const uint32_t bl0 = b0 + (NPASS == 3 ? IMG_BYTES : 0), bl1 = b1 + (NPASS == 3 ? IMG_BYTES : 0);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
                         const uint32_t ao = kc * ATOM_BYTES + kk * 32, bo = kk * 32, acc = (kc | kk) ? 1u : 0u;
@@ -353,22 +367,31 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
                     }
             }
             umma_commit(&S.dbar[1]);
-            // heads: this rank's 64 columns of each, D2_h -> cols 64h..64h+63 (D0 has been drained)
+            // heads: this rank's 64 columns of each head as ONE N = 192 accumulator, cols 0..191 (D0 has been drained):
+            // the A operand (h2) is read once per k step for all three heads, a third of the shared-memory operand
+            // traffic of three N = 64 chains.  Column 64 h + c of the accumulator = head h, column 64 rank + c.
             mbar_wait(&S.a_ready, st.a_phase); st.a_phase ^= 1;
             tc_fence_after();
-            for (int h = 0; h < 3; ++h) {
-                for (int j = 0; j < 2; ++j) {
-                    next_chunk();
+            for (int kc = 0; kc < 4; ++kc) {
+                next_chunk();   // hi image
 #pragma unroll
-                    for (int sb = 0; sb < 2; ++sb)
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint32_t ao = kc * ATOM_BYTES + kk * 32;
+                    umma_bf16(tmem, make_desc(a_hi + ao), make_desc(b_hi + kk * 32), kIdescN192, (kc | kk) ? 1u : 0u);
+                    if (NPASS == 3) umma_bf16(tmem, make_desc(a_lo + ao), make_desc(b_hi + kk * 32), kIdescN192, 1u);
+                }
+                chunk_done();
+                if (NPASS == 3) {
+                    next_chunk();   // lo image
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            mma(tmem + h * HC, (2 * j + sb) * ATOM_BYTES + kk * 32, sb * (IMG_BYTES / 2) + kk * 32, kIdescN64,
-                                (j | sb | kk) ? 1u : 0u);
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(tmem, make_desc(a_hi + kc * ATOM_BYTES + kk * 32), make_desc(b_hi + kk * 32), kIdescN192, 1u);
                     chunk_done();
                 }
-                umma_commit(&S.dbar[2 + h]);
             }
+            umma_commit(&S.dbar[2]);
+            umma_commit(&S.dbar[3]);
+            umma_commit(&S.dbar[4]);
         }
         __syncwarp();
     } else {

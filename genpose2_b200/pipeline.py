@@ -131,7 +131,9 @@ class PosePipeline:
             st["pts"].copy_(pts); st["center"].copy_(center)
             if init_x is not None:
                 st["init"].copy_(init_x)
-            st["noise"].copy_(real_prior((B * R, 9), T=T0))
+            # warm-up / capture noise from a private generator: building the graph must not consume the global CPU
+            # generator (the first graphed step has to see the same draw as an eager step would)
+            st["noise"].copy_(torch.randn((B * R, 9), generator=torch.Generator().manual_seed(0)))
             sdata = {"pts": st["pts"], "pts_center": st["center"]}
             net.prior_fn = lambda shape, T=1.0: st["noise"]    # device tensor: no host work inside the capture
             try:
