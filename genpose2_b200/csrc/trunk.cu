@@ -6,7 +6,7 @@
 
 #include <cstdlib>
 
-#include "trunk_solo.cuh"
+#include "trunk_solo_t.cuh"
 
 namespace gp {
 
@@ -282,6 +282,46 @@ struct TcSolo {
         }
     }
 };
+// The same shape with the A operand in tensor memory (trunk_solo_t.cuh).
+template <int NPASS>
+struct TcSoloT {
+    static constexpr int RT = tc::RT;
+    static constexpr int NT = tc::NTHREADS;
+    static constexpr int XS = tc::XS;
+    static constexpr int TQW = 768;
+    static constexpr int CLUSTER = 1;
+    using Smem = solot::Smem<NPASS>;
+    using Ctx = solot::State;
+    static constexpr size_t smem_bytes() { return sizeof(Smem) + 1024; }
+    static __device__ __forceinline__ Smem &smem(unsigned char *raw) {
+        return *reinterpret_cast<Smem *>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    }
+    static __device__ __forceinline__ int tile_first() { return blockIdx.x; }
+    static __device__ __forceinline__ int tile_step() { return gridDim.x; }
+    static __device__ __forceinline__ bool writer(const Ctx &) { return true; }
+    static __device__ __forceinline__ size_t replica_index(const Ctx &) { return 0; }
+    static __device__ __forceinline__ void tile_sync() {}
+    static __device__ __forceinline__ float *xin(Smem &S) { return S.x; }
+    static __device__ __forceinline__ float *outp(Smem &S) { return S.x; }
+    static __device__ __forceinline__ float *tq(Smem &S) { return S.tq; }
+    static __device__ __forceinline__ void setup(Smem &S, Ctx &c, const float *P) { solot::setup<NPASS>(S, c, P); }
+    static __device__ __forceinline__ void teardown(Smem &S, Ctx &c) { solot::teardown<NPASS>(S, c); }
+    static __device__ __forceinline__ void stage_tq(const float *P, Smem &S, Ctx &, int ns) { solot::compute_tq_all<NPASS>(P, S, ns); }
+    static __device__ __forceinline__ void begin_tile(Smem &S, Ctx &c, const float *proj, int r0, int N, int rpo) {
+        solot::begin_tile<NPASS>(S, c, proj, r0, N, rpo);
+    }
+    static __device__ __forceinline__ void forward(const float *P, const float *proj, Smem &S, Ctx &c, const float *tq) {
+        solot::forward<NPASS>(P, proj, S, c, tq);
+    }
+    static __device__ __forceinline__ void report(Ctx &c, double *stats) {
+        if (blockIdx.x == 0 && threadIdx.x == 64) {
+            stats[8] = (double)c.cyc_fwd; stats[9] = (double)c.cyc_l1; stats[10] = (double)c.cyc_wait1;
+            stats[11] = (double)c.cyc_epi1; stats[12] = (double)c.cyc_waith; stats[13] = (double)c.cyc_epi2;
+            stats[20] = (double)c.cyc_tail;
+        }
+    }
+};
+static_assert(sizeof(solot::Smem<3>) + 1024 + 768 <= 227 * 1024, "solo (TMEM A) evaluator shared memory exceeds 227 KB");
 // static shared memory of the kernels built on the evaluators (stage constants, per-row t) must fit beside it
 static_assert(sizeof(solo::Smem<3>) + 1024 + 768 <= 227 * 1024, "solo evaluator shared memory exceeds 227 KB");
 static_assert(sizeof(solo::Smem<1>) + 1024 + 768 <= 227 * 1024, "solo evaluator shared memory exceeds 227 KB");
@@ -1145,14 +1185,16 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 // `mode` of the public entries: bits 0..1 = arithmetic (0 FFMA, 1 bf16, 2 split-bf16), GP_MODE_SOLO / GP_MODE_CLUSTER
 // force the shape of the tensor-core evaluator; by default a batch of more 128-row tiles than the GPU holds 4-CTA
 // clusters at once (33 on a B200) runs one CTA per tile.
-static bool use_solo(int mode, int N) {
-    if (mode & GP_MODE_SOLO) return true;
-    if (mode & GP_MODE_CLUSTER) return false;
-    return (N + tc::RT - 1) / tc::RT > 32;
+// 0: cluster shape, 1: one CTA per tile (A operand in shared memory), 2: one CTA per tile, A operand in tensor memory
+static int use_solo(int mode, int N) {
+    if (mode & GP_MODE_SOLO) return (mode & GP_MODE_SMEM_A) ? 1 : 2;
+    if (mode & GP_MODE_CLUSTER) return 0;
+    return (N + tc::RT - 1) / tc::RT > 32 ? ((mode & GP_MODE_SMEM_A) ? 1 : 2) : 0;
 }
 static bool mode_ok(int mode) {
     const int a = mode & 3;
-    return a <= 2 && (mode & ~(3 | GP_MODE_SOLO | GP_MODE_CLUSTER)) == 0 && (mode & (GP_MODE_SOLO | GP_MODE_CLUSTER)) != (GP_MODE_SOLO | GP_MODE_CLUSTER);
+    return a <= 2 && (mode & ~(3 | GP_MODE_SOLO | GP_MODE_CLUSTER | GP_MODE_SMEM_A)) == 0 &&
+           (mode & (GP_MODE_SOLO | GP_MODE_CLUSTER)) != (GP_MODE_SOLO | GP_MODE_CLUSTER);
 }
 
 // Rows per compute thread of the FFMA evaluator (tile = 4x that many rows): the choice that minimises the
@@ -1214,9 +1256,11 @@ static int launch_eval(const void *packed, const float *proj, const float *x, co
                        cudaStream_t st, const char *name) {
     if (N == 0) return GP_OK;
     int rc;
-    const bool solo_shape = use_solo(mode, N);
+    const int solo_shape = use_solo(mode, N);
     mode &= 3;
-    if (mode == 1 && solo_shape) rc = launch_eval_ev<TcSolo<1>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
+    if (mode == 1 && solo_shape == 2) rc = launch_eval_ev<TcSoloT<1>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
+    else if (mode == 2 && solo_shape == 2) rc = launch_eval_ev<TcSoloT<3>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
+    else if (mode == 1 && solo_shape) rc = launch_eval_ev<TcSolo<1>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
     else if (mode == 2 && solo_shape) rc = launch_eval_ev<TcSolo<3>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
     else if (mode == 1) rc = launch_eval_ev<TcEval<1>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
     else if (mode == 2) rc = launch_eval_ev<TcEval<3>, MODE>(packed, proj, x, poses, center, t, N, rpo, out, st);
@@ -1231,7 +1275,7 @@ extern "C" int gp_scorenet_eval(const void *packed, const float *proj, const flo
     GP_REQUIRE(N >= 0 && rows_per_object >= 1, "gp_scorenet_eval: bad sizes");
     if (N == 0) return GP_OK;
     GP_REQUIRE(packed && proj && x && t && score, "gp_scorenet_eval: null pointer");
-    GP_REQUIRE(mode_ok(mode), "gp_scorenet_eval: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05) [| GP_MODE_SOLO / GP_MODE_CLUSTER]");
+    GP_REQUIRE(mode_ok(mode), "gp_scorenet_eval: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05) [| GP_MODE_SOLO / GP_MODE_CLUSTER / GP_MODE_SMEM_A]");
     return launch_eval<0>(packed, proj, x, nullptr, nullptr, t, N, rows_per_object, score, mode, as_stream(s), "gp_scorenet_eval");
 }
 
@@ -1240,7 +1284,7 @@ extern "C" int gp_energy(const void *packed, const float *proj, const double *po
     GP_REQUIRE(N >= 0 && rows_per_object >= 1, "gp_energy: bad sizes");
     if (N == 0) return GP_OK;
     GP_REQUIRE(packed && proj && poses && pts_center && t_rows && energy, "gp_energy: null pointer");
-    GP_REQUIRE(mode_ok(mode), "gp_energy: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05) [| GP_MODE_SOLO / GP_MODE_CLUSTER]");
+    GP_REQUIRE(mode_ok(mode), "gp_energy: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05) [| GP_MODE_SOLO / GP_MODE_CLUSTER / GP_MODE_SMEM_A]");
     return launch_eval<1>(packed, proj, nullptr, poses, pts_center, t_rows, N, rows_per_object, energy, mode, as_stream(s), "gp_energy");
 }
 
@@ -1263,7 +1307,7 @@ static int scorenet_ode_impl(const void *packed, const float *proj, const double
     GP_REQUIRE(N >= 1 && rows_per_object >= 1, "gp_scorenet_ode: bad sizes N=%d rows_per_object=%d", N, rows_per_object);
     GP_REQUIRE(rtol > 0 && atol > 0, "gp_scorenet_ode: tolerances must be positive");
     GP_REQUIRE(traj == nullptr || max_traj >= 1, "gp_scorenet_ode: max_traj < 1");
-    GP_REQUIRE(mode_ok(mode), "gp_scorenet_ode: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05) [| GP_MODE_SOLO / GP_MODE_CLUSTER]");
+    GP_REQUIRE(mode_ok(mode), "gp_scorenet_ode: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05) [| GP_MODE_SOLO / GP_MODE_CLUSTER / GP_MODE_SMEM_A]");
     GP_REQUIRE((t_eval == nullptr) == (dense == nullptr) && (t_eval == nullptr || n_eval >= 1), "gp_scorenet_ode_dense: t_eval / dense / n_eval inconsistent");
     if (workspace_bytes < gp_scorenet_ode_workspace_bytes(N)) {
         set_error("gp_scorenet_ode: workspace too small (%zu < %zu)", workspace_bytes, gp_scorenet_ode_workspace_bytes(N));
@@ -1289,10 +1333,10 @@ static int scorenet_ode_impl(const void *packed, const float *proj, const double
     cudaStream_t st = as_stream(s);
     GP_CUDA(cudaMemsetAsync(a.gbar, 0, 256, st));
     const int sms = num_sms();
-    const bool solo_shape = use_solo(mode, N);
+    const int solo_shape = use_solo(mode, N);
     mode &= 3;
-    if (mode == 1) return solo_shape ? launch_ode<TcSolo<1>>(a, st) : launch_ode<TcEval<1>>(a, st);
-    if (mode == 2) return solo_shape ? launch_ode<TcSolo<3>>(a, st) : launch_ode<TcEval<3>>(a, st);
+    if (mode == 1) return solo_shape == 2 ? launch_ode<TcSoloT<1>>(a, st) : solo_shape ? launch_ode<TcSolo<1>>(a, st) : launch_ode<TcEval<1>>(a, st);
+    if (mode == 2) return solo_shape == 2 ? launch_ode<TcSoloT<3>>(a, st) : solo_shape ? launch_ode<TcSolo<3>>(a, st) : launch_ode<TcEval<3>>(a, st);
     switch (simt_rows_per_thread(N, sms)) {
         case 2: return launch_ode<SimtEval<2>>(a, st);
         case 4: return launch_ode<SimtEval<4>>(a, st);
@@ -1345,7 +1389,7 @@ extern "C" int gp_scorenet_pc(const void *packed, const float *proj, const float
                               size_t workspace_bytes, int mode, gp_stream_t s) {
     GP_REQUIRE(packed && proj && x0 && noise && pts_center && time_steps && mean_x && workspace, "gp_scorenet_pc: null pointer");
     GP_REQUIRE(N >= 1 && rows_per_object >= 1 && num_steps >= 2, "gp_scorenet_pc: bad sizes");
-    GP_REQUIRE(mode_ok(mode), "gp_scorenet_pc: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05) [| GP_MODE_SOLO / GP_MODE_CLUSTER]");
+    GP_REQUIRE(mode_ok(mode), "gp_scorenet_pc: mode must be 0 (fp32 FFMA), 1 (bf16 tcgen05) or 2 (split-bf16 x3 tcgen05) [| GP_MODE_SOLO / GP_MODE_CLUSTER / GP_MODE_SMEM_A]");
     if (workspace_bytes < gp_scorenet_pc_workspace_bytes(N)) {
         set_error("gp_scorenet_pc: workspace too small");
         return GP_ERR_WORKSPACE;
@@ -1361,10 +1405,10 @@ extern "C" int gp_scorenet_pc(const void *packed, const float *proj, const float
     cudaStream_t st = as_stream(s);
     GP_CUDA(cudaMemsetAsync(a.gbar, 0, 256, st));
     const int sms = num_sms();
-    const bool solo_shape = use_solo(mode, N);
+    const int solo_shape = use_solo(mode, N);
     mode &= 3;
-    if (mode == 1) return solo_shape ? launch_pc<TcSolo<1>>(a, st) : launch_pc<TcEval<1>>(a, st);
-    if (mode == 2) return solo_shape ? launch_pc<TcSolo<3>>(a, st) : launch_pc<TcEval<3>>(a, st);
+    if (mode == 1) return solo_shape == 2 ? launch_pc<TcSoloT<1>>(a, st) : solo_shape ? launch_pc<TcSolo<1>>(a, st) : launch_pc<TcEval<1>>(a, st);
+    if (mode == 2) return solo_shape == 2 ? launch_pc<TcSoloT<3>>(a, st) : solo_shape ? launch_pc<TcSolo<3>>(a, st) : launch_pc<TcEval<3>>(a, st);
     switch (simt_rows_per_thread(N, sms)) {
         case 2: return launch_pc<SimtEval<2>>(a, st);
         case 4: return launch_pc<SimtEval<4>>(a, st);

@@ -24,7 +24,7 @@ from . import _lib
 MLP_MODES = {"fp32_ffma": 0, "bf16": 1, "fp32": 2}
 # shape of the tensor-core evaluator (include/genpose_b200.h, gp_mode_flag): "auto" = one CTA per 128-row tile for
 # batches of more than 32 tiles, a 4-CTA cluster per tile below; "solo" / "cluster" force one
-EVAL_SHAPES = {"auto": 0, "solo": 16, "cluster": 32}
+EVAL_SHAPES = {"auto": 0, "solo": 16, "cluster": 32, "solo_smem_a": 16 | 64}
 
 
 def zero_module(module):

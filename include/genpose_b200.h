@@ -215,7 +215,8 @@ GP_API int gp_scorenet_eval(const void *packed, const float *proj, const float *
  * batch has more than 32 tiles (more than the GPU holds clusters at once), clusters otherwise. */
 enum gp_mode_flag {
     GP_MODE_SOLO = 16,    /* force one CTA per tile */
-    GP_MODE_CLUSTER = 32  /* force a 4-CTA cluster per tile */
+    GP_MODE_CLUSTER = 32, /* force a 4-CTA cluster per tile */
+    GP_MODE_SMEM_A = 64   /* one-CTA-per-tile shape: keep the activations (A operand) in shared memory instead of tensor memory */
 };
 
 /* Integrator statistics written by gp_scorenet_ode (device, 16 doubles). */

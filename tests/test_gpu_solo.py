@@ -1,4 +1,5 @@
-"""GPU: the one-CTA-per-tile ("solo") shape of the tensor-core ScoreNet evaluator (csrc/trunk_solo.cuh), forced
+"""GPU: the one-CTA-per-tile ("solo") shape of the tensor-core ScoreNet evaluator -- with the A operand in tensor
+memory (csrc/trunk_solo_t.cuh, the default) and in shared memory (csrc/trunk_solo.cuh, GP_MODE_SMEM_A) -- forced
 through the GP_MODE_SOLO flag of the C ABI at sizes where the default is the cluster shape, against the same
 reference goldens / oracle and with the same gates as the cluster shape; and at a batch where CTAs own several
 tiles (more tiles than SMs) against the cluster shape."""
@@ -20,9 +21,13 @@ def solo_net(seed, mlp_mode, agent_type="score", shape="solo"):
     return net
 
 
+SHAPES = ["solo", "solo_smem_a"]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("mlp_mode,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
-def test_solo_scorenet_eval_matches_oracle(mlp_mode, tol):
-    net = solo_net(100, mlp_mode)
+def test_solo_scorenet_eval_matches_oracle(mlp_mode, tol, shape):
+    net = solo_net(100, mlp_mode, shape=shape)
     trunk = po.Trunk(synthetic.random_gfobjectpose_state_dict(100))
     g = torch.Generator().manual_seed(0)
     B, R = 7, 50   # 350 rows: three tiles, the last one partial; tiles span up to four objects
@@ -43,12 +48,13 @@ def test_solo_scorenet_eval_matches_oracle(mlp_mode, tol):
     assert float((got - want).abs().max() / want.abs().max()) <= tol
 
 
+@pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("mlp_mode", ["fp32", "bf16"])
 @pytest.mark.parametrize("name", ["ode_b4_T055", "ode_track_T025"])
-def test_solo_ode_sampler_matches_reference_golden(name, mlp_mode):
+def test_solo_ode_sampler_matches_reference_golden(name, mlp_mode, shape):
     from genpose2_b200 import samplers
     g = load_golden(name)
-    net = solo_net(int(g["score_seed"]), mlp_mode)
+    net = solo_net(int(g["score_seed"]), mlp_mode, shape=shape)
     R, B = int(g["R"]), int(g["B"])
     feat, center = torch.from_numpy(g["feat"]).cuda(), torch.from_numpy(g["center"]).cuda()
     noise = torch.from_numpy(g["noise"])
@@ -59,7 +65,7 @@ def test_solo_ode_sampler_matches_reference_golden(name, mlp_mode):
                                       device="cuda", eps=1e-5, T=float(g["T0"]), pose_mode="rot_matrix", init_x=init)
     st = samplers.ode_stats()
     rot, trans = pose_errors(x.cpu().numpy(), g["x"])
-    print(f"solo {name} [{mlp_mode}]: rot {rot:.3e} trans {trans:.3e} nfev {st['nfev'] + 1} (reference {int(g['nfev'])})")
+    print(f"{shape} {name} [{mlp_mode}]: rot {rot:.3e} trans {trans:.3e} nfev {st['nfev'] + 1} (reference {int(g['nfev'])})")
     assert st["status"] == 0
     if mlp_mode == "fp32":
         assert st["nfev"] + 1 == int(g["nfev"]) and xs.shape == (B * R, int(g["S"]), 9)
@@ -131,7 +137,7 @@ def test_solo_many_tiles_per_cta_vs_cluster_shape(mlp_mode):
     data = {"pts": torch.zeros(B * R, 1, 3), "pts_center": rep(center, R), "_gp_pts_feat_obj": feat,
             "_gp_rows_per_object": R}
     res = {}
-    for shape in ("solo", "cluster", "auto"):
+    for shape in ("solo", "cluster", "auto", "solo_smem_a"):
         net = solo_net(100, mlp_mode, shape=shape)
         _, x = samplers.cond_ode_sampler(net, dict(data), lambda s, T: noise.clone(), net.sde_fn, device="cuda", T=T0,
                                          pose_mode="rot_matrix", return_trajectory=False)
@@ -144,6 +150,12 @@ def test_solo_many_tiles_per_cta_vs_cluster_shape(mlp_mode):
     trans = np.linalg.norm(a[:, 6:] - b[:, 6:], axis=1)
     print(f"solo vs cluster [{mlp_mode}] 157 tiles: rot max {rot.max():.3e} median {np.median(rot):.3e}; trans max "
           f"{trans.max():.3e}; nfev {res['solo'][1]['nfev']} / {res['cluster'][1]['nfev']}")
+    # the two solo variants differ only in the summation order of the 256 -> 3 output layer
+    c = res["solo_smem_a"][0]
+    rot2 = geodesic_6d(a[:, :6], c[:, :6])
+    trans2 = np.linalg.norm(a[:, 6:] - c[:, 6:], axis=1)
+    print(f"solo (TMEM A) vs solo (smem A): rot max {rot2.max():.3e} trans max {trans2.max():.3e}")
+    assert rot2.max() <= (ROT_TOL if mlp_mode == "fp32" else BF16_ROT_TOL) and trans2.max() <= (TRANS_TOL if mlp_mode == "fp32" else BF16_TRANS_TOL)
     if mlp_mode == "fp32":
         assert res["solo"][1]["nfev"] == res["cluster"][1]["nfev"]
         assert rot.max() <= ROT_TOL and trans.max() <= TRANS_TOL, (rot.max(), trans.max())
