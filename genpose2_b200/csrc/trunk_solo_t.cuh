@@ -28,7 +28,7 @@ using namespace tc;
 constexpr int NCHUNKS = 34;          // 2 (pose_encoder.0) + 8 (pose_encoder.2) + 3 x 8 (heads)
 constexpr int SLOTS = 4;             // objects a tile may span for the shared-memory proj table
 constexpr int NSTAGE = 8;            // ring depth (single 16 KB images)
-constexpr uint32_t COL_A_HI = 0, COL_A_LO = 128, COL_ACC = 256;
+// TMEM columns COL_A_HI / COL_A_LO / COL_ACC and epi_hidden_t come from trunk_tc.cuh (shared with the cluster shape)
 
 template <int NPASS>
 struct Smem {
@@ -146,40 +146,6 @@ __device__ __forceinline__ void begin_tile(Smem<NPASS> &S, State &st, const floa
         float4 *dst = reinterpret_cast<float4 *>(S.pj);
         for (int i = tid; i < st.nslots * 192; i += NTHREADS) dst[i] = __ldg(src + i);
     }
-}
-
-// accumulator columns [acc + c0, acc + c0 + 128) of this thread's row -> relu(. + bias) -> packed bf16 (hi / lo)
-// -> the A operand in TMEM (k = output column)
-template <int NPASS>
-__device__ __forceinline__ void epi_hidden_t(uint32_t lane_addr, uint32_t acc, const float *sbias, int c0) {
-    uint32_t r[2][32];
-    tmem_ld32_nowait(lane_addr + acc + c0, r[0]);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        if (g + 1 < 4) tmem_ld32_nowait(lane_addr + acc + c0 + (g + 1) * 32, r[(g + 1) & 1]);
-        tmem_ld_wait();
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-            const int n0 = c0 + g * 32 + j4 * 4;
-            const float4 b = *reinterpret_cast<const float4 *>(sbias + n0);
-            const float v0 = fmaxf(__uint_as_float(r[g & 1][j4 * 4 + 0]) + b.x, 0.f), v1 = fmaxf(__uint_as_float(r[g & 1][j4 * 4 + 1]) + b.y, 0.f);
-            const float v2 = fmaxf(__uint_as_float(r[g & 1][j4 * 4 + 2]) + b.z, 0.f), v3 = fmaxf(__uint_as_float(r[g & 1][j4 * 4 + 3]) + b.w, 0.f);
-            const __nv_bfloat162 p0 = __floats2bfloat162_rn(v0, v1), p1 = __floats2bfloat162_rn(v2, v3);
-            hi[j4 * 2 + 0] = *reinterpret_cast<const uint32_t *>(&p0);
-            hi[j4 * 2 + 1] = *reinterpret_cast<const uint32_t *>(&p1);
-            if (NPASS == 3) {
-                const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
-                const __nv_bfloat162 l0 = __floats2bfloat162_rn(v0 - f0.x, v1 - f0.y), l1 = __floats2bfloat162_rn(v2 - f1.x, v3 - f1.y);
-                lo[j4 * 2 + 0] = *reinterpret_cast<const uint32_t *>(&l0);
-                lo[j4 * 2 + 1] = *reinterpret_cast<const uint32_t *>(&l1);
-            }
-        }
-        const uint32_t kcol = (uint32_t)(c0 + g * 32) >> 1;   // 32 output columns = 16 packed columns of the next A operand
-        tmem_st16(lane_addr + COL_A_HI + kcol, hi);
-        if (NPASS == 3) tmem_st16(lane_addr + COL_A_LO + kcol, lo);
-    }
-    tmem_st_wait();
 }
 
 // f_theta for the 128 rows in S.x -> S.x [r*9 + c]; `tq` is this stage's t-branch (768 floats in shared memory).

@@ -17,8 +17,12 @@
 //   warp 1      MMA issuer   : one lane issues tcgen05.mma chains (M128, N128 for the encoder, N64 for the
 //                              head slices, K16), accumulators in TMEM, commits to mbarriers
 //   warps 2..9  epilogue     : 256 threads.  Inputs -> bf16 A operand; TMEM -> registers (tcgen05.ld), bias,
-//                              ReLU, bf16 (hi / lo) re-pack into the swizzled A-operand buffers; heads:
-//                              + proj + tq from shared memory, ReLU, 256 -> 3 output layer, cluster exchange.
+//                              ReLU, bf16 (hi / lo) re-pack into the A operand, which lives in TENSOR MEMORY
+//                              (tcgen05.st; the MMAs read it from there): no A buffer in shared memory, so the
+//                              weight ring is 5-6 stages deep; heads: + proj + tq from shared memory, ReLU,
+//                              256 -> 3 output layer, cluster exchange.
+// TMEM map: columns 0..127 A hi (256 k as packed bf16 pairs), 128..255 A lo, 256..511 accumulators (D0 / D1: N = 256;
+// heads: N = 192).
 //
 // NPASS = 1 ("bf16" mode): operands rounded to bf16.
 // NPASS = 3 ("fp32" mode): every operand is split x = hi + lo (two bf16) and each product is accumulated as
@@ -54,19 +58,20 @@ constexpr int MAX_SLOTS = 5;          // objects a tile may span for the shared-
 constexpr uint32_t kIdescN128 = make_idesc_bf16(128, 128);
 constexpr uint32_t kIdescN64 = make_idesc_bf16(128, 64);
 constexpr uint32_t kIdescN192 = make_idesc_bf16(128, NHC);
+constexpr uint32_t COL_A_HI = 0, COL_A_LO = 128, COL_ACC = 256;   // TMEM columns: A operand (hi, lo), accumulators
 static_assert(TrunkLayout::TC_CHUNKS == NCOMMON + CL * NRANK, "packed chunk count");
 static_assert(TrunkLayout::WIDE_IMG_FLOATS * 4 == WIDE_BYTES, "wide head image size");
 
 template <int NPASS>
 struct Smem {
     static constexpr int IMAGES = NPASS == 3 ? 2 : 1;
-    static constexpr int NSTAGE = NPASS == 3 ? 2 : 4;
+    static constexpr int NSTAGE = NPASS == 3 ? 5 : 6;
     // one ring slot holds a pose-encoder chunk ([128][64] image; hi + lo in split mode) or ONE wide head image (24 KB)
     static constexpr int SLOT = NPASS == 3 ? 2 * IMG_BYTES : WIDE_BYTES;
     // ring entries per evaluation: 10 pose-encoder chunks + 4 k-atoms of the wide head image (hi, lo separately)
     static constexpr int ENTRIES = NCOMMON + 4 * IMAGES;
-    uint8_t ring[NSTAGE][SLOT];               // 64 / 96 KB; the struct sits on a 1024-byte boundary
-    uint8_t abuf[IMAGES][4][ATOM_BYTES];      // x / h1 / h2 as A operand (hi, lo), 4 k-atoms each
+    uint8_t ring[NSTAGE][SLOT];               // 160 / 144 KB; the struct sits on a 1024-byte boundary
+    float stage[9 * RT];                      // this CTA's combined partial [c][row], source of the bulk copies to the peers
     float part[CL - 1][9 * RT];               // [peer][c][row] partial outputs, written by the other CTAs of the cluster;
                                               // compute_tq scratch between evaluations
     float4 wo[NHC];                           // output-layer weights of this rank's head columns
@@ -254,6 +259,40 @@ __device__ __forceinline__ void epi_hidden(uint32_t taddr, const float *sbias, i
     }
 }
 
+// accumulator columns [acc + c0, acc + c0 + 128) of this thread's row -> relu(. + bias) -> packed bf16 (hi / lo)
+// -> the A operand in TMEM (k = output column: 32 output columns = 16 packed 32-bit columns)
+template <int NPASS>
+__device__ __forceinline__ void epi_hidden_t(uint32_t lane_addr, uint32_t acc, const float *sbias, int c0) {
+    uint32_t r[2][32];
+    tmem_ld32_nowait(lane_addr + acc + c0, r[0]);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (g + 1 < 4) tmem_ld32_nowait(lane_addr + acc + c0 + (g + 1) * 32, r[(g + 1) & 1]);
+        tmem_ld_wait();
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const int n0 = c0 + g * 32 + j4 * 4;
+            const float4 b = *reinterpret_cast<const float4 *>(sbias + n0);
+            const float v0 = fmaxf(__uint_as_float(r[g & 1][j4 * 4 + 0]) + b.x, 0.f), v1 = fmaxf(__uint_as_float(r[g & 1][j4 * 4 + 1]) + b.y, 0.f);
+            const float v2 = fmaxf(__uint_as_float(r[g & 1][j4 * 4 + 2]) + b.z, 0.f), v3 = fmaxf(__uint_as_float(r[g & 1][j4 * 4 + 3]) + b.w, 0.f);
+            const __nv_bfloat162 p0 = __floats2bfloat162_rn(v0, v1), p1 = __floats2bfloat162_rn(v2, v3);
+            hi[j4 * 2 + 0] = *reinterpret_cast<const uint32_t *>(&p0);
+            hi[j4 * 2 + 1] = *reinterpret_cast<const uint32_t *>(&p1);
+            if (NPASS == 3) {
+                const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
+                const __nv_bfloat162 l0 = __floats2bfloat162_rn(v0 - f0.x, v1 - f0.y), l1 = __floats2bfloat162_rn(v2 - f1.x, v3 - f1.y);
+                lo[j4 * 2 + 0] = *reinterpret_cast<const uint32_t *>(&l0);
+                lo[j4 * 2 + 1] = *reinterpret_cast<const uint32_t *>(&l1);
+            }
+        }
+        const uint32_t kcol = (uint32_t)(c0 + g * 32) >> 1;
+        tmem_st16(lane_addr + COL_A_HI + kcol, hi);
+        if (NPASS == 3) tmem_st16(lane_addr + COL_A_LO + kcol, lo);
+    }
+    tmem_st_wait();
+}
+
 // f_theta for the 128 rows in S.x -> S.x [r*9 + c]; `tq` is this stage's t-branch (NHC floats in shared memory,
 // this rank's columns).  All 320 threads of all CL CTAs of the cluster call; ends with __syncthreads().
 template <int NPASS>
@@ -283,20 +322,19 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
             // one, copy it into their S.part slot (async proxy, completes on their xfull: no thread fences)
             mbar_wait(&S.stage_ready, xph);
             if (st.evals > 0) mbar_wait(&S.xfree, xph ^ 1);
-            const float *stage = reinterpret_cast<const float *>(&S.abuf[0][0][0]);
+            const float *stage = S.stage;
             for (uint32_t d = 0; d < (uint32_t)CL; ++d) {
                 if (d == rank) continue;
                 bulk_s2peer(mapa(smem_u32(&S.part[rank < d ? rank : rank - 1][0]), d), stage, 9 * RT * sizeof(float),
                             mapa(smem_u32(&S.xfull), d));
             }
-            bulk_wait_read();  // the staging area (A-operand buffer) is free again when forward() returns
+            bulk_wait_read();  // the staging area is free again when forward() returns
         }
         __syncwarp();
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
-            const uint32_t a_hi = smem_u32(&S.abuf[0][0][0]);
-            const uint32_t a_lo = smem_u32(&S.abuf[NPASS == 3 ? 1 : 0][0][0]);
+            const uint32_t a_hi = tmem + COL_A_HI, a_lo = tmem + COL_A_LO, acc = tmem + COL_ACC;
             uint32_t b_hi = 0, b_lo = 0, stage = 0;
             auto next_chunk = [&]() {
                 const uint32_t g = st.consumed;
@@ -310,82 +348,72 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
                 umma_commit(&S.empty[stage]);
                 st.consumed += 1;
             };
-            auto mma = [&](uint32_t d, uint32_t ao, uint32_t bo, uint32_t idesc, uint32_t acc) {
-                umma_bf16(d, make_desc(a_hi + ao), make_desc(b_hi + bo), idesc, acc);
+            // the 1 / 3 products of one k step (A columns `ac`: 8 packed TMEM columns = 16 k) against the chunk's B images
+            auto mma = [&](uint32_t d, uint32_t ac, uint32_t bo, uint32_t idesc, uint32_t accum) {
+                umma_bf16_ts(d, a_hi + ac, make_desc(b_hi + bo), idesc, accum);
                 if (NPASS == 3) {
-                    umma_bf16(d, make_desc(a_lo + ao), make_desc(b_hi + bo), idesc, 1u);
-                    umma_bf16(d, make_desc(a_hi + ao), make_desc(b_lo + bo), idesc, 1u);
+                    umma_bf16_ts(d, a_lo + ac, make_desc(b_hi + bo), idesc, 1u);
+                    umma_bf16_ts(d, a_hi + ac, make_desc(b_lo + bo), idesc, 1u);
                 }
             };
-            // pose_encoder.0: K = 16 (9 used), D0 -> cols 0..255
+            // pose_encoder.0: K = 16 (9 used), D0 -> accumulator cols 0..255
             mbar_wait(&S.a_ready, st.a_phase); st.a_phase ^= 1;
             tc_fence_after();
             for (int nh = 0; nh < 2; ++nh) {
                 next_chunk();
-                mma(tmem + nh * 128, 0, 0, kIdescN128, 0u);
+                mma(acc + nh * 128, 0, 0, kIdescN128, 0u);
                 chunk_done();
             }
             umma_commit(&S.dbar[0]);
-            // pose_encoder.2: D1 -> cols 256..511
+            // pose_encoder.2: D1 -> the same accumulator columns (D0 has been read out).  Consecutive MMAs into one
+            // accumulator form a dependent chain (~90 cycles each, an N128 MMA occupies the pipe for 64): the two column
+            // halves of a k-atom are multiplied interleaved, two independent accumulators in flight.
             mbar_wait(&S.a_ready, st.a_phase); st.a_phase ^= 1;
             tc_fence_after();
-            if (NST >= 4) {
-                // Consecutive MMAs into one accumulator form a dependent chain (~90-130 cycles each, an N128 MMA
-                // occupies the pipe for 64): with a deep ring the two column halves of a k-atom are multiplied
-                // interleaved, two independent accumulators in flight.
-                for (int kc = 0; kc < 4; ++kc) {
-                    const uint32_t g = st.consumed, s0 = g % NST, s1 = (g + 1) % NST;
-                    mbar_wait(&S.full[s0], (g / NST) & 1);
-                    mbar_wait(&S.full[s1], ((g + 1) / NST) & 1);
-                    tc_fence_after();
-                    const uint32_t b0 = smem_u32(&S.ring[s0][0]), b1 = smem_u32(&S.ring[s1][0]);
-                    const uint32_t bl0 = b0 + (NPASS == 3 ? IMG_BYTES : 0), bl1 = b1 + (NPASS == 3 ? IMG_BYTES : 0);
+            for (int kc = 0; kc < 4; ++kc) {
+                const uint32_t g = st.consumed, s0 = g % NST, s1 = (g + 1) % NST;
+                mbar_wait(&S.full[s0], (g / NST) & 1);
+                mbar_wait(&S.full[s1], ((g + 1) / NST) & 1);
+                tc_fence_after();
+                const uint32_t b0 = smem_u32(&S.ring[s0][0]), b1 = smem_u32(&S.ring[s1][0]);
+                const uint32_t bl0 = b0 + (NPASS == 3 ? IMG_BYTES : 0), bl1 = b1 + (NPASS == 3 ? IMG_BYTES : 0);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t ao = kc * ATOM_BYTES + kk * 32, bo = kk * 32, acc = (kc | kk) ? 1u : 0u;
-                        umma_bf16(tmem + 256, make_desc(a_hi + ao), make_desc(b0 + bo), kIdescN128, acc);
-                        umma_bf16(tmem + 384, make_desc(a_hi + ao), make_desc(b1 + bo), kIdescN128, acc);
-                        if (NPASS == 3) {
-                            umma_bf16(tmem + 256, make_desc(a_lo + ao), make_desc(b0 + bo), kIdescN128, 1u);
-                            umma_bf16(tmem + 384, make_desc(a_lo + ao), make_desc(b1 + bo), kIdescN128, 1u);
-                            umma_bf16(tmem + 256, make_desc(a_hi + ao), make_desc(bl0 + bo), kIdescN128, 1u);
-                            umma_bf16(tmem + 384, make_desc(a_hi + ao), make_desc(bl1 + bo), kIdescN128, 1u);
-                        }
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint32_t ac = kc * 32 + kk * 8, bo = kk * 32, accum = (kc | kk) ? 1u : 0u;
+                    umma_bf16_ts(acc, a_hi + ac, make_desc(b0 + bo), kIdescN128, accum);
+                    umma_bf16_ts(acc + 128, a_hi + ac, make_desc(b1 + bo), kIdescN128, accum);
+                    if (NPASS == 3) {
+                        umma_bf16_ts(acc, a_lo + ac, make_desc(b0 + bo), kIdescN128, 1u);
+                        umma_bf16_ts(acc + 128, a_lo + ac, make_desc(b1 + bo), kIdescN128, 1u);
+                        umma_bf16_ts(acc, a_hi + ac, make_desc(bl0 + bo), kIdescN128, 1u);
+                        umma_bf16_ts(acc + 128, a_hi + ac, make_desc(bl1 + bo), kIdescN128, 1u);
                     }
-                    umma_commit(&S.empty[s0]);
-                    umma_commit(&S.empty[s1]);
-                    st.consumed = g + 2;
                 }
-            } else {
-                for (int kc = 0; kc < 4; ++kc)
-                    for (int nh = 0; nh < 2; ++nh) {
-                        next_chunk();
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            mma(tmem + 256 + nh * 128, kc * ATOM_BYTES + kk * 32, kk * 32, kIdescN128, (kc | kk) ? 1u : 0u);
-                        chunk_done();
-                    }
+                umma_commit(&S.empty[s0]);
+                umma_commit(&S.empty[s1]);
+                st.consumed = g + 2;
             }
             umma_commit(&S.dbar[1]);
-            // heads: this rank's 64 columns of each head as ONE N = 192 accumulator, cols 0..191 (D0 has been drained):
-            // the A operand (h2) is read once per k step for all three heads, a third of the shared-memory operand
-            // traffic of three N = 64 chains.  Column 64 h + c of the accumulator = head h, column 64 rank + c.
+            // heads: this rank's 64 columns of each head as ONE N = 192 accumulator, accumulator cols 0..191 (D1 has
+            // been read out): the A operand (h2) is read once per k step for all three heads, and an N = 192 MMA occupies
+            // the pipe for 96 cycles >= the accumulate latency, so one chain keeps the pipe busy.
+            // Column 64 h + c of the accumulator = head h, column 64 rank + c.
             mbar_wait(&S.a_ready, st.a_phase); st.a_phase ^= 1;
             tc_fence_after();
             for (int kc = 0; kc < 4; ++kc) {
                 next_chunk();   // hi image
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    const uint32_t ao = kc * ATOM_BYTES + kk * 32;
-                    umma_bf16(tmem, make_desc(a_hi + ao), make_desc(b_hi + kk * 32), kIdescN192, (kc | kk) ? 1u : 0u);
-                    if (NPASS == 3) umma_bf16(tmem, make_desc(a_lo + ao), make_desc(b_hi + kk * 32), kIdescN192, 1u);
+                    const uint32_t ac = kc * 32 + kk * 8;
+                    umma_bf16_ts(acc, a_hi + ac, make_desc(b_hi + kk * 32), kIdescN192, (kc | kk) ? 1u : 0u);
+                    if (NPASS == 3) umma_bf16_ts(acc, a_lo + ac, make_desc(b_hi + kk * 32), kIdescN192, 1u);
                 }
                 chunk_done();
                 if (NPASS == 3) {
                     next_chunk();   // lo image
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
-                        umma_bf16(tmem, make_desc(a_hi + kc * ATOM_BYTES + kk * 32), make_desc(b_hi + kk * 32), kIdescN192, 1u);
+                        umma_bf16_ts(acc, a_hi + kc * 32 + kk * 8, make_desc(b_hi + kk * 32), kIdescN192, 1u);
                     chunk_done();
                 }
             }
@@ -400,8 +428,6 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
         const int row = 32 * (warp & 3) + lane;   // TMEM lane quarter is fixed by warp % 4
         const int half = e >> 2;                  // column half 0 / 1
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-        const uint32_t A_hi = smem_u32(&S.abuf[0][0][0]);
-        const uint32_t A_lo = smem_u32(&S.abuf[NPASS == 3 ? 1 : 0][0][0]);
         const uint32_t dph = st.d_phase;
         st.d_phase ^= 1;
         // Views derived from the dynamic shared array itself: the compiler then knows the address space (LDS,
@@ -432,24 +458,19 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
                 hi[p] = *reinterpret_cast<const uint32_t *>(&h2);
                 lo[p] = *reinterpret_cast<const uint32_t *>(&l2);
             }
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int off = row * 128 + ((j ^ (row & 7)) << 4);
-                sts_u4(A_hi + off, make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]));
-                if (NPASS == 3) sts_u4(A_lo + off, make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]));
-            }
+            tmem_st8(lane_addr + COL_A_HI, hi);
+            if (NPASS == 3) tmem_st8(lane_addr + COL_A_LO, lo);
+            tmem_st_wait();
         }
         tc_fence_before();
-        fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.a_ready);
 
         // h1 = relu(D0 + b1) -> A buffers
         mbar_wait(&S.dbar[0], dph);
         tc_fence_after();
-        epi_hidden<NPASS>(lane_addr, sb1, row, half * 128, A_hi, A_lo);
+        epi_hidden_t<NPASS>(lane_addr, COL_ACC, sb1, half * 128);
         tc_fence_before();
-        fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.a_ready);
         {
@@ -465,9 +486,8 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
             st.cyc_wait1 += t1 - t0;
             t0 = t1;
         }
-        epi_hidden<NPASS>(lane_addr + 256, sb2, row, half * 128, A_hi, A_lo);
+        epi_hidden_t<NPASS>(lane_addr, COL_ACC, sb2, half * 128);
         tc_fence_before();
-        fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.a_ready);
         {
@@ -493,7 +513,7 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
             const int cb = h * HC + half * 32;                      // local column base
             const int gcol = h * 256 + HC * (int)rank + half * 32;  // global head column base
             uint32_t r[32];
-            tmem_ld32(lane_addr + cb, r);
+            tmem_ld32(lane_addr + COL_ACC + cb, r);
             float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
@@ -538,8 +558,8 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
         }
         { const long long t1 = clock64(); st.cyc_x[0] += t1 - tx; tx = t1; }
         if (half == 0) {
-            // stage the row's partial [c][row] in the (now idle) A-operand buffer for the producer thread's bulk copies
-            float *stage = reinterpret_cast<float *>(gp_dyn_smem + (smem_u32(&S.abuf[0][0][0]) - dyn0));
+            // stage the row's partial [c][row] for the producer thread's bulk copies
+            float *stage = reinterpret_cast<float *>(gp_dyn_smem + (smem_u32(S.stage) - dyn0));
 #pragma unroll
             for (int c = 0; c < 9; ++c) stage[c * RT + row] = acc[c];
             fence_proxy_async();

@@ -174,3 +174,51 @@ def test_get_energy_random_T_branch_vs_reference(ref_ns):
     torch.manual_seed(18)
     other = agent.get_energy(dict(data), poses.cuda(), T=None, mode="test", extract_feature=True)
     assert not torch.equal(other, got)
+
+
+def test_integration_stub_under_the_reference_wrappers(ref_ns, tmp_path):
+    """the ctypes stub a maintainer drops in as `pointnet2_cuda.py`.  The code block is taken
+    from INTEGRATION.md itself, installed as the `pointnet2_cuda` module, and the REFERENCE's own pointnet2_utils.py
+    (FurthestPointSampling / GatherOperation / BallQuery / GroupingOperation / QueryAndGroup, unmodified) runs on top of
+    it; results are compared with the same wrappers on the reference's own extension."""
+    import importlib.util
+    import os
+    import re
+    import sys
+    from oracle import ref_shim
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(# pointnet2_cuda.py.*?)```", md, re.S).group(1)
+    code = code.replace("/path/to/genpose2_b200/libgenpose_b200.so", os.path.join(root, "genpose2_b200", "libgenpose_b200.so"))
+    stub_path = tmp_path / "pointnet2_cuda.py"
+    stub_path.write_text(code)
+    spec = importlib.util.spec_from_file_location("pointnet2_cuda_stub", stub_path)
+    stub = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(stub)
+    # a second copy of the reference's wrapper module, bound to the stub instead of the reference ext
+    ref_utils = ref_ns.pointnet2_utils
+    real_ext = sys.modules["pointnet2_cuda"]
+    sys.modules["pointnet2_cuda"] = stub
+    try:
+        spec2 = importlib.util.spec_from_file_location("ref_pointnet2_utils_on_stub", ref_utils.__file__)
+        on_stub = importlib.util.module_from_spec(spec2)
+        spec2.loader.exec_module(on_stub)
+    finally:
+        sys.modules["pointnet2_cuda"] = real_ext
+    assert on_stub.pointnet2 is stub and ref_utils.pointnet2 is real_ext
+    pts, _ = synthetic.make_point_clouds(6, 1024, seed=77, dup_fraction=0.5)
+    xyz = pts.cuda().contiguous()
+    feats = torch.randn(6, 32, 1024, device="cuda")
+    for mod_a, mod_b in ((on_stub, ref_utils),):
+        idx_a, idx_b = mod_a.furthest_point_sample(xyz, 512), mod_b.furthest_point_sample(xyz, 512)
+        assert torch.equal(idx_a, idx_b)
+        flipped = xyz.transpose(1, 2).contiguous()
+        new_a = mod_a.gather_operation(flipped, idx_a).transpose(1, 2).contiguous()
+        new_b = mod_b.gather_operation(flipped, idx_b).transpose(1, 2).contiguous()
+        assert torch.equal(new_a, new_b)
+        bq_a, bq_b = mod_a.ball_query(0.02, 32, xyz, new_a), mod_b.ball_query(0.02, 32, xyz, new_b)
+        assert torch.equal(bq_a, bq_b)
+        assert torch.equal(mod_a.grouping_operation(feats, bq_a), mod_b.grouping_operation(feats, bq_b))
+        ga = mod_a.QueryAndGroup(0.02, 32, use_xyz=True)(xyz, new_a, feats)
+        gb = mod_b.QueryAndGroup(0.02, 32, use_xyz=True)(xyz, new_b, feats)
+        assert torch.equal(ga, gb)
