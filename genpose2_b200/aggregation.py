@@ -12,7 +12,23 @@ import torch
 from . import _lib
 
 
+MAX_HYPOTHESES = 64          # AG_MAXR of csrc/aggregate.cu: hypotheses per object the kernel ranks in one warp
+MAX_RETAIN_CLUSTERED = 32    # AG_MAXK: retained hypotheses when DBSCAN runs (neighbourhoods are 32-bit masks)
+
+
 def _run(poses, energy, retain, clustering, eps, min_samples, want_sorted=False, want_labels=False):
+    """Limits of the kernel that the reference's host loop does not have: at most 64 hypotheses per object, at most 32
+    retained ones when clustering (64 without).  The evaluation scripts use 50 / 20.  Outside them this raises
+    NotImplementedError instead of silently doing something else."""
+    R = poses.shape[1]
+    if R > MAX_HYPOTHESES:
+        raise NotImplementedError(f"aggregation of {R} hypotheses per object: the kernel handles at most {MAX_HYPOTHESES}")
+    if retain > (MAX_RETAIN_CLUSTERED if clustering else MAX_HYPOTHESES):
+        raise NotImplementedError(f"retain_num={retain}: the kernel keeps at most {MAX_RETAIN_CLUSTERED} hypotheses with "
+                                  f"clustering ({MAX_HYPOTHESES} without)")
+    if clustering and min_samples < 1:
+        # sklearn.cluster.DBSCAN(min_samples=0) raises InvalidParameterError (the reference would crash here)
+        raise ValueError(f"clustering_minpts * retain_num = {min_samples} < 1: DBSCAN needs min_samples >= 1")
     poses = _lib.check_cuda(poses.to(torch.float64).contiguous(), "poses", torch.float64)
     energy = _lib.check_cuda(energy.to(poses.device, torch.float32).contiguous(), "energy", torch.float32)
     B, R, D = poses.shape
@@ -28,7 +44,8 @@ def _run(poses, energy, retain, clustering, eps, min_samples, want_sorted=False,
 
 
 def sort_poses_by_energy(poses, energy):
-    """reward.py:131-155 -> (sorted_poses [bs,R,9], sorted_energy [bs,R,2])."""
+    """reward.py:131-155 -> (sorted_poses [bs,R,9], sorted_energy [bs,R,2]).  Equal energies are ranked
+    stable-descending (torch.sort(descending=True) leaves their order unspecified, and its CPU and CUDA kernels differ)."""
     R = poses.shape[1]
     _, _, sorted_p = _run(poses, energy, min(R, 32), False, 0.0, 1, want_sorted=True)
     sorted_energy = torch.sort(energy.to(poses.device), descending=True, dim=1)[0]

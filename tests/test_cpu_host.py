@@ -281,3 +281,17 @@ def test_load_ckpt_reads_a_checkpoint_written_by_the_reference(tmp_path):
             assert torch.equal(got[k].cpu(), want[k].cpu()), k
             if k in sd:
                 assert torch.equal(got[k].cpu(), sd[k]), k
+
+
+def test_aggregation_limits_raise_instead_of_misbehaving():
+    """the aggregation kernel's caps (64 hypotheses, 32 retained with clustering) and DBSCAN's
+    min_samples >= 1 are enforced loudly on the Python side, before any device work."""
+    from genpose2_b200.aggregation import aggregate_pose, sort_poses_by_energy
+    poses = torch.zeros(2, 80, 9, dtype=torch.float64)
+    energy = torch.zeros(2, 80, 2)
+    with pytest.raises(NotImplementedError):
+        sort_poses_by_energy(poses, energy)
+    with pytest.raises(NotImplementedError):
+        aggregate_pose(poses[:, :64], energy[:, :64], eval_repeat_num=64, retain_ratio=0.75)   # 48 retained, clustering on
+    with pytest.raises(ValueError):
+        aggregate_pose(poses[:, :50], energy[:, :50], eval_repeat_num=50, retain_ratio=0.1)    # int(0.1667 * 5) = 0
