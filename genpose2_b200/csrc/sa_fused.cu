@@ -6,16 +6,35 @@
 //   out[g]  = max over the pool_ns rows of group g of relu(H . W2^T + b2)      [rows / pool_ns, c3]
 //
 // The (centre, sample) activation matrices of the reference -- c2 and c3 floats for each of B*npoint*nsample
-// rows -- never exist in HBM: a tile of 128 rows is gathered from the (L2 resident) per-point table P,
-// converted to bf16 (hi / lo) A-operand atoms in shared memory, multiplied on tcgen05 into TMEM, re-packed as
-// the next A operand by the epilogue warps, multiplied again and pooled straight out of TMEM.
+// rows -- never exist in HBM.  Per 128-row tile:
+//   gather   worker warps read P rows by ball-query index (coalesced: 16 lanes per row), subtract Q, ReLU, split to
+//            bf16 (hi / lo) and store swizzled A-operand atoms in shared memory;
+//   GEMM 1   A (shared memory) x W1 chunks -> D (TMEM);
+//   hidden   H = relu(D + b1) -> packed bf16 pairs written straight into TENSOR MEMORY (tcgen05.st): the second GEMM
+//            takes its A operand from TMEM (tcgen05.mma [d], [a_tmem], b_desc), so H never touches shared memory;
+//   GEMM 2   H (TMEM) x W2 chunks -> D (TMEM, the same columns: D of GEMM 1 has been read out);
+//   pool     max over the pool_ns rows of each group = over lanes of a warp (row = TMEM lane): a recursive-halving
+//            butterfly in registers (31 shuffles per 32 x 32 block), bias + ReLU once per pooled value
+//            (relu(max(x) + b) == max(relu(x + b)) bit for bit), coalesced stores.  No shared-memory staging.
+// What the TMEM-resident H buys (round 2): the shared-memory A buffer only holds the GATHERED operand, which GEMM 1 has
+// finished reading long before the tile is done -- so the worker warps gather tile t + 1 while the tensor pipe runs
+// GEMM 2 of tile t (they used to idle there), the buffer is half as large at levels 3-4, and the freed shared memory
+// deepens the weight ring (5-10 single 16 KB images instead of 2 hi+lo stages: the weight stream, ~1.3 k cycles round
+// trip per image, was what bounded GEMM 2 at level 4).  Accumulators are processed in passes of at most 256 columns =
+// two 128-column chunks whose MMA chains are issued interleaved (a chain into one accumulator retires one MMA per ~90
+// cycles, an N = 128 MMA occupies the pipe for 64: two chains keep it busy).
 //
-// CTA = 10 warps, persistent over tiles: warp 0 streams the weight chunks (cp.async.bulk, [<=128 n][64 k]
-// images from the gp_gemm_pack layout) through a shared-memory ring and runs ahead across tiles; warp 1 issues
-// the MMAs (M128, N <= 128 per chunk, K16); warps 2..9 gather / convert / run both epilogues.
+// TMEM map: [0, hcols) H (hi: 32 columns per 64-wide k-atom, then lo in split mode) | [hcols, hcols + DN) accumulators.
+// CTA = NW worker warps + producer + MMA issuer, persistent over tiles: warp 0 streams the weight chunks
+// (cp.async.bulk, [<=128 n][64 k] images from the gp_gemm_pack layout) through a shared-memory ring and runs ahead
+// across tiles; warp 1 issues the MMAs; warps 2.. gather / convert / run both epilogues.
 // NPASS = 1: bf16 operands; NPASS = 3: split-bf16 (hi*hi + lo*hi + hi*lo), fp32-class.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+
+#ifndef GP_SAF_VARIANT
+#define GP_SAF_VARIANT 0
+#endif
 
 namespace gp {
 namespace saf {
@@ -24,7 +43,8 @@ using namespace gp::tc;
 
 constexpr int BM = 128;
 constexpr int ATOM = 128 * 128;   // [128 rows][64 k] bf16
-constexpr int HALF = 128 * 128;   // weight chunk: up to [128 n][64 k] bf16
+constexpr int SLOT = 128 * 128;   // ring slot: one weight image of up to [128 n][64 k] bf16
+constexpr int MAX_NST = 12;
 
 struct Args {
     const float *P;
@@ -44,9 +64,11 @@ struct Args {
     float *pooled;
     int ld_pooled;
     int ntiles;
-    // launch configuration (host): ring stages, bytes per weight image slot, TMEM columns, TMEM column of D2
-    int nst, slot_bytes, tmem_cols, d2col;
-    int chunk_rows;      // output columns per weight chunk: 128, or 64 when shared memory is tight
+    // launch configuration (host)
+    int nst;             // ring slots
+    int tmem_cols;       // allocated TMEM columns (256 or 512)
+    int hcols;           // TMEM columns of H (hi + lo)
+    int dn;              // accumulator columns per pass (128 or 256)
     int bias_smem;       // biases staged in shared memory (else read through L1)
     int tile_in_batch;   // rows_per_batch % 128 == 0: all rows of a tile belong to one batch
     int q_shift;         // log2(q_ns) if q_ns is a power of two, else -1
@@ -56,67 +78,72 @@ template <int NPASS>
 struct Cfg {
     static constexpr int IMAGES = NPASS == 3 ? 2 : 1;
 };
-constexpr int MAX_NST = 4;
 
 __host__ __device__ inline int round16(int n) { return (n + 15) & ~15; }
 __host__ __device__ inline int atoms_of(int k) { return (k + 63) / 64; }
 
-// shared memory carve-up (bytes from a 1024-aligned base): weight ring | A buffer (= pool staging) | biases | barriers
+// shared memory carve-up (bytes from a 1024-aligned base): weight ring | gathered A buffer | biases | barriers
 template <int NPASS>
 struct Layout {
-    int natoms, nst, slot, bias_smem;
-    __host__ __device__ Layout(int c1, int c2, int nst_, int slot_, int bias_smem_)
-        : natoms(atoms_of(c1) > atoms_of(c2) ? atoms_of(c1) : atoms_of(c2)), nst(nst_), slot(slot_), bias_smem(bias_smem_) {}
+    int k1, nst, bias_smem;
+    __host__ __device__ Layout(int c1, int nst_, int bias_smem_) : k1(atoms_of(c1)), nst(nst_), bias_smem(bias_smem_) {}
     __host__ __device__ size_t ring() const { return 0; }
-    __host__ __device__ size_t abuf() const { return (size_t)nst * Cfg<NPASS>::IMAGES * slot; }
-    // the A buffer doubles as the pooling stage (8 x [32][32] f32) once the second GEMM has read it
-    __host__ __device__ size_t abuf_bytes() const {
-        const size_t b = (size_t)Cfg<NPASS>::IMAGES * natoms * ATOM;
-        return b < 8 * 4096 ? 8 * 4096 : b;
-    }
+    __host__ __device__ size_t abuf() const { return (size_t)nst * SLOT; }
+    __host__ __device__ size_t abuf_bytes() const { return (size_t)Cfg<NPASS>::IMAGES * k1 * ATOM; }
     __host__ __device__ size_t bias() const { return abuf() + abuf_bytes(); }
     __host__ __device__ size_t bars() const { return bias() + (bias_smem ? (384 + 512) * sizeof(float) : 0); }
-    __host__ __device__ size_t total() const { return bars() + 256 + 1024; }
+    __host__ __device__ size_t total() const { return bars() + 512 + 1024; }
 };
 
-// Max-pool of one warp's 32 rows x 32 columns block of raw accumulators (v = this lane's row; -inf for rows that
-// do not exist) over groups of `ns` consecutive rows, then bias + ReLU once per pooled value: the bias is per
-// column and x -> relu(x + b) is monotone, so relu(max_r(x_r) + b) == max_r(relu(x_r + b)) bit for bit.
-// Transposed through a swizzled [32][32] shared-memory tile (bank = col ^ row on both sides); lane c reduces
-// column c and stores it -- no cross-lane instructions, coalesced 128-byte stores.
-__device__ __forceinline__ void pool_block(const float (&v)[32], float *stg, int lane, long long grow0, long long R, int ns,
-                                           int nbase, int N, const float *bias, float *pooled, int ld_pooled) {
+// Max-pool of one warp's 32 rows (lane = row; -inf for rows that do not exist) x 32 columns of raw accumulators over
+// groups of NS consecutive rows (= lanes), then bias + ReLU once per pooled value.  Recursive halving over the lanes of
+// a group: at every butterfly step a lane keeps one half of its columns and hands the other half to its partner, so
+// the 32 x 32 block is reduced with 31 shuffles per lane (not 32 x log2 NS) and without shared memory; lane l of a
+// group ends up with the 32 / NS consecutive columns (l % NS) * 32 / NS .. of its group's pooled row (coalesced stores).
+template <int NS>
+__device__ __forceinline__ void pool_block(const uint32_t (&r)[32], bool row_ok, int lane, long long grow0, long long R,
+                                           int nbase, int N, const float *bias, float *pooled, int ld_pooled, bool vec_ok) {
+    float v[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) stg[lane * 32 + (j ^ lane)] = v[j];
-    __syncwarp();
-    const int n = nbase + lane;
-    const float bn = n < N ? bias[n] : 0.f;
-    float m8[4];  // maxima of rows 0-7, 8-15, 16-23, 24-31 of column `lane` (all loads independent)
+    for (int j = 0; j < 32; ++j) v[j] = row_ok ? __uint_as_float(r[j]) : -INFINITY;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        float t[8];
+    for (int bit = NS / 2, h = 16; bit >= 1; bit >>= 1, h >>= 1) {
+        const bool up = (lane & bit) != 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t[i] = stg[(8 * q + i) * 32 + (lane ^ (8 * q + i))];
-        m8[q] = fmaxf(fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3])), fmaxf(fmaxf(t[4], t[5]), fmaxf(t[6], t[7])));
-    }
-    if (n < N) {
-        if (ns == 32) {
-            if (grow0 < R) pooled[(grow0 / 32) * (long long)ld_pooled + n] = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])) + bn, 0.f);
-        } else if (ns == 16) {
-            if (grow0 < R) pooled[(grow0 / 16) * (long long)ld_pooled + n] = fmaxf(fmaxf(m8[0], m8[1]) + bn, 0.f);
-            if (grow0 + 16 < R) pooled[(grow0 / 16 + 1) * (long long)ld_pooled + n] = fmaxf(fmaxf(m8[2], m8[3]) + bn, 0.f);
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (grow0 + 8 * q < R) pooled[(grow0 / 8 + q) * (long long)ld_pooled + n] = fmaxf(m8[q] + bn, 0.f);
+        for (int j = 0; j < h; ++j) {
+            const float mine = up ? v[j + h] : v[j];
+            const float theirs = up ? v[j] : v[j + h];
+            v[j] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, theirs, bit));
         }
     }
-    __syncwarp();
+    constexpr int KEEP = 32 / NS;                 // consecutive columns this lane ends up with
+    const int grp = lane / NS;                    // pooled row of this lane's group inside the 32-row block
+    const long long prow = grow0 / NS + grp;
+    if (grow0 + (long long)grp * NS < R) {
+        const int n0 = nbase + (lane & (NS - 1)) * KEEP;
+        float *dst = pooled + prow * (long long)ld_pooled + n0;
+        float o[KEEP];
+#pragma unroll
+        for (int i = 0; i < KEEP; ++i) o[i] = n0 + i < N ? fmaxf(v[i] + bias[n0 + i], 0.f) : 0.f;
+#if GP_SAF_VARIANT == 2
+        if (o[0] == 12345.f) dst[0] = o[0];
+#else
+        // a lane's KEEP columns are consecutive: one 8- / 16-byte store when the row allows it
+        if (KEEP == 2 && vec_ok && n0 + 1 < N) {
+            *reinterpret_cast<float2 *>(dst) = make_float2(o[0], o[1]);
+        } else if (KEEP == 4 && vec_ok && n0 + 3 < N) {
+            *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < KEEP; ++i)
+                if (n0 + i < N) dst[i] = o[i];
+        }
+#endif
+    }
 }
 
 // NW worker warps (gather / convert / epilogues) + producer + MMA issuer.  NW = 8: one CTA per SM; NW = 4: 192-thread
-// CTAs, two per SM when a CTA needs at most half of the shared memory and 256 TMEM columns -- two tiles in flight per
-// SM, each CTA's serial gather -> MMA -> epilogue -> MMA -> pool chain overlapping the other's.
+// CTAs, two per SM when a CTA needs at most half of the shared memory and 256 TMEM columns.
 template <int NPASS, int NW>
 __global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel(Args a) {
     using C = Cfg<NPASS>;
@@ -128,30 +155,35 @@ __global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel
     const int NST = a.nst;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const Layout<NPASS> L(a.c1, a.c2, a.nst, a.slot_bytes, a.bias_smem);
+    const Layout<NPASS> L(a.c1, a.nst, a.bias_smem);
     uint8_t *ring = base + L.ring();
     uint8_t *abuf = base + L.abuf();
-    float *stage_all = reinterpret_cast<float *>(abuf);
     float *sb1 = reinterpret_cast<float *>(base + L.bias());
     float *sb2 = sb1 + 384;
     const float *b1p = a.bias_smem ? sb1 : a.b1, *b2p = a.bias_smem ? sb2 : a.b2;   // valid for n < c2 / n < c3
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(base + L.bars());
-    unsigned long long *full = bars, *empty = bars + MAX_NST, *a_ready = bars + 2 * MAX_NST, *dbar = bars + 2 * MAX_NST + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_NST + 3);
+    unsigned long long *full = bars, *empty = bars + MAX_NST;
+    unsigned long long *a_ready = bars + 2 * MAX_NST;       // gathered rows of the next tile are in the A buffer (NW arrivals)
+    unsigned long long *d1bar = a_ready + 1;                // a pass of GEMM 1 is complete (commit)
+    unsigned long long *e1_done = a_ready + 2;              // that pass has been read out into H (NW arrivals)
+    unsigned long long *d2bar = a_ready + 3;                // a pass of GEMM 2 is complete (commit)
+    unsigned long long *p_done = a_ready + 4;               // that pass has been pooled (NW arrivals)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 5);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int k1 = atoms_of(a.c1), k2 = atoms_of(a.c2);
     const int bn1 = round16(a.c2), bn2 = round16(a.c3);
-    const int CR = a.chunk_rows;
-    const int nh1 = (bn1 + CR - 1) / CR, nh2 = (bn2 + CR - 1) / CR;
-    const int nper = k1 * nh1 + k2 * nh2;   // weight chunks per tile
+    const int DN = a.dn;
+    const int np1 = (bn1 + DN - 1) / DN, np2 = (bn2 + DN - 1) / DN;     // accumulator passes of the two GEMMs
     const int my_tiles = a.ntiles > (int)blockIdx.x ? (a.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(a_ready, NW);
-        mbar_init(&dbar[0], 1);
-        mbar_init(&dbar[1], 1);
+        mbar_init(d1bar, 1);
+        mbar_init(e1_done, NW);
+        mbar_init(d2bar, 1);
+        mbar_init(p_done, NW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (a.bias_smem) {
@@ -167,72 +199,177 @@ __global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t abuf_a = smem_u32(abuf);
+    const uint32_t h_hi = tmem, h_lo = tmem + (uint32_t)(k2 * 32);   // H: 32 packed columns per k-atom
+    const uint32_t dcol = (uint32_t)a.hcols;                         // accumulators start after H
+
+    // number of 128-column chunks of pass `p` of a GEMM whose (rounded) width is bn, and the rows (= columns) of chunk nh
+    auto pass_chunks = [&](int bn, int p) { const int w = min(DN, bn - p * DN); return (w + 127) / 128; };
+    auto chunk_rows = [&](int bn, int p, int nh) { return min(128, bn - p * DN - nh * 128); };
 
     if (warp == 0) {
         // ---------------- weight producer ----------------
+        // entry order per tile = consumption order: GEMM 1 passes, then GEMM 2 passes; per pass: k-atom c, image
+        // (hi, lo), chunk nh
         if (lane == 0) {
-            const long long total = (long long)my_tiles * nper;
-            for (long long Lc = 0; Lc < total; ++Lc) {
-                const int s = (int)(Lc % NST);
-                if (Lc >= NST) mbar_wait(&empty[s], (uint32_t)((Lc / NST) + 1) & 1);
-                int i = (int)(Lc % nper);
-                const uint8_t *wp;
-                int bn, c, nh, kat;
-                if (i < k1 * nh1) { wp = a.W1p; bn = bn1; kat = k1; c = i / nh1; nh = i % nh1; }
-                else { i -= k1 * nh1; wp = a.W2p; bn = bn2; kat = k2; c = i / nh2; nh = i % nh2; }
-                // gp_gemm_pack layout: n-tiles of 256 columns, per tile and k-chunk one image [bn_tile x 128 B] (hi, lo)
-                const int ncol = nh * CR, jt = ncol >> 8, within = ncol & 255;
-                const int bnj = min(256, bn - 256 * jt);
-                const uint32_t rows = (uint32_t)min(CR, bnj - within);
-                const size_t img = (size_t)bnj * 128;
-                const uint8_t *tile = wp + (size_t)jt * kat * IM * (256 * 128);
-                mbar_arrive_expect_tx(&full[s], IM * rows * 128);
-                for (int w = 0; w < IM; ++w)
-                    bulk_g2s(ring + ((size_t)s * IM + w) * a.slot_bytes, tile + ((size_t)c * IM + w) * img + (size_t)within * 128,
-                             rows * 128, &full[s]);
+            uint32_t slot = 0, wrap = 0;   // ring position of the next entry; `wrap` = how often the ring has been filled
+#ifdef GP_SAF_PROBE
+            long long pw = 0, pt0 = clock64(), nent = 0;
+#endif
+            for (int t = 0; t < my_tiles; ++t) {
+                for (int gm = 0; gm < 2; ++gm) {
+                    const uint8_t *wp = gm ? a.W2p : a.W1p;
+                    const int bn = gm ? bn2 : bn1, kat = gm ? k2 : k1, np = gm ? np2 : np1;
+                    for (int p = 0; p < np; ++p) {
+                        const int nch = pass_chunks(bn, p);
+                        for (int c = 0; c < kat; ++c)
+                            for (int w = 0; w < IM; ++w)
+                                for (int nh = 0; nh < nch; ++nh) {
+#ifdef GP_SAF_PROBE
+                                    const long long w0 = clock64();
+                                    ++nent;
+#endif
+                                    if (wrap) mbar_wait(&empty[slot], (wrap + 1) & 1);
+#ifdef GP_SAF_PROBE
+                                    pw += clock64() - w0;
+#endif
+                                    // gp_gemm_pack layout: n-tiles of 256 columns, per tile and k-chunk one image
+                                    // [bn_tile x 128 B] (hi, lo)
+                                    const int ncol = p * DN + nh * 128, jt = ncol >> 8, within = ncol & 255;
+                                    const int bnj = min(256, bn - 256 * jt);
+                                    const uint32_t rows = (uint32_t)chunk_rows(bn, p, nh);
+                                    const size_t img = (size_t)bnj * 128;
+                                    const uint8_t *tile = wp + (size_t)jt * kat * IM * (256 * 128);
+                                    mbar_arrive_expect_tx(&full[slot], rows * 128);
+                                    bulk_g2s(ring + (size_t)slot * SLOT, tile + ((size_t)c * IM + w) * img + (size_t)within * 128,
+                                             rows * 128, &full[slot]);
+                                    if (++slot == (uint32_t)NST) { slot = 0; ++wrap; }
+                                }
+                    }
+                }
             }
+#ifdef GP_SAF_PROBE
+            if (blockIdx.x == 0 && my_tiles)
+                printf("saf producer: entries/tile %lld, cycles/tile %lld of which waiting for a free slot %lld (nst %d)\n", nent / my_tiles,
+                       (clock64() - pt0) / my_tiles, pw / my_tiles, NST);
+#endif
         }
         __syncwarp();
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
-        if (lane == 0) {
-            const uint32_t a_hi = abuf_a, a_lo = abuf_a + (NPASS == 3 ? L.natoms * ATOM : 0);
-            long long consumed = 0;
-            uint32_t a_phase = 0;
-            auto gemm = [&](int kat, int nh_cnt, int bn, uint32_t dcol) {
-                for (int c = 0; c < kat; ++c)
-                    for (int nh = 0; nh < nh_cnt; ++nh) {
-                        const int s = (int)(consumed % NST);
-                        mbar_wait(&full[s], (uint32_t)(consumed / NST) & 1);
-                        tc_fence_after();
-                        const uint32_t b_hi = smem_u32(ring + (size_t)s * IM * a.slot_bytes);
-                        const uint32_t b_lo = b_hi + (NPASS == 3 ? a.slot_bytes : 0);
-                        const int ncol = nh * CR;
-                        const uint32_t idesc = make_idesc_bf16(128, (uint32_t)min(CR, min(256, bn - (ncol & ~255)) - (ncol & 255)));
-                        const uint32_t d = tmem + dcol + ncol;
+        // The whole warp runs this code with identical state; one elected lane issues each MMA / commit (tc_ptx.cuh).
+        {
+            const uint32_t a_hi = abuf_a, a_lo = abuf_a + (NPASS == 3 ? k1 * ATOM : 0);
+            const uint32_t ring_a = smem_u32(ring);
+            uint32_t slot = 0, fph = 0;     // ring position of the next entry to consume, parity of its `full` barrier
+            uint32_t ph_a = 0, ph_e1 = 0, ph_p = 0;
+#ifdef GP_SAF_PROBE
+            long long mw_full = 0, mw_other = 0, mt0 = clock64();
+#endif
+            // Everything the MMA thread touches stays in (uniform) registers: no arrays, no 64-bit arithmetic -- an MMA
+            // whose descriptors come from local memory is issued through a R2UR waterfall, ~400 cycles apiece.
+            // next ring entry: wait for it, return its shared-memory address; `done` hands it back to the producer
+            auto take = [&](uint32_t &s_out) -> uint32_t {
+                const uint32_t sl = slot;
+                mbar_wait(&full[sl], fph);
+                if (++slot == (uint32_t)NST) { slot = 0; fph ^= 1; }
+                s_out = sl;
+                return ring_a + sl * SLOT;
+            };
+            // one accumulator pass: kat k-atoms, one or two chunks of <= 128 columns (two chunks = two interleaved chains)
+            auto pass = [&](const bool second, const int kat, const int bn, const int p) {
+                const bool two = pass_chunks(bn, p) == 2;
+                const uint32_t id0 = make_idesc_bf16(128, (uint32_t)chunk_rows(bn, p, 0));
+                const uint32_t id1 = two ? make_idesc_bf16(128, (uint32_t)chunk_rows(bn, p, 1)) : id0;
+                const uint32_t d0 = tmem + dcol, d1 = d0 + 128;
+                for (int c = 0; c < kat; ++c) {
+                    uint32_t s0 = 0, s1 = 0, b0, b1 = 0;
+#ifdef GP_SAF_PROBE
+                    long long w0 = clock64();
+#endif
+                    b0 = take(s0);            // hi images of the chunk(s)
+                    if (two) b1 = take(s1);
+                    tc_fence_after();
+#ifdef GP_SAF_PROBE
+                    mw_full += clock64() - w0;
+#endif
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const uint32_t ao = c * ATOM + kk * 32, bo = kk * 32;
-                            umma_bf16(d, make_desc(a_hi + ao), make_desc(b_hi + bo), idesc, (c | kk) ? 1u : 0u);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t accum = (c | kk) ? 1u : 0u;
+                        const uint32_t ah = second ? h_hi + c * 32 + kk * 8 : a_hi + c * ATOM + kk * 32;
+                        const uint32_t al = second ? h_lo + c * 32 + kk * 8 : a_lo + c * ATOM + kk * 32;
+                        if (second) {
+                            umma_bf16_ts_w(d0, ah, make_desc(b0 + kk * 32), id0, accum);
+                            if (two) umma_bf16_ts_w(d1, ah, make_desc(b1 + kk * 32), id1, accum);
                             if (NPASS == 3) {
-                                umma_bf16(d, make_desc(a_lo + ao), make_desc(b_hi + bo), idesc, 1u);
-                                umma_bf16(d, make_desc(a_hi + ao), make_desc(b_lo + bo), idesc, 1u);
+                                umma_bf16_ts_w(d0, al, make_desc(b0 + kk * 32), id0, 1u);
+                                if (two) umma_bf16_ts_w(d1, al, make_desc(b1 + kk * 32), id1, 1u);
+                            }
+                        } else {
+                            umma_bf16_w(d0, make_desc(ah), make_desc(b0 + kk * 32), id0, accum);
+                            if (two) umma_bf16_w(d1, make_desc(ah), make_desc(b1 + kk * 32), id1, accum);
+                            if (NPASS == 3) {
+                                umma_bf16_w(d0, make_desc(al), make_desc(b0 + kk * 32), id0, 1u);
+                                if (two) umma_bf16_w(d1, make_desc(al), make_desc(b1 + kk * 32), id1, 1u);
                             }
                         }
-                        umma_commit(&empty[s]);
-                        ++consumed;
                     }
+                    umma_commit_w(&empty[s0]);
+                    if (two) umma_commit_w(&empty[s1]);
+                    if (NPASS == 3) {
+#ifdef GP_SAF_PROBE
+                        w0 = clock64();
+#endif
+                        b0 = take(s0);        // lo images
+                        if (two) b1 = take(s1);
+                        tc_fence_after();
+#ifdef GP_SAF_PROBE
+                        mw_full += clock64() - w0;
+#endif
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint32_t ah = second ? h_hi + c * 32 + kk * 8 : a_hi + c * ATOM + kk * 32;
+                            if (second) {
+                                umma_bf16_ts_w(d0, ah, make_desc(b0 + kk * 32), id0, 1u);
+                                if (two) umma_bf16_ts_w(d1, ah, make_desc(b1 + kk * 32), id1, 1u);
+                            } else {
+                                umma_bf16_w(d0, make_desc(ah), make_desc(b0 + kk * 32), id0, 1u);
+                                if (two) umma_bf16_w(d1, make_desc(ah), make_desc(b1 + kk * 32), id1, 1u);
+                            }
+                        }
+                        umma_commit_w(&empty[s0]);
+                        if (two) umma_commit_w(&empty[s1]);
+                    }
+                }
             };
             for (int t = 0; t < my_tiles; ++t) {
-                mbar_wait(a_ready, a_phase); a_phase ^= 1;   // gathered rows are in the A buffer
+#ifdef GP_SAF_PROBE
+                const long long w0 = clock64();
+#endif
+                mbar_wait(a_ready, ph_a); ph_a ^= 1;        // gathered rows of tile t are in the A buffer
                 tc_fence_after();
-                gemm(k1, nh1, bn1, 0);
-                umma_commit(&dbar[0]);
-                mbar_wait(a_ready, a_phase); a_phase ^= 1;   // hidden activations are in the A buffer
+#ifdef GP_SAF_PROBE
+                mw_other += clock64() - w0;
+#endif
+                for (int p = 0; p < np1; ++p) {
+                    if (p > 0) { mbar_wait(e1_done, ph_e1); ph_e1 ^= 1; tc_fence_after(); }   // accumulators read out
+                    pass(false, k1, bn1, p);
+                    umma_commit_w(d1bar);
+                }
+                mbar_wait(e1_done, ph_e1); ph_e1 ^= 1;     // H is complete in TMEM, accumulators free
                 tc_fence_after();
-                gemm(k2, nh2, bn2, (uint32_t)a.d2col);
-                umma_commit(&dbar[1]);
+                for (int q = 0; q < np2; ++q) {
+                    if (q > 0) { mbar_wait(p_done, ph_p); ph_p ^= 1; tc_fence_after(); }
+                    pass(true, k2, bn2, q);
+                    umma_commit_w(d2bar);
+                }
+                mbar_wait(p_done, ph_p); ph_p ^= 1;        // last pass pooled: accumulators free for the next tile
+                tc_fence_after();
             }
+#ifdef GP_SAF_PROBE
+            if (blockIdx.x == 0 && my_tiles && lane == 0)
+                printf("saf mma: cycles/tile %lld, waiting for weights %lld, waiting for a_ready %lld\n", (clock64() - mt0) / my_tiles,
+                       mw_full / my_tiles, mw_other / my_tiles);
+#endif
         }
         __syncwarp();
     } else {
@@ -243,13 +380,15 @@ __global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel
         const int half = e >> 2;                   // which 32-column groups (odd / even)
         const int row = 32 * quarter + lane;       // epilogue row
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * quarter) << 16);
-        const uint32_t A_hi = abuf_a, A_lo = abuf_a + (NPASS == 3 ? L.natoms * ATOM : 0);
+        const uint32_t A_hi = abuf_a, A_lo = abuf_a + (NPASS == 3 ? k1 * ATOM : 0);
         const int jv = w & 15;                     // float4 inside a 64-float chunk
         const int rsub = w >> 4;                   // row inside a pass
         const int ns = a.pool_ns;
-        // Rows rsub + RSTEP p (p < RP) of a tile belong to this thread's gather.  Their ball-query indices for tile
-        // t + 1 are requested while tile t is in its epilogues and only consumed at the next gather: the index load is
-        // the head of the gather's latency chain.
+        // pooled rows can take 16-byte vector stores (every row start and every 32-column block is 16-byte aligned)
+        const bool vec_ok = (reinterpret_cast<uintptr_t>(a.pooled) & 15) == 0 && (a.ld_pooled & 3) == 0;
+        // Rows rsub + RSTEP p (p < RP) of a tile belong to this thread's gather.  Their ball-query indices for the
+        // next tile are requested early and only consumed at the gather: the index load is the head of the gather's
+        // latency chain.
         int gi[RP];
         auto request = [&](int t) {
             const long long row0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * BM;
@@ -260,16 +399,12 @@ __global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel
                 if (t < my_tiles && gr < a.R) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(gi[p]) : "l"(a.gidx + gr));
             }
         };
-        request(0);
-        long long cy[6] = {0, 0, 0, 0, 0, 0};
-        long long tt = clock64();
-        auto lap = [&](int i) { const long long n = clock64(); cy[i] += n - tt; tt = n; };
-        for (int t = 0; t < my_tiles; ++t) {
+        // gather k-atoms [kc_lo, kc_hi) of tile t into the A buffer (its indices are in gi[]): thread handles rows
+        // rsub + RSTEP p (p < RP), 16 bytes of every 64-float chunk, 8 rows at a time; `last` publishes the tile
+        auto gather = [&](int t, int kc_lo, int kc_hi, bool last) {
             const long long row0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * BM;
-            const uint32_t dph = (uint32_t)t & 1;
-            // ---- gather: thread handles rows rsub + RSTEP p (p < RP), 16 bytes of every 64-float chunk, 8 rows at a time ----
             const int tile_batch = (int)(row0 / a.rows_per_batch);
-#pragma unroll 1
+#pragma unroll
             for (int pb = 0; pb < RP; pb += 8) {
                 long long src[8];
                 int qoff[8];
@@ -282,7 +417,7 @@ __global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel
                     src[p] = gidx >= 0 ? ((long long)batch * a.n_src + gidx) * a.ldp : -1;
                     qoff[p] = gidx >= 0 ? qrow * a.ldq : 0;
                 }
-                for (int kc = 0; kc < k1; ++kc) {
+                for (int kc = kc_lo; kc < kc_hi; ++kc) {
                     const int k = kc * 64 + 4 * jv;
                     const bool k_ok = k < a.c1;
                     float4 pv[8], qv[8];
@@ -311,75 +446,97 @@ __global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel
                     }
                 }
             }
-            tc_fence_before();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_ready);
-            lap(0);
+            if (last) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_ready);
+            }
+        };
+        long long cy[7] = {0, 0, 0, 0, 0, 0, 0};
+        long long tt = clock64();
+        auto lap = [&](int i) { const long long n = clock64(); cy[i] += n - tt; tt = n; };
+        uint32_t ph_d1 = 0, ph_d2 = 0;
+        // the gather of the next tile is spread over the passes of the second GEMM (one part before each pooling pass),
+        // so that the tensor pipe always has the next pass to run while the workers gather
+        const int nparts = np2 < k1 ? np2 : k1;
+        request(0);
+        gather(0, 0, k1, true);
+        lap(0);
+        for (int t = 0; t < my_tiles; ++t) {
+            const long long row0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * BM;
             request(t + 1);
             lap(1);
-
-            // ---- hidden layer: H = relu(D1 + b1) -> A buffer (zero beyond c2, up to whole k-atoms) ----
-            mbar_wait(&dbar[0], dph);
-            tc_fence_after();
-            lap(2);
-            for (int g = half; g < 2 * k2; g += HALVES) {
-                uint32_t r[32];
-                tmem_ld32(lane_addr + g * 32, r);
+            // ---- hidden layer: H = relu(D + b1) -> TMEM A operand of the second GEMM (zero beyond c2, up to whole k-atoms) ----
+            for (int p = 0; p < np1; ++p) {
+                mbar_wait(d1bar, ph_d1); ph_d1 ^= 1;
+                tc_fence_after();
+                lap(2);
+                const int g_lo = p * DN / 32, g_hi = min(2 * k2, (p + 1) * DN / 32);
+                for (int g = g_lo + half; g < g_hi; g += HALVES) {
+                    uint32_t hi[16], lo[16];
+                    if (g * 32 < bn1) {
+                        uint32_t r[32];
+                        tmem_ld32(lane_addr + dcol + (g * 32 - p * DN), r);
 #pragma unroll
-                for (int j8 = 0; j8 < 4; ++j8) {
-                    const int n0 = g * 32 + j8 * 8;
-                    float v[8];
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const int n0 = g * 32 + j4 * 4;
+                            float v[4];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = n0 + j < a.c2 ? fmaxf(__uint_as_float(r[j8 * 8 + j]) + b1p[n0 + j], 0.f) : 0.f;
-                    const __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-                    const __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
-                    uint4 pk;
-                    pk.x = *reinterpret_cast<const uint32_t *>(&p0); pk.y = *reinterpret_cast<const uint32_t *>(&p1);
-                    pk.z = *reinterpret_cast<const uint32_t *>(&p2); pk.w = *reinterpret_cast<const uint32_t *>(&p3);
-                    const uint32_t off = (n0 >> 6) * ATOM + row * 128 + ((((n0 & 63) >> 3) ^ (row & 7)) << 4);
-                    sts_u4(A_hi + off, pk);
-                    if (NPASS == 3) {
-                        const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
-                        const float2 f2 = __bfloat1622float2(p2), f3 = __bfloat1622float2(p3);
-                        const __nv_bfloat162 l0 = __floats2bfloat162_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2bfloat162_rn(v[2] - f1.x, v[3] - f1.y);
-                        const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[4] - f2.x, v[5] - f2.y), l3 = __floats2bfloat162_rn(v[6] - f3.x, v[7] - f3.y);
-                        uint4 pl;
-                        pl.x = *reinterpret_cast<const uint32_t *>(&l0); pl.y = *reinterpret_cast<const uint32_t *>(&l1);
-                        pl.z = *reinterpret_cast<const uint32_t *>(&l2); pl.w = *reinterpret_cast<const uint32_t *>(&l3);
-                        sts_u4(A_lo + off, pl);
+                            for (int j = 0; j < 4; ++j) v[j] = n0 + j < a.c2 ? fmaxf(__uint_as_float(r[j4 * 4 + j]) + b1p[n0 + j], 0.f) : 0.f;
+                            const __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+                            hi[j4 * 2 + 0] = *reinterpret_cast<const uint32_t *>(&p0);
+                            hi[j4 * 2 + 1] = *reinterpret_cast<const uint32_t *>(&p1);
+                            if (NPASS == 3) {
+                                const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
+                                const __nv_bfloat162 l0 = __floats2bfloat162_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2bfloat162_rn(v[2] - f1.x, v[3] - f1.y);
+                                lo[j4 * 2 + 0] = *reinterpret_cast<const uint32_t *>(&l0);
+                                lo[j4 * 2 + 1] = *reinterpret_cast<const uint32_t *>(&l1);
+                            }
+                        }
+                    } else {   // padding columns of the last k-atom beyond the accumulator width: zeros
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { hi[j] = 0u; lo[j] = 0u; }
                     }
+                    tmem_st16(lane_addr + (uint32_t)(g * 16), hi);                       // H hi: column n / 2
+                    if (NPASS == 3) tmem_st16(lane_addr + (uint32_t)(k2 * 32 + g * 16), lo);
                 }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(e1_done);
+                lap(3);
             }
-            tc_fence_before();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_ready);
-
-            // ---- output layer + max-pool over the pool_ns rows of each group ----
-            lap(3);
-            mbar_wait(&dbar[1], dph);
-            tc_fence_after();
-            lap(4);
+            // ---- output layer + max-pool over the pool_ns rows of each group; before each pooling pass a part of the NEXT
+            // tile is gathered while the tensor pipe runs that pass of the second GEMM (GEMM 1 of this tile has retired) ----
             const long long grow = row0 + row;
             const bool row_ok = grow < a.R;
-            for (int g = half; g * 32 < a.c3; g += HALVES) {
-                uint32_t r[32];
-                tmem_ld32(lane_addr + a.d2col + g * 32, r);
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = row_ok ? __uint_as_float(r[j]) : -INFINITY;
-                pool_block(v, stage_all + e * 1024, lane, row0 + 32 * quarter, a.R, ns, g * 32, a.c3, b2p, a.pooled, a.ld_pooled);
+            for (int q = 0; q < np2; ++q) {
+                if (t + 1 < my_tiles && q < nparts) gather(t + 1, q * k1 / nparts, (q + 1) * k1 / nparts, q == nparts - 1);
+                lap(0);
+                mbar_wait(d2bar, ph_d2); ph_d2 ^= 1;
+                tc_fence_after();
+                lap(4);
+                const int g_lo = q * DN / 32, g_hi = min((a.c3 + 31) / 32, (q + 1) * DN / 32);
+                for (int g = g_lo + half; g < g_hi; g += HALVES) {
+                    uint32_t r[32];
+                    tmem_ld32(lane_addr + dcol + (g * 32 - q * DN), r);
+#ifdef GP_SAF_PROBE
+                    { const long long n = clock64(); cy[6] += n - tt; }
+#endif
+                    if (ns == 32) pool_block<32>(r, row_ok, lane, row0 + 32 * quarter, a.R, g * 32, a.c3, b2p, a.pooled, a.ld_pooled, vec_ok);
+                    else if (ns == 16) pool_block<16>(r, row_ok, lane, row0 + 32 * quarter, a.R, g * 32, a.c3, b2p, a.pooled, a.ld_pooled, vec_ok);
+                    else pool_block<8>(r, row_ok, lane, row0 + 32 * quarter, a.R, g * 32, a.c3, b2p, a.pooled, a.ld_pooled, vec_ok);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_done);
+                lap(5);
             }
-            tc_fence_before();
-            // the pooling stage lives in the A buffer: nobody gathers the next tile into it before all warps are done
-            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
-            lap(5);
         }
 #ifdef GP_SAF_PROBE
         if (blockIdx.x == 0 && tid == 64)
-            printf("saf c=(%d,%d,%d) ns=%d tiles=%d per tile: gather %lld locate %lld wait_d0 %lld hidden %lld wait_d1 %lld pool %lld\n", a.c1, a.c2,
-                   a.c3, a.pool_ns, my_tiles, cy[0] / my_tiles, cy[1] / my_tiles, cy[2] / my_tiles, cy[3] / my_tiles, cy[4] / my_tiles, cy[5] / my_tiles);
+            printf("saf c=(%d,%d,%d) ns=%d tiles=%d per tile: gather %lld locate %lld wait_d0 %lld hidden %lld wait_d1 %lld pool %lld (cumulative to each ldtm %lld)\n", a.c1, a.c2,
+                   a.c3, a.pool_ns, my_tiles, cy[0] / my_tiles, cy[1] / my_tiles, cy[2] / my_tiles, cy[3] / my_tiles, cy[4] / my_tiles, cy[5] / my_tiles, cy[6] / my_tiles);
 #endif
     }
     tc_fence_before();
@@ -387,57 +544,56 @@ __global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel
     if (warp == 1) tmem_dealloc(tmem, (uint32_t)a.tmem_cols);
 }
 
+// TMEM / shared-memory plan of a shape.  Returns false when it does not fit (the caller reports GP_ERR_UNSUPPORTED).
+template <int NPASS>
+static bool plan(Args &a, bool two_per_sm, size_t smem_budget) {
+    constexpr int IM = Cfg<NPASS>::IMAGES;
+    const int k2 = atoms_of(a.c2);
+    a.tmem_cols = two_per_sm ? 256 : 512;
+    a.hcols = k2 * 32 * IM;
+    const int avail = a.tmem_cols - a.hcols;
+    if (avail < 128) return false;
+    a.dn = avail >= 256 ? 256 : 128;
+    for (int bias_smem = 1; bias_smem >= 0; --bias_smem) {
+        a.bias_smem = bias_smem;
+        const size_t fixed = Layout<NPASS>(a.c1, 0, bias_smem).total();
+        if (fixed + 2 * (size_t)SLOT * IM > smem_budget) continue;
+        const int nst = (int)((smem_budget - fixed) / SLOT);
+        a.nst = nst > MAX_NST ? MAX_NST : nst;
+        return true;
+    }
+    return false;
+}
+
 template <int NPASS>
 static int launch(Args a, cudaStream_t st) {
-    constexpr int IM = Cfg<NPASS>::IMAGES;
-    const int bn1 = round16(a.c2), bn2 = round16(a.c3);
-    // D2 reuses D1's TMEM columns (D1 is drained before the second GEMM starts)
-    a.tmem_cols = (bn1 > 256 || bn2 > 256) ? 512 : 256;
-    a.d2col = 0;
     a.tile_in_batch = a.rows_per_batch % BM == 0;
     a.q_shift = -1;
     for (int sh = 0; sh < 31; ++sh)
         if ((1 << sh) == a.q_ns) a.q_shift = sh;
-    // One CTA per SM (its 10 warps are allocated as 12, two CTAs would leave 80 registers per thread).  The weight
-    // ring wants >= 2 stages: 128-column chunks and biases in shared memory if that fits, else 64-column chunks,
-    // else biases through L1.
-    const size_t full_sm = 227 * 1024;
-    int nst = 0;
-    size_t fixed = 0, stage = 0;
-    const int tries[3][2] = {{128, 1}, {64, 1}, {64, 0}};
-    for (int t = 0; t < 3; ++t) {
-        const int widest = bn1 > bn2 ? bn1 : bn2;
-        a.chunk_rows = tries[t][0];
-        a.bias_smem = tries[t][1];
-        a.slot_bytes = (widest < a.chunk_rows ? widest : a.chunk_rows) * 128;
-        fixed = Layout<NPASS>(a.c1, a.c2, 0, a.slot_bytes, a.bias_smem).total();
-        stage = (size_t)IM * a.slot_bytes;
-        nst = fixed + stage <= full_sm ? (int)((full_sm - fixed) / stage) : 0;
-        if (nst >= 2) break;
-    }
-    GP_REQUIRE(nst >= 1, "gp_sa_mlp2_fused: layer widths need %zu bytes of shared memory", fixed + stage);
-    a.nst = nst > MAX_NST ? MAX_NST : nst;
-    // two 192-thread CTAs per SM when one of them (with at least one ring stage of 128-column chunks) fits in half
-    // of the shared memory and 256 TMEM columns
-    const size_t half_sm = 113 * 1024;
-    if (a.tmem_cols == 256 && a.chunk_rows == 128 && fixed + stage <= half_sm) {
-        const int nst2 = (int)((half_sm - fixed) / stage);
-        a.nst = nst2 > MAX_NST ? MAX_NST : nst2;
-        const Layout<NPASS> L2(a.c1, a.c2, a.nst, a.slot_bytes, a.bias_smem);
+    // two 192-thread CTAs per SM when one of them fits in half of the shared memory and 256 TMEM columns with both
+    // GEMMs in a single accumulator pass (the narrow levels: their tiles are gather / pool bound, a second CTA doubles
+    // the warps that hide those latencies)
+    Args a2 = a;
+    if (plan<NPASS>(a2, true, 113 * 1024) && round16(a.c2) <= a2.dn && round16(a.c3) <= a2.dn) {
+        const Layout<NPASS> L2(a2.c1, a2.nst, a2.bias_smem);
         auto kern = sa_mlp2_kernel<NPASS, 4>;
         GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         const int cap = 2 * num_sms();
-        kern<<<a.ntiles < cap ? a.ntiles : cap, 6 * 32, L2.total(), st>>>(a);
+        kern<<<a2.ntiles < cap ? a2.ntiles : cap, 6 * 32, L2.total(), st>>>(a2);
         GP_CHECK_LAUNCH("gp_sa_mlp2_fused");
         return GP_OK;
     }
-    const Layout<NPASS> L(a.c1, a.c2, a.nst, a.slot_bytes, a.bias_smem);
+    if (!plan<NPASS>(a, false, 227 * 1024)) {
+        set_error("gp_sa_mlp2_fused: widths (%d, %d, %d) do not fit tensor / shared memory", a.c1, a.c2, a.c3);
+        return GP_ERR_UNSUPPORTED;
+    }
+    const Layout<NPASS> L(a.c1, a.nst, a.bias_smem);
     auto kern = sa_mlp2_kernel<NPASS, 8>;
-    const size_t smem = L.total();
     GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const int grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
-    kern<<<grid, 10 * 32, smem, st>>>(a);
+    kern<<<grid, 10 * 32, L.total(), st>>>(a);
     GP_CHECK_LAUNCH("gp_sa_mlp2_fused");
     return GP_OK;
 }

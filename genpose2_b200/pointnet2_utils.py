@@ -285,16 +285,15 @@ def sa_mlp2_fused(P, n_src, gidx, rows_per_batch, Q, q_ns, packed1, bias1, c1, c
 
 
 def sa_mlp2_fused_fits(c1, c2, c3, npass, pool_ns):
-    """Shapes for which the fused kernel is used: its own limits (c2 <= 384, shared-memory budget) and, for hidden
-    widths above 256 in split-bf16 mode, the measured fact that the hi + lo A buffer then leaves room only for
-    64-column weight chunks and the two-kernel path (gather GEMM + pooled GEMM) is faster (0.37 vs 0.48 ms at
-    level 4); in bf16 mode the buffer is half as large and the fused kernel wins."""
-    if c1 % 4 or c1 > 256 or c2 > (384 if npass == 1 else 256) or c3 > 512 or pool_ns not in (8, 16, 32):
+    """Shapes the fused kernel takes (the plan of csrc/sa_fused.cu): H = relu(layer 2) lives in tensor memory as packed
+    bf16 (32 columns per 64-wide k-atom, hi + lo in split mode) next to at least 128 accumulator columns, and the
+    gathered A operand plus a ring of at least two weight chunks (hi + lo) must fit in shared memory."""
+    if c1 % 4 or c1 > 256 or c2 > 384 or c3 > 512 or pool_ns not in (8, 16, 32):
         return False
     images = 2 if npass == 3 else 1
-    natoms = max((c1 + 63) // 64, (c2 + 63) // 64)
-    slot = min(64, (max(c2, c3) + 15) // 16 * 16) * 128   # the smallest configuration the launcher falls back to
-    return images * slot + max(images * natoms * 16384, 32768) + 256 + 1024 <= 227 * 1024
+    if 512 - ((c2 + 63) // 64) * 32 * images < 128:
+        return False
+    return images * ((c1 + 63) // 64) * 16384 + 2 * images * 16384 + 2048 + 1536 <= 227 * 1024
 
 
 class QueryAndGroup(nn.Module):

@@ -59,15 +59,16 @@ def test_encoder_gemm_engines_vs_cpu_restatement(mode, tol):
                                         ((128, 196, 256), 32, 100),   # fused, level-3 widths, partial last tile
                                         ((64, 64, 128), 8, 128),      # fused, pool over 8
                                         ((256, 256, 512), 16, 64),    # fused, level-4 widths (two output n-tiles)
-                                        ((256, 384, 512), 16, 64)])   # hidden width > 256: gather GEMM + pooled GEMM (faster than
-                                                                      # the fused kernel with the tiny weight chunks that would fit)
+                                        ((256, 384, 512), 16, 64),    # hidden width > 256: accumulator passes of 128 columns in split mode
+                                        ((64, 64, 128), 32, 200),     # two CTAs per SM shape, partial last tile
+                                        ((128, 130, 250), 8, 96)])    # widths that are not multiples of 16 / 64
 def test_hoisted_scale_matches_direct_scale(npass, tol, spec, ns, M):
     """the hoisted first layer + gather loader (+ fused layers 2, 3 and max-pool where the widths allow) vs the
     direct (gather rows, 3 GEMMs, max) evaluation in float64"""
     from genpose2_b200 import pointnet2_utils as pu
     from genpose2_b200.pointnet2 import SharedMLP
     B, N, C = 3, 256, 96
-    assert pu.sa_mlp2_fused_fits(*spec, npass, ns) == (spec[1] <= (384 if npass == 1 else 256))
+    assert pu.sa_mlp2_fused_fits(*spec, npass, ns)    # every encoder shape is fused (H in tensor memory), both modes
     g = torch.Generator().manual_seed(4)
     pts, _ = synthetic.make_point_clouds(B, N, seed=21)
     xyz = pts.cuda()
