@@ -44,6 +44,8 @@ SIGNATURES = {
     "gp_ball_query": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
     "gp_ball_query2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p,
                                c_float, c_int, c_void_p, c_void_p]),
+    "gp_ball_query2_tails": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p,
+                                     c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "gp_group": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gp_query_group": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p]),
@@ -54,6 +56,9 @@ SIGNATURES = {
                                 ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "gp_sa_small_mlp_hostw": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p),
                                 ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "gp_sa_small_mlp_hostw_tail": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p),
+                                ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "gp_zero": (c_int, [c_void_p, c_size_t, c_void_p]),
     "gp_gemm_packed_bytes": (c_size_t, [c_int, c_int, c_int]),
     "gp_gemm_pack": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gp_gemm_bias_relu": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
@@ -64,6 +69,8 @@ SIGNATURES = {
                                          c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                          c_void_p, c_int, c_void_p]),
     "gp_centre_term": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "gp_centre_term_tail": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                    c_void_p, c_int, c_void_p]),
     "gp_sa_mlp2_fused": (c_int, [c_void_p, c_int, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_int, c_int,
                                  c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                  c_int, c_void_p]),

@@ -39,3 +39,10 @@ extern "C" int gp_version(void) { return 1; }
 extern "C" const char *gp_last_error(void) { return gp::last_error_buf(); }
 extern "C" long long gp_launch_count(void) { return gp::t_launches; }
 extern "C" void gp_launch_count_reset(void) { gp::t_launches = 0; }
+
+extern "C" int gp_zero(void *dst, size_t bytes, gp_stream_t s) {
+    if (bytes == 0) return GP_OK;
+    GP_REQUIRE(dst, "gp_zero: null pointer");
+    GP_CUDA(cudaMemsetAsync(dst, 0, bytes, gp::as_stream(s)));
+    return GP_OK;
+}

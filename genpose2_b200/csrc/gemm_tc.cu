@@ -419,11 +419,14 @@ namespace gp {
 namespace gemm {
 // Q[r][k] = sum_j xyz[r][j] * Wt[j][k] - b[k] for k < c1, zero up to ldq: the per-centre term of a hoisted first layer
 __global__ void centre_term_kernel(const float *__restrict__ xyz, long long rows, const float *__restrict__ Wt,
-                                   const float *__restrict__ b, int c1, float *__restrict__ Q, int ldq) {
+                                   const float *__restrict__ b, int c1, float *__restrict__ Q, int ldq,
+                                   const float *__restrict__ tail_src, float *__restrict__ tail_dst, int ld_tail) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * ldq) return;
     const long long r = i / ldq;
     const int k = (int)(i - r * ldq);
+    // by-product: the centre's [x y z 0] row into the tail of this level's buffer
+    if (tail_dst && k < 4) tail_dst[r * ld_tail + k] = __ldg(tail_src + r * 4 + k);
     float v = 0.f;
     if (k < c1) {
         const float x = __ldg(xyz + r * 3), y = __ldg(xyz + r * 3 + 1), z = __ldg(xyz + r * 3 + 2);
@@ -441,8 +444,21 @@ extern "C" int gp_centre_term(const float *new_xyz, long long rows, const float 
     if (rows == 0) return GP_OK;
     GP_REQUIRE(new_xyz && w0_xyz_t && b0 && Q, "gp_centre_term: null pointer");
     const long long total = rows * ldq;
-    gemm::centre_term_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(s)>>>(new_xyz, rows, w0_xyz_t, b0, c1, Q, ldq);
+    gemm::centre_term_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(s)>>>(new_xyz, rows, w0_xyz_t, b0, c1, Q, ldq,
+                                                                                            nullptr, nullptr, 0);
     GP_CHECK_LAUNCH("gp_centre_term");
+    return GP_OK;
+}
+
+extern "C" int gp_centre_term_tail(const float *new_xyz, long long rows, const float *w0_xyz_t, const float *b0, int c1,
+                                   float *Q, int ldq, const float *tail_src, float *tail_dst, int ld_tail, gp_stream_t s) {
+    GP_REQUIRE(rows >= 0 && c1 >= 1 && ldq >= c1 && ldq >= 4, "gp_centre_term_tail: bad sizes");
+    if (rows == 0) return GP_OK;
+    GP_REQUIRE(new_xyz && w0_xyz_t && b0 && Q && tail_src && tail_dst && ld_tail >= 4, "gp_centre_term_tail: null pointer");
+    const long long total = rows * ldq;
+    gemm::centre_term_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(s)>>>(new_xyz, rows, w0_xyz_t, b0, c1, Q, ldq,
+                                                                                            tail_src, tail_dst, ld_tail);
+    GP_CHECK_LAUNCH("gp_centre_term_tail");
     return GP_OK;
 }
 

@@ -278,11 +278,20 @@ constexpr int BQ_CHUNK = 3072;                  // points staged per pass (48 KB
 // branches per point; an earlier warp-per-centre version of this
 // kernel (ballot + popc compaction) was latency-bound on its ballot -> count -> branch chain
 // (116 us for level 1 at 64 objects, 1 % of HBM bandwidth, profiles/README.md).
+// Optional by-products of the scan for the encoder's level buffers (one thread owns one centre): the centre relative
+// to a per-object shift, and the [x y z 0] tail row (relative or absolute) the next level's GEMM rows end with.
+struct BqTails {
+    const float *shift;   // [B,3] or nullptr
+    float *rel;           // [B,M,3] = new_xyz - shift, or nullptr
+    float *tail;          // [B,M,4] = [rel | 0] (tail_abs == 0) or [new_xyz | 0], or nullptr
+    int tail_abs;
+};
+
 template <bool TWO>
 __global__ void __launch_bounds__(BQ_THREADS)
 ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz, int N, int M,
                   float r0sq, int ns0, int *__restrict__ idx0, float r1sq, int ns1,
-                  int *__restrict__ idx1) {
+                  int *__restrict__ idx1, BqTails tails) {
     extern __shared__ __align__(16) float4 s_pts4[];  // [CH] (x, y, z, -)
     const int CH = min(N, BQ_CHUNK);
     const int b = blockIdx.y;
@@ -295,6 +304,15 @@ ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ x
     if (active) {
         const float *p = new_xyz + ((size_t)b * M + c) * 3;
         cx = __ldg(p + 0); cy = __ldg(p + 1); cz = __ldg(p + 2);
+        if (tails.rel || tails.tail) {
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+            if (tails.shift) { sx = __ldg(tails.shift + b * 3); sy = __ldg(tails.shift + b * 3 + 1); sz = __ldg(tails.shift + b * 3 + 2); }
+            const float rx = cx - sx, ry = cy - sy, rz = cz - sz;
+            const size_t bc = (size_t)b * M + c;
+            if (tails.rel) { tails.rel[bc * 3] = rx; tails.rel[bc * 3 + 1] = ry; tails.rel[bc * 3 + 2] = rz; }
+            if (tails.tail)
+                *reinterpret_cast<float4 *>(tails.tail + bc * 4) = tails.tail_abs ? make_float4(cx, cy, cz, 0.f) : make_float4(rx, ry, rz, 0.f);
+        }
     }
     int *o0 = idx0 + ((size_t)b * M + (active ? c : 0)) * ns0;
     int *o1 = TWO ? idx1 + ((size_t)b * M + (active ? c : 0)) * ns1 : nullptr;
@@ -350,14 +368,14 @@ ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ x
 
 template <bool TWO>
 static int launch_bq(const float *new_xyz, const float *xyz, int B, int N, int M, float r0,
-                     int ns0, int *idx0, float r1, int ns1, int *idx1, cudaStream_t st) {
+                     int ns0, int *idx0, float r1, int ns1, int *idx1, cudaStream_t st, BqTails tails = BqTails{nullptr, nullptr, nullptr, 0}) {
     const int CH = N < BQ_CHUNK ? N : BQ_CHUNK;
     size_t smem = (size_t)((CH + 31) & ~31) * sizeof(float4);
     dim3 grid((M + BQ_THREADS - 1) / BQ_THREADS, B);
     // radius2 = radius * radius in float32 (ball_query_gpu.cu:23)
     const float r0sq = r0 * r0, r1sq = r1 * r1;
     ball_query_kernel<TWO><<<grid, BQ_THREADS, smem, st>>>(new_xyz, xyz, N, M, r0sq, ns0, idx0,
-                                                              r1sq, ns1, idx1);
+                                                              r1sq, ns1, idx1, tails);
     GP_CHECK_LAUNCH("gp_ball_query");
     return GP_OK;
 }
@@ -381,6 +399,19 @@ extern "C" int gp_ball_query2(const float *new_xyz, const float *xyz, int B, int
     GP_REQUIRE(B <= 65535, "gp_ball_query2: B=%d > 65535", B);
     return launch_bq<true>(new_xyz, xyz, B, N, M, radius0, nsample0, idx0, radius1, nsample1, idx1,
                            as_stream(s));
+}
+
+extern "C" int gp_ball_query2_tails(const float *new_xyz, const float *xyz, int B, int N, int M,
+                                    float radius0, int nsample0, int32_t *idx0, float radius1,
+                                    int nsample1, int32_t *idx1, const float *shift, float *rel, float *tail,
+                                    int tail_absolute, gp_stream_t s) {
+    GP_REQUIRE(new_xyz && xyz && idx0 && idx1, "gp_ball_query2_tails: null pointer");
+    GP_REQUIRE(B >= 0 && N >= 1 && M >= 0 && nsample0 >= 1 && nsample1 >= 1, "gp_ball_query2_tails: bad sizes");
+    GP_REQUIRE(!tail || ((uintptr_t)tail & 15) == 0, "gp_ball_query2_tails: tail must be 16-byte aligned");
+    if (B == 0 || M == 0) return GP_OK;
+    GP_REQUIRE(B <= 65535, "gp_ball_query2_tails: B=%d > 65535", B);
+    return launch_bq<true>(new_xyz, xyz, B, N, M, radius0, nsample0, idx0, radius1, nsample1, idx1,
+                           as_stream(s), BqTails{shift, rel, tail, tail_absolute});
 }
 
 // ------------------------------------------------------------------------------------------
@@ -686,7 +717,7 @@ template <int C1, int C2, int C3, int NS>
 __global__ void __launch_bounds__(256)
 sa_small_const_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz, const int *__restrict__ idx,
                       int N, int M, long long rows_total, const __grid_constant__ SaSmallConst<C1, C2, C3> W,
-                      float *__restrict__ out, int ld_out) {
+                      float *__restrict__ out, int ld_out, const float *__restrict__ tail_src, int tail_col) {
     const int tid = threadIdx.x, lane = tid & 31;
     const long long row = (long long)blockIdx.x * 256 + tid;
     const bool ok = row < rows_total;
@@ -713,12 +744,15 @@ sa_small_const_kernel(const float *__restrict__ xyz, const float *__restrict__ n
         float *dst = out + bp * (long long)ld_out;
 #pragma unroll
         for (int q = 0; q < C3 / GL; ++q) dst[q * GL + (lane % GL)] = keep[q];
+        // the centre's [x y z 0] row for the tail of the level buffer (what the next level's GEMM rows end with)
+        if (tail_src && (lane % GL) < 4) dst[tail_col + (lane % GL)] = __ldg(tail_src + bp * 4 + (lane % GL));
     }
 }
 
 template <int C1, int C2, int C3>
 static int launch_sa_small_const(const float *xyz, const float *new_xyz, const int *idx, int B, int N, int M, int ns,
-                                 const float *const *w, const float *const *b, float *out, int ld_out, cudaStream_t st) {
+                                 const float *const *w, const float *const *b, float *out, int ld_out, cudaStream_t st,
+                                 const float *tail_src = nullptr, int tail_col = 0) {
     SaSmallConst<C1, C2, C3> W;   // host weights [Cout][Cin] -> [k][n]
     for (int n = 0; n < C1; ++n) { for (int k = 0; k < 3; ++k) W.w0[k * C1 + n] = w[0][n * 3 + k]; W.b0[n] = b[0][n]; }
     for (int n = 0; n < C2; ++n) { for (int k = 0; k < C1; ++k) W.w1[k * C2 + n] = w[1][n * C1 + k]; W.b1[n] = b[1][n]; }
@@ -726,9 +760,9 @@ static int launch_sa_small_const(const float *xyz, const float *new_xyz, const i
     const long long rows = (long long)B * M * ns;
     const unsigned grid = (unsigned)((rows + 255) / 256);
     if (ns == 16)
-        sa_small_const_kernel<C1, C2, C3, 16><<<grid, 256, 0, st>>>(xyz, new_xyz, idx, N, M, rows, W, out, ld_out);
+        sa_small_const_kernel<C1, C2, C3, 16><<<grid, 256, 0, st>>>(xyz, new_xyz, idx, N, M, rows, W, out, ld_out, tail_src, tail_col);
     else
-        sa_small_const_kernel<C1, C2, C3, 32><<<grid, 256, 0, st>>>(xyz, new_xyz, idx, N, M, rows, W, out, ld_out);
+        sa_small_const_kernel<C1, C2, C3, 32><<<grid, 256, 0, st>>>(xyz, new_xyz, idx, N, M, rows, W, out, ld_out, tail_src, tail_col);
     GP_CHECK_LAUNCH("gp_sa_small_mlp_hostw");
     return GP_OK;
 }
@@ -775,5 +809,23 @@ extern "C" int gp_sa_small_mlp_hostw(const float *xyz, const float *new_xyz, con
     if (C1 == 32 && C2 == 32 && C3 == 64)
         return gp::launch_sa_small_const<32, 32, 64>(xyz, new_xyz, idx, B, N, M, nsample, host_weights, host_biases, out, ld_out, gp::as_stream(s));
     gp::set_error("gp_sa_small_mlp_hostw: channel spec %d-%d-%d is not instantiated (16-16-32, 32-32-64)", C1, C2, C3);
+    return GP_ERR_UNSUPPORTED;
+}
+
+extern "C" int gp_sa_small_mlp_hostw_tail(const float *xyz, const float *new_xyz, const int32_t *idx, int B, int N, int M,
+                                          int nsample, const float *const *host_weights, const float *const *host_biases,
+                                          int C1, int C2, int C3, float *out, int ld_out, const float *tail_src,
+                                          int tail_col, gp_stream_t s) {
+    GP_REQUIRE(B >= 0 && N >= 1 && M >= 0 && (nsample == 16 || nsample == 32), "gp_sa_small_mlp_hostw_tail: nsample must be 16 or 32");
+    if ((long long)B * M == 0) return GP_OK;
+    GP_REQUIRE(xyz && new_xyz && idx && host_weights && host_biases && out && ld_out >= C3,
+               "gp_sa_small_mlp_hostw_tail: null pointer / bad ld_out");
+    GP_REQUIRE(!tail_src || (tail_col >= 0 && tail_col + 4 <= ld_out), "gp_sa_small_mlp_hostw_tail: the tail does not fit the row");
+    for (int i = 0; i < 3; ++i) GP_REQUIRE(host_weights[i] && host_biases[i], "gp_sa_small_mlp_hostw_tail: null layer %d", i);
+    if (C1 == 16 && C2 == 16 && C3 == 32)
+        return gp::launch_sa_small_const<16, 16, 32>(xyz, new_xyz, idx, B, N, M, nsample, host_weights, host_biases, out, ld_out, gp::as_stream(s), tail_src, tail_col);
+    if (C1 == 32 && C2 == 32 && C3 == 64)
+        return gp::launch_sa_small_const<32, 32, 64>(xyz, new_xyz, idx, B, N, M, nsample, host_weights, host_biases, out, ld_out, gp::as_stream(s), tail_src, tail_col);
+    gp::set_error("gp_sa_small_mlp_hostw_tail: channel spec %d-%d-%d is not instantiated (16-16-32, 32-32-64)", C1, C2, C3);
     return GP_ERR_UNSUPPORTED;
 }

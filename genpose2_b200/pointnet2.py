@@ -180,7 +180,7 @@ class SharedMLP(nn.Module):
         pu.gemm_bias_relu(h2, t["p2"], t["b2"], t["c3"], t["c2"], npass, pool_ns=ns, pooled_out=out)
         return out
 
-    def forward_rows_pooled(self, rows, groups, nsample, out, gemm_mode, feat_first=False):
+    def forward_rows_pooled(self, rows, groups, nsample, out, gemm_mode, feat_first=False, zeroed=False):
         """rows (R, ld) -> SharedMLP -> max over `nsample` rows per group, written into `out` (groups, Cout).
         gemm_mode: "bf16x3" (tcgen05, split-bf16, fp32-class) or "bf16" (tcgen05).
         feat_first: the rows are [feat | xyz | 0] (the encoder's level buffers) instead of [xyz | feat]."""
@@ -191,7 +191,8 @@ class SharedMLP(nn.Module):
             if i + 1 < len(layers):
                 h = pu.gemm_bias_relu(h, packed, b, N, K, npass)
             else:
-                out.zero_()
+                if not zeroed:
+                    out.zero_()
                 pu.gemm_bias_relu(h, packed, b, N, K, npass, pool_ns=nsample, pooled_out=out)
         return out
 
@@ -255,6 +256,11 @@ class PointnetSAModuleMSG(nn.Module):
             off = 0
             hoist = feat_cl is not None and tc and feat_cl.shape[2] % 4 == 0
             P_all = Q_all = None
+            # [x y z 0] of the centres for the tail of the level buffer: written by a kernel of this level as a by-product
+            tail = None
+            if pad_rows:
+                tail = geometry[3] if len(geometry) > 3 else torch.nn.functional.pad(new_xyz, (0, 1))
+            tail_written = False
             if hoist:
                 shifted = len(geometry) > 5      # compute_geometry's per-object shift (see there)
                 q_xyz = geometry[4] if shifted else new_xyz
@@ -268,7 +274,9 @@ class PointnetSAModuleMSG(nn.Module):
                     mf = self._merged_first_layer(npass)
                     if mf is not None:
                         P_all = pu.gemm_linear(pts_rows, mf["p0"], mf["n"], mf["k0"], npass)
-                        Q_all = pu.centre_term(q_xyz.reshape(B * M, 3), mf["w0_xyz_t"], mf["b0"], P_all.shape[1])
+                        Q_all = pu.centre_term(q_xyz.reshape(B * M, 3), mf["w0_xyz_t"], mf["b0"], P_all.shape[1],
+                                               tail=tail, tail_dst=None if tail is None else out2d[:, C:C + 4])
+                        tail_written = tail is not None
             col = 0
             for i, mlp in enumerate(self.mlps):
                 if hoist and mlp.n_layers == 3:
@@ -286,20 +294,21 @@ class PointnetSAModuleMSG(nn.Module):
                 if (feat_cl is None and tc and self.nsamples[i] in (16, 32)
                         and spec in ((16, 16, 32), (32, 32, 64))):
                     # first level: the whole scale in one FP32 kernel (channels too narrow for tensor cores)
-                    pu.sa_small_mlp_hostw(xyz, new_xyz, bq[i], mlp._folded_layers_host(), out2d[:, off:off + couts[i]])
+                    first = tail is not None and not tail_written
+                    pu.sa_small_mlp_hostw(xyz, new_xyz, bq[i], mlp._folded_layers_host(), out2d[:, off:off + couts[i]],
+                                          tail=tail if first else None, tail_col=C - off)
+                    tail_written = tail_written or first
                     off += couts[i]
                     continue
                 rows = pu.group_rows(xyz, new_xyz, feat_cl, bq[i], pad_to=4 if tc else 1)
                 mlp.forward_rows_pooled(rows, B * M, self.nsamples[i], out2d[:, off:off + couts[i]], self.gemm_mode)
                 off += couts[i]
-            if pad_rows:
-                tail = geometry[3] if len(geometry) > 3 else torch.nn.functional.pad(new_xyz, (0, 1))
+            if pad_rows and not tail_written:
                 out_full[..., C:].copy_(tail)  # [x y z 0] of the centres
             res = (new_xyz, out, geometry)
             return res + (out2d if pad_rows else None,) if return_rows else res
         # GroupAll (pointnet2_utils.py:306-328): every point of the level is one sample of a single group
         N = xyz.shape[1]
-        out = torch.empty((B, 1, C), dtype=torch.float32, device=xyz.device)
         if not (N % 32 == 0 or 32 % N == 0):
             raise NotImplementedError(
                 f"GroupAll over {N} points: the pooled tensor-core GEMM needs N to divide or be a multiple of 32 "
@@ -314,9 +323,10 @@ class PointnetSAModuleMSG(nn.Module):
                 parts.append(torch.zeros((B, N, 4 - width % 4), dtype=torch.float32, device=xyz.device))
             rows = torch.cat(parts, dim=-1).reshape(B * N, -1)
             gm = self.gemm_mode
+        out = pu.zeros((B, 1, C), xyz.device)   # the pooled GEMMs take the max into a zero-initialised output
         off = 0
         for i, mlp in enumerate(self.mlps):
-            mlp.forward_rows_pooled(rows, B, N, out.view(B, -1)[:, off:off + couts[i]], gm, feat_first=feat_first)
+            mlp.forward_rows_pooled(rows, B, N, out.view(B, -1)[:, off:off + couts[i]], gm, feat_first=feat_first, zeroed=True)
             off += couts[i]
         res = (None, out, geometry)
         return res + (None,) if return_rows else res
@@ -372,11 +382,11 @@ class Pointnet2ClsMSG(nn.Module):
             # each level samples the previous level's centres: an FPS-ordered cloud, whose FPS is its own prefix
             # unless the earlier sampling hit an exact tie (pointnet2_utils.furthest_point_sample_chain)
             idx, new_xyz, tie_free = pu.furthest_point_sample_chain(xyz, sa.npoint, tie_free)
-            rel = new_xyz - shift
-            # tail of this level's buffer = the xyz columns the NEXT level reads: shifted for a hoisted level, absolute
-            # for the GroupAll level (its SharedMLP sees the coordinates themselves, pointnet2_utils.py:321-326)
-            tail = torch.nn.functional.pad(rel if k + 1 < n_levels else new_xyz, (0, 1))   # [x y z 0]
-            geometry.append((idx, new_xyz, pu.ball_query2(sa.radii, sa.nsamples, xyz, new_xyz), tail, rel, shift))
+            # rel = new_xyz - shift and the tail of this level's buffer = the [x y z 0] columns the NEXT level reads
+            # (shifted for a hoisted level, absolute for the GroupAll level: its SharedMLP sees the coordinates
+            # themselves, pointnet2_utils.py:321-326) come out of the ball-query launch
+            bq, rel, tail = pu.ball_query2_tails(sa.radii, sa.nsamples, xyz, new_xyz, shift, k + 1 >= n_levels)
+            geometry.append((idx, new_xyz, bq, tail, rel, shift))
             xyz = new_xyz
         return geometry
 

@@ -97,6 +97,25 @@ def ball_query2(radii, nsamples, xyz: torch.Tensor, new_xyz: torch.Tensor):
     return idx0, idx1
 
 
+def ball_query2_tails(radii, nsamples, xyz: torch.Tensor, new_xyz: torch.Tensor, shift: torch.Tensor, tail_absolute: bool):
+    """ball_query2 plus the encoder's per-centre by-products from the same launch (gp_ball_query2_tails):
+    returns ((idx0, idx1), rel [B,M,3] = new_xyz - shift, tail [B,M,4] = [rel | 0] or [new_xyz | 0])."""
+    _lib.check_cuda(xyz, "xyz", torch.float32)
+    _lib.check_cuda(new_xyz, "new_xyz", torch.float32)
+    _lib.check_cuda(shift, "shift", torch.float32)
+    B, N, _ = xyz.size()
+    npoint = new_xyz.size(1)
+    assert shift.numel() == 3 * B
+    idx0 = torch.empty((B, npoint, nsamples[0]), dtype=torch.int32, device=xyz.device)
+    idx1 = torch.empty((B, npoint, nsamples[1]), dtype=torch.int32, device=xyz.device)
+    rel = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz.device)
+    tail = torch.empty((B, npoint, 4), dtype=torch.float32, device=xyz.device)
+    _lib.call("gp_ball_query2_tails", _lib.ptr(new_xyz), _lib.ptr(xyz), B, N, npoint, float(radii[0]),
+              int(nsamples[0]), _lib.ptr(idx0), float(radii[1]), int(nsamples[1]), _lib.ptr(idx1),
+              _lib.ptr(shift), _lib.ptr(rel), _lib.ptr(tail), int(bool(tail_absolute)), device=xyz.device)
+    return (idx0, idx1), rel, tail
+
+
 def grouping_operation(features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     """pointnet2_utils.py:179-203.  features (B, C, N), idx (B, npoint, nsample) -> (B, C, npoint, nsample)."""
     assert features.is_contiguous()
@@ -179,9 +198,10 @@ def sa_small_mlp(xyz, new_xyz, idx, layers, out):
     return out
 
 
-def sa_small_mlp_hostw(xyz, new_xyz, idx, host_layers, out):
+def sa_small_mlp_hostw(xyz, new_xyz, idx, host_layers, out, tail=None, tail_col=0):
     """sa_small_mlp with HOST copies of the folded weights (gp_sa_small_mlp_hostw): they travel in the launch's
-    parameter space and the kernel reads them as constant operands.  `host_layers` = [(W, b)] x 3, CPU fp32."""
+    parameter space and the kernel reads them as constant operands.  `host_layers` = [(W, b)] x 3, CPU fp32.
+    tail [B,M,4] (optional): also copied to out[..., tail_col : tail_col + 4] (gp_sa_small_mlp_hostw_tail)."""
     import ctypes
     _lib.check_cuda(xyz, "xyz", torch.float32)
     _lib.check_cuda(new_xyz, "new_xyz", torch.float32)
@@ -194,9 +214,21 @@ def sa_small_mlp_hostw(xyz, new_xyz, idx, host_layers, out):
     ws = (ctypes.c_void_p * 3)(*[w.data_ptr() for w, _ in host_layers])
     bs = (ctypes.c_void_p * 3)(*[b.data_ptr() for _, b in host_layers])
     C1, C2, C3 = (w.shape[0] for w, _ in host_layers)
+    if tail is not None:
+        _lib.check_cuda(tail, "tail", torch.float32)
+        _lib.call("gp_sa_small_mlp_hostw_tail", _lib.ptr(xyz), _lib.ptr(new_xyz), _lib.ptr(idx), B, N, M, ns, ws, bs, C1, C2,
+                  C3, _lib.ptr(out), int(out.stride(-2)), _lib.ptr(tail), int(tail_col), device=xyz.device)
+        return out
     _lib.call("gp_sa_small_mlp_hostw", _lib.ptr(xyz), _lib.ptr(new_xyz), _lib.ptr(idx), B, N, M, ns, ws, bs, C1, C2, C3,
               _lib.ptr(out), int(out.stride(-2)), device=xyz.device)
     return out
+
+
+def zeros(shape, device):
+    """A zero-filled fp32 tensor through a stream-ordered memset (gp_zero), not a fill kernel."""
+    t = torch.empty(shape, dtype=torch.float32, device=device)
+    _lib.call("gp_zero", _lib.ptr(t), t.numel() * 4, device=t.device)
+    return t
 
 
 def gemm_pack(weight: torch.Tensor, npass: int) -> torch.Tensor:
@@ -260,11 +292,19 @@ def gemm_gather_bias_relu(P, n_src, gidx, rows_per_batch, Q, q_ns, packed, bias,
     return y
 
 
-def centre_term(new_xyz_rows, w0_xyz_t, b0, ldq):
-    """Q [rows, ldq]: per-centre term  new_xyz @ W0_xyz^T - b0  of a hoisted first layer, zero-padded (gp_centre_term)."""
+def centre_term(new_xyz_rows, w0_xyz_t, b0, ldq, tail=None, tail_dst=None):
+    """Q [rows, ldq]: per-centre term  new_xyz @ W0_xyz^T - b0  of a hoisted first layer, zero-padded (gp_centre_term).
+    With tail [rows,4] and tail_dst (a 4-column slice of the level buffer) the same launch copies the tail rows
+    (gp_centre_term_tail)."""
     _lib.check_cuda(new_xyz_rows, "new_xyz", torch.float32)
     rows, c1 = new_xyz_rows.shape[0], w0_xyz_t.shape[1]
     Q = torch.empty((rows, ldq), dtype=torch.float32, device=new_xyz_rows.device)
+    if tail is not None:
+        _lib.check_cuda(tail, "tail", torch.float32)
+        assert tail_dst.shape[-1] == 4 and tail_dst.stride(-1) == 1 and tail.numel() == rows * 4
+        _lib.call("gp_centre_term_tail", _lib.ptr(new_xyz_rows), rows, _lib.ptr(w0_xyz_t), _lib.ptr(b0), int(c1), _lib.ptr(Q),
+                  int(ldq), _lib.ptr(tail), _lib.ptr(tail_dst), int(tail_dst.stride(-2)), device=new_xyz_rows.device)
+        return Q
     _lib.call("gp_centre_term", _lib.ptr(new_xyz_rows), rows, _lib.ptr(w0_xyz_t), _lib.ptr(b0), int(c1), _lib.ptr(Q),
               int(ldq), device=new_xyz_rows.device)
     return Q

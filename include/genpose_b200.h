@@ -82,6 +82,15 @@ GP_API int gp_ball_query2(const float *new_xyz, const float *xyz, int B, int N, 
                    int nsample0, int32_t *idx0, float radius1, int nsample1, int32_t *idx1,
                    gp_stream_t s);
 
+/* gp_ball_query2 with the encoder's per-centre by-products written by the same launch (one thread owns one
+ * centre): rel [B,M,3] = new_xyz - shift[b] (the centres in the object frame the hoisted first layers use,
+ * replaces a torch subtraction) and tail [B,M,4] = [rel | 0] or, with tail_absolute, [new_xyz | 0] -- the last
+ * four columns of the next level's channels-last rows [feat | xyz | 0] (replaces the torch.cat of
+ * P2/pointnet2_utils.py:286-291).  shift [B,3] (NULL: zero), rel / tail may be NULL. */
+GP_API int gp_ball_query2_tails(const float *new_xyz, const float *xyz, int B, int N, int M, float radius0,
+                         int nsample0, int32_t *idx0, float radius1, int nsample1, int32_t *idx1,
+                         const float *shift, float *rel, float *tail, int tail_absolute, gp_stream_t s);
+
 /* Replaces pointnet2_cuda.group_points_wrapper(b, c, n, npoints, nsample, points, idx, out)
  * (P2/src/group_points.cpp:26-37 -> group_points_gpu.cu:47-89).
  * points [B,C,N], idx [B,M,nsample] -> out [B,C,M,nsample]. */
@@ -123,6 +132,15 @@ GP_API int gp_sa_small_mlp_hostw(const float *xyz, const float *new_xyz, const i
                     int nsample, const float *const *host_weights, const float *const *host_biases, int C1, int C2,
                     int C3, float *out, int ld_out, gp_stream_t s);
 
+/* gp_sa_small_mlp_hostw that also copies tail_src[(b*M + p), 0:4] ([x y z 0] of the centre) to
+ * out[(b*M + p) * ld_out + tail_col .. + 3]: the level buffer [feat | xyz | 0] is complete after the launch. */
+GP_API int gp_sa_small_mlp_hostw_tail(const float *xyz, const float *new_xyz, const int32_t *idx, int B, int N, int M,
+                    int nsample, const float *const *host_weights, const float *const *host_biases, int C1, int C2,
+                    int C3, float *out, int ld_out, const float *tail_src, int tail_col, gp_stream_t s);
+
+/* Stream-ordered zero fill (a memset node, no kernel): the zero-initialisation the pooled GEMM outputs need. */
+GP_API int gp_zero(void *dst, size_t bytes, gp_stream_t s);
+
 /* One SharedMLP layer (P2/pytorch_utils.py:5-33: conv1x1 + BatchNorm(eval) folded + ReLU) on channels-last
  * rows, on the tcgen05 tensor cores: Y = relu(X . W^T + bias), optionally fused with the max-pool over
  * `pool_ns` consecutive rows (P2/pointnet2_modules.py:59-61).
@@ -150,6 +168,10 @@ GP_API int gp_gemm_linear(const float *X, long long R, int ldx, const void *pack
  * transposed. */
 GP_API int gp_centre_term(const float *new_xyz, long long rows, const float *w0_xyz_t, const float *b0, int c1,
                    float *Q, int ldq, gp_stream_t s);
+/* The same, and tail_dst[r * ld_tail + 0..3] = tail_src[r * 4 + 0..3]: the centres' [x y z 0] rows land in the
+ * tail of this level's buffer in the same launch. */
+GP_API int gp_centre_term_tail(const float *new_xyz, long long rows, const float *w0_xyz_t, const float *b0, int c1,
+                        float *Q, int ldq, const float *tail_src, float *tail_dst, int ld_tail, gp_stream_t s);
 
 /* Second SharedMLP layer with the hoisted first layer applied on the fly in the operand loader:
  *   A[r][k] = relu(P[(r / rows_per_batch) * n_src + gidx[r]][k] - Q[r / q_ns][k]),   Y = relu(A . W^T + bias)

@@ -241,3 +241,36 @@ def test_group_rows_and_maxpool_rows():
         assert torch.equal(out[:, 20:60], h.view(B * M, ns, 40).amax(1)) and (out[:, :20] == 0).all() and (out[:, 60:] == 0).all()
         h3 = torch.randn(B * M * ns, 3, device="cuda")  # scalar path
         assert torch.equal(pu.maxpool_rows(h3, B * M, ns), h3.view(B * M, ns, 3).amax(1))
+
+
+@pytest.mark.parametrize("absolute", [False, True])
+def test_ball_query2_tails_equals_ball_query2_plus_torch(absolute):
+    """the per-centre by-products of gp_ball_query2_tails (centres relative to the per-object shift, [x y z 0] tail
+    rows) are exactly what the torch subtraction / pad they replace produce; the indices are gp_ball_query2's"""
+    from genpose2_b200 import pointnet2_utils as pu
+    xyz = clouds(5, 1000, 23)
+    _, new_xyz = pu.furthest_point_sample_gather(xyz, 300)
+    shift = xyz[:, 0:1, :].contiguous()
+    (i0, i1), rel, tail = pu.ball_query2_tails((0.02, 0.05), (16, 32), xyz, new_xyz, shift, absolute)
+    j0, j1 = pu.ball_query2((0.02, 0.05), (16, 32), xyz, new_xyz)
+    assert torch.equal(i0, j0) and torch.equal(i1, j1)
+    assert torch.equal(rel, new_xyz - shift)
+    assert torch.equal(tail, torch.nn.functional.pad(new_xyz if absolute else new_xyz - shift, (0, 1)))
+
+
+def test_level_buffer_tails_written_by_the_level_kernels():
+    """every level buffer [feat | xyz | 0] of the encoder ends with the centres' tail rows (written by the level-1
+    kernel / the centre-term kernel, not by a separate copy)"""
+    from genpose2_b200.pointnet2 import Pointnet2ClsMSG
+    enc = Pointnet2ClsMSG(0).cuda().eval()
+    enc.load_state_dict(synthetic.random_encoder_state_dict(3, prefix=""))
+    pts = clouds(4, 1024, 5)
+    geo = enc.compute_geometry(pts)
+    with torch.no_grad():
+        xyz, feat, rows = pts, None, None
+        for k, sa in enumerate(enc.SA_modules[:4]):
+            xyz, feat, _, rows = sa.forward_cl(xyz, feat, geo[k], pts_rows=rows, return_rows=True)
+            C = feat.shape[-1]
+            assert rows.shape[1] == C + 4
+            assert torch.equal(rows[:, C:], geo[k][3].reshape(-1, 4))
+            assert torch.equal(rows[:, :C], feat.reshape(-1, C))
