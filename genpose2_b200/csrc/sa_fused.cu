@@ -32,10 +32,6 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
-#ifndef GP_SAF_VARIANT
-#define GP_SAF_VARIANT 0
-#endif
-
 namespace gp {
 namespace saf {
 
@@ -125,9 +121,6 @@ __device__ __forceinline__ void pool_block(const uint32_t (&r)[32], bool row_ok,
         float o[KEEP];
 #pragma unroll
         for (int i = 0; i < KEEP; ++i) o[i] = n0 + i < N ? fmaxf(v[i] + bias[n0 + i], 0.f) : 0.f;
-#if GP_SAF_VARIANT == 2
-        if (o[0] == 12345.f) dst[0] = o[0];
-#else
         // a lane's KEEP columns are consecutive: one 8- / 16-byte store when the row allows it
         if (KEEP == 2 && vec_ok && n0 + 1 < N) {
             *reinterpret_cast<float2 *>(dst) = make_float2(o[0], o[1]);
@@ -138,7 +131,6 @@ __device__ __forceinline__ void pool_block(const uint32_t (&r)[32], bool row_ok,
             for (int i = 0; i < KEEP; ++i)
                 if (n0 + i < N) dst[i] = o[i];
         }
-#endif
     }
 }
 

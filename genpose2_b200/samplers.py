@@ -16,7 +16,15 @@ from . import _lib
 from .scorenet import _object_features
 
 POSE_DIM = 9  # get_pose_dim("rot_matrix"), utils/genpose_utils.py:34-35
-MAX_TRAJ = 512  # accepted-step slots recorded when the trajectory is requested
+MAX_TRAJ = 512  # accepted-step slots recorded when the trajectory is requested (upper bound)
+TRAJ_BYTES_BUDGET = 2 << 30   # the recording buffer [slots, N, 9] f64 is capped at this size (never below 64 slots)
+
+
+def _traj_slots(batch_size):
+    """Slots of the trajectory buffer: MAX_TRAJ for small batches, fewer when [slots, N, 9] f64 would exceed
+    TRAJ_BYTES_BUDGET (the evaluation settings accept 9 - 62 steps; a longer trajectory raises)."""
+    per_slot = max(1, batch_size) * POSE_DIM * 8
+    return int(max(64, min(MAX_TRAJ, TRAJ_BYTES_BUDGET // per_slot)))
 
 last_ode_stats = {}  # statistics of the most recent cond_ode_sampler call (nfev, accepted, ...)
 
@@ -132,17 +140,19 @@ def cond_ode_sampler(score_model, data, prior, sde_coeff, atol=1e-5, rtol=1e-5, 
         _watch(stats)
         return xs, x_out
     traj = None
+    slots = _traj_slots(batch_size)
     if return_trajectory:
-        traj = torch.empty((MAX_TRAJ, batch_size, POSE_DIM), dtype=torch.float64, device=dev)
+        traj = torch.empty((slots, batch_size, POSE_DIM), dtype=torch.float64, device=dev)
     _lib.call("gp_scorenet_ode", _lib.ptr(net.packed()), _lib.ptr(proj), _lib.ptr(x0), _lib.ptr(center),
               batch_size, rpo, float(T), float(eps), float(rtol), float(atol), 1 if denoise else 0,
-              _lib.ptr(x_out), _lib.ptr(traj), MAX_TRAJ if traj is not None else 0, _lib.ptr(stats),
+              _lib.ptr(x_out), _lib.ptr(traj), slots if traj is not None else 0, _lib.ptr(stats),
               _lib.ptr(ws), ws_bytes, _mlp_mode(score_model), device=dev)
     if return_trajectory:
         st = stats.cpu()
         S = int(st[_lib.STAT_ACCEPTED].item()) + 1
-        if S > MAX_TRAJ:
-            raise RuntimeError(f"trajectory longer than {MAX_TRAJ} accepted steps")
+        if S > slots:
+            raise RuntimeError(f"trajectory of {S} accepted steps does not fit the {slots} recorded slots "
+                               "(raise samplers.TRAJ_BYTES_BUDGET, or pass return_trajectory=False)")
         xs = torch.empty((batch_size, S, POSE_DIM), dtype=torch.float64, device=dev)
         _lib.call("gp_traj_finalize", _lib.ptr(traj), _lib.ptr(center), S, batch_size, _lib.ptr(xs), device=dev)
         _record_stats(st)

@@ -295,3 +295,14 @@ def test_aggregation_limits_raise_instead_of_misbehaving():
         aggregate_pose(poses[:, :64], energy[:, :64], eval_repeat_num=64, retain_ratio=0.75)   # 48 retained, clustering on
     with pytest.raises(ValueError):
         aggregate_pose(poses[:, :50], energy[:, :50], eval_repeat_num=50, retain_ratio=0.1)    # int(0.1667 * 5) = 0
+
+
+def test_trajectory_buffer_is_bounded_by_a_byte_budget():
+    """return_trajectory=True records accepted steps into [slots, N, 9] f64: 512 slots for small batches, capped by
+    TRAJ_BYTES_BUDGET for large ones (15 GB at 8192 x 50 rows in round 1), never below 64 slots"""
+    from genpose2_b200 import samplers
+    assert samplers._traj_slots(50) == samplers.MAX_TRAJ
+    n = 8192 * 50
+    slots = samplers._traj_slots(n)
+    assert 64 <= slots < samplers.MAX_TRAJ and slots * n * 72 <= samplers.TRAJ_BYTES_BUDGET + 64 * n * 72
+    assert samplers._traj_slots(10 ** 9) == 64
