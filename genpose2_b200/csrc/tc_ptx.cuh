@@ -130,6 +130,20 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 16 TMEM lanes x 32 columns in the 16x256b fragment layout (verified on the device, scratch/ldshape.cu): thread T of the
+// warp receives, for i < 4, v[4i + 0, 1] = (lane T / 4, columns 8i + 2 (T % 4) + {0, 1}) and v[4i + 2, 3] = (lane T / 4 + 8, same
+// columns), lanes counted from the lane field of taddr (a multiple of 16 inside the warp's own quarter).  Unlike the
+// 32x32b shape (one row per thread) a thread holds FOUR columns-pairs of TWO rows: per-column operands (weights) are
+// loaded once per 2 rows.  No wait: read the registers after tmem_ld_wait().
+__device__ __forceinline__ void tmem_ld_16x256b_x4_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+
 // registers -> TMEM: this thread's lane, 16 / 8 consecutive 32-bit columns starting at taddr (warp-collective)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
     asm volatile(

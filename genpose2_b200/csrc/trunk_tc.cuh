@@ -77,6 +77,7 @@ struct Smem {
     float4 wo[NHC];                           // output-layer weights of this rank's head columns
     float x[RT * XS];                         // inputs [RT][9]; overwritten with f_theta [RT][9] by forward()
     float pj[MAX_SLOTS * NHC];                // proj[obj][this rank's columns] for the objects of the tile
+    float pjq[MAX_SLOTS * NHC];               // ... + this evaluation's t-branch (what the head epilogue adds to the accumulators)
     float tq[6 * NHC];                        // t-branch, up to 6 stages x this rank's columns
     float b1[256], b2[256];
     float bo[12];
@@ -293,6 +294,65 @@ __device__ __forceinline__ void epi_hidden_t(uint32_t lane_addr, uint32_t acc, c
     tmem_st_wait();
 }
 
+// Head epilogue of one head for a warp's 32 rows x 32 accumulator columns: z = relu(D + e) and the 256 -> 3 output layer over
+// these columns.  The accumulators are read in the 16x256b fragment layout: a thread holds 8 columns (8 i + 2 (lane & 3) + {0, 1})
+// of 4 rows (TMEM lanes (lane >> 2) + 8 k of the warp's quarter), so an output-layer weight is loaded once per 4 rows -- with
+// one row per thread (32x32b) the broadcast LDS.128 per column (512 B of register write-back each) bound the epilogue.
+// The 4 lanes that share rows then reduce-scatter their partial sums: thread (lane) ends up with the 3 outputs of ONE row,
+// TMEM lane (lane >> 2) + 8 (lane & 3).  e_k: the row's proj + tq columns (shared-memory table, or global proj + tq when TABLE
+// is false).  Split into load / compute / reduce so that the TMEM load of the next block is in flight under the FMAs of this one.
+struct HeadFrag {
+    uint32_t ra[16], rb[16];   // rows k = 0, 1 (TMEM lanes + 0..15 of the quarter) and k = 2, 3 (lanes + 16..31)
+};
+// request a 32-row x 32-column accumulator block of the warp's quarter (no wait: tmem_ld_wait() before head_compute)
+__device__ __forceinline__ void head_load(uint32_t quarter_addr, uint32_t col, HeadFrag &f) {
+    tmem_ld_16x256b_x4_nowait(quarter_addr + col, f.ra);
+    tmem_ld_16x256b_x4_nowait(quarter_addr + (16u << 16) + col, f.rb);
+}
+// a[k][o] += sum over this thread's 8 columns of relu(D[row k][c] + e_k[c]) * Wo[c][o]
+template <bool TABLE>
+__device__ __forceinline__ void head_compute(const HeadFrag &f, const float4 *swo_cb, const float *const (&erow)[4],
+                                             const float *stq_cb, int lane, float (&a)[4][3]) {
+    const int tq4 = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int cc = 8 * i + 2 * tq4;
+        const float4 w0 = swo_cb[cc], w1 = swo_cb[cc + 1];
+        float2 tqv = make_float2(0.f, 0.f);
+        if (!TABLE) tqv = *reinterpret_cast<const float2 *>(stq_cb + cc);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float2 e;
+            if (TABLE) {
+                e = *reinterpret_cast<const float2 *>(erow[k] + cc);
+            } else {
+                const float2 g = __ldg(reinterpret_cast<const float2 *>(erow[k] + cc));
+                e = make_float2(g.x + tqv.x, g.y + tqv.y);
+            }
+            const uint32_t d0 = k < 2 ? f.ra[4 * i + 2 * (k & 1)] : f.rb[4 * i + 2 * (k & 1)];
+            const uint32_t d1 = k < 2 ? f.ra[4 * i + 2 * (k & 1) + 1] : f.rb[4 * i + 2 * (k & 1) + 1];
+            const float z0 = fmaxf(__uint_as_float(d0) + e.x, 0.f), z1 = fmaxf(__uint_as_float(d1) + e.y, 0.f);
+            a[k][0] = fmaf(z1, w1.x, fmaf(z0, w0.x, a[k][0]));
+            a[k][1] = fmaf(z1, w1.y, fmaf(z0, w0.y, a[k][1]));
+            a[k][2] = fmaf(z1, w1.z, fmaf(z0, w0.z, a[k][2]));
+        }
+    }
+}
+// reduce-scatter over the 4 lanes of a row group (xor 2 halves the rows a lane keeps, xor 1 again): out = the 3 sums of
+// row k = lane & 3
+__device__ __forceinline__ void head_reduce(const float (&a)[4][3], int lane, float (&out)[3]) {
+    const bool up2 = (lane & 2) != 0, up1 = (lane & 1) != 0;
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+        const float s0 = up2 ? a[0][o] : a[2][o], s1 = up2 ? a[1][o] : a[3][o];
+        float k0 = up2 ? a[2][o] : a[0][o], k1 = up2 ? a[3][o] : a[1][o];
+        k0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        k1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        const float s = up1 ? k0 : k1, kk = up1 ? k1 : k0;
+        out[o] = kk + __shfl_xor_sync(0xffffffffu, s, 1);
+    }
+}
+
 // f_theta for the 128 rows in S.x -> S.x [r*9 + c]; `tq` is this stage's t-branch (NHC floats in shared memory,
 // this rank's columns).  All 320 threads of all CL CTAs of the cluster call; ends with __syncthreads().
 template <int NPASS>
@@ -438,6 +498,7 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
         const float *sb1 = reinterpret_cast<const float *>(gp_dyn_smem + (smem_u32(S.b1) - dyn0));
         const float *sb2 = reinterpret_cast<const float *>(gp_dyn_smem + (smem_u32(S.b2) - dyn0));
         const float *spj = reinterpret_cast<const float *>(gp_dyn_smem + (smem_u32(S.pj) - dyn0));
+        float *spjq = reinterpret_cast<float *>(gp_dyn_smem + (smem_u32(S.pjq) - dyn0));
         const float *stq = reinterpret_cast<const float *>(gp_dyn_smem + (smem_u32(tq) - dyn0));
         const float4 *swo = reinterpret_cast<const float4 *>(gp_dyn_smem + (smem_u32(S.wo) - dyn0));
         float *sxw = reinterpret_cast<float *>(gp_dyn_smem + (smem_u32(S.x) - dyn0));
@@ -465,6 +526,11 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.a_ready);
+        // while the first layer runs: proj + this stage's t-branch for the objects of the tile (consumed by the head epilogue
+        // after the named barrier below)
+        const bool use_pj = st.nslots <= MAX_SLOTS;
+        if (use_pj)
+            for (int i = tid - 64; i < st.nslots * NHC; i += 256) spjq[i] = spj[i] + stq[i % NHC];
 
         // h1 = relu(D0 + b1) -> A buffers
         mbar_wait(&S.dbar[0], dph);
@@ -496,65 +562,68 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
             t0 = t1;
         }
 
-        // heads: z = relu(D + proj + tq), partial out = z . Wo^T over this thread's 32 columns of each head
-        const int o = S.obj[row];
-        const bool use_pj = st.nslots <= MAX_SLOTS;
-        const float *pjrow = spj + (use_pj && o >= 0 ? o - st.slot_base : 0) * NHC;
-        const float *prow = proj + (size_t)(o < 0 ? 0 : o) * 768;
+        // heads: z = relu(D + proj + tq), partial out = z . Wo^T over this warp's 32 columns of each head (head_block)
+        asm volatile("bar.sync 3, 256;" ::: "memory");   // S.pjq is complete (the 8 epilogue warps)
+        const int tq4 = lane & 3, tr = lane >> 2;
+        const int q32 = 32 * (warp & 3);
+        const float *erow[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int o = S.obj[q32 + tr + 8 * k];
+            erow[k] = use_pj ? spjq + (o >= 0 ? o - st.slot_base : 0) * NHC : proj + (size_t)(o < 0 ? 0 : o) * 768;
+        }
+        float out9[9];
+        // the three heads complete together (one commit): request head h + 1 while head h is multiplied
+        mbar_wait(&S.dbar[2], dph);
+        mbar_wait(&S.dbar[3], dph);
+        mbar_wait(&S.dbar[4], dph);
+        tc_fence_after();
+        {
+            const long long t1 = clock64();
+            st.cyc_waith += t1 - t0;
+            t0 = t1;
+        }
+        HeadFrag frag[2];
+        head_load(lane_addr, COL_ACC + half * 32, frag[0]);
 #pragma unroll
         for (int h = 0; h < 3; ++h) {
-            mbar_wait(&S.dbar[2 + h], dph);
-            tc_fence_after();
-            {
-                const long long t1 = clock64();
-                st.cyc_waith += t1 - t0;
-                t0 = t1;
-            }
+            tmem_ld_wait();
+            if (h + 1 < 3) head_load(lane_addr, COL_ACC + (h + 1) * HC + half * 32, frag[(h + 1) & 1]);
             const int cb = h * HC + half * 32;                      // local column base
             const int gcol = h * 256 + HC * (int)rank + half * 32;  // global head column base
-            uint32_t r[32];
-            tmem_ld32(lane_addr + COL_ACC + cb, r);
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            const float *e4[4];
 #pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-                // output-layer weights of 8 columns (shared-memory broadcasts)
-                float4 w[8];
+            for (int k = 0; k < 4; ++k) e4[k] = erow[k] + (use_pj ? cb : gcol);
+            float a[4][3];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) w[j] = swo[cb + j8 * 8 + j];
-                float ev[8];
-                const float4 ta = *reinterpret_cast<const float4 *>(stq + cb + j8 * 8);
-                const float4 tb = *reinterpret_cast<const float4 *>(stq + cb + j8 * 8 + 4);
-                // the object's proj columns: the shared-memory table, or (a tile spanning > MAX_SLOTS objects) global memory
-                const float *ebase = use_pj ? pjrow + cb : prow + gcol;
-                const float4 ea = *reinterpret_cast<const float4 *>(ebase + j8 * 8);
-                const float4 eb = *reinterpret_cast<const float4 *>(ebase + j8 * 8 + 4);
-                ev[0] = ea.x + ta.x; ev[1] = ea.y + ta.y; ev[2] = ea.z + ta.z; ev[3] = ea.w + ta.w;
-                ev[4] = eb.x + tb.x; ev[5] = eb.y + tb.y; ev[6] = eb.z + tb.z; ev[7] = eb.w + tb.w;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float z = fmaxf(__uint_as_float(r[j8 * 8 + j]) + ev[j], 0.f);
-                    a0 = fmaf(z, w[j].x, a0); a1 = fmaf(z, w[j].y, a1); a2 = fmaf(z, w[j].z, a2);
-                }
-            }
-            acc[h * 3 + 0] = a0; acc[h * 3 + 1] = a1; acc[h * 3 + 2] = a2;
-            {
-                const long long t1 = clock64();
-                st.cyc_epi2 += t1 - t0;
-                t0 = t1;
-            }
+            for (int k = 0; k < 4; ++k) a[k][0] = a[k][1] = a[k][2] = 0.f;
+            if (use_pj) head_compute<true>(frag[h & 1], swo + cb, e4, stq + cb, lane, a);
+            else head_compute<false>(frag[h & 1], swo + cb, e4, stq + cb, lane, a);
+            float o3[3];
+            head_reduce(a, lane, o3);
+            out9[h * 3 + 0] = o3[0]; out9[h * 3 + 1] = o3[1]; out9[h * 3 + 2] = o3[2];
+        }
+        {
+            const long long t1 = clock64();
+            st.cyc_epi2 += t1 - t0;
+            t0 = t1;
         }
         tc_fence_before();
         tx = clock64();
-        // the two column halves of a row meet through S.x (dead since the inputs were converted), then the row's
-        // partial goes to the three peers
-        if (half == 1) {
+        // the two column halves of a row meet through shared memory: this thread holds the partial of row q32 + tr + 8 tq4;
+        // half 0 parks it in the staging area (free: the previous evaluation's copies have read it), half 1 in S.x (dead since
+        // the inputs were converted); then the row's owner thread of half 0 adds the two
+        float *stage_w = reinterpret_cast<float *>(gp_dyn_smem + (smem_u32(S.stage) - dyn0));
+        {
+            float *dst = half ? sxw : stage_w;
+            const int prow_l = q32 + tr + 8 * tq4;
 #pragma unroll
-            for (int c = 0; c < 9; ++c) sxw[c * RT + row] = acc[c];
+            for (int c = 0; c < 9; ++c) dst[c * RT + prow_l] = out9[c];
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
         if (half == 0) {
 #pragma unroll
-            for (int c = 0; c < 9; ++c) acc[c] += sxw[c * RT + row];
+            for (int c = 0; c < 9; ++c) acc[c] = stage_w[c * RT + row] + sxw[c * RT + row];
         }
         { const long long t1 = clock64(); st.cyc_x[0] += t1 - tx; tx = t1; }
         if (half == 0) {
