@@ -71,6 +71,9 @@ SIGNATURES = {
     "gp_centre_term": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "gp_centre_term_tail": (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                     c_void_p, c_int, c_void_p]),
+    "gp_sa_mlp2_fused_xyz": (c_int, [c_void_p, c_void_p, c_int, c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                     c_int, c_void_p]),
     "gp_sa_mlp2_fused": (c_int, [c_void_p, c_int, c_int, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_int, c_int,
                                  c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                  c_int, c_void_p]),

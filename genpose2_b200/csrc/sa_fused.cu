@@ -60,6 +60,11 @@ struct Args {
     float *pooled;
     int ld_pooled;
     int ntiles;
+    // first-level mode (xyz != nullptr; P / Q unused): A[r][k] = relu(W0[k] . (xyz[batch(r)][gidx[r]] - centres[r / q_ns]) + b0[k]),
+    // the K = 3 first layer evaluated in the operand loader
+    const float *xyz;        // [batches, n_src, 3]
+    const float *centres;    // [R / q_ns, 3]
+    float w0c[64 * 3], b0c[64];   // folded first layer [c1][3], [c1]: travels in the launch's parameter space (constant operands)
     // launch configuration (host)
     int nst;             // ring slots
     int tmem_cols;       // allocated TMEM columns (256 or 512)
@@ -134,10 +139,47 @@ __device__ __forceinline__ void pool_block(const uint32_t (&r)[32], bool row_ok,
     }
 }
 
+// First-level mode: one thread = one row.  x[k] = relu(W0[k] . d + b0[k]) for the thread's C1 / PARTS output channels
+// (weights from the parameter space: uniform operands), split to bf16 hi / lo and stored as 16-byte chunks of the
+// swizzled A operand atom.
+template <int NPASS, int C1, int PARTS>
+__device__ __forceinline__ void xyz_first_layer(const Args &a, int part, float dx, float dy, float dz, bool valid, int rl,
+                                                uint32_t A_hi, uint32_t A_lo) {
+    constexpr int NC = C1 / PARTS;
+    static_assert(NC % 8 == 0, "a thread writes whole 16-byte chunks");
+#pragma unroll
+    for (int c8 = 0; c8 < NC / 8; ++c8) {
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = part * NC + c8 * 8 + j;
+            // same operation order as the FP32 level-1 kernel (dense_relu_c): ((b + dx w0) + dy w1) + dz w2
+            const float v = fmaf(dz, a.w0c[k * 3 + 2], fmaf(dy, a.w0c[k * 3 + 1], fmaf(dx, a.w0c[k * 3], a.b0c[k])));
+            x[j] = valid ? fmaxf(v, 0.f) : 0.f;
+        }
+        const int j16 = (part * NC) / 8 + c8;
+        const uint32_t off = rl * 128 + ((j16 ^ (rl & 7)) << 4);
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+            hi[j] = *reinterpret_cast<const uint32_t *>(&h);
+            if (NPASS == 3) {
+                const float2 f = __bfloat1622float2(h);
+                const __nv_bfloat162 l = __floats2bfloat162_rn(x[2 * j] - f.x, x[2 * j + 1] - f.y);
+                lo[j] = *reinterpret_cast<const uint32_t *>(&l);
+            }
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(A_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]));
+        if (NPASS == 3)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(A_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]));
+    }
+}
+
 // NW worker warps (gather / convert / epilogues) + producer + MMA issuer.  NW = 8: one CTA per SM; NW = 4: 192-thread
 // CTAs, two per SM when a CTA needs at most half of the shared memory and 256 TMEM columns.
 template <int NPASS, int NW>
-__global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel(Args a) {
+__global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel(const __grid_constant__ Args a) {
     using C = Cfg<NPASS>;
     constexpr int IM = C::IMAGES;
     constexpr int NTHREADS = (NW + 2) * 32;
@@ -268,7 +310,8 @@ __global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel
                 return ring_a + sl * SLOT;
             };
             // one accumulator pass: kat k-atoms, one or two chunks of <= 128 columns (two chunks = two interleaved chains)
-            auto pass = [&](const bool second, const int kat, const int bn, const int p) {
+            // `kdim`: the populated K (c1 / c2 rounded up to 16): the last k-atom multiplies only its populated 16-wide steps
+            auto pass = [&](const bool second, const int kat, const int kdim, const int bn, const int p) {
                 const bool two = pass_chunks(bn, p) == 2;
                 const uint32_t id0 = make_idesc_bf16(128, (uint32_t)chunk_rows(bn, p, 0));
                 const uint32_t id1 = two ? make_idesc_bf16(128, (uint32_t)chunk_rows(bn, p, 1)) : id0;
@@ -284,8 +327,8 @@ __global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel
 #ifdef GP_SAF_PROBE
                     mw_full += clock64() - w0;
 #endif
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
+                    const int nk = min(4, (kdim - 64 * c + 15) >> 4);
+                    for (int kk = 0; kk < nk; ++kk) {
                         const uint32_t accum = (c | kk) ? 1u : 0u;
                         const uint32_t ah = second ? h_hi + c * 32 + kk * 8 : a_hi + c * ATOM + kk * 32;
                         const uint32_t al = second ? h_lo + c * 32 + kk * 8 : a_lo + c * ATOM + kk * 32;
@@ -317,8 +360,7 @@ __global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel
 #ifdef GP_SAF_PROBE
                         mw_full += clock64() - w0;
 #endif
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
+                        for (int kk = 0; kk < nk; ++kk) {
                             const uint32_t ah = second ? h_hi + c * 32 + kk * 8 : a_hi + c * ATOM + kk * 32;
                             if (second) {
                                 umma_bf16_ts_w(d0, ah, make_desc(b0 + kk * 32), id0, 1u);
@@ -344,14 +386,14 @@ __global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel
 #endif
                 for (int p = 0; p < np1; ++p) {
                     if (p > 0) { mbar_wait(e1_done, ph_e1); ph_e1 ^= 1; tc_fence_after(); }   // accumulators read out
-                    pass(false, k1, bn1, p);
+                    pass(false, k1, round16(a.c1), bn1, p);
                     umma_commit_w(d1bar);
                 }
                 mbar_wait(e1_done, ph_e1); ph_e1 ^= 1;     // H is complete in TMEM, accumulators free
                 tc_fence_after();
                 for (int q = 0; q < np2; ++q) {
                     if (q > 0) { mbar_wait(p_done, ph_p); ph_p ^= 1; tc_fence_after(); }
-                    pass(true, k2, bn2, q);
+                    pass(true, k2, bn1, bn2, q);
                     umma_commit_w(d2bar);
                 }
                 mbar_wait(p_done, ph_p); ph_p ^= 1;        // last pass pooled: accumulators free for the next tile
@@ -382,8 +424,15 @@ __global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel
         // next tile are requested early and only consumed at the gather: the index load is the head of the gather's
         // latency chain.
         int gi[RP];
+        int gx = -1;     // first-level mode: the ball-query index of THIS thread's row (row w % 128 of the tile)
         auto request = [&](int t) {
             const long long row0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * BM;
+            if (a.xyz) {
+                const long long gr = row0 + (w & 127);
+                gx = -1;
+                if (t < my_tiles && gr < a.R) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(gx) : "l"(a.gidx + gr));
+                return;
+            }
 #pragma unroll
             for (int p = 0; p < RP; ++p) {
                 const long long gr = row0 + rsub + RSTEP * p;
@@ -393,7 +442,31 @@ __global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel
         };
         // gather k-atoms [kc_lo, kc_hi) of tile t into the A buffer (its indices are in gi[]): thread handles rows
         // rsub + RSTEP p (p < RP), 16 bytes of every 64-float chunk, 8 rows at a time; `last` publishes the tile
+        // first-level mode: one row per thread (all NW * 32 worker threads: with 8 worker warps two threads split a row's channels)
+        auto gather_xyz = [&](int t) {
+            const long long row0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * BM;
+            const int rl = w & 127, part = w >> 7;
+            const int g32 = (int)(row0 + rl);
+            const bool valid = gx >= 0;
+            float dx = 0.f, dy = 0.f, dz = 0.f;
+            if (valid) {
+                const int batch = g32 / a.rows_per_batch;
+                const int qrow = a.q_shift >= 0 ? g32 >> a.q_shift : g32 / a.q_ns;
+                const float *pt = a.xyz + ((long long)batch * a.n_src + gx) * 3;
+                const float *ct = a.centres + (long long)qrow * 3;
+                dx = __ldg(pt) - __ldg(ct); dy = __ldg(pt + 1) - __ldg(ct + 1); dz = __ldg(pt + 2) - __ldg(ct + 2);
+            }
+            if (a.c1 == 32) xyz_first_layer<NPASS, 32, HALVES>(a, part, dx, dy, dz, valid, rl, A_hi, A_lo);
+            else xyz_first_layer<NPASS, 16, HALVES>(a, part, dx, dy, dz, valid, rl, A_hi, A_lo);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
+        };
         auto gather = [&](int t, int kc_lo, int kc_hi, bool last) {
+            if (a.xyz) {   // c1 <= 64: one k-atom, one part
+                if (last) gather_xyz(t);
+                return;
+            }
             const long long row0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * BM;
             const int tile_batch = (int)(row0 / a.rows_per_batch);
 #pragma unroll
@@ -618,5 +691,35 @@ extern "C" int gp_sa_mlp2_fused(const float *P, int n_src, int ldp, const int32_
     a.W2p = (const uint8_t *)packed2; a.b2 = bias2; a.c3 = c3;
     a.pool_ns = pool_ns; a.pooled = pooled; a.ld_pooled = ld_pooled;
     a.ntiles = (int)((R + saf::BM - 1) / saf::BM);
+    a.xyz = nullptr; a.centres = nullptr;
+    return npass == 3 ? saf::launch<3>(a, as_stream(s)) : saf::launch<1>(a, as_stream(s));
+}
+
+extern "C" int gp_sa_mlp2_fused_xyz(const float *xyz, const float *centres, int n_src, const int32_t *gidx, long long R,
+                                    int rows_per_batch, int q_ns, const float *host_W0, const float *host_b0, const void *packed1,
+                                    const float *bias1, int c1, int c2, const void *packed2, const float *bias2, int c3, int npass,
+                                    int pool_ns, float *pooled, int ld_pooled, gp_stream_t s) {
+    GP_REQUIRE(R >= 0 && (npass == 1 || npass == 3), "gp_sa_mlp2_fused_xyz: bad arguments");
+    if (R == 0) return GP_OK;
+    GP_REQUIRE(xyz && centres && gidx && host_W0 && host_b0 && packed1 && bias1 && packed2 && bias2 && pooled, "gp_sa_mlp2_fused_xyz: null pointer");
+    GP_REQUIRE((c1 == 16 || c1 == 32) && c2 >= 1 && c2 <= 384 && c3 >= 1 && c3 <= 512,
+               "gp_sa_mlp2_fused_xyz: c1 must be 16 or 32, c2 <= 384 and c3 <= 512 (got %d, %d, %d)", c1, c2, c3);
+    GP_REQUIRE(((uintptr_t)packed1 & 15) == 0 && ((uintptr_t)packed2 & 15) == 0, "gp_sa_mlp2_fused_xyz: packed weights must be 16-byte aligned");
+    GP_REQUIRE(rows_per_batch >= 1 && n_src >= 1 && q_ns >= 1, "gp_sa_mlp2_fused_xyz: bad gather geometry");
+    GP_REQUIRE((pool_ns == 8 || pool_ns == 16 || pool_ns == 32) && R % pool_ns == 0 && ld_pooled >= c3,
+               "gp_sa_mlp2_fused_xyz: pool_ns must be 8, 16 or 32 and divide R");
+    GP_REQUIRE(R < 2147483647LL, "gp_sa_mlp2_fused_xyz: too many rows");
+    saf::Args a;
+    a.P = nullptr; a.n_src = n_src; a.ldp = 0; a.gidx = gidx; a.R = R; a.rows_per_batch = rows_per_batch;
+    a.Q = nullptr; a.ldq = 0; a.q_ns = q_ns;
+    a.W1p = (const uint8_t *)packed1; a.b1 = bias1; a.c1 = c1; a.c2 = c2;
+    a.W2p = (const uint8_t *)packed2; a.b2 = bias2; a.c3 = c3;
+    a.pool_ns = pool_ns; a.pooled = pooled; a.ld_pooled = ld_pooled;
+    a.ntiles = (int)((R + saf::BM - 1) / saf::BM);
+    a.xyz = xyz; a.centres = centres;
+    for (int k = 0; k < 64; ++k) {
+        a.b0c[k] = k < c1 ? host_b0[k] : 0.f;
+        for (int d = 0; d < 3; ++d) a.w0c[k * 3 + d] = k < c1 ? host_W0[k * 3 + d] : 0.f;
+    }
     return npass == 3 ? saf::launch<3>(a, as_stream(s)) : saf::launch<1>(a, as_stream(s));
 }

@@ -204,6 +204,8 @@ class PointnetSAModuleMSG(nn.Module):
         super().__init__()
         self.npoint, self.radii, self.nsamples = npoint, radii, nsamples
         self.gemm_mode = "bf16x3"  # "bf16x3" | "bf16" (see SharedMLP.forward_rows_pooled)
+        # feature-less scales (first level) that take the fused tensor-core kernel instead of the FP32 kernel
+        self.level1_tc_specs = ((32, 32, 64),)
         self.groupers = nn.ModuleList(
             [pu.QueryAndGroup(r, n) if npoint is not None else pu.GroupAll() for r, n in zip(radii, nsamples)])
         self.mlps = nn.ModuleList([SharedMLP([spec[0] + 3] + spec[1:]) for spec in mlps])
@@ -291,6 +293,17 @@ class PointnetSAModuleMSG(nn.Module):
                     off += couts[i]
                     continue
                 spec = tuple(getattr(mlp, f"layer{j}").conv.out_channels for j in range(mlp.n_layers))
+                if (feat_cl is None and tc and self.nsamples[i] in (16, 32) and spec in self.level1_tc_specs
+                        and pu.sa_mlp2_fused_fits(*spec, {"bf16x3": 3, "bf16": 1}[self.gemm_mode], self.nsamples[i])):
+                    # first level, wide scale: layers 2, 3 and the max-pool on the tensor cores, the K = 3 first layer
+                    # evaluated in the fused kernel's operand loader
+                    npass = {"bf16x3": 3, "bf16": 1}[self.gemm_mode]
+                    t = mlp._tc_hoisted(npass)
+                    w0, b0 = mlp._folded_layers_host()[0]
+                    pu.sa_mlp2_fused_xyz(xyz, new_xyz, bq[i], w0, b0, t["p1"], t["b1"], t["c1"], t["c2"], t["p2"], t["b2"],
+                                         t["c3"], npass, out2d[:, off:off + couts[i]])
+                    off += couts[i]
+                    continue
                 if (feat_cl is None and tc and self.nsamples[i] in (16, 32)
                         and spec in ((16, 16, 32), (32, 32, 64))):
                     # first level: the whole scale in one FP32 kernel (channels too narrow for tensor cores)

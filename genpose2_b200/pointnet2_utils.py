@@ -224,6 +224,12 @@ def sa_small_mlp_hostw(xyz, new_xyz, idx, host_layers, out, tail=None, tail_col=
     return out
 
 
+def ctypes_ptr(host_tensor):
+    """Pointer to a CPU tensor's storage (host-side operands that travel in a launch's parameter space)."""
+    import ctypes
+    return ctypes.c_void_p(host_tensor.data_ptr())
+
+
 def zeros(shape, device):
     """A zero-filled fp32 tensor through a stream-ordered memset (gp_zero), not a fill kernel."""
     t = torch.empty(shape, dtype=torch.float32, device=device)
@@ -321,6 +327,25 @@ def sa_mlp2_fused(P, n_src, gidx, rows_per_batch, Q, q_ns, packed1, bias1, c1, c
               int(rows_per_batch), _lib.ptr(Q), int(Q.stride(0)), int(q_ns), _lib.ptr(packed1), _lib.ptr(bias1), int(c1),
               int(c2), _lib.ptr(packed2), _lib.ptr(bias2), int(c3), int(npass), int(pool_ns), _lib.ptr(pooled_out),
               int(pooled_out.stride(-2)), device=P.device)
+    return pooled_out
+
+
+def sa_mlp2_fused_xyz(xyz, new_xyz, bq_idx, w0, b0, packed1, bias1, c1, c2, packed2, bias2, c3, npass, pooled_out):
+    """A feature-less scale (first level) on the fused tensor-core kernel (gp_sa_mlp2_fused_xyz): the K = 3 first layer
+    relu(W0 . (xyz[idx] - new_xyz) + b0) is evaluated in the operand loader, layers 2, 3 and the max-pool as sa_mlp2_fused.
+    xyz [B,N,3], new_xyz [B,M,3], bq_idx [B,M,ns]; w0 [c1,3], b0 [c1]: HOST copies of the folded first layer."""
+    _lib.check_cuda(xyz, "xyz", torch.float32)
+    _lib.check_cuda(new_xyz, "new_xyz", torch.float32)
+    _lib.check_cuda(bq_idx, "bq_idx", torch.int32)
+    for t in (w0, b0):
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise TypeError("w0 / b0 must be contiguous fp32 CPU tensors (they travel in the launch's parameter space)")
+    B, N, _ = xyz.shape
+    _, M, ns = bq_idx.shape
+    _lib.call("gp_sa_mlp2_fused_xyz", _lib.ptr(xyz), _lib.ptr(new_xyz), int(N), _lib.ptr(bq_idx), bq_idx.numel(), int(M * ns),
+              int(ns), ctypes_ptr(w0), ctypes_ptr(b0), _lib.ptr(packed1), _lib.ptr(bias1), int(c1), int(c2), _lib.ptr(packed2),
+              _lib.ptr(bias2), int(c3), int(npass), int(ns), _lib.ptr(pooled_out), int(pooled_out.stride(-2)),
+              device=xyz.device)
     return pooled_out
 
 

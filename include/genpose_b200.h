@@ -194,6 +194,15 @@ GP_API int gp_sa_mlp2_fused(const float *P, int n_src, int ldp, const int32_t *g
                      const float *Q, int ldq, int q_ns, const void *packed1, const float *bias1, int c1, int c2,
                      const void *packed2, const float *bias2, int c3, int npass, int pool_ns, float *pooled,
                      int ld_pooled, gp_stream_t s);
+/* The same kernel for a scale WITHOUT point features (the first level): the K = 3 first layer is evaluated in the
+ * operand loader, A[r][k] = relu(W0[k] . (xyz[batch(r), gidx[r]] - centres[r / q_ns]) + b0[k]), one row per thread, so
+ * neither the per-point table P nor Q exists.  xyz [batches, n_src, 3], centres [R / q_ns, 3] (new_xyz) on the device;
+ * host_W0 [c1, 3] / host_b0 [c1] = HOST copies of the folded first layer (they travel in the launch's parameter space,
+ * like gp_sa_small_mlp_hostw), c1 = 16 or 32; the rest as gp_sa_mlp2_fused. */
+GP_API int gp_sa_mlp2_fused_xyz(const float *xyz, const float *centres, int n_src, const int32_t *gidx, long long R,
+                         int rows_per_batch, int q_ns, const float *host_W0, const float *host_b0, const void *packed1,
+                         const float *bias1, int c1, int c2, const void *packed2, const float *bias2, int c3, int npass,
+                         int pool_ns, float *pooled, int ld_pooled, gp_stream_t s);
 
 /* ---------------------------------------------------------------------------------------------
  * (2)(3) ScoreNet / EnergyNet trunk.  Raw parameters in the reference's state-dict layout

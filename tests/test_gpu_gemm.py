@@ -134,3 +134,35 @@ def test_first_level_scale_kernels_match_float64_and_each_other(spec, ns):
     assert (a[:, spec[2]:] == -1).all()  # the column slice only
     err = float((a[:, : spec[2]].double() - want).abs().max() / want.abs().max())
     assert err < 1e-5, err
+
+
+@pytest.mark.parametrize("npass,tol", [(3, 1e-4), (1, 3e-2)])
+@pytest.mark.parametrize("spec,ns", [((32, 32, 64), 32), ((16, 16, 32), 16), ((32, 32, 64), 16)])
+def test_first_level_on_the_fused_kernel_matches_the_fp32_kernel(npass, tol, spec, ns):
+    """gp_sa_mlp2_fused_xyz (first layer K = 3 in the operand loader, layers 2 / 3 + max-pool on tcgen05) vs the FP32
+    level-1 kernel gp_sa_small_mlp_hostw on the same ball-query groups, incl. a partial last tile and empty balls"""
+    from genpose2_b200 import pointnet2_utils as pu
+    from genpose2_b200.pointnet2 import SharedMLP
+    B, N, M = 3, 1000, 200 if ns == 32 else 203
+    pts, _ = synthetic.make_point_clouds(B, N, seed=31)
+    xyz = pts.cuda()
+    _, new_xyz = pu.furthest_point_sample_gather(xyz, M)
+    idx = pu.ball_query(0.02, ns, xyz, new_xyz)
+    mlp = SharedMLP([3, *spec]).cuda().eval()
+    g = torch.Generator().manual_seed(9)
+    with torch.no_grad():
+        for p in mlp.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+        for i in range(3):
+            bn = getattr(mlp, f"layer{i}").bn.bn
+            bn.running_mean.copy_(torch.randn(bn.running_mean.shape, generator=g) * 0.1)
+            bn.running_var.copy_(torch.rand(bn.running_var.shape, generator=g) + 0.5)
+    ref = torch.empty((B * M, spec[2]), dtype=torch.float32, device="cuda")
+    pu.sa_small_mlp_hostw(xyz, new_xyz, idx, mlp._folded_layers_host(), ref)
+    t = mlp._tc_hoisted(npass)
+    w0, b0 = mlp._folded_layers_host()[0]
+    got = torch.empty((B * M, spec[2] + 4), dtype=torch.float32, device="cuda")   # a column slice of a wider buffer
+    pu.sa_mlp2_fused_xyz(xyz, new_xyz, idx, w0, b0, t["p1"], t["b1"], t["c1"], t["c2"], t["p2"], t["b2"], t["c3"], npass,
+                         got[:, :spec[2]])
+    err = (got[:, :spec[2]] - ref).abs().max().item() / ref.abs().max().item()
+    assert err < tol, err
