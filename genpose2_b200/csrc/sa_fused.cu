@@ -32,6 +32,10 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
+#ifndef GP_SAF_ROW_MODE
+#define GP_SAF_ROW_MODE 1
+#endif
+
 namespace gp {
 namespace saf {
 
@@ -424,10 +428,13 @@ __global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel
         // next tile are requested early and only consumed at the gather: the index load is the head of the gather's
         // latency chain.
         int gi[RP];
-        int gx = -1;     // first-level mode: the ball-query index of THIS thread's row (row w % 128 of the tile)
+        int gx = -1;     // one-row-per-thread loaders: the ball-query index of THIS thread's row (row w % 128 of the tile)
+        // a single k-atom (c1 <= 64): one thread converts one whole row (its 8 / HALVES 16-byte chunks) -- per-row address
+        // arithmetic once instead of once per 16 lanes
+        const bool row_mode = !a.xyz && k1 == 1 && GP_SAF_ROW_MODE;
         auto request = [&](int t) {
             const long long row0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * BM;
-            if (a.xyz) {
+            if (a.xyz || row_mode) {
                 const long long gr = row0 + (w & 127);
                 gx = -1;
                 if (t < my_tiles && gr < a.R) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(gx) : "l"(a.gidx + gr));
@@ -462,9 +469,55 @@ __global__ void __launch_bounds__((NW + 2) * 32, NW == 4 ? 2 : 1) sa_mlp2_kernel
             __syncwarp();
             if (lane == 0) mbar_arrive(a_ready);
         };
+        auto gather_row = [&](int t) {
+            const long long row0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * BM;
+            const int rl = w & 127, part = w >> 7;
+            const int g32 = (int)(row0 + rl);
+            constexpr int NCH = 8 / HALVES;          // 16-byte bf16 chunks (8 columns) of this thread
+            float4 pv[NCH][2], qv[NCH][2];
+            const bool valid = gx >= 0;
+            const int batch = g32 / a.rows_per_batch;
+            const int qrow = a.q_shift >= 0 ? g32 >> a.q_shift : g32 / a.q_ns;
+            const float *prow = a.P + ((long long)batch * a.n_src + (valid ? gx : 0)) * a.ldp + part * NCH * 8;
+            const float *qrowp = a.Q + (long long)(valid ? qrow : 0) * a.ldq + part * NCH * 8;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const bool ok = valid && part * NCH * 8 + c * 8 + h * 4 < a.c1;
+                    pv[c][h] = ok ? __ldg(reinterpret_cast<const float4 *>(prow + c * 8 + h * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    qv[c][h] = ok ? __ldg(reinterpret_cast<const float4 *>(qrowp + c * 8 + h * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const float x[8] = {fmaxf(pv[c][0].x - qv[c][0].x, 0.f), fmaxf(pv[c][0].y - qv[c][0].y, 0.f),
+                                    fmaxf(pv[c][0].z - qv[c][0].z, 0.f), fmaxf(pv[c][0].w - qv[c][0].w, 0.f),
+                                    fmaxf(pv[c][1].x - qv[c][1].x, 0.f), fmaxf(pv[c][1].y - qv[c][1].y, 0.f),
+                                    fmaxf(pv[c][1].z - qv[c][1].z, 0.f), fmaxf(pv[c][1].w - qv[c][1].w, 0.f)};
+                const int j16 = part * NCH + c;
+                const uint32_t off = rl * 128 + ((j16 ^ (rl & 7)) << 4);
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+                    hi[j] = *reinterpret_cast<const uint32_t *>(&h);
+                    if (NPASS == 3) {
+                        const float2 f = __bfloat1622float2(h);
+                        const __nv_bfloat162 l = __floats2bfloat162_rn(x[2 * j] - f.x, x[2 * j + 1] - f.y);
+                        lo[j] = *reinterpret_cast<const uint32_t *>(&l);
+                    }
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(A_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]));
+                if (NPASS == 3)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(A_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]));
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
+        };
         auto gather = [&](int t, int kc_lo, int kc_hi, bool last) {
-            if (a.xyz) {   // c1 <= 64: one k-atom, one part
-                if (last) gather_xyz(t);
+            if (a.xyz || row_mode) {   // c1 <= 64: one k-atom, one part
+                if (last) { if (a.xyz) gather_xyz(t); else gather_row(t); }
                 return;
             }
             const long long row0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * BM;
