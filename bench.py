@@ -499,7 +499,7 @@ def bench_c4(dev):
     from genpose2_b200 import synthetic
     from genpose2_b200.pipeline import PosePipeline
     B, F, T = 32, 100, 0.25
-    pipe = PosePipeline(device=str(dev), mlp_mode="fp32").load_synthetic_weights((100, 200, 300))
+    pipe = PosePipeline(device=str(dev), mlp_mode="fp32", use_graph=True).load_synthetic_weights((100, 200, 300))
     frames = []
     base, base_c = synthetic.make_point_clouds(B, NUM_POINTS, seed=900)
     gen = torch.Generator().manual_seed(901)
@@ -537,7 +537,8 @@ def bench_c4(dev):
     torch.cuda.synchronize()
     ms = s.elapsed_time(e)
     return {"workload": f"{B} objects/frame x {REPEAT} hypotheses, T0 = {T}, {F} frames, pose feedback, host clouds in / pose out per frame",
-            "ms_per_frame": ms / F, "frames_per_s": F / (ms * 1e-3), "objects_per_s": B * F / (ms * 1e-3), "mlp_mode": "fp32"}
+            "ms_per_frame": ms / F, "frames_per_s": F / (ms * 1e-3), "objects_per_s": B * F / (ms * 1e-3), "mlp_mode": "fp32",
+            "cuda_graph": "one graph replay per frame (PosePipeline(use_graph=True))"}
 
 
 def bench_reference_gpu(dev, c1_feat, c1_center):
