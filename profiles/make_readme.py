@@ -146,8 +146,8 @@ def main():
         md.append(launch_table(c5) + "\n")
     sa = os.path.join(GO, "sa_mlp2.ncu-rep")
     if os.path.exists(sa):
-        md.append("## sa_mlp2 — `ncu --set full` of the fused set-abstraction kernel, the six launches of one encoder\n")
-        md.append("`ncu --set full -k regex:sa_mlp2 -c 6 python profiles/profile_step.py` (levels 2, 3, 4 x 2 scales, fp32 mode)\n")
+        md.append("## sa_mlp2 — `ncu --set full` of the fused set-abstraction kernel, the seven launches of one encoder\n")
+        md.append("`ncu --set full -k regex:sa_mlp2 -c 7 python profiles/profile_step.py` (the wide scale of level 1 in first-level mode, then levels 2, 3, 4 x 2 scales; fp32 mode)\n")
         ms = raw_metrics(sa)
         keys = ["gpu__time_duration.sum", "launch__shared_mem_per_block_dynamic", "dram__bytes_read.sum", "dram__bytes_write.sum",
                 "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
@@ -155,7 +155,7 @@ def main():
         md.append("|---|" + "---|" * len(keys))
         for i, d in enumerate(ms):
             md.append(f"| {i} | " + " | ".join(d.get(k, "") for k in keys) + " |")
-        md.append(f"\n### top source lines — all six launches\n\n```\n{top_lines(sa)}\n```\n")
+        md.append(f"\n### top source lines — all seven launches\n\n```\n{top_lines(sa)}\n```\n")
     sas = os.path.join(GO, "sa_small.ncu-rep")
     if os.path.exists(sas):
         md.append("## sa_small — `ncu --set full` of the level-1 kernel (weights as uniform operands from the launch's parameter space)\n")

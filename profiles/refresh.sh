@@ -8,7 +8,7 @@ R=r02
 mkdir -p $O
 if [ "${1:-core}" = "extra" ]; then
 export GP_NONCOOPERATIVE_LAUNCH=1
-ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:sa_mlp2 -c 6 \
+ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:sa_mlp2 -c 7 \
     -o $O/sa_mlp2 -f python profiles/profile_step.py > $O/ncu_sa.log 2>&1
 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:sa_small -c 2 \
     -o $O/sa_small -f python profiles/profile_step.py > $O/ncu_sa_small.log 2>&1
