@@ -284,6 +284,11 @@ GP_API size_t gp_scorenet_ode_workspace_bytes(int N);
  *               2 = tcgen05 with every operand split into two bf16 (hi*hi + lo*hi + hi*lo, fp32 accumulation in
  *               TMEM: 16 mantissa bits per operand, indistinguishable from fp32 on the reference's fixtures).
  *               Modes 1 and 2 run as 4-CTA clusters per 128-row tile (cooperative launch).
+ * The sampler kernels (this entry, gp_scorenet_ode_dense, gp_scorenet_pc) are persistent grids with a spin grid barrier,
+ * launched cooperatively so that every CTA is resident.  The one process-wide switch this library reads is the
+ * environment variable GP_NONCOOPERATIVE_LAUNCH=1 (read once): it drops the cooperative attribute for profilers that
+ * cannot replay cooperative cluster launches; with it set NOTHING else may share the GPU with such a launch (the grid
+ * is sized for an otherwise idle device).  Leave it unset in production.
  */
 GP_API int gp_scorenet_ode(const void *packed, const float *proj, const double *x0,
                     const float *pts_center, int N, int rows_per_object, double T, double eps,
