@@ -190,10 +190,14 @@ class PosePipeline:
         self._side.wait_event(fork)
         with torch.cuda.stream(self._side):
             energy_feat, _ = self._encode(self.energy_agent, data["pts"], geometries=geometry)
+            # everything of the energy evaluation that does not need the sampled poses, still beside the sampler
+            energy_pre = self.energy_agent.energy_prepare(energy_feat, data["pts_center"], R, 1e-5)
             if not capturing:
-                energy_feat.record_stream(main)
+                for t in (energy_feat,) + tuple(energy_pre):
+                    t.record_stream(main)
         main.wait_stream(self._side)
-        energy = self.energy_agent.get_energy(data={"pts_feat": energy_feat, "pts_center": data["pts_center"]},
+        energy = self.energy_agent.get_energy(data={"pts_feat": energy_feat, "pts_center": data["pts_center"],
+                                                    "_gp_energy_pre": energy_pre},
                                               pose_samples=pred_pose, T=1e-5, mode="test", extract_feature=False)
         agg = aggregate_pose(pred_pose, energy, eval_repeat_num=R, retain_ratio=cfg.retain_ratio,
                              clustering=cfg.clustering, clustering_eps=cfg.clustering_eps,

@@ -122,6 +122,18 @@ class PoseNet(nn.Module):
             pred_len = self.net(data)
         return data["axes"], pred_len
 
+    def energy_prepare(self, pts_feat, pts_center, repeat_num, T):
+        """The pose-independent inputs of get_energy(T=T, extract_feature=False) for `data["_gp_energy_pre"]`:
+        (per-row centres [N,3], per-row times [N], per-object head projection [B,768])."""
+        bs, dev = pts_feat.shape[0], pts_feat.device
+        N = bs * repeat_num
+        with torch.no_grad():
+            t_rows = torch.ones(N, dtype=torch.float32, device=dev) * T
+            center = pts_center.to(dev, torch.float32)
+            center_rows = center.unsqueeze(1).expand(bs, repeat_num, 3).reshape(N, 3).contiguous()
+            proj = self.net.pose_score_net.project(pts_feat)
+        return center_rows, t_rows, proj
+
     def get_energy(self, data, pose_samples, T=None, mode="test", extract_feature=True, geometry=None):
         """posenet_agent.py:608-705 -> energy [bs, repeat_num, 2] f32."""
         if mode != "test":
@@ -135,16 +147,24 @@ class PoseNet(nn.Module):
             self.pts_feature = True
             dev = pts_feat.device
             N = bs * repeat_num
-            if T is not None:
+            pre = data.get("_gp_energy_pre") if T is not None else None
+            if pre is not None:
+                pass
+            elif T is not None:
                 t_rows = torch.ones(N, dtype=torch.float32, device=dev) * T
             else:  # posenet_agent.py:677-687: one random T in [1e-5, 1e-4) per object
                 T_samples = torch.randint(int(1e-5 * 1e5), int(1e-4 * 1e5), (bs, 1)).to(dev).type_as(pts_feat) / 1e5
                 t_rows = T_samples.repeat([1, repeat_num]).view(N).contiguous()
-            center = data["pts_center"].to(dev, torch.float32)
-            center_rows = center.unsqueeze(1).expand(bs, repeat_num, 3).reshape(N, 3).contiguous()
-            poses = _lib.check_cuda(pose_samples.to(dev, torch.float64).reshape(N, -1).contiguous(), "pose_samples")
             net = self.net.pose_score_net
-            proj = net.project(pts_feat)
+            # what does not depend on the poses may come precomputed (PosePipeline prepares it beside the sampler, on the
+            # stream of the energy encoder): the per-row centres and times, the per-object head projection
+            if pre is not None:
+                center_rows, t_rows, proj = pre
+            else:
+                center = data["pts_center"].to(dev, torch.float32)
+                center_rows = center.unsqueeze(1).expand(bs, repeat_num, 3).reshape(N, 3).contiguous()
+                proj = net.project(pts_feat)
+            poses = _lib.check_cuda(pose_samples.to(dev, torch.float64).reshape(N, -1).contiguous(), "pose_samples")
             energy = net.energy_from_poses(proj, poses, center_rows, t_rows, repeat_num)
         return energy.reshape(bs, repeat_num, -1)
 
