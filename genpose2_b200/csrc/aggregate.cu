@@ -235,24 +235,33 @@ struct ScaleSmem {
 };
 
 // out[o][n] = act(b[n] + sum_k W[n][k] in[o][k]); one warp per output n, every lane takes 4 consecutive k per step
-// (16-byte loads, up to 10 of them in flight: the weight row streams from L2 once per CTA).  K % 4 == 0.
+// (16-byte loads: the weight row streams from L2 once per CTA).  A warp works on NB outputs at a time -- all their weight
+// loads are in flight together, so a layer costs NOUT / (8 NB) L2 round trips per warp instead of NOUT / 8 (the kernel is
+// bound by that latency chain: 64 CTAs, one object each at C2).  K % 4 == 0.
 template <int OB, int K, int LD, bool RELU>
 __device__ __forceinline__ void dense_rows(const float *__restrict__ W, const float *__restrict__ bias, int NOUT,
                                            const float *in, float *out, int out_ld) {
     static_assert(K % 4 == 0 && LD % 4 == 0, "16-byte rows");
     constexpr int STEPS = (K / 4 + 31) / 32;
+    constexpr int NB = STEPS * OB <= 2 ? 8 : (STEPS * OB <= 4 ? 4 : (STEPS <= 12 && OB <= 2 ? 2 : 1));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int n = warp; n < NOUT; n += nw) {
-        const float4 *w = reinterpret_cast<const float4 *>(W + (size_t)n * K);
-        float4 wv[STEPS];
+    for (int n0 = warp * NB; n0 < NOUT; n0 += nw * NB) {
+        float4 wv[NB][STEPS];
 #pragma unroll
-        for (int i = 0; i < STEPS; ++i) {
-            const int k4 = lane + 32 * i;
-            wv[i] = k4 < K / 4 ? __ldg(w + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < NB; ++j) {
+            const int n = n0 + j < NOUT ? n0 + j : NOUT - 1;
+            const float4 *w = reinterpret_cast<const float4 *>(W + (size_t)n * K);
+#pragma unroll
+            for (int i = 0; i < STEPS; ++i) {
+                const int k4 = lane + 32 * i;
+                wv[j][i] = k4 < K / 4 ? __ldg(w + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
-        float acc[OB];
+        float acc[NB][OB];
 #pragma unroll
-        for (int o = 0; o < OB; ++o) acc[o] = 0.f;
+        for (int j = 0; j < NB; ++j)
+#pragma unroll
+            for (int o = 0; o < OB; ++o) acc[j][o] = 0.f;
 #pragma unroll
         for (int i = 0; i < STEPS; ++i) {
             const int k4 = lane + 32 * i;
@@ -260,18 +269,25 @@ __device__ __forceinline__ void dense_rows(const float *__restrict__ W, const fl
 #pragma unroll
                 for (int o = 0; o < OB; ++o) {
                     const float4 x = *reinterpret_cast<const float4 *>(in + o * LD + 4 * k4);
-                    acc[o] = fmaf(x.x, wv[i].x, fmaf(x.y, wv[i].y, fmaf(x.z, wv[i].z, fmaf(x.w, wv[i].w, acc[o]))));
+#pragma unroll
+                    for (int j = 0; j < NB; ++j)
+                        acc[j][o] = fmaf(x.x, wv[j][i].x, fmaf(x.y, wv[j][i].y, fmaf(x.z, wv[j][i].z, fmaf(x.w, wv[j][i].w, acc[j][o]))));
                 }
             }
         }
-        const float bv = __ldg(bias + n);
 #pragma unroll
-        for (int o = 0; o < OB; ++o) {
-            float v = acc[o];
+        for (int j = 0; j < NB; ++j) {
+            const int n = n0 + j;
+            if (n >= NOUT) break;
+            const float bv = __ldg(bias + n);
 #pragma unroll
-            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-            v += bv;
-            if (lane == 0) out[o * out_ld + n] = RELU ? fmaxf(v, 0.f) : v;
+            for (int o = 0; o < OB; ++o) {
+                float v = acc[j][o];
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+                v += bv;
+                if (lane == 0) out[o * out_ld + n] = RELU ? fmaxf(v, 0.f) : v;
+            }
         }
     }
 }
