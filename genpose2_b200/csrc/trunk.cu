@@ -131,31 +131,46 @@ project_kernel(const float *__restrict__ P, const float *__restrict__ feat, int 
         reinterpret_cast<float4 *>(&s_f[o][0])[c4] = v;
     }
     __syncthreads();
-    for (int j = warp; j < PJ_OUT; j += 8) {
-        const int n = n0 + j;
-        const float4 *w = reinterpret_cast<const float4 *>(P + TrunkLayout::WHF + (size_t)n * 1024);
-        float acc[PJ_OBJ];
+    // a warp takes two outputs at a time and requests both weight rows (2 x 8 16-byte loads per lane) before the first FMA:
+    // 4 L2 round trips per warp instead of 32 (the launch sits between the encoder and the sampler: latency is what counts)
+    for (int j = 2 * warp; j < PJ_OUT; j += 16) {
+        float4 wv[2][8];
 #pragma unroll
-        for (int o = 0; o < PJ_OBJ; ++o) acc[o] = 0.f;
-#pragma unroll 2
-        for (int c4 = lane; c4 < 256; c4 += 32) {
-            const float4 wv = __ldg(w + c4);
+        for (int u = 0; u < 2; ++u) {
+            const float4 *w = reinterpret_cast<const float4 *>(P + TrunkLayout::WHF + (size_t)(n0 + j + u) * 1024);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) wv[u][i] = __ldg(w + lane + 32 * i);
+        }
+        float acc[2][PJ_OBJ];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int o = 0; o < PJ_OBJ; ++o) acc[u][o] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
 #pragma unroll
             for (int o = 0; o < PJ_OBJ; ++o) {
-                const float4 f = reinterpret_cast<const float4 *>(&s_f[o][0])[c4];
-                acc[o] = fmaf(f.x, wv.x, acc[o]);
-                acc[o] = fmaf(f.y, wv.y, acc[o]);
-                acc[o] = fmaf(f.z, wv.z, acc[o]);
-                acc[o] = fmaf(f.w, wv.w, acc[o]);
+                const float4 f = reinterpret_cast<const float4 *>(&s_f[o][0])[lane + 32 * i];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    acc[u][o] = fmaf(f.x, wv[u][i].x, acc[u][o]);
+                    acc[u][o] = fmaf(f.y, wv[u][i].y, acc[u][o]);
+                    acc[u][o] = fmaf(f.z, wv[u][i].z, acc[u][o]);
+                    acc[u][o] = fmaf(f.w, wv[u][i].w, acc[u][o]);
+                }
             }
         }
-        const float bias = __ldg(P + TrunkLayout::BH + n);
 #pragma unroll
-        for (int o = 0; o < PJ_OBJ; ++o) {
-            float v = acc[o];
+        for (int u = 0; u < 2; ++u) {
+            const int n = n0 + j + u;
+            const float bias = __ldg(P + TrunkLayout::BH + n);
 #pragma unroll
-            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-            if (lane == 0 && b0 + o < B) proj[(size_t)(b0 + o) * 768 + n] = v + bias;
+            for (int o = 0; o < PJ_OBJ; ++o) {
+                float v = acc[u][o];
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+                if (lane == 0 && b0 + o < B) proj[(size_t)(b0 + o) * 768 + n] = v + bias;
+            }
         }
     }
 }
