@@ -233,6 +233,27 @@ class PointnetSAModuleMSG(nn.Module):
             self._mf_key = key
         return self._mf
 
+    def _merged_groupall_first(self, npass, feat_first):
+        """GroupAll level with two-layer scales: the first layers of all scales as ONE GEMM (they read the same rows).
+        None when the scales are not two-layer MLPs of equal input width with hidden widths that keep every slice on a
+        64-column boundary."""
+        if len(self.mlps) < 2 or any(m.n_layers != 2 for m in self.mlps):
+            return None
+        lays = [(m._tc_layers_featfirst(npass) if feat_first else m._tc_layers(npass)) for m in self.mlps]
+        if len({l[0][3] for l in lays}) != 1 or any(l[0][2] % 64 or l[1][3] != l[0][2] for l in lays):
+            return None
+        key = (tuple(m._fold_key for m in self.mlps), npass, feat_first)
+        if getattr(self, "_mg_key", None) != key:
+            ws, bs = [], []
+            for m in self.mlps:
+                w0, b0 = m._folded_layers()[0]
+                ws.append(torch.cat([w0[:, 3:], w0[:, :3]], dim=1) if feat_first else w0)
+                bs.append(b0)
+            w = torch.cat(ws, dim=0).contiguous()
+            self._mg = dict(p0=pu.gemm_pack(w, npass), b0=torch.cat(bs).contiguous(), n=w.shape[0], k=w.shape[1])
+            self._mg_key = key
+        return self._mg
+
     def forward_cl(self, xyz, feat_cl=None, geometry=None, pts_rows=None, return_rows=False):
         """Channels-last fast path: feat_cl (B,N,C) -> new_xyz (B,npoint,3), out (B,npoint,sum Cout).
         FPS+gather, one two-radius ball query, then per scale: fused gather into GEMM rows, the SharedMLP
@@ -338,6 +359,22 @@ class PointnetSAModuleMSG(nn.Module):
             gm = self.gemm_mode
         out = pu.zeros((B, 1, C), xyz.device)   # the pooled GEMMs take the max into a zero-initialised output
         off = 0
+        npass = {"bf16x3": 3, "bf16": 1}[gm]
+        mg = self._merged_groupall_first(npass, feat_first)
+        if mg is not None:
+            # the scales read the same rows: their first layers are ONE GEMM (weights stacked along the output channels,
+            # twice the CTAs of a launch per scale -- at 64 objects a scale alone covers 64 of the 148 SMs); each scale's
+            # pooled second layer then reads its column slice
+            h = pu.gemm_bias_relu(rows, mg["p0"], mg["b0"], mg["n"], mg["k"], npass)
+            col = 0
+            for i, mlp in enumerate(self.mlps):
+                packed, b, N2, K2 = (mlp._tc_layers_featfirst(npass) if feat_first else mlp._tc_layers(npass))[1]
+                pu.gemm_bias_relu(h[:, col:col + K2], packed, b, N2, K2, npass, pool_ns=N,
+                                  pooled_out=out.view(B, -1)[:, off:off + couts[i]])
+                col += K2
+                off += couts[i]
+            res = (None, out, geometry)
+            return res + (None,) if return_rows else res
         for i, mlp in enumerate(self.mlps):
             mlp.forward_rows_pooled(rows, B, N, out.view(B, -1)[:, off:off + couts[i]], gm, feat_first=feat_first, zeroed=True)
             off += couts[i]

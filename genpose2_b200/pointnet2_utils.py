@@ -253,8 +253,8 @@ def gemm_bias_relu(x, packed, bias, N, K, npass, pool_ns=0, pooled_out=None):
     pool_ns == 0 -> returns y [R, round_up(N, 32)] (columns >= N are zero);
     pool_ns  > 0 -> max over each pool_ns consecutive rows into `pooled_out` (zero-initialised,
     [R / pool_ns, >= N] row-major, may be a column slice) and returns it."""
-    _lib.check_cuda(x, "x", torch.float32)
-    R, ldx = x.shape
+    _lib.check_cuda(x, "x", torch.float32, rows=True)    # may be a column slice of a wider row-major matrix
+    R, ldx = x.shape[0], int(x.stride(0))
     if pool_ns:
         if pooled_out is None:
             pooled_out = torch.zeros((R // pool_ns, N), dtype=torch.float32, device=x.device)
