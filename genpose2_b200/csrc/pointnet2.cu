@@ -49,9 +49,12 @@ struct FpsOrder {
 template <int NWARPS, int PPT, bool COORDS_IN_REGS, bool CHAIN>
 __global__ void __launch_bounds__(NWARPS * 32)
 fps_kernel(const float *__restrict__ xyz, int N, int m, FpsOrder order, int *__restrict__ idx,
-           float *__restrict__ new_xyz, const int *__restrict__ tie_in, int *__restrict__ tie_out) {
+           float *__restrict__ new_xyz, const int *__restrict__ tie_in, int *__restrict__ tie_out, int sel_smem) {
     constexpr int T = NWARPS * 32;
-    extern __shared__ __align__(16) float s_raw[];  // [3*N] AoS copy of this object's cloud
+    extern __shared__ __align__(16) float s_raw[];  // [3*N] AoS copy of this object's cloud (+ [m] selected indices)
+    // sel_smem: the winners are parked in shared memory (one store per step) and idx / new_xyz are written by all
+    // threads after the loop -- thread 0's three dependent loads + four global stores per step are off the critical path
+    int *s_sel = reinterpret_cast<int *>(s_raw + ((3 * N + 3) & ~3));
     __shared__ uint2 s_part[2][32];
     __shared__ int s_tie;
 
@@ -104,11 +107,15 @@ fps_kernel(const float *__restrict__ xyz, int N, int m, FpsOrder order, int *__r
     unsigned prev_whi = 0u;
     int first_bad = m;
     if (tid == 0) {
-        out[0] = 0;
-        if (out_xyz) {
-            out_xyz[0] = s_raw[0];
-            out_xyz[1] = s_raw[1];
-            out_xyz[2] = s_raw[2];
+        if (sel_smem) {
+            s_sel[0] = 0;
+        } else {
+            out[0] = 0;
+            if (out_xyz) {
+                out_xyz[0] = s_raw[0];
+                out_xyz[1] = s_raw[1];
+                out_xyz[2] = s_raw[2];
+            }
         }
     }
     const int lane = tid & 31, warp = tid >> 5;
@@ -153,13 +160,23 @@ fps_kernel(const float *__restrict__ xyz, int N, int m, FpsOrder order, int *__r
             prev_whi = whi;
         }
         if (tid == 0) {
-            out[j] = old;
-            if (out_xyz) {
-                out_xyz[3 * j + 0] = s_raw[3 * old + 0];
-                out_xyz[3 * j + 1] = s_raw[3 * old + 1];
-                out_xyz[3 * j + 2] = s_raw[3 * old + 2];
+            if (sel_smem) {
+                s_sel[j] = old;
+            } else {
+                out[j] = old;
+                if (out_xyz) {
+                    out_xyz[3 * j + 0] = s_raw[3 * old + 0];
+                    out_xyz[3 * j + 1] = s_raw[3 * old + 1];
+                    out_xyz[3 * j + 2] = s_raw[3 * old + 2];
+                }
             }
         }
+    }
+    if (sel_smem) {
+        __syncthreads();
+        for (int i = tid; i < m; i += T) out[i] = s_sel[i];
+        if (out_xyz)
+            for (int i = tid; i < 3 * m; i += T) out_xyz[i] = s_raw[3 * s_sel[i / 3] + i % 3];
     }
     if (CHAIN && tie_out) {  // the last step is not checked: the prefix is vouched for up to m - 1 samples
         first_bad = __reduce_min_sync(0xffffffffu, first_bad);
@@ -181,9 +198,12 @@ static int launch_fps(const float *xyz, int B, int N, int m, FpsOrder order, int
                       float *new_xyz, bool chain, const int *tie_in, int *tie_out, cudaStream_t st) {
     size_t smem = (size_t)N * 3 * sizeof(float);
     smem = (smem + 15) & ~(size_t)15;
+    // the selected indices go through shared memory when they fit next to the cloud
+    const int sel_smem = smem + (size_t)m * sizeof(int) <= 200 * 1024 ? 1 : 0;
+    if (sel_smem) smem += ((size_t)m * sizeof(int) + 15) & ~(size_t)15;
     auto kern = chain ? fps_kernel<NWARPS, PPT, REGS, true> : fps_kernel<NWARPS, PPT, REGS, false>;
     if (smem > 40 * 1024) GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<B, NWARPS * 32, smem, st>>>(xyz, N, m, order, idx, new_xyz, tie_in, tie_out);
+    kern<<<B, NWARPS * 32, smem, st>>>(xyz, N, m, order, idx, new_xyz, tie_in, tie_out, sel_smem);
     GP_CHECK_LAUNCH("gp_fps");
     return GP_OK;
 }
