@@ -166,3 +166,24 @@ def test_first_level_on_the_fused_kernel_matches_the_fp32_kernel(npass, tol, spe
                          got[:, :spec[2]])
     err = (got[:, :spec[2]] - ref).abs().max().item() / ref.abs().max().item()
     assert err < tol, err
+
+
+def test_centre_term_tail_and_zero_fill():
+    """gp_centre_term_tail = gp_centre_term + the tail rows copied into a 4-column slice of a wider buffer; gp_zero is a
+    stream-ordered zero fill"""
+    from genpose2_b200 import pointnet2_utils as pu
+    g = torch.Generator().manual_seed(12)
+    rows, c1, ldq = 300, 64, 128
+    xyz = torch.randn(rows, 3, generator=g).cuda()
+    w0t = torch.randn(3, c1, generator=g).cuda()
+    b0 = torch.randn(c1, generator=g).cuda()
+    tail = torch.randn(rows, 4, generator=g).cuda()
+    buf = torch.full((rows, 260), 7.0, device="cuda")
+    q_ref = pu.centre_term(xyz, w0t, b0, ldq)
+    q = pu.centre_term(xyz, w0t, b0, ldq, tail=tail, tail_dst=buf[:, 256:260])
+    assert torch.equal(q, q_ref)
+    assert torch.equal(buf[:, 256:], tail) and bool((buf[:, :256] == 7.0).all())
+    want = xyz.double() @ w0t.double() - b0.double()
+    assert (q[:, :c1].double() - want).abs().max().item() < 1e-5 and bool((q[:, c1:] == 0).all())
+    z = pu.zeros((5, 1, 1024), xyz.device)
+    assert z.shape == (5, 1, 1024) and bool((z == 0).all())
