@@ -255,6 +255,7 @@ struct TcEval {
             stats[11] = (double)c.cyc_epi1; stats[12] = (double)c.cyc_waith; stats[13] = (double)c.cyc_epi2;
             for (int i = 0; i < 5; ++i) stats[20 + i] = (double)c.cyc_x[i];
         }
+        if (blockIdx.x == 0 && threadIdx.x == 32) stats[15] = (double)c.cyc_wfull;   // the MMA issuer's own counter
     }
 };
 // One CTA per 128-row tile, no cluster: the throughput shape for batches of more tiles than the GPU has clusters

@@ -104,6 +104,7 @@ struct State {
     // cycle counters of one epilogue thread (phase breakdown of an evaluation, reported through `stats`)
     long long cyc_l1 = 0, cyc_wait1 = 0, cyc_epi1 = 0, cyc_waith = 0, cyc_epi2 = 0, cyc_fwd = 0;
     long long cyc_x[5] = {0, 0, 0, 0, 0};  // tail: combine halves, barrier A, scatter, barrier B, final sum
+    long long cyc_wfull = 0;               // MMA issuer: cycles spent waiting for weight chunks (ring `full` barriers)
 };
 
 // global head column (0..767) of this rank's local column i (0..191)
@@ -399,7 +400,9 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
             auto next_chunk = [&]() {
                 const uint32_t g = st.consumed;
                 stage = g % NST;
+                const long long w0 = clock64();
                 mbar_wait(&S.full[stage], (g / NST) & 1);
+                st.cyc_wfull += clock64() - w0;
                 tc_fence_after();
                 b_hi = smem_u32(&S.ring[stage][0]);
                 b_lo = b_hi + (NPASS == 3 ? IMG_BYTES : 0);
@@ -432,8 +435,10 @@ __device__ __noinline__ void forward(const float *__restrict__ P, const float *_
             tc_fence_after();
             for (int kc = 0; kc < 4; ++kc) {
                 const uint32_t g = st.consumed, s0 = g % NST, s1 = (g + 1) % NST;
+                const long long w0 = clock64();
                 mbar_wait(&S.full[s0], (g / NST) & 1);
                 mbar_wait(&S.full[s1], ((g + 1) / NST) & 1);
+                st.cyc_wfull += clock64() - w0;
                 tc_fence_after();
                 const uint32_t b0 = smem_u32(&S.ring[s0][0]), b1 = smem_u32(&S.ring[s1][0]);
                 const uint32_t bl0 = b0 + (NPASS == 3 ? IMG_BYTES : 0), bl1 = b1 + (NPASS == 3 ? IMG_BYTES : 0);

@@ -35,5 +35,6 @@ for mode in ("bf16", "fp32"):
         if shape == "cluster":
             for n, v in zip(["x:combine", "x:barrierA", "x:scatter", "x:barrierB", "x:final"], st[20:25]):
                 print(f"   {n:12s} {v / nf:10.0f} cycles/eval")
+            print(f"   {'mma:wait_w':12s} {st[15] / nf:10.0f} cycles/eval   (MMA issuer waiting for weight chunks of the ring)")
         else:
             print(f"   {'tail':12s} {st[20] / nf:10.0f} cycles/eval")
